@@ -1,0 +1,231 @@
+/*
+ * go1_b200.h — C-ABI of libgo1b200.so: the B200-native replacement for the hot path of
+ * Improbable-AI/walk-these-ways (LeggedRobot.step() + the ppo_cse learner).
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; every device buffer is allocated and owned by the caller
+ *     (torch on the Python side), the library only borrows pointers;
+ *   - every call returns 0 on success, non-zero on failure; the message is in go1_last_error();
+ *   - calls are stream-ordered on the cudaStream_t passed as `void* stream` and never synchronise
+ *     the device themselves (except go1_sim_create / *_destroy);
+ *   - no CPU fallback: without a CUDA device every compute entry point fails with an error.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference root).
+ */
+#ifndef GO1_B200_H
+#define GO1_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GO1_NUM_DOF 12
+#define GO1_NUM_COMMANDS 15
+#define GO1_MAX_OBS 128
+#define GO1_MAX_PRIV_OBS 32
+#define GO1_EVENT_STRIDE 6        /* floats per event record */
+
+/* reward term ids: one per CoRLRewards._reward_<name> (go1_gym/envs/rewards/corl_rewards.py:15-201) */
+enum Go1RewardTerm {
+    GO1_REW_TRACKING_LIN_VEL = 0, GO1_REW_TRACKING_ANG_VEL, GO1_REW_LIN_VEL_Z, GO1_REW_ANG_VEL_XY,
+    GO1_REW_ORIENTATION, GO1_REW_TORQUES, GO1_REW_DOF_ACC, GO1_REW_ACTION_RATE, GO1_REW_COLLISION,
+    GO1_REW_DOF_POS_LIMITS, GO1_REW_JUMP, GO1_REW_TRACKING_CONTACTS_SHAPED_FORCE,
+    GO1_REW_TRACKING_CONTACTS_SHAPED_VEL, GO1_REW_DOF_POS, GO1_REW_DOF_VEL, GO1_REW_ACTION_SMOOTHNESS_1,
+    GO1_REW_ACTION_SMOOTHNESS_2, GO1_REW_FEET_SLIP, GO1_REW_FEET_CONTACT_VEL, GO1_REW_FEET_CONTACT_FORCES,
+    GO1_REW_FEET_CLEARANCE_CMD_LINEAR, GO1_REW_FEET_IMPACT_VEL, GO1_REW_ORIENTATION_CONTROL,
+    GO1_REW_RAIBERT_HEURISTIC, GO1_REW_TERMINATION, GO1_NUM_REWARD_TERMS
+};
+
+/* Resolved configuration of the env hot path.  Field-by-field mirror of what LeggedRobot reads from
+ * Cfg (go1_gym/envs/base/legged_robot_config.py) after _parse_cfg (legged_robot.py:1716-1732). */
+typedef struct Go1SimConfig {
+    int32_t num_envs, num_train_envs;
+    float sim_dt;                       /* Cfg.sim.dt (0.005) */
+    int32_t decimation;                 /* Cfg.control.decimation (4) */
+    float clip_actions, clip_obs;       /* Cfg.normalization */
+    int32_t control_type;               /* 0 = actuator_net, 1 = P   (legged_robot.py:928-943) */
+    float action_scale, hip_scale_reduction, kp, kd;
+    int32_t use_lag;                    /* Cfg.domain_rand.randomize_lag_timesteps (lag_timesteps must be 6) */
+    float default_dof_pos[GO1_NUM_DOF];
+    float soft_limit_lo[GO1_NUM_DOF], soft_limit_hi[GO1_NUM_DOF];   /* legged_robot.py:603-607 */
+    float torque_limit;
+    /* gait clock (legged_robot.py:826-905) */
+    int32_t num_commands, observe_gait_commands, pacing_offset;
+    float kappa_gait_probs;
+    /* observations (legged_robot.py:302-376) */
+    int32_t observe_vel, observe_only_ang_vel, observe_only_lin_vel, observe_command, observe_two_prev_actions,
+            observe_timing_parameter, observe_clock_inputs, observe_yaw, observe_contact_states;
+    int32_t num_obs, num_priv_obs, add_noise;
+    float commands_scale[GO1_NUM_COMMANDS];
+    float obs_scale_lin_vel, obs_scale_ang_vel, obs_scale_dof_pos, obs_scale_dof_vel;
+    float noise_scale_vec[GO1_MAX_OBS]; /* legged_robot.py:1053-1120 */
+    /* privileged observations (legged_robot.py:378-491); scale/shift from get_scale_shift */
+    int32_t priv_friction, priv_restitution, priv_base_mass, priv_com_displacement, priv_motor_strength,
+            priv_motor_offset, priv_body_height, priv_body_velocity, priv_gravity, priv_clock_inputs,
+            priv_desired_contact_states;
+    float friction_ss[2], restitution_ss[2], mass_ss[2], com_ss[2], motor_strength_ss[2], motor_offset_ss[2],
+          body_height_ss[2], body_velocity_ss[2], gravity_ss[2];
+    /* rewards (legged_robot.py:263-300, 1385-1429) */
+    float reward_scale[GO1_NUM_REWARD_TERMS];   /* already multiplied by dt; 0 = inactive */
+    int32_t reward_order[GO1_NUM_REWARD_TERMS]; /* active term ids in the reference's iteration order */
+    int32_t num_active_rewards, only_positive_rewards, only_positive_rewards_ji22_style;
+    float sigma_rew_neg, tracking_sigma, tracking_sigma_yaw, gait_force_sigma, gait_vel_sigma,
+          base_height_target, max_contact_force;
+    /* termination (legged_robot.py:138-148) */
+    int32_t use_terminal_body_height, max_episode_length;
+    float terminal_body_height;
+    /* domain randomisation (legged_robot.py:645-665) and command resampling interval (:684-686) */
+    int32_t randomize_motor_strength, randomize_motor_offset, randomize_Kp_factor, randomize_Kd_factor,
+            rand_interval, resampling_interval;
+    float motor_strength_range[2], motor_offset_range[2], Kp_factor_range[2], Kd_factor_range[2];
+    /* reset (legged_robot.py:948-1001) */
+    float base_init_state[13];
+    float x_init_range, y_init_range, yaw_init_range, x_init_offset, y_init_offset;
+    int32_t custom_origins;
+    /* rigid-body solver (our algorithm; PhysX parameters legged_robot_config.py:402-421) */
+    float erp, cfm, max_depen_vel, contact_margin, bounce_threshold;
+    int32_t pgs_iters;
+    float terrain_friction, terrain_restitution;
+    float pen_k[4], pen_c[4], pen_mt, limit_k, limit_c;
+    /* heightfield terrain (NULL/0 = flat): int16 samples [rows][cols] in device memory */
+    const int16_t* hf; int32_t hf_rows, hf_cols; float hf_hscale, hf_vscale, hf_border;
+    uint64_t seed;                      /* Philox key for device-side randomisation */
+} Go1SimConfig;
+
+/* Device buffers borrowed from the caller.  State is SoA: row-major [rows][num_envs] for per-env rows
+ * and [rows][4*num_envs] (index env*4+leg, legs FL,FR,RL,RR) for per-leg rows; row indices are
+ * queried by name with go1_sim_row().  obs/priv_obs are the reference's AoS outputs. */
+typedef struct Go1SimBuffers {
+    float* env_f32;      /* [go1_sim_num_rows(0)][N]  */
+    float* leg_f32;      /* [go1_sim_num_rows(1)][4N] */
+    int32_t* env_i32;    /* [go1_sim_num_rows(2)][N]  */
+    float* obs;          /* [N][num_obs]       LeggedRobot.obs_buf */
+    float* priv_obs;     /* [N][num_priv_obs]  LeggedRobot.privileged_obs_buf */
+    float* rew;          /* [N]                LeggedRobot.rew_buf */
+    uint8_t* reset;      /* [N]                LeggedRobot.reset_buf (bool after check_termination) */
+    uint8_t* time_out;   /* [N]                LeggedRobot.time_out_buf */
+    int32_t* event_count;/* [2]  number of records in `events` (reset envs, interval-resample envs) */
+    float* events;       /* [2][N][GO1_EVENT_STRIDE]: env id + 4 curriculum command_sums + ep_len */
+    float* episode_acc;  /* [GO1_NUM_REWARD_TERMS+2] sum of episode_sums over envs reset this step, + count */
+    const float* noise;  /* optional [N][num_obs] uniform(0,1) draws injected for parity tests, or NULL */
+    const float* reset_rand; /* optional [N][40] uniform(0,1) draws injected for reset/DR parity tests, or NULL */
+} Go1SimBuffers;
+
+typedef struct Go1Sim Go1Sim;
+
+const char* go1_last_error(void);
+int go1_version(void);
+int go1_device_count(void);
+/* sizeof(Go1SimConfig) / sizeof(Go1SimBuffers) as compiled, so FFI bindings can verify their struct mirrors */
+int go1_sizeof_config(void);
+int go1_sizeof_buffers(void);
+
+/* Layout queries: kind 0 = env_f32, 1 = leg_f32, 2 = env_i32. go1_sim_row returns the first row of the
+ * named field or -1. */
+int go1_sim_num_rows(int kind);
+int go1_sim_row(int kind, const char* name);
+
+/* Replaces BaseTask.__init__/create_sim/_init_buffers (base_task.py:16-86, legged_robot.py:1123-1258):
+ * uploads the model/actuator/config table.  actuator_weights: 1313 floats
+ * (W1[32x6] b1[32] W2[32x32] b2[32] W3[32] b3[1]) of resources/actuator_nets/unitree_go1.pt. */
+int go1_sim_create(const Go1SimConfig* cfg, const float* actuator_weights, int device, Go1Sim** out);
+int go1_sim_destroy(Go1Sim* sim);
+int go1_sim_bind(Go1Sim* sim, const Go1SimBuffers* bufs);
+/* Re-upload a changed config (e.g. reward scales after Cfg mutation) */
+int go1_sim_update_config(Go1Sim* sim, const Go1SimConfig* cfg, void* stream);
+
+/* Replaces LeggedRobot.step + post_physics_step for all envs that do not reset this step
+ * (legged_robot.py:60-136): clip actions, 4x{_compute_torques -> rigid-body substep}, base-frame
+ * quantities, _step_contact_targets, check_termination, compute_reward, compute_observations, history
+ * of last_* buffers; envs that terminate are recorded in `events[0]`, envs due for the periodic
+ * command resample next step in `events[1]`.  gravity = Cfg gravity + randomised offset
+ * (legged_robot.py:546-561); gravity_vec = normalised gravity used for projected_gravity.
+ * mode: 0 = full step; 1 = torques only (test hook for _compute_torques: one substep of control,
+ * no dynamics); 2 = post-physics only (test hook: physics outputs already in the buffers). */
+int go1_sim_step(Go1Sim* sim, const float* actions /*[N][12]*/, const float gravity[3],
+                 const float gravity_vec[3], int64_t common_step, int mode, void* stream);
+
+/* Replaces LeggedRobot.reset_idx (+ _resample_commands' device part, _randomize_dof_props,
+ * _reset_dofs, _reset_root_states; legged_robot.py:150-239, 645-665, 948-1001) for `k` envs, followed —
+ * when post_step != 0 — by compute_observations and the last_* rolls for those envs
+ * (legged_robot.py:124-131).  new_commands: [k][15] sampled by the host curriculum. */
+int go1_sim_reset_idx(Go1Sim* sim, const int32_t* env_ids, int k, const float* new_commands,
+                      const float* actions, int post_step, int64_t common_step, void* stream);
+
+/* Replaces the device part of LeggedRobot._resample_commands for the periodic resample
+ * (legged_robot.py:684-686, 756-824): write new commands, zero command_sums. */
+int go1_sim_set_commands(Go1Sim* sim, const int32_t* env_ids, int k, const float* new_commands, void* stream);
+
+/* Replaces HistoryWrapper.step's torch.cat roll (go1_gym/envs/wrappers/history_wrapper.py:23):
+ * hist_out[n] = concat(hist_in[n][num_obs:], obs[n]). */
+int go1_history_roll(const float* hist_in, const float* obs, float* hist_out, int n, int num_obs,
+                     int history_len, void* stream);
+
+/* ------------------------------------------------------------------ ppo_cse learner ---------- */
+
+/* Replaces RolloutStorage.compute_returns (go1_gym_learn/ppo_cse/rollout_storage.py:74-88): GAE scan
+ * over T steps for n envs ([T][n] row-major), then advantage normalisation (global mean / unbiased std).
+ * dones: uint8.  stats (device, 2 doubles) receives sum and sum of squares of the raw advantages so that
+ * multi-GPU callers can all-reduce before go1_ppo_normalize_advantages. */
+int go1_ppo_gae(const float* rewards, const uint8_t* dones, const float* values, const float* last_values,
+                float* returns, float* advantages, double* stats, int T, int n, float gamma, float lam,
+                void* stream);
+int go1_ppo_normalize_advantages(float* advantages, const double* stats, int64_t global_count, int64_t local_count,
+                                 void* stream);
+
+/* GEMM primitive behind every nn.Linear of ActorCritic (actor_critic.py:38-77; replaces the cuBLAS sgemm
+ * calls issued by F.linear and its autograd): C[M][N] (+)= opA(A) opB(B) (+ bias[n]), optional ELU.
+ *   transA == 0: A is row-major [M][K] (row stride lda);  transA == 1: A is [K][M]
+ *   transB == 0: B is row-major [K][N] (row stride ldb);  transB == 1: B is [N][K] (torch Linear weight)
+ * forward  y  = act(x W^T + b):  go1_gemm(0,1, M,N,K, x,ldx, W,ldw, y,ldy, b, act, 0, impl)
+ * dgrad    dx = dz W          :  go1_gemm(0,0, M,K,N, dz,lddz, W,ldw, dx,lddx, NULL,0, acc, impl)
+ * wgrad    dW = dz^T x        :  go1_gemm(1,0, N,K,M, dz,lddz, x,ldx, dW,lddw, NULL,0, acc, impl)
+ * Row strides let a layer read/write column slices of wider buffers, so cat(obs_history, latent)
+ * (actor_critic.py:115) is never materialised.  accumulate: add into C instead of overwriting
+ * (bias/act are applied after the accumulation).  act: 0 none, 1 ELU(alpha=1).
+ * impl: 0 = fp32 CUDA cores (exact-fp32 path), 1 = tcgen05 TF32 tensor cores with fp32 accumulation. */
+int go1_gemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+             float* C, int ldc, const float* bias, int act, int accumulate, int impl, void* stream);
+/* dz = dy * ELU'(z) computed from the saved layer output y (autograd of nn.ELU). dz may alias dy. */
+int go1_elu_backward(const float* y, int ldy, const float* dy, int lddy, float* dz, int lddz, int M, int N, void* stream);
+/* out[n] (+)= sum_m x[m][n]: bias gradient of nn.Linear. */
+int go1_colsum(const float* x, int ldx, float* out, int M, int N, int accumulate, void* stream);
+
+/* Replaces the Normal(mean,std) sample + log-prob of ActorCritic.act / get_actions_log_prob
+ * (actor_critic.py:113-126): actions = mean + std*eps (eps ~ N(0,1) from Philox(seed,counter) or the
+ * injected `eps` for parity tests), logp = sum_j log N(a_j). */
+int go1_ppo_sample_actions(const float* mean, int ldm, const float* std, const float* eps, uint64_t seed,
+                           uint64_t counter, float* actions, float* logp, int n, int num_actions, void* stream);
+
+/* Replaces the loss block of PPO.update (ppo.py:113-152): from the minibatch forward outputs computes the
+ * clipped surrogate, clipped value loss, entropy bonus, their gradients w.r.t. mean / value / std, and the
+ * KL(old||new) mean used by the adaptive LR schedule.  scalars (device, 8 floats): surrogate_loss,
+ * value_loss, entropy_mean, kl_mean, ... ; inv_count = 1/global minibatch size. */
+int go1_ppo_loss(const float* mean, int ldm, const float* std, const float* value, const float* actions,
+                 const float* old_logp, const float* old_mean, const float* old_std, const float* advantages,
+                 const float* returns, const float* old_values, float* dmean, int lddm, float* dvalue,
+                 float* dstd, float* scalars, int n, int num_actions, float clip_param,
+                 float value_loss_coef, float entropy_coef, int use_clipped_value_loss, float inv_count,
+                 void* stream);
+
+/* Replaces F.mse_loss(adaptation_pred[:num_train], target[:num_train]) fwd+bwd and the test-split loss
+ * (ppo.py:168-186). scalars: [0] train loss, [1] test loss. */
+int go1_ppo_mse(const float* pred, int ldp, const float* target, int ldt, float* dpred, int lddp, float* scalars,
+                int n, int num_train, int dim, void* stream);
+
+/* Replaces nn.utils.clip_grad_norm_ + Adam.step over one flat parameter/gradient buffer
+ * (ppo.py:155-158, 187-189).  grad_sq (device double) = sum of squared gradients (computed by
+ * go1_ppo_grad_sqnorm, all-reducible).  max_grad_norm <= 0 disables clipping. */
+int go1_ppo_grad_sqnorm(const float* grad, int64_t count, double* grad_sq, void* stream);
+int go1_ppo_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count,
+                      const double* grad_sq, float max_grad_norm, float lr, float beta1, float beta2, float eps,
+                      int step, void* stream);
+
+/* Replaces the fancy-index gathers of RolloutStorage.mini_batch_generator (rollout_storage.py:98-137):
+ * dst[i][0:width] = src[idx[i]][0:width]; ldd = row stride of dst in floats (>= width). */
+int go1_gather_rows(const float* src, const int64_t* idx, float* dst, int64_t rows, int width, int ldd, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Generates the golden vectors under tests/golden/ by running the REFERENCE's own Python
+(/root/reference, imported through tests/_stubs) on seeded inputs.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+Outputs (committed):
+  cfg_trees.json     Cfg defaults / after config_go1 / after scripts/train.py's overrides (key order kept)
+  env_logic.npz      inputs + outputs of LeggedRobot._compute_torques (x2), _step_contact_targets,
+                     check_termination, compute_reward, compute_observations on a mock env (N=64)
+  kats.npz           known-answer tests of SURVEY.md §8c: actuator net, gait clock, curriculum, policy MLPs
+  ppo.npz            one full ppo_cse act->process_env_step->compute_returns->update cycle (BASELINE config 1)
+"""
+import io
+import json
+import os
+import pickle
+import re
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, os.path.join(ROOT, "tests", "_stubs"))
+sys.path.insert(1, REF)
+np.int = int            # the reference pins numpy 1.23 (legged_robot.py:1362)
+import torch  # noqa: E402
+
+torch.set_num_threads(1)
+
+
+def clean(d):
+    return {k: v for k, v in dict(d).items() if not k.startswith("_")}
+
+
+def tree(C):
+    out = {}
+    for s, v in clean(vars(C)).items():
+        if isinstance(v, type):
+            out[s] = {k: (clean(vars(x)) if isinstance(x, type) else x) for k, x in clean(vars(v)).items()}
+    return out
+
+
+def jsonable(o):
+    if isinstance(o, dict):
+        return {k: jsonable(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [jsonable(v) for v in o]
+    if isinstance(o, (np.floating, np.integer)):
+        return o.item()
+    return o
+
+
+def reference_train_cfg():
+    """Cfg after config_go1 + the assignments of scripts/train.py (exec'd from the reference source)."""
+    from go1_gym.envs.base.legged_robot_config import Cfg
+    from go1_gym.envs.go1.go1_config import config_go1
+    trees = {"defaults": jsonable(tree(Cfg))}
+    config_go1(Cfg)
+    trees["go1"] = jsonable(tree(Cfg))
+    src = open(f"{REF}/scripts/train.py").read().splitlines()
+    lines = [l.strip() for l in src if re.match(r"\s*Cfg\.\w+\.\w+\s*=", l)]
+    exec("\n".join(lines), {"Cfg": Cfg})
+    trees["train"] = jsonable(tree(Cfg))
+    return Cfg, trees
+
+
+def make_env_logic(Cfg):
+    from go1_gym.envs.base.legged_robot import LeggedRobot
+    from isaacgym.torch_utils import quat_rotate_inverse
+
+    N = 64
+    g = torch.Generator().manual_seed(1234)
+    R = lambda *s, lo=-1.0, hi=1.0: torch.rand(*s, generator=g) * (hi - lo) + lo
+    dt = 4 * float(np.float32(0.005))
+    env = types.SimpleNamespace()
+    env.cfg = Cfg
+    env.dt = dt
+    env.num_envs = N
+    env.num_dof = env.num_dofs = env.num_actions = env.num_actuated_dof = 12
+    env.device = "cpu"
+    env.num_bodies = 17
+    env.obs_scales = Cfg.obs_scales
+    env.feet_indices = torch.tensor([4, 8, 12, 16])
+    env.penalised_contact_indices = torch.tensor([2, 6, 10, 14, 3, 7, 11, 15])
+    env.termination_contact_indices = torch.tensor([0])
+    names = [f"{l}_{p}_joint" for l in ("FL", "FR", "RL", "RR") for p in ("hip", "thigh", "calf")]
+    env.default_dof_pos = torch.tensor([Cfg.init_state.default_joint_angles[n] for n in names]).unsqueeze(0)
+    lim = torch.tensor([[-0.802851455917, 0.802851455917], [-1.0471975512, 4.18879020479], [-2.69653369433, -0.916297857297]] * 4)
+    m = (lim[:, 0] + lim[:, 1]) / 2
+    r = lim[:, 1] - lim[:, 0]
+    env.dof_pos_limits = torch.stack((m - 0.5 * r * Cfg.rewards.soft_dof_pos_limit, m + 0.5 * r * Cfg.rewards.soft_dof_pos_limit), 1)
+    env.torque_limits = torch.full((12,), 33.5)
+    # ---- state
+    quat = torch.randn(N, 4, generator=g) * torch.tensor([0.15, 0.15, 1.0, 1.0])
+    quat = quat / quat.norm(dim=1, keepdim=True)
+    env.root_states = torch.cat((R(N, 2, lo=-3, hi=3), R(N, 1, lo=0.02, hi=0.45), quat, R(N, 3, lo=-1.5, hi=1.5), R(N, 3, lo=-2, hi=2)), 1)
+    env.base_pos = env.root_states[:, 0:3]
+    env.base_quat = env.root_states[:, 3:7]
+    env.dof_pos = env.default_dof_pos + R(N, 12, lo=-0.9, hi=0.9)
+    env.dof_vel = R(N, 12, lo=-8, hi=8)
+    env.actions = R(N, 12, lo=-3, hi=3)
+    env.last_actions = R(N, 12, lo=-3, hi=3)
+    env.last_actions[:5] = 0.0
+    env.last_actions[5:10, ::2] = 0.0
+    env.last_last_actions = R(N, 12, lo=-3, hi=3)
+    env.last_last_actions[3:8] = 0.0
+    env.last_dof_vel = R(N, 12, lo=-8, hi=8)
+    env.last_joint_pos_target = env.default_dof_pos + R(N, 12, lo=-0.5, hi=0.5)
+    env.last_last_joint_pos_target = env.default_dof_pos + R(N, 12, lo=-0.5, hi=0.5)
+    env.lag_buffer = [R(N, 12, lo=-0.6, hi=0.6) for _ in range(7)]
+    env.joint_pos_err_last = R(N, 12, lo=-0.5, hi=0.5)
+    env.joint_pos_err_last_last = R(N, 12, lo=-0.5, hi=0.5)
+    env.joint_vel_last = R(N, 12, lo=-8, hi=8)
+    env.joint_vel_last_last = R(N, 12, lo=-8, hi=8)
+    env.motor_offsets = R(N, 12, lo=-0.02, hi=0.02)
+    env.motor_strengths = R(N, 1, lo=0.9, hi=1.1).repeat(1, 12)
+    env.Kp_factors = torch.ones(N, 12)
+    env.Kd_factors = torch.ones(N, 12)
+    env.p_gains = torch.full((12,), 20.0)
+    env.d_gains = torch.full((12,), 0.5)
+    env.friction_coeffs = R(N, 1, lo=0.1, hi=3.0).repeat(1, 4)
+    env.restitutions = R(N, 1, lo=0.0, hi=0.4).repeat(1, 4)
+    env.payloads = R(N, lo=-1, hi=3)
+    env.com_displacements = torch.zeros(N, 3)
+    env.gravities = torch.zeros(N, 3)
+    gv = torch.tensor([0.05, -0.03, -9.8])
+    env.gravity_vec = (gv / gv.norm()).repeat(N, 1)
+    cmd_lo = torch.tensor([-1, -0.6, -1, -0.25, 2.0, 0, 0, 0, 0.5, 0.03, -0.4, 0.0, 0.10, 0.35, 0.0])
+    cmd_hi = torch.tensor([1, 0.6, 1, 0.15, 4.0, 1, 1, 1, 0.5, 0.35, 0.4, 0.0, 0.45, 0.45, 0.01])
+    env.commands = torch.rand(N, 15, generator=g) * (cmd_hi - cmd_lo) + cmd_lo
+    env.commands[:, 5:8] = torch.round(2 * env.commands[:, 5:8]) / 2.0 % 1
+    env.commands[::7, 8] = 0.35                      # a few non-default stance durations
+    env.gait_indices = torch.rand(N, generator=g)
+    env.gait_indices[0] = 0.0
+    env.clock_inputs = torch.zeros(N, 4)
+    env.doubletime_clock_inputs = torch.zeros(N, 4)
+    env.halftime_clock_inputs = torch.zeros(N, 4)
+    env.desired_contact_states = torch.zeros(N, 4)
+    env.contact_forces = torch.zeros(N, 17, 3)
+    env.contact_forces[:, [4, 8, 12, 16]] = R(N, 4, 3, lo=-15, hi=15) * (torch.rand(N, 4, 1, generator=g) > 0.4)
+    env.contact_forces[:, [4, 8, 12, 16], 2] = env.contact_forces[:, [4, 8, 12, 16], 2].abs() * 6
+    env.contact_forces[:, [2, 6, 10, 14, 3, 7, 11, 15]] = R(N, 8, 3, lo=-2, hi=2) * (torch.rand(N, 8, 1, generator=g) > 0.8)
+    env.contact_forces[:, 0] = R(N, 3, lo=-3, hi=3) * (torch.rand(N, 1, generator=g) > 0.8)
+    env.foot_positions = torch.cat((R(N, 4, 2, lo=-3.5, hi=3.5), R(N, 4, 1, lo=0.0, hi=0.15)), 2)
+    env.foot_positions[:, :, :2] = env.root_states[:, None, :2] + R(N, 4, 2, lo=-0.35, hi=0.35)
+    env.foot_velocities = R(N, 4, 3, lo=-2, hi=2)
+    env.prev_foot_velocities = R(N, 4, 3, lo=-2, hi=2)
+    env.last_contacts = torch.rand(N, 4, generator=g) > 0.5
+    env.episode_length_buf = torch.randint(0, 1010, (N,), generator=g)
+    env.episode_length_buf[:3] = torch.tensor([1001, 1002, 1000])
+    env.measured_heights = 0
+    env.add_noise = True
+    env.commands_scale = torch.tensor([2.0, 2.0, 0.25, 2.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.15, 0.3, 0.3, 1.0, 1.0, 1.0])
+    env.noise_scale_vec = LeggedRobot._get_noise_scale_vec(env, Cfg)
+    env.torques = torch.zeros(N, 12)
+    env.joint_pos_target = torch.zeros(N, 12)
+    env.rew_buf = torch.zeros(N); env.rew_buf_pos = torch.zeros(N); env.rew_buf_neg = torch.zeros(N)
+    env.sim_params = types.SimpleNamespace(dt=float(np.float32(Cfg.sim.dt)))      # gymapi.SimParams.dt is a C float
+    LeggedRobot._parse_cfg(env, Cfg)                                              # derives max_episode_length etc.
+    assert abs(env.dt - dt) < 1e-12
+    env.reward_scales = clean(vars(Cfg.reward_scales))
+    env.curriculum_thresholds = clean(vars(Cfg.curriculum_thresholds))
+
+    # actuator net evaluation closure as in _init_buffers (legged_robot.py:1238-1253)
+    net = torch.jit.load(f"{REF}/resources/actuator_nets/unitree_go1.pt", map_location="cpu")
+
+    def eval_actuator_network(jp, jpl, jpll, jv, jvl, jvll):
+        xs = torch.cat((jp.unsqueeze(-1), jpl.unsqueeze(-1), jpll.unsqueeze(-1), jv.unsqueeze(-1), jvl.unsqueeze(-1), jvll.unsqueeze(-1)), dim=-1)
+        return net(xs.view(N * 12, 6)).view(N, 12)
+    env.actuator_network = eval_actuator_network
+
+    out = {}
+
+    def snap(prefix, names):
+        for n in names:
+            v = getattr(env, n)
+            if isinstance(v, list):
+                v = torch.stack(v)
+            out[f"{prefix}/{n}"] = v.detach().clone().numpy()
+
+    state_in = ["root_states", "dof_pos", "dof_vel", "actions", "last_actions", "last_last_actions", "last_dof_vel",
+                "last_joint_pos_target", "last_last_joint_pos_target", "lag_buffer", "joint_pos_err_last", "joint_pos_err_last_last",
+                "joint_vel_last", "joint_vel_last_last", "motor_offsets", "motor_strengths", "friction_coeffs", "restitutions",
+                "payloads", "gravity_vec", "commands", "gait_indices", "contact_forces", "foot_positions", "foot_velocities",
+                "prev_foot_velocities", "last_contacts", "episode_length_buf", "noise_scale_vec", "dof_pos_limits"]
+    snap("in", state_in)
+    with torch.no_grad():
+        # ---- two control substeps (legged_robot.py:74-80 without the physics)
+        for sub in range(2):
+            tq = LeggedRobot._compute_torques(env, env.actions).view(N, 12)
+            out[f"torques/sub{sub}"] = tq.numpy().copy()
+            out[f"joint_pos_target/sub{sub}"] = env.joint_pos_target.numpy().copy()
+        env.torques = tq
+        snap("after_torques", ["lag_buffer", "joint_pos_err_last", "joint_pos_err_last_last", "joint_vel_last", "joint_vel_last_last"])
+        # ---- post physics quantities (legged_robot.py:106-110)
+        env.base_lin_vel = quat_rotate_inverse(env.base_quat, env.root_states[:, 7:10])
+        env.base_ang_vel = quat_rotate_inverse(env.base_quat, env.root_states[:, 10:13])
+        env.projected_gravity = quat_rotate_inverse(env.base_quat, env.gravity_vec)
+        snap("post", ["base_lin_vel", "base_ang_vel", "projected_gravity"])
+        LeggedRobot._step_contact_targets(env)
+        snap("gait", ["gait_indices", "foot_indices", "clock_inputs", "doubletime_clock_inputs", "halftime_clock_inputs", "desired_contact_states"])
+        LeggedRobot.check_termination(env)
+        out["term/reset_buf"] = env.reset_buf.numpy().copy()
+        out["term/time_out_buf"] = env.time_out_buf.numpy().copy()
+        LeggedRobot._prepare_reward_function(env)
+        scales = dict(env.reward_scales)
+        out["reward/names"] = np.array(env.reward_names)
+        out["reward/scales"] = np.array([scales[n] for n in env.reward_names])
+        for n, fn in zip(env.reward_names, env.reward_functions):
+            if n == "feet_slip":
+                keep = env.last_contacts.clone()
+            out[f"reward_raw/{n}"] = fn().numpy().copy()
+            if n == "feet_slip":
+                env.last_contacts = keep
+        LeggedRobot.compute_reward(env)
+        out["reward/rew_buf"] = env.rew_buf.numpy().copy()
+        out["reward/rew_buf_pos"] = env.rew_buf_pos.numpy().copy()
+        out["reward/rew_buf_neg"] = env.rew_buf_neg.numpy().copy()
+        out["reward/last_contacts"] = env.last_contacts.numpy().copy()
+        for k, v in env.episode_sums.items():
+            out[f"episode_sums/{k}"] = v.numpy().copy()
+        for k, v in env.command_sums.items():
+            out[f"command_sums/{k}"] = v.numpy().copy()
+        # ---- observations with injected noise: torch.rand_like is replaced for the call
+        u = torch.rand(N, 70, generator=g)
+        out["obs/noise_u"] = u.numpy().copy()
+        orig = torch.rand_like
+        torch.rand_like = lambda t, **k: u
+        try:
+            LeggedRobot.compute_observations(env)
+        finally:
+            torch.rand_like = orig
+        out["obs/obs_buf"] = torch.clip(env.obs_buf, -100, 100).numpy().copy()
+        out["obs/privileged_obs_buf"] = torch.clip(env.privileged_obs_buf, -100, 100).numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "env_logic.npz"), **out)
+    print("env_logic.npz:", len(out), "arrays")
+
+
+def make_kats(Cfg):
+    from go1_gym.envs.base.legged_robot import LeggedRobot
+    from go1_gym.envs.base.curriculum import RewardThresholdCurriculum
+    out = {}
+    net = torch.jit.load(f"{REF}/resources/actuator_nets/unitree_go1.pt", map_location="cpu")
+    torch.manual_seed(0)
+    x = torch.randn(3, 6)
+    out["actuator/x"] = x.numpy(); out["actuator/y"] = net(x).detach().numpy(); out["actuator/y0"] = net(torch.zeros(1, 6)).detach().numpy()
+    # hardware log replay: MAE of the net vs measured tau_est
+    class U(pickle.Unpickler):
+        def find_class(self, mod, name):
+            if mod == "torch.storage" and name == "_load_from_bytes":
+                return lambda b: torch.load(io.BytesIO(b), map_location="cpu", weights_only=False)
+            return super().find_class(mod, name)
+    # gait clock KAT: f = 3 Hz, phase .5, 3 steps
+    env = types.SimpleNamespace(cfg=Cfg, dt=0.02)
+    env.commands = torch.zeros(1, 15); env.commands[0, 4] = 3.0; env.commands[0, 5] = 0.5; env.commands[0, 8] = 0.5
+    env.gait_indices = torch.zeros(1)
+    for n in ("clock_inputs", "doubletime_clock_inputs", "halftime_clock_inputs", "desired_contact_states"):
+        setattr(env, n, torch.zeros(1, 4))
+    for _ in range(3):
+        LeggedRobot._step_contact_targets(env)
+    out["gait/gait_indices"] = env.gait_indices.numpy().copy(); out["gait/clock_inputs"] = env.clock_inputs.numpy().copy()
+    out["gait/desired_contact_states"] = env.desired_contact_states.numpy().copy()
+    # curriculum KAT
+    c = RewardThresholdCurriculum(100, x_vel=(-5, 5, 21), y_vel=(-.6, .6, 1), yaw_vel=(-5, 5, 21))
+    c.set_to(np.array([-1, -.6, -1]), np.array([1, .6, 1]))
+    cmds, bins = c.sample(5)
+    out["curriculum/sample_cmds"] = cmds; out["curriculum/sample_bins"] = bins
+    c.update(bins, [torch.tensor([1.0, 0.1, 1.0, 1.0, 0.2]), torch.tensor([1.0, 1.0, 1.0, 0.0, 1.0])], [0.5, 0.5],
+             local_range=np.array([0.55, 0.55, 0.55]))
+    out["curriculum/weights_after_update"] = c.weights.copy()
+    cmds2, bins2 = c.sample(7)
+    out["curriculum/sample2_cmds"] = cmds2; out["curriculum/sample2_bins"] = bins2
+    # full 15-D train.py curriculum: a few samples/updates
+    lim = Cfg.commands
+    kw = dict(x_vel=(*lim.limit_vel_x, lim.num_bins_vel_x), y_vel=(*lim.limit_vel_y, lim.num_bins_vel_y), yaw_vel=(*lim.limit_vel_yaw, lim.num_bins_vel_yaw),
+              body_height=(*lim.limit_body_height, lim.num_bins_body_height), gait_frequency=(*lim.limit_gait_frequency, lim.num_bins_gait_frequency),
+              gait_phase=(*lim.limit_gait_phase, lim.num_bins_gait_phase), gait_offset=(*lim.limit_gait_offset, lim.num_bins_gait_offset),
+              gait_bounds=(*lim.limit_gait_bound, lim.num_bins_gait_bound), gait_duration=(*lim.limit_gait_duration, lim.num_bins_gait_duration),
+              footswing_height=(*lim.limit_footswing_height, lim.num_bins_footswing_height), body_pitch=(*lim.limit_body_pitch, lim.num_bins_body_pitch),
+              body_roll=(*lim.limit_body_roll, lim.num_bins_body_roll), stance_width=(*lim.limit_stance_width, lim.num_bins_stance_width),
+              stance_length=(*lim.limit_stance_length, lim.num_bins_stance_length), aux_reward_coef=(*lim.limit_aux_reward_coef, lim.num_bins_aux_reward_coef))
+    c15 = RewardThresholdCurriculum(100, **kw)
+    low = np.array([lim.lin_vel_x[0], lim.lin_vel_y[0], lim.ang_vel_yaw[0], lim.body_height_cmd[0], lim.gait_frequency_cmd_range[0], lim.gait_phase_cmd_range[0],
+                    lim.gait_offset_cmd_range[0], lim.gait_bound_cmd_range[0], lim.gait_duration_cmd_range[0], lim.footswing_height_range[0],
+                    lim.body_pitch_range[0], lim.body_roll_range[0], lim.stance_width_range[0], lim.stance_length_range[0], lim.aux_reward_coef_range[0]])
+    high = np.array([lim.lin_vel_x[1], lim.lin_vel_y[1], lim.ang_vel_yaw[1], lim.body_height_cmd[1], lim.gait_frequency_cmd_range[1], lim.gait_phase_cmd_range[1],
+                     lim.gait_offset_cmd_range[1], lim.gait_bound_cmd_range[1], lim.gait_duration_cmd_range[1], lim.footswing_height_range[1],
+                     lim.body_pitch_range[1], lim.body_roll_range[1], lim.stance_width_range[1], lim.stance_length_range[1], lim.aux_reward_coef_range[1]])
+    c15.set_to(low=low, high=high)
+    out["curriculum15/weights0"] = c15.weights.copy()
+    cm, bi = c15.sample(batch_size=6)
+    out["curriculum15/cmds"] = cm; out["curriculum15/bins"] = bi
+    lr = np.array([0.55, 0.55, 0.55, 0.55, 0.35, 0.25, 0.25, 0.25, 0.25, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0])
+    c15.update(bi, [torch.tensor([1., 0, 1, 1, 0, 1]), torch.tensor([1., 1, 1, 1, 1, 0]), torch.tensor([1., 1, 1, 1, 1, 1]), torch.tensor([1., 1, 0, 1, 1, 1])],
+               [0.5, 0.5, 0.5, 0.5], local_range=lr)
+    out["curriculum15/weights1"] = c15.weights.copy()
+    cm, bi = c15.sample(batch_size=9)
+    out["curriculum15/cmds2"] = cm; out["curriculum15/bins2"] = bi
+    # pretrained policy KAT
+    run = f"{REF}/runs/gait-conditioned-agility/pretrain-v0/train/025417.456545/checkpoints"
+    body = torch.jit.load(f"{run}/body_latest.jit", map_location="cpu")
+    adapt = torch.jit.load(f"{run}/adaptation_module_latest.jit", map_location="cpu")
+    h = torch.zeros(1, 2100)
+    lat = adapt(h)
+    out["policy/latent0"] = lat.detach().numpy(); out["policy/action0"] = body(torch.cat((h, lat), -1)).detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "kats.npz"), **out)
+    print("kats.npz:", len(out), "arrays")
+
+
+def make_ppo():
+    """BASELINE.json config 1: ppo_cse GAE + ActorCritic + Adam update on a synthetic rollout (num_envs=4, T=24)."""
+    from go1_gym_learn.ppo_cse.actor_critic import ActorCritic
+    from go1_gym_learn.ppo_cse.ppo import PPO, PPO_Args
+    N, T, NOBS, NH, NP, NA = 4, 24, 70, 2100, 2, 12
+    torch.manual_seed(0)
+    ac = ActorCritic(NOBS, NP, NH, NA)
+    # deterministic, platform-independent initial weights (numpy PCG64), so the 12 MB need not be stored:
+    # tests re-create them with the same helper (tests/ppo_golden_util.py)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from ppo_golden_util import seeded_weights, sample_tensor
+    with torch.no_grad():
+        for k, v in seeded_weights({k: tuple(v.shape) for k, v in ac.state_dict().items()}).items():
+            ac.state_dict()[k].copy_(torch.from_numpy(v))
+    out = {}
+    alg = PPO(ac, device="cpu")
+    alg.init_storage(N, T, [NOBS], [NP], [NH], [NA])
+    g = torch.Generator().manual_seed(7)
+    obs = torch.randn(N, NOBS, generator=g); hist = torch.randn(N, NH, generator=g) * 0.3; priv = torch.randn(N, NP, generator=g)
+    eps_all, rew_all, done_all = [], [], []
+    hist_all, priv_all, obs_all = [], [], []
+    import torch.distributions.normal as tn
+    for t in range(T):
+        hist_all.append(hist.numpy().copy()); priv_all.append(priv.numpy().copy()); obs_all.append(obs.numpy().copy())
+        eps = torch.randn(N, NA, generator=g)
+        eps_all.append(eps.numpy().copy())
+        orig = tn.Normal.sample
+        tn.Normal.sample = lambda self, sample_shape=torch.Size(): (self.mean + self.stddev * eps).detach()
+        try:
+            with torch.inference_mode():
+                alg.act(obs, priv, hist)
+        finally:
+            tn.Normal.sample = orig
+        rew = torch.randn(N, generator=g); done = (torch.rand(N, generator=g) < 0.1)
+        rew_all.append(rew.numpy().copy()); done_all.append(done.numpy().copy())
+        infos = {"env_bins": torch.zeros(N), "time_outs": torch.zeros(N, dtype=torch.bool)}
+        with torch.inference_mode():
+            alg.process_env_step(rew, done, infos)
+        obs = torch.randn(N, NOBS, generator=g); hist = torch.randn(N, NH, generator=g) * 0.3; priv = torch.randn(N, NP, generator=g)
+    out["last/hist"] = hist.numpy().copy(); out["last/priv"] = priv.numpy().copy()
+    with torch.inference_mode():
+        alg.compute_returns(hist, priv)
+    st = alg.storage
+    for n in ("actions", "values", "actions_log_prob", "mu", "sigma", "returns", "advantages", "rewards"):
+        out[f"storage/{n}"] = getattr(st, n).detach().numpy().copy()
+    out["storage/dones"] = st.dones.numpy().copy()
+    out["in/eps"] = np.stack(eps_all); out["in/rew"] = np.stack(rew_all); out["in/done"] = np.stack(done_all)
+    out["in/hist"] = np.stack(hist_all); out["in/priv"] = np.stack(priv_all); out["in/obs"] = np.stack(obs_all)
+    # fix the minibatch permutation so it can be injected on the other side
+    perm = torch.randperm(N * T, generator=g)
+    out["in/perm"] = perm.numpy().copy()
+    orig_rp = torch.randperm
+    torch.randperm = lambda n, **k: perm
+    try:
+        losses = alg.update()
+    finally:
+        torch.randperm = orig_rp
+    out["update/losses"] = np.array(losses, dtype=np.float64)
+    out["update/learning_rate"] = np.array(alg.learning_rate)
+    for k, v in ac.state_dict().items():
+        out[f"final/{k}"] = sample_tensor(v.detach().numpy())     # strided samples + sum + sum of squares
+    np.savez_compressed(os.path.join(HERE, "ppo.npz"), **out)
+    print("ppo.npz:", len(out), "arrays; losses", losses[:3], "lr", alg.learning_rate)
+
+
+if __name__ == "__main__":
+    Cfg, trees = reference_train_cfg()
+    with open(os.path.join(HERE, "cfg_trees.json"), "w") as f:
+        json.dump(trees, f, indent=0, sort_keys=False)
+    make_env_logic(Cfg)
+    make_kats(Cfg)
+    make_ppo()

@@ -1,0 +1,534 @@
+// ppo_kernels.cu — learner-side kernels of go1_gym_learn/ppo_cse for sm_100a:
+//   GAE warp-scan (rollout_storage.py:74-88), fp32 CUDA-core GEMM with fused bias/ELU epilogue (the
+//   exact-fp32 path next to the tcgen05 TF32 path in gemm_tf32.cu), ELU backward, column sums, Normal
+//   sampling/log-prob (actor_critic.py:113-126), PPO loss + gradients (ppo.py:113-152), MSE
+//   (ppo.py:168-186), global grad-norm + clip + Adam (ppo.py:155-158), row gather
+//   (rollout_storage.py:98-137).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/go1_b200.h"
+#include "sim_math.cuh"
+
+extern int go1_set_error(const char* m);
+static int cuda_rc(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return 0;
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    go1_set_error(buf);
+    return (int)e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GAE: A_t = delta_t + c_t A_{t+1} is a scan over affine maps x -> b + a x.  One warp per env, lanes = time
+// steps (reversed), composed with a 5-step Kogge-Stone shuffle scan; tiles of 32 envs are staged through
+// shared memory so global loads/stores stay coalesced along the env axis.  T <= 32 per pass; longer
+// rollouts chain passes through the carry.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) gae_kernel(const float* __restrict__ rew, const uint8_t* __restrict__ done,
+                                                   const float* __restrict__ val, const float* __restrict__ last_val,
+                                                   float* __restrict__ ret, float* __restrict__ adv, double* __restrict__ stats,
+                                                   int T, int n, float gamma, float lam) {
+    __shared__ float s_a[32][33], s_b[32][33], s_v[32][33];
+    __shared__ double s_red[2][32];
+    const int lane = threadIdx.x, w = threadIdx.y;        // block = (32, 32)
+    const int env0 = blockIdx.x * 32;
+    double lsum = 0.0, lsq = 0.0;
+    float carry = 0.f;                                     // A_{t+1} entering the current chunk (per env = per warp)
+    for (int t_hi = T; t_hi > 0; t_hi -= 32) {
+        const int t_lo = max(t_hi - 32, 0), len = t_hi - t_lo;
+        // load: thread (lane = env offset, w = time offset) -> coalesced over envs
+        {
+            const int t = t_lo + w, e = env0 + lane;
+            float a = 0.f, b = 0.f, v = 0.f;
+            if (w < len && e < n) {
+                const size_t i = (size_t)t * n + e;
+                v = val[i];
+                const float nv = (t == T - 1) ? last_val[e] : val[i + n];
+                const float nt = 1.0f - (float)done[i];
+                b = rew[i] + nt * gamma * nv - v;          // delta_t
+                a = nt * gamma * lam;                      // c_t
+            }
+            s_a[w][lane] = a; s_b[w][lane] = b; s_v[w][lane] = v;
+        }
+        __syncthreads();
+        // scan: warp w = env offset, lane j = reversed time (j = 0 is the last step of the chunk)
+        {
+            const int tt = len - 1 - lane;
+            float a = (lane < len) ? s_a[tt][w] : 1.f, b = (lane < len) ? s_b[tt][w] : 0.f;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const float ap = __shfl_up_sync(0xffffffffu, a, d), bp = __shfl_up_sync(0xffffffffu, b, d);
+                if (lane >= d) { b = b + a * bp; a = a * ap; }
+            }
+            const float A = b + a * carry;                 // advantage at time t_lo + tt
+            if (lane < len) s_b[tt][w] = A;
+            carry = __shfl_sync(0xffffffffu, A, len - 1);  // A at t_lo feeds the next (earlier) chunk
+        }
+        __syncthreads();
+        {
+            const int t = t_lo + w, e = env0 + lane;
+            if (w < len && e < n) {
+                const size_t i = (size_t)t * n + e;
+                const float A = s_b[w][lane];
+                ret[i] = A + s_v[w][lane];
+                adv[i] = A;                                // == returns - values (rollout_storage.py:87)
+                lsum += (double)A; lsq += (double)A * (double)A;
+            }
+        }
+        __syncthreads();
+    }
+    // block reduce of the statistics
+    for (int d = 16; d > 0; d >>= 1) { lsum += __shfl_xor_sync(0xffffffffu, lsum, d); lsq += __shfl_xor_sync(0xffffffffu, lsq, d); }
+    if (lane == 0) { s_red[0][w] = lsum; s_red[1][w] = lsq; }
+    __syncthreads();
+    if (w == 0) {
+        double a = s_red[0][lane], b = s_red[1][lane];
+        for (int d = 16; d > 0; d >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, d); b += __shfl_xor_sync(0xffffffffu, b, d); }
+        if (lane == 0) { atomicAdd(stats, a); atomicAdd(stats + 1, b); }
+    }
+}
+
+__global__ void normalize_adv_kernel(float* __restrict__ adv, const double* __restrict__ stats, long long global_count, long long local_count) {
+    const double mean = stats[0] / (double)global_count;
+    const double var = (stats[1] - (double)global_count * mean * mean) / (double)(global_count - 1);   // unbiased (torch.std)
+    const float m = (float)mean, inv = 1.0f / ((float)sqrt(fmax(var, 0.0)) + 1e-8f);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < local_count; i += (long long)gridDim.x * blockDim.x)
+        adv[i] = (adv[i] - m) * inv;
+}
+
+extern "C" int go1_ppo_gae(const float* rewards, const uint8_t* dones, const float* values, const float* last_values,
+                           float* returns, float* advantages, double* stats, int T, int n, float gamma, float lam, void* stream) {
+    if (!rewards || !dones || !values || !last_values || !returns || !advantages || !stats || T <= 0 || n <= 0) return go1_set_error("go1_ppo_gae: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(stats, 0, 2 * sizeof(double), st);
+    gae_kernel<<<(n + 31) / 32, dim3(32, 32), 0, st>>>(rewards, dones, values, last_values, returns, advantages, stats, T, n, gamma, lam);
+    return cuda_rc("go1_ppo_gae");
+}
+extern "C" int go1_ppo_normalize_advantages(float* advantages, const double* stats, int64_t global_count, int64_t local_count, void* stream) {
+    if (!advantages || !stats || global_count < 2 || local_count <= 0) return go1_set_error("go1_ppo_normalize_advantages: bad arguments");
+    normalize_adv_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(advantages, stats, global_count, local_count);
+    return cuda_rc("go1_ppo_normalize_advantages");
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 CUDA-core GEMM: C[M][N] (+)= opA(A) opB(B) (+ bias[n]) with optional ELU.
+//   TA == 0: A is [M][K] (lda), TA == 1: A is [K][M];  TB == 0: B is [K][N] (ldb), TB == 1: B is [N][K].
+// 128x128x8 tiles, 256 threads, 8x8 register micro-tiles; split-K over gridDim.z with atomicAdd.
+// ---------------------------------------------------------------------------------------------
+DI float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+
+template <int TA, int TB>
+__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                                    float* __restrict__ Cm, int ldc, const float* __restrict__ bias,
+                                                    int M, int N, int K, int act, int accumulate, int kchunk) {
+    constexpr int BM = 128, BN = 128, BK = 8;
+    __shared__ float As[2][BK][BM + 4], Bs[2][BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
+    const int tx = tid & 15, ty = tid >> 4;                 // 16 x 16 threads, each 8 (m) x 8 (n)
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+
+    auto load_tile = [&](int buf, int k0) {
+        // A tile: BM x BK
+        if (TA == 0) {      // A[m][k]: thread -> (m = tid/2, k half = tid%2 * 4 .. +4)
+            const int m = tid >> 1, kk = (tid & 1) * 4;
+            const int gm = m0 + m;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int gk = k0 + kk + c;
+                As[buf][kk + c][m] = (gm < M && gk < kend) ? A[(size_t)gm * lda + gk] : 0.f;
+            }
+        } else {            // A[k][m]: thread -> (k = tid/32, m = (tid%32)*4 .. +4), coalesced over m
+            const int kk = tid >> 5, m = (tid & 31) * 4;
+            const int gk = k0 + kk;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int gm = m0 + m + c;
+                As[buf][kk][m + c] = (gm < M && gk < kend) ? A[(size_t)gk * lda + gm] : 0.f;
+            }
+        }
+        if (TB == 1) {      // B[n][k]
+            const int n = tid >> 1, kk = (tid & 1) * 4;
+            const int gn = n0 + n;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int gk = k0 + kk + c;
+                Bs[buf][kk + c][n] = (gn < N && gk < kend) ? B[(size_t)gn * ldb + gk] : 0.f;
+            }
+        } else {            // B[k][n]
+            const int kk = tid >> 5, n = (tid & 31) * 4;
+            const int gk = k0 + kk;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int gn = n0 + n + c;
+                Bs[buf][kk][n + c] = (gn < N && gk < kend) ? B[(size_t)gk * ldb + gn] : 0.f;
+            }
+        }
+    };
+
+    int buf = 0;
+    if (kbeg < kend) load_tile(0, kbeg);
+    __syncthreads();
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+        if (k0 + BK < kend) load_tile(buf ^ 1, k0 + BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; kk++) {
+            float a[8], b[8];
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+        buf ^= 1;
+    }
+    const bool split = gridDim.z > 1;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            if (gn >= N) continue;
+            float* c = Cm + (size_t)gm * ldc + gn;
+            float v = acc[i][j];
+            if (split) { atomicAdd(c, v); continue; }      // caller pre-initialised C (zero or accumulate target)
+            if (accumulate) v += *c;
+            if (bias) v += bias[gn];
+            if (act == 1) v = elu1(v);
+            *c = v;
+        }
+    }
+}
+
+__global__ void bias_act_kernel(float* __restrict__ Cm, int ldc, const float* __restrict__ bias, int M, int N, int act) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)M * N) return;
+    const int m = (int)(i / N), n = (int)(i - (size_t)m * N);
+    float v = Cm[(size_t)m * ldc + n];
+    if (bias) v += bias[n];
+    if (act == 1) v = elu1(v);
+    Cm[(size_t)m * ldc + n] = v;
+}
+__global__ void zero_strided_kernel(float* __restrict__ Cm, int ldc, int M, int N) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)M * N) return;
+    const int m = (int)(i / N), n = (int)(i - (size_t)m * N);
+    Cm[(size_t)m * ldc + n] = 0.f;
+}
+
+extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                             float* Cm, int ldc, const float* bias, int act, int accumulate, cudaStream_t st);
+
+extern "C" int go1_gemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                        float* Cm, int ldc, const float* bias, int act, int accumulate, int impl, void* stream) {
+    if (!A || !B || !Cm || M <= 0 || N <= 0 || K <= 0) return go1_set_error("go1_gemm: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (impl == 1) return go1_gemm_tf32(transA, transB, M, N, K, A, lda, B, ldb, Cm, ldc, bias, act, accumulate, st);
+    if (impl != 0) return go1_set_error("go1_gemm: unknown impl");
+    const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
+    int splitk = 1;
+    if (tiles < 148 && K >= 2048) { splitk = min((148 * 2 + tiles - 1) / tiles, (K + 255) / 256); if (splitk < 1) splitk = 1; }
+    int kchunk = ((K + splitk - 1) / splitk + 7) / 8 * 8;
+    splitk = (K + kchunk - 1) / kchunk;
+    dim3 grid((N + 127) / 128, (M + 127) / 128, splitk);
+    if (splitk > 1 && !accumulate) {
+        const size_t tot = (size_t)M * N;
+        zero_strided_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cm, ldc, M, N);
+    }
+#define LAUNCH(TA, TB) sgemm_kernel<TA, TB><<<grid, 256, 0, st>>>(A, lda, B, ldb, Cm, ldc, bias, M, N, K, act, accumulate, kchunk)
+    if (!transA && !transB) LAUNCH(0, 0); else if (!transA && transB) LAUNCH(0, 1); else if (transA && !transB) LAUNCH(1, 0); else LAUNCH(1, 1);
+#undef LAUNCH
+    if (splitk > 1 && (bias || act)) {
+        const size_t tot = (size_t)M * N;
+        bias_act_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cm, ldc, bias, M, N, act);
+    }
+    return cuda_rc("go1_gemm");
+}
+
+// dz = dy * ELU'(y) from the saved output y (alpha = 1: ELU' = 1 for y > 0 else y + 1)
+__global__ void elu_bwd_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ dy, int lddy, float* __restrict__ dz, int lddz, int M, int N) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)M * N) return;
+    const int m = (int)(i / N), n = (int)(i - (size_t)m * N);
+    const float yv = y[(size_t)m * ldy + n];
+    dz[(size_t)m * lddz + n] = dy[(size_t)m * lddy + n] * (yv > 0.f ? 1.0f : yv + 1.0f);
+}
+extern "C" int go1_elu_backward(const float* y, int ldy, const float* dy, int lddy, float* dz, int lddz, int M, int N, void* stream) {
+    if (!y || !dy || !dz || M <= 0 || N <= 0) return go1_set_error("go1_elu_backward: bad arguments");
+    const size_t tot = (size_t)M * N;
+    elu_bwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(y, ldy, dy, lddy, dz, lddz, M, N);
+    return cuda_rc("go1_elu_backward");
+}
+
+// out[n] (+)= sum_m x[m][n]   (bias gradients)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int ldx, float* __restrict__ out, int M, int N, int rows_per_block) {
+    __shared__ float s[8][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + lane;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    float acc = 0.f;
+    if (n < N) for (int m = r0 + w; m < r1; m += 8) acc += x[(size_t)m * ldx + n];
+    s[w][lane] = acc;
+    __syncthreads();
+    if (w == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) t += s[k][lane];
+        atomicAdd(out + n, t);
+    }
+}
+extern "C" int go1_colsum(const float* x, int ldx, float* out, int M, int N, int accumulate, void* stream) {
+    if (!x || !out || M <= 0 || N <= 0) return go1_set_error("go1_colsum: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * N, st);
+    const int rpb = 512;
+    dim3 grid((N + 31) / 32, (M + rpb - 1) / rpb);
+    colsum_kernel<<<grid, 256, 0, st>>>(x, ldx, out, M, N, rpb);
+    return cuda_rc("go1_colsum");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Normal(mean, std): sample + log-prob  (actor_critic.py:113-126)
+// ---------------------------------------------------------------------------------------------
+__global__ void sample_actions_kernel(const float* __restrict__ mean, int ldm, const float* __restrict__ std, const float* __restrict__ eps,
+                                      uint64_t seed, uint64_t counter, float* __restrict__ actions, float* __restrict__ logp, int n, int na) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float lp = 0.f;
+    for (int j = 0; j < na; j++) {
+        float e;
+        if (eps) e = eps[(size_t)i * na + j];
+        else {   // Box-Muller on two Philox uniforms
+            float u1 = philox_uniform(seed, (uint32_t)i, counter, 2u * j), u2 = philox_uniform(seed, (uint32_t)i, counter, 2u * j + 1u);
+            u1 = fmaxf(u1, 5.9604645e-8f);
+            e = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+        }
+        const float mu = mean[(size_t)i * ldm + j], sd = std[j];
+        const float a = mu + sd * e;
+        actions[(size_t)i * na + j] = a;
+        const float d = a - mu;
+        lp += -(d * d) / (2.0f * sd * sd) - logf(sd) - 0.91893853320467274178f;
+    }
+    logp[i] = lp;
+}
+extern "C" int go1_ppo_sample_actions(const float* mean, int ldm, const float* std, const float* eps, uint64_t seed, uint64_t counter,
+                                      float* actions, float* logp, int n, int num_actions, void* stream) {
+    if (!mean || !std || !actions || !logp || n <= 0 || num_actions <= 0) return go1_set_error("go1_ppo_sample_actions: bad arguments");
+    sample_actions_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean, ldm, std, eps, seed, counter, actions, logp, n, num_actions);
+    return cuda_rc("go1_ppo_sample_actions");
+}
+
+// ---------------------------------------------------------------------------------------------
+// PPO loss + gradients (ppo.py:113-152).  scalars[0..3] += inv_count * {surrogate, value loss, entropy, kl} sums.
+// ---------------------------------------------------------------------------------------------
+#define PPO_MAX_ACT 16
+__global__ void __launch_bounds__(256) ppo_loss_kernel(const float* __restrict__ mean, int ldm, const float* __restrict__ std, const float* __restrict__ value,
+        const float* __restrict__ actions, const float* __restrict__ old_logp, const float* __restrict__ old_mean, const float* __restrict__ old_std,
+        const float* __restrict__ adv, const float* __restrict__ returns, const float* __restrict__ old_values,
+        float* __restrict__ dmean, int lddm, float* __restrict__ dvalue, float* __restrict__ dstd, float* __restrict__ scalars,
+        int n, int na, float clip, float vcoef, float ecoef, int clipped_v, float inv_count) {
+    __shared__ float s_red[8][PPO_MAX_ACT + 4];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float dsd[PPO_MAX_ACT];
+#pragma unroll
+    for (int j = 0; j < PPO_MAX_ACT; j++) dsd[j] = 0.f;
+    float surr = 0.f, vloss = 0.f, kl = 0.f;
+    if (i < n) {
+        float lp = 0.f;
+        for (int j = 0; j < na; j++) {
+            const float mu = mean[(size_t)i * ldm + j], sd = std[j], a = actions[(size_t)i * na + j];
+            const float d = a - mu;
+            lp += -(d * d) / (2.0f * sd * sd) - logf(sd) - 0.91893853320467274178f;
+            const float om = old_mean[(size_t)i * na + j], os = old_std[(size_t)i * na + j];
+            kl += logf(sd / os + 1.e-5f) + (os * os + (om - mu) * (om - mu)) / (2.0f * sd * sd) - 0.5f;
+        }
+        const float A = adv[i];
+        const float ratio = expf(lp - old_logp[i]);
+        const float s1 = -A * ratio, s2 = -A * fminf(fmaxf(ratio, 1.0f - clip), 1.0f + clip);
+        surr = fmaxf(s1, s2);
+        const bool inside = ratio >= 1.0f - clip && ratio <= 1.0f + clip;
+        // d max(s1,s2)/d ratio (torch: ties split evenly; inside the clip range both branches carry -A)
+        float gr = (s1 > s2) ? -A : ((s1 == s2) ? (inside ? -A : -0.5f * A) : (inside ? -A : 0.f));
+        const float glp = gr * ratio * inv_count;
+        for (int j = 0; j < na; j++) {
+            const float mu = mean[(size_t)i * ldm + j], sd = std[j], a = actions[(size_t)i * na + j];
+            const float d = a - mu;
+            dmean[(size_t)i * lddm + j] = glp * d / (sd * sd);
+            dsd[j] = glp * (d * d / (sd * sd * sd) - 1.0f / sd);
+        }
+        const float v = value[i], R = returns[i];
+        float gv;
+        if (clipped_v) {
+            const float vt = old_values[i];
+            const float dv = v - vt;
+            const float vc = vt + fminf(fmaxf(dv, -clip), clip);
+            const float l1 = (v - R) * (v - R), l2 = (vc - R) * (vc - R);
+            vloss = fmaxf(l1, l2);
+            const float g1 = 2.0f * (v - R), g2 = (dv >= -clip && dv <= clip) ? 2.0f * (vc - R) : 0.f;
+            gv = (l1 > l2) ? g1 : ((l1 == l2) ? 0.5f * (g1 + g2) : g2);
+        } else { vloss = (R - v) * (R - v); gv = 2.0f * (v - R); }
+        dvalue[i] = vcoef * gv * inv_count;
+    }
+    // reductions: 12 dstd partials + 3 scalars
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float red[PPO_MAX_ACT + 3];
+#pragma unroll
+    for (int j = 0; j < PPO_MAX_ACT; j++) red[j] = dsd[j];
+    red[PPO_MAX_ACT] = surr; red[PPO_MAX_ACT + 1] = vloss; red[PPO_MAX_ACT + 2] = kl;
+#pragma unroll
+    for (int j = 0; j < PPO_MAX_ACT + 3; j++) {
+        float v = red[j];
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if (lane == 0) s_red[w][j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < PPO_MAX_ACT + 3) {
+        float t = 0.f;
+        for (int k = 0; k < 8; k++) t += s_red[k][threadIdx.x];
+        const int j = threadIdx.x;
+        if (j < PPO_MAX_ACT) { if (j < na) atomicAdd(dstd + j, t); }
+        else atomicAdd(scalars + (j == PPO_MAX_ACT ? 0 : (j == PPO_MAX_ACT + 1 ? 1 : 3)), t * inv_count);
+    }
+}
+__global__ void ppo_entropy_kernel(const float* __restrict__ std, float* __restrict__ dstd, float* __restrict__ scalars, int na, float ecoef, float local_frac) {
+    // entropy of Normal(mean, std) summed over actions is the same for every sample: sum_j 0.5 + 0.5 log(2 pi) + log std_j
+    const int j = threadIdx.x;
+    float h = 0.f;
+    if (j < na) { h = 1.4189385332046727f + logf(std[j]); atomicAdd(dstd + j, -ecoef * local_frac / std[j]); }
+    for (int d = 16; d > 0; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
+    if (j == 0) atomicAdd(scalars + 2, h * local_frac);
+}
+extern "C" int go1_ppo_loss(const float* mean, int ldm, const float* std, const float* value, const float* actions,
+                            const float* old_logp, const float* old_mean, const float* old_std, const float* advantages,
+                            const float* returns, const float* old_values, float* dmean, int lddm, float* dvalue,
+                            float* dstd, float* scalars, int n, int num_actions, float clip_param,
+                            float value_loss_coef, float entropy_coef, int use_clipped_value_loss, float inv_count, void* stream) {
+    if (!mean || !std || !value || !actions || !old_logp || !old_mean || !old_std || !advantages || !returns || !old_values || !dmean || !dvalue || !dstd || !scalars)
+        return go1_set_error("go1_ppo_loss: null argument");
+    if (n <= 0 || num_actions <= 0 || num_actions > PPO_MAX_ACT) return go1_set_error("go1_ppo_loss: bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(dstd, 0, sizeof(float) * num_actions, st);
+    cudaMemsetAsync(scalars, 0, sizeof(float) * 8, st);
+    ppo_loss_kernel<<<(n + 255) / 256, 256, 0, st>>>(mean, ldm, std, value, actions, old_logp, old_mean, old_std, advantages, returns, old_values,
+                                                    dmean, lddm, dvalue, dstd, scalars, n, num_actions, clip_param, value_loss_coef, entropy_coef,
+                                                    use_clipped_value_loss, inv_count);
+    ppo_entropy_kernel<<<1, 32, 0, st>>>(std, dstd, scalars, num_actions, entropy_coef, (float)n * inv_count);
+    return cuda_rc("go1_ppo_loss");
+}
+
+// MSE (ppo.py:168-186): train split [0, num_train) gets loss + gradient, the rest only the test loss
+__global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ pred, int ldp, const float* __restrict__ tgt, int ldt, float* __restrict__ dpred, int lddp,
+                                                  float* __restrict__ scalars, int n, int num_train, int dim) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float ltr = 0.f, lte = 0.f;
+    if (i < n) {
+        const bool train = i < num_train;
+        const float inv_tr = 1.0f / ((float)num_train * dim);
+        for (int j = 0; j < dim; j++) {
+            const float d = pred[(size_t)i * ldp + j] - tgt[(size_t)i * ldt + j];
+            if (train) { ltr += d * d; dpred[(size_t)i * lddp + j] = 2.0f * d * inv_tr; }
+            else { lte += d * d; dpred[(size_t)i * lddp + j] = 0.f; }
+        }
+    }
+    __shared__ float s[2][8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int d = 16; d > 0; d >>= 1) { ltr += __shfl_xor_sync(0xffffffffu, ltr, d); lte += __shfl_xor_sync(0xffffffffu, lte, d); }
+    if (lane == 0) { s[0][w] = ltr; s[1][w] = lte; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        float t = 0.f;
+        for (int k = 0; k < 8; k++) t += s[threadIdx.x][k];
+        const float cnt = threadIdx.x == 0 ? (float)num_train * dim : (float)(n - num_train) * dim;
+        if (cnt > 0.f) atomicAdd(scalars + threadIdx.x, t / cnt);
+    }
+}
+extern "C" int go1_ppo_mse(const float* pred, int ldp, const float* target, int ldt, float* dpred, int lddp, float* scalars,
+                           int n, int num_train, int dim, void* stream) {
+    if (!pred || !target || !dpred || !scalars || n <= 0 || dim <= 0 || num_train < 0 || num_train > n) return go1_set_error("go1_ppo_mse: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(scalars, 0, sizeof(float) * 2, st);
+    mse_kernel<<<(n + 255) / 256, 256, 0, st>>>(pred, ldp, target, ldt, dpred, lddp, scalars, n, num_train, dim);
+    return cuda_rc("go1_ppo_mse");
+}
+
+// ---------------------------------------------------------------------------------------------
+// clip_grad_norm_ + Adam over a flat buffer (ppo.py:155-158)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g, long long count, double* __restrict__ out) {
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) { const float v = g[i]; acc += (double)v * (double)v; }
+    __shared__ double s[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane == 0) s[w] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0; for (int k = 0; k < 8; k++) t += s[k]; atomicAdd(out, t); }
+}
+extern "C" int go1_ppo_grad_sqnorm(const float* grad, int64_t count, double* grad_sq, void* stream) {
+    if (!grad || !grad_sq || count <= 0) return go1_set_error("go1_ppo_grad_sqnorm: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(grad_sq, 0, sizeof(double), st);
+    sqnorm_kernel<<<296, 256, 0, st>>>(grad, count, grad_sq);
+    return cuda_rc("go1_ppo_grad_sqnorm");
+}
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long count,
+                                                   const double* __restrict__ grad_sq, float max_norm, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt) {
+    float coef = 1.0f;
+    if (max_norm > 0.f && grad_sq) {
+        const float total = (float)sqrt(*grad_sq);
+        coef = fminf(max_norm / (total + 1e-6f), 1.0f);
+    }
+    const float step_size = lr / bc1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        const float gi = g[i] * coef;
+        const float mi = b1 * m[i] + (1.0f - b1) * gi;
+        const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] -= step_size * (mi / denom);
+    }
+}
+extern "C" int go1_ppo_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count, const double* grad_sq,
+                                 float max_grad_norm, float lr, float beta1, float beta2, float eps, int step, void* stream) {
+    if (!param || !grad || !exp_avg || !exp_avg_sq || count <= 0 || step <= 0) return go1_set_error("go1_ppo_adam_step: bad arguments");
+    const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
+    adam_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, count, grad_sq, max_grad_norm, lr, beta1, beta2, eps, bc1, sqrtf(bc2));
+    return cuda_rc("go1_ppo_adam_step");
+}
+
+// ---------------------------------------------------------------------------------------------
+// row gather: dst[i][0:width] = src[idx[i]][0:width]   (dst row stride ldd)
+// ---------------------------------------------------------------------------------------------
+__global__ void gather_rows_kernel(const float* __restrict__ src, const long long* __restrict__ idx, float* __restrict__ dst, long long rows, int width, int ldd) {
+    const long long r = blockIdx.x;
+    if (r >= rows) return;
+    const float* s = src + (size_t)idx[r] * width;
+    float* d = dst + (size_t)r * ldd;
+    if ((width & 3) == 0 && (ldd & 3) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+        for (int c = threadIdx.x; c < width / 4; c += blockDim.x) reinterpret_cast<float4*>(d)[c] = reinterpret_cast<const float4*>(s)[c];
+    } else {
+        for (int c = threadIdx.x; c < width; c += blockDim.x) d[c] = s[c];
+    }
+}
+extern "C" int go1_gather_rows(const float* src, const int64_t* idx, float* dst, int64_t rows, int width, int ldd, void* stream) {
+    if (!src || !idx || !dst || rows <= 0 || width <= 0 || ldd < width) return go1_set_error("go1_gather_rows: bad arguments");
+    const int threads = width >= 1024 ? 256 : (width >= 128 ? 64 : 32);
+    gather_rows_kernel<<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(src, (const long long*)idx, dst, rows, width, ldd);
+    return cuda_rc("go1_gather_rows");
+}

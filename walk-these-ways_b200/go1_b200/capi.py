@@ -1,0 +1,160 @@
+"""ctypes binding of libgo1b200.so (include/go1_b200.h).
+
+The product has no CPU fallback: importing this module works anywhere (so the build can be checked
+on a CPU box), but every compute call goes through the CUDA library and raises Go1Error if the
+library is missing or no CUDA device is present.
+"""
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "lib", "libgo1b200.so")
+
+NUM_DOF = 12
+NUM_COMMANDS = 15
+MAX_OBS = 128
+MAX_PRIV_OBS = 32
+EVENT_STRIDE = 6
+
+REWARD_TERMS = [
+    "tracking_lin_vel", "tracking_ang_vel", "lin_vel_z", "ang_vel_xy", "orientation", "torques", "dof_acc",
+    "action_rate", "collision", "dof_pos_limits", "jump", "tracking_contacts_shaped_force",
+    "tracking_contacts_shaped_vel", "dof_pos", "dof_vel", "action_smoothness_1", "action_smoothness_2",
+    "feet_slip", "feet_contact_vel", "feet_contact_forces", "feet_clearance_cmd_linear", "feet_impact_vel",
+    "orientation_control", "raibert_heuristic", "termination",
+]
+NUM_REWARD_TERMS = len(REWARD_TERMS)
+NUM_EPISODE_SUMS = NUM_REWARD_TERMS + 1
+NUM_COMMAND_SUMS = NUM_REWARD_TERMS + 5
+COMMAND_SUM_EXTRAS = ["lin_vel_raw", "ang_vel_raw", "lin_vel_residual", "ang_vel_residual", "ep_timesteps"]
+
+_i, _f = C.c_int32, C.c_float
+
+
+class Go1SimConfig(C.Structure):
+    _fields_ = [
+        ("num_envs", _i), ("num_train_envs", _i), ("sim_dt", _f), ("decimation", _i),
+        ("clip_actions", _f), ("clip_obs", _f), ("control_type", _i),
+        ("action_scale", _f), ("hip_scale_reduction", _f), ("kp", _f), ("kd", _f), ("use_lag", _i),
+        ("default_dof_pos", _f * NUM_DOF), ("soft_limit_lo", _f * NUM_DOF), ("soft_limit_hi", _f * NUM_DOF),
+        ("torque_limit", _f),
+        ("num_commands", _i), ("observe_gait_commands", _i), ("pacing_offset", _i), ("kappa_gait_probs", _f),
+        ("observe_vel", _i), ("observe_only_ang_vel", _i), ("observe_only_lin_vel", _i), ("observe_command", _i),
+        ("observe_two_prev_actions", _i), ("observe_timing_parameter", _i), ("observe_clock_inputs", _i),
+        ("observe_yaw", _i), ("observe_contact_states", _i),
+        ("num_obs", _i), ("num_priv_obs", _i), ("add_noise", _i),
+        ("commands_scale", _f * NUM_COMMANDS),
+        ("obs_scale_lin_vel", _f), ("obs_scale_ang_vel", _f), ("obs_scale_dof_pos", _f), ("obs_scale_dof_vel", _f),
+        ("noise_scale_vec", _f * MAX_OBS),
+        ("priv_friction", _i), ("priv_restitution", _i), ("priv_base_mass", _i), ("priv_com_displacement", _i),
+        ("priv_motor_strength", _i), ("priv_motor_offset", _i), ("priv_body_height", _i), ("priv_body_velocity", _i),
+        ("priv_gravity", _i), ("priv_clock_inputs", _i), ("priv_desired_contact_states", _i),
+        ("friction_ss", _f * 2), ("restitution_ss", _f * 2), ("mass_ss", _f * 2), ("com_ss", _f * 2),
+        ("motor_strength_ss", _f * 2), ("motor_offset_ss", _f * 2), ("body_height_ss", _f * 2),
+        ("body_velocity_ss", _f * 2), ("gravity_ss", _f * 2),
+        ("reward_scale", _f * NUM_REWARD_TERMS), ("reward_order", _i * NUM_REWARD_TERMS),
+        ("num_active_rewards", _i), ("only_positive_rewards", _i), ("only_positive_rewards_ji22_style", _i),
+        ("sigma_rew_neg", _f), ("tracking_sigma", _f), ("tracking_sigma_yaw", _f), ("gait_force_sigma", _f),
+        ("gait_vel_sigma", _f), ("base_height_target", _f), ("max_contact_force", _f),
+        ("use_terminal_body_height", _i), ("max_episode_length", _i), ("terminal_body_height", _f),
+        ("randomize_motor_strength", _i), ("randomize_motor_offset", _i), ("randomize_Kp_factor", _i),
+        ("randomize_Kd_factor", _i), ("rand_interval", _i), ("resampling_interval", _i),
+        ("motor_strength_range", _f * 2), ("motor_offset_range", _f * 2), ("Kp_factor_range", _f * 2),
+        ("Kd_factor_range", _f * 2),
+        ("base_init_state", _f * 13),
+        ("x_init_range", _f), ("y_init_range", _f), ("yaw_init_range", _f), ("x_init_offset", _f), ("y_init_offset", _f),
+        ("custom_origins", _i),
+        ("erp", _f), ("cfm", _f), ("max_depen_vel", _f), ("contact_margin", _f), ("bounce_threshold", _f),
+        ("pgs_iters", _i), ("terrain_friction", _f), ("terrain_restitution", _f),
+        ("pen_k", _f * 4), ("pen_c", _f * 4), ("pen_mt", _f), ("limit_k", _f), ("limit_c", _f),
+        ("hf", C.c_void_p), ("hf_rows", _i), ("hf_cols", _i), ("hf_hscale", _f), ("hf_vscale", _f), ("hf_border", _f),
+        ("seed", C.c_uint64),
+    ]
+
+
+class Go1SimBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "env_f32", "leg_f32", "env_i32", "obs", "priv_obs", "rew", "reset", "time_out", "event_count", "events",
+        "episode_acc", "noise", "reset_rand")]
+
+
+class Go1Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libgo1b200.so (built by __graft_entry__.build() / csrc/Makefile). Fails loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Go1Error(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       f"(nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.go1_last_error.restype = C.c_char_p
+    vp, ip, i64 = C.c_void_p, C.c_int, C.c_int64
+    sig = {
+        "go1_version": ([], ip), "go1_device_count": ([], ip), "go1_sizeof_config": ([], ip), "go1_sizeof_buffers": ([], ip),
+        "go1_sim_num_rows": ([ip], ip), "go1_sim_row": ([ip, C.c_char_p], ip),
+        "go1_sim_create": ([C.POINTER(Go1SimConfig), vp, ip, C.POINTER(vp)], ip),
+        "go1_sim_destroy": ([vp], ip), "go1_sim_bind": ([vp, C.POINTER(Go1SimBuffers)], ip),
+        "go1_sim_update_config": ([vp, C.POINTER(Go1SimConfig), vp], ip),
+        "go1_sim_step": ([vp, vp, C.POINTER(_f * 3), C.POINTER(_f * 3), i64, ip, vp], ip),
+        "go1_sim_reset_idx": ([vp, vp, ip, vp, vp, ip, i64, vp], ip),
+        "go1_sim_set_commands": ([vp, vp, ip, vp, vp], ip),
+        "go1_history_roll": ([vp, vp, vp, ip, ip, ip, vp], ip),
+        "go1_ppo_gae": ([vp, vp, vp, vp, vp, vp, vp, ip, ip, _f, _f, vp], ip),
+        "go1_ppo_normalize_advantages": ([vp, vp, i64, i64, vp], ip),
+        "go1_gemm": ([ip, ip, ip, ip, ip, vp, ip, vp, ip, vp, ip, vp, ip, ip, ip, vp], ip),
+        "go1_elu_backward": ([vp, ip, vp, ip, vp, ip, ip, ip, vp], ip),
+        "go1_colsum": ([vp, ip, vp, ip, ip, ip, vp], ip),
+        "go1_ppo_sample_actions": ([vp, ip, vp, vp, C.c_uint64, C.c_uint64, vp, vp, ip, ip, vp], ip),
+        "go1_ppo_loss": ([vp, ip, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ip, vp, vp, vp, ip, ip, _f, _f, _f, ip, _f, vp], ip),
+        "go1_ppo_mse": ([vp, ip, vp, ip, vp, ip, vp, ip, ip, ip, vp], ip),
+        "go1_ppo_grad_sqnorm": ([vp, i64, vp, vp], ip),
+        "go1_ppo_adam_step": ([vp, vp, vp, vp, i64, vp, _f, _f, _f, _f, _f, ip, vp], ip),
+        "go1_gather_rows": ([vp, vp, vp, i64, ip, ip, vp], ip),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(L, name)          # AttributeError here = header/library mismatch: fail loudly
+        fn.argtypes = args
+        fn.restype = res
+    if L.go1_sizeof_config() != C.sizeof(Go1SimConfig):
+        raise Go1Error(f"Go1SimConfig mirror out of date: C {L.go1_sizeof_config()} vs ctypes {C.sizeof(Go1SimConfig)}")
+    if L.go1_sizeof_buffers() != C.sizeof(Go1SimBuffers):
+        raise Go1Error("Go1SimBuffers mirror out of date")
+    _lib = L
+    return L
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise Go1Error(f"{what} failed ({rc}): {lib().go1_last_error().decode()}")
+
+
+def exported_symbols():
+    """Names every entry point include/go1_b200.h declares (used by the CPU-side ABI test)."""
+    import re
+    hdr = os.path.join(os.path.dirname(_PKG), "include", "go1_b200.h")
+    txt = open(hdr).read()
+    return sorted(set(re.findall(r"\b(go1_[a-z0-9_]+)\s*\(", txt)))
+
+
+def row(kind, name):
+    r = lib().go1_sim_row(kind, name.encode())
+    if r < 0:
+        raise KeyError(name)
+    return r
+
+
+def ptr(t):
+    """Raw device pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
