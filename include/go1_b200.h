@@ -218,8 +218,13 @@ int go1_ppo_mse(const float* pred, int ldp, const float* target, int ldt, float*
  * go1_ppo_grad_sqnorm, all-reducible).  max_grad_norm <= 0 disables clipping. */
 int go1_ppo_grad_sqnorm(const float* grad, int64_t count, double* grad_sq, void* stream);
 int go1_ppo_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count,
-                      const double* grad_sq, float max_grad_norm, float lr, float beta1, float beta2, float eps,
-                      int step, void* stream);
+                      const double* grad_sq, float max_grad_norm, float lr, const float* lr_dev, float beta1, float beta2,
+                      float eps, int step, void* stream);
+/* Replaces the adaptive-KL learning-rate schedule of PPO.update (ppo.py:118-132) without a host sync:
+ * lr_dev <- max(lr_min, lr/1.5) if kl > 2*desired_kl; min(lr_max, lr*1.5) if 0 < kl < desired_kl/2.
+ * kl = scalars[3] written by go1_ppo_loss (all-reduced first on multi-GPU).  go1_ppo_adam_step reads the
+ * learning rate from lr_dev when it is non-NULL. */
+int go1_ppo_adaptive_lr(const float* scalars, float* lr_dev, float desired_kl, float lr_min, float lr_max, void* stream);
 
 /* Replaces the fancy-index gathers of RolloutStorage.mini_batch_generator (rollout_storage.py:98-137):
  * dst[i][0:width] = src[idx[i]][0:width]; ldd = row stride of dst in floats (>= width). */

@@ -1,0 +1,169 @@
+"""GPU parity tests of the learner kernels (through the C-ABI) against torch fp32 references and against the
+vectors produced by the reference's own ppo_cse code (tests/golden/ppo.npz: BASELINE.json config 1)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "walk-these-ways_b200", "compat"))
+
+
+def _gemm(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, bias=None, act=0, acc=0, impl=0):
+    from go1_b200 import capi
+    capi.check(capi.lib().go1_gemm(ta, tb, M, N, K, capi.ptr(A), lda, capi.ptr(B), ldb, capi.ptr(C), ldc, capi.ptr(bias), act, acc, impl,
+                                   capi.stream_ptr()), "gemm")
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 1), (0, 0), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(4, 12, 128), (96, 2, 2100), (300, 257, 70), (129, 130, 2102), (512, 256, 4096)])
+def test_gemm_fp32_matches_torch(ta, tb, M, N, K):
+    torch.manual_seed(M + N + K)
+    A = torch.randn((K, M) if ta else (M, K), device="cuda")
+    B = torch.randn((N, K) if tb else (K, N), device="cuda")
+    bias = torch.randn(N, device="cuda")
+    ref = (A.t() if ta else A).double() @ (B.t() if tb else B).double()
+    C = torch.full((M, N + 3), 7.0, device="cuda")            # ldc > N: the pad columns must stay untouched
+    _gemm(ta, tb, M, N, K, A, A.stride(0), B, B.stride(0), C, N + 3)
+    assert torch.allclose(C[:, :N].double(), ref, rtol=1e-4, atol=1e-3 * np.sqrt(K) / 30) and (C[:, N:] == 7.0).all()
+    C2 = torch.randn(M, N, device="cuda"); C0 = C2.clone()
+    _gemm(ta, tb, M, N, K, A, A.stride(0), B, B.stride(0), C2, N, bias=bias, act=1, acc=1)
+    want = torch.nn.functional.elu(C0.double() + ref + bias.double())
+    assert torch.allclose(C2.double(), want, rtol=1e-4, atol=1e-3 * np.sqrt(K) / 30)
+
+
+def test_gemm_split_k_wgrad_shape():
+    M, N, K = 256, 128, 24576          # dW of a 256->128 layer over a 24576-row minibatch
+    A = torch.randn(K, M, device="cuda") * 0.1; B = torch.randn(K, N, device="cuda") * 0.1
+    C = torch.zeros(M, N, device="cuda")
+    _gemm(1, 0, M, N, K, A, M, B, N, C, N)
+    assert torch.allclose(C.double(), A.t().double() @ B.double(), rtol=1e-4, atol=2e-3)
+
+
+def test_elu_backward_colsum_gather():
+    from go1_b200 import capi
+    L, st = capi.lib(), capi.stream_ptr()
+    y = torch.randn(1000, 37, device="cuda"); y = torch.nn.functional.elu(y); dy = torch.randn_like(y)
+    dz = torch.empty_like(y)
+    capi.check(L.go1_elu_backward(capi.ptr(y), 37, capi.ptr(dy), 37, capi.ptr(dz), 37, 1000, 37, st), "elu")
+    assert torch.allclose(dz, dy * torch.where(y > 0, torch.ones_like(y), y + 1), atol=1e-6)
+    out = torch.empty(37, device="cuda")
+    capi.check(L.go1_colsum(capi.ptr(dz), 37, capi.ptr(out), 1000, 37, 0, st), "colsum")
+    assert torch.allclose(out, dz.sum(0), rtol=1e-4, atol=1e-4)
+    src = torch.randn(500, 2100, device="cuda"); idx = torch.randperm(500, device="cuda")[:200]
+    dst = torch.empty(200, 2100, device="cuda")
+    capi.check(L.go1_gather_rows(capi.ptr(src), capi.ptr(idx), capi.ptr(dst), 200, 2100, 2100, st), "gather")
+    assert torch.equal(dst, src[idx])          # copies are bit-exact
+
+
+@pytest.mark.parametrize("T,n", [(24, 4), (24, 4096), (70, 100), (5, 33)])
+def test_gae_matches_reference_loop(T, n):
+    """rollout_storage.py:74-88 restated as the literal reversed loop (fp32 torch) vs the warp-scan kernel."""
+    from go1_b200 import capi
+    torch.manual_seed(T * n)
+    rew = torch.randn(T, n, 1, device="cuda"); val = torch.randn(T, n, 1, device="cuda"); last = torch.randn(n, 1, device="cuda")
+    done = (torch.rand(T, n, 1, device="cuda") < 0.1).byte()
+    ret = torch.zeros_like(rew); adv_k = torch.zeros_like(rew); stats = torch.zeros(2, dtype=torch.float64, device="cuda")
+    L, st = capi.lib(), capi.stream_ptr()
+    capi.check(L.go1_ppo_gae(capi.ptr(rew), capi.ptr(done), capi.ptr(val), capi.ptr(last), capi.ptr(ret), capi.ptr(adv_k), capi.ptr(stats), T, n, 0.99, 0.95, st), "gae")
+    capi.check(L.go1_ppo_normalize_advantages(capi.ptr(adv_k), capi.ptr(stats), T * n, T * n, st), "norm")
+    adv, returns = 0, torch.zeros_like(rew)
+    for step in reversed(range(T)):
+        nv = last if step == T - 1 else val[step + 1]
+        nt = 1.0 - done[step].float()
+        delta = rew[step] + nt * 0.99 * nv - val[step]
+        adv = delta + nt * 0.99 * 0.95 * adv
+        returns[step] = adv + val[step]
+    a = returns - val
+    a = (a - a.mean()) / (a.std() + 1e-8)
+    assert torch.allclose(ret, returns, rtol=1e-5, atol=2e-5)
+    assert torch.allclose(adv_k, a, rtol=1e-4, atol=2e-5)
+
+
+def test_ppo_loss_kernel_matches_autograd():
+    """Loss values and gradients of ppo.py:113-152 from torch autograd (the reference's own formulae)."""
+    from go1_b200 import capi
+    torch.manual_seed(0)
+    n, A = 5000, 12
+    mean = torch.randn(n, A, device="cuda", requires_grad=True); std = (torch.rand(A, device="cuda") + 0.5).requires_grad_()
+    value = torch.randn(n, 1, device="cuda", requires_grad=True)
+    actions = torch.randn(n, A, device="cuda"); old_mu = mean.detach() + 0.1 * torch.randn(n, A, device="cuda")
+    old_sigma = (std.detach() * (1 + 0.05 * torch.randn(A, device="cuda"))).expand(n, A).contiguous()
+    old_logp = torch.distributions.Normal(old_mu, old_sigma).log_prob(actions).sum(-1, keepdim=True)
+    adv = torch.randn(n, 1, device="cuda"); returns = torch.randn(n, 1, device="cuda"); old_v = value.detach() + 0.3 * torch.randn(n, 1, device="cuda")
+    dist = torch.distributions.Normal(mean, mean * 0. + std)
+    logp = dist.log_prob(actions).sum(-1)
+    ratio = torch.exp(logp - old_logp.squeeze())
+    surr = torch.max(-adv.squeeze() * ratio, -adv.squeeze() * torch.clamp(ratio, 0.8, 1.2)).mean()
+    vc = old_v + (value - old_v).clamp(-0.2, 0.2)
+    vloss = torch.max((value - returns).pow(2), (vc - returns).pow(2)).mean()
+    ent = dist.entropy().sum(-1).mean()
+    loss = surr + 1.0 * vloss - 0.01 * ent
+    loss.backward()
+    kl = torch.sum(torch.log(std / old_sigma + 1.e-5) + (old_sigma ** 2 + (old_mu - mean) ** 2) / (2.0 * std ** 2) - 0.5, -1).mean()
+    dmean = torch.empty(n, A, device="cuda"); dvalue = torch.empty(n, 1, device="cuda"); dstd = torch.empty(A, device="cuda"); sc = torch.empty(8, device="cuda")
+    capi.check(capi.lib().go1_ppo_loss(capi.ptr(mean.detach()), A, capi.ptr(std.detach()), capi.ptr(value.detach()), capi.ptr(actions), capi.ptr(old_logp),
+                                       capi.ptr(old_mu), capi.ptr(old_sigma), capi.ptr(adv), capi.ptr(returns), capi.ptr(old_v), capi.ptr(dmean), A,
+                                       capi.ptr(dvalue), capi.ptr(dstd), capi.ptr(sc), n, A, 0.2, 1.0, 0.01, 1, 1.0 / n, capi.stream_ptr()), "loss")
+    assert torch.allclose(sc[0], surr.detach(), rtol=1e-4, atol=1e-5) and torch.allclose(sc[1], vloss.detach(), rtol=1e-4)
+    assert torch.allclose(sc[2], ent.detach(), rtol=1e-5) and torch.allclose(sc[3], kl.detach(), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(dmean, mean.grad, rtol=1e-4, atol=1e-7) and torch.allclose(dvalue, value.grad, rtol=1e-4, atol=1e-8)
+    assert torch.allclose(dstd, std.grad, rtol=1e-3, atol=1e-5)
+
+
+def test_clip_adam_matches_torch_optim():
+    from go1_b200 import capi
+    torch.manual_seed(1)
+    p = torch.randn(100003, device="cuda"); ref = torch.nn.Parameter(p.clone()); opt = torch.optim.Adam([ref], lr=1e-3)
+    m = torch.zeros_like(p); v = torch.zeros_like(p); gsq = torch.zeros(1, dtype=torch.float64, device="cuda")
+    for t in range(1, 4):
+        g = torch.randn_like(p) * 0.01 * t
+        ref.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_([ref], 1.0)
+        opt.step()
+        capi.check(capi.lib().go1_ppo_grad_sqnorm(capi.ptr(g), g.numel(), capi.ptr(gsq), capi.stream_ptr()), "sq")
+        capi.check(capi.lib().go1_ppo_adam_step(capi.ptr(p), capi.ptr(g), capi.ptr(m), capi.ptr(v), p.numel(), capi.ptr(gsq), 1.0, 1e-3, None, 0.9, 0.999, 1e-8, t,
+                                                capi.stream_ptr()), "adam")
+        assert torch.allclose(p, ref.detach(), rtol=1e-5, atol=1e-7)
+
+
+def test_full_ppo_cycle_matches_reference_golden():
+    """BASELINE config 1: act x24 -> process_env_step -> compute_returns -> update (5 epochs x 4 minibatches + adaptation
+    steps) on the reference's own vectors.  fp32 CUDA-core GEMMs; tolerances stated per quantity."""
+    from ppo_golden_util import seeded_weights, sample_tensor
+    from go1_gym_learn.ppo_cse import ActorCritic
+    from go1_gym_learn.ppo_cse.ppo import PPO
+    g = np.load(os.path.join(HERE, "golden", "ppo.npz"))
+    N, T, NOBS, NH, NP, NA = 4, 24, 70, 2100, 2, 12
+    ac = ActorCritic(NOBS, NP, NH, NA)
+    w = seeded_weights({k: tuple(v.shape) for k, v in ac.state_dict().items()})
+    ac.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+    alg = PPO(ac, device="cuda:0")
+    alg.init_storage(N, T, [NOBS], [NP], [NH], [NA])
+    C = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    for t in range(T):
+        ac.injected_eps = C(g["in/eps"][t])
+        alg.act(C(g["in/obs"][t]), C(g["in/priv"][t]), C(g["in/hist"][t]))
+        infos = {"env_bins": torch.zeros(N, device="cuda"), "time_outs": torch.zeros(N, dtype=torch.bool, device="cuda")}
+        alg.process_env_step(C(g["in/rew"][t]), C(g["in/done"][t]), infos)
+    alg.compute_returns(C(g["last/hist"]), C(g["last/priv"]))
+    st = alg.storage
+    for name, tol in (("actions", 2e-5), ("values", 2e-5), ("actions_log_prob", 1e-4), ("mu", 2e-5), ("returns", 5e-5), ("advantages", 2e-4)):
+        got, want = getattr(st, name).cpu().numpy(), g[f"storage/{name}"]
+        assert np.allclose(got, want, rtol=1e-4, atol=tol), (name, np.abs(got - want).max())
+    assert np.array_equal(st.dones.cpu().numpy(), g["storage/dones"])
+    alg.fixed_minibatch_indices = C(g["in/perm"])
+    losses = alg.update()
+    ref = g["update/losses"]
+    assert abs(losses[0] - ref[0]) < 2e-3 * abs(ref[0]) and abs(losses[1] - ref[1]) < 2e-3 and abs(losses[2] - ref[2]) < 2e-3 * abs(ref[2])
+    assert abs(losses[5] - ref[5]) < 2e-3 * abs(ref[5])
+    assert abs(alg.learning_rate - float(g["update/learning_rate"])) < 1e-12
+    sd = ac.state_dict()
+    for k, v in sd.items():
+        got, want = sample_tensor(v.cpu().numpy()), g[f"final/{k}"]
+        # 20 PPO + 20 adaptation Adam steps; lr <= 1e-3 so each weight moves <= ~0.02: compare the MOVED weights tightly
+        assert np.allclose(got[:-2], want[:-2], rtol=0, atol=3e-4), (k, np.abs(got[:-2] - want[:-2]).max())
+        assert abs(got[-1] - want[-1]) <= 2e-4 * max(1.0, abs(want[-1])), k

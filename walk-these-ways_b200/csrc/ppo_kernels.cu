@@ -488,7 +488,8 @@ extern "C" int go1_ppo_grad_sqnorm(const float* grad, int64_t count, double* gra
     return cuda_rc("go1_ppo_grad_sqnorm");
 }
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long count,
-                                                   const double* __restrict__ grad_sq, float max_norm, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt) {
+                                                   const double* __restrict__ grad_sq, float max_norm, float lr, const float* __restrict__ lr_dev, float b1, float b2, float eps, float bc1, float bc2_sqrt) {
+    if (lr_dev) lr = *lr_dev;
     float coef = 1.0f;
     if (max_norm > 0.f && grad_sq) {
         const float total = (float)sqrt(*grad_sq);
@@ -504,11 +505,23 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
         p[i] -= step_size * (mi / denom);
     }
 }
+__global__ void adaptive_lr_kernel(const float* __restrict__ scalars, float* __restrict__ lr, float desired_kl, float lo, float hi) {
+    const float kl = scalars[3];
+    float v = *lr;
+    if (kl > desired_kl * 2.0f) v = fmaxf(lo, v / 1.5f);
+    else if (kl < desired_kl / 2.0f && kl > 0.0f) v = fminf(hi, v * 1.5f);
+    *lr = v;
+}
+extern "C" int go1_ppo_adaptive_lr(const float* scalars, float* lr_dev, float desired_kl, float lr_min, float lr_max, void* stream) {
+    if (!scalars || !lr_dev) return go1_set_error("go1_ppo_adaptive_lr: bad arguments");
+    adaptive_lr_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(scalars, lr_dev, desired_kl, lr_min, lr_max);
+    return cuda_rc("go1_ppo_adaptive_lr");
+}
 extern "C" int go1_ppo_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count, const double* grad_sq,
-                                 float max_grad_norm, float lr, float beta1, float beta2, float eps, int step, void* stream) {
+                                 float max_grad_norm, float lr, const float* lr_dev, float beta1, float beta2, float eps, int step, void* stream) {
     if (!param || !grad || !exp_avg || !exp_avg_sq || count <= 0 || step <= 0) return go1_set_error("go1_ppo_adam_step: bad arguments");
     const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
-    adam_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, count, grad_sq, max_grad_norm, lr, beta1, beta2, eps, bc1, sqrtf(bc2));
+    adam_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, count, grad_sq, max_grad_norm, lr, lr_dev, beta1, beta2, eps, bc1, sqrtf(bc2));
     return cuda_rc("go1_ppo_adam_step");
 }
 

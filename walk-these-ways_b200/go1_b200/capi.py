@@ -115,7 +115,8 @@ def lib():
         "go1_ppo_loss": ([vp, ip, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ip, vp, vp, vp, ip, ip, _f, _f, _f, ip, _f, vp], ip),
         "go1_ppo_mse": ([vp, ip, vp, ip, vp, ip, vp, ip, ip, ip, vp], ip),
         "go1_ppo_grad_sqnorm": ([vp, i64, vp, vp], ip),
-        "go1_ppo_adam_step": ([vp, vp, vp, vp, i64, vp, _f, _f, _f, _f, _f, ip, vp], ip),
+        "go1_ppo_adam_step": ([vp, vp, vp, vp, i64, vp, _f, _f, vp, _f, _f, _f, ip, vp], ip),
+        "go1_ppo_adaptive_lr": ([vp, vp, _f, _f, _f, vp], ip),
         "go1_gather_rows": ([vp, vp, vp, i64, ip, ip, vp], ip),
     }
     for name, (args, res) in sig.items():

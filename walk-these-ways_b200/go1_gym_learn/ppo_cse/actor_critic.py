@@ -1,0 +1,320 @@
+"""ActorCritic of ppo_cse (reference go1_gym_learn/ppo_cse/actor_critic.py:19-147) on hand-written kernels.
+
+Same public surface (AC_Args, ActorCritic(num_obs, num_privileged_obs, num_obs_history, num_actions),
+.adaptation_module / .actor_body / .critic_body as nn.Sequential so checkpoints and TorchScript exports keep
+the reference's names, .act / .evaluate / .act_student / .act_teacher / .get_actions_log_prob / .action_mean /
+.action_std / .entropy), but:
+  * all parameters are views into ONE flat fp32 buffer (adaptation module first), gradients into one flat
+    gradient buffer -> one grad-norm, one Adam launch, one NCCL all-reduce per optimizer step;
+  * forward and backward are explicit go1_gemm calls (fp32 CUDA-core or tcgen05 TF32) with fused
+    bias+ELU epilogues; cat(obs_history, latent) is never materialised (the 2 extra input columns are a
+    second, K=2 GEMM accumulated into the first layer's pre-activation);
+  * no autograd graph: the backward pass is written out (see `backward_ppo`, `backward_adaptation`).
+"""
+import torch
+import torch.nn as nn
+from params_proto import PrefixProto
+
+from go1_b200 import capi
+
+
+class AC_Args(PrefixProto, cli=False):
+    # policy
+    init_noise_std = 1.0
+    actor_hidden_dims = [512, 256, 128]
+    critic_hidden_dims = [512, 256, 128]
+    activation = 'elu'  # only elu runs on the fused kernels
+    adaptation_module_branch_hidden_dims = [256, 128]
+    use_decoder = False
+    gemm_impl = 0       # 0 = fp32 CUDA cores (exact), 1 = tcgen05 TF32 tensor cores
+
+
+def _mlp(in_dim, hidden, out_dim):
+    layers, d = [], in_dim
+    for h in hidden:
+        layers += [nn.Linear(d, h), nn.ELU()]
+        d = h
+    layers.append(nn.Linear(d, out_dim))
+    return nn.Sequential(*layers)
+
+
+class _Net:
+    """Forward/backward of one MLP whose first layer reads [x (K0 columns) | extra (E columns)]."""
+
+    def __init__(self, seq, flat, grad, offset):
+        self.linears = [m for m in seq if isinstance(m, nn.Linear)]
+        self.specs = []                       # (w_off, b_off, out, in)
+        off = offset
+        for lin in self.linears:
+            o, i = lin.weight.shape
+            self.specs.append((off, off + o * i, o, i))
+            off += o * i + o
+        self.end = off
+        self.flat, self.grad = flat, grad
+        self.acts = {}
+
+    def _buf(self, key, M, width):
+        t = self.acts.get(key)
+        if t is None or t.shape[0] < M or t.shape[1] != width:
+            t = torch.empty(M, width, device=self.flat.device)
+            self.acts[key] = t
+        return t[:M]
+
+    def forward(self, x, ldx, K0, extra, M, impl, tag="a"):
+        """x: [M][K0] rows with stride ldx; extra: [M][E] contiguous or None. Returns list of layer outputs."""
+        L, st = capi.lib(), capi.stream_ptr()
+        outs, inp, ld_in = [], x, ldx
+        n = len(self.specs)
+        for li, (wo, bo, o, i) in enumerate(self.specs):
+            y = self._buf((tag, li), M, o)
+            W = self.flat[wo:wo + o * i]
+            b = self.flat[bo:bo + o]
+            act = 1 if li < n - 1 else 0
+            if li == 0 and extra is not None:
+                E = i - K0
+                capi.check(L.go1_gemm(0, 1, M, o, K0, capi.ptr(inp), ld_in, capi.ptr(W), i, capi.ptr(y), o, None, 0, 0, impl, st), "gemm")
+                capi.check(L.go1_gemm(0, 1, M, o, E, capi.ptr(extra), extra.stride(0), W.data_ptr() + 4 * K0, i, capi.ptr(y), o, capi.ptr(b), act, 1, 0, st), "gemm")
+            else:
+                K = i
+                capi.check(L.go1_gemm(0, 1, M, o, K, capi.ptr(inp), ld_in, capi.ptr(W), i, capi.ptr(y), o, capi.ptr(b), act, 0, impl, st), "gemm")
+            outs.append(y)
+            inp, ld_in = y, o
+        return outs
+
+    def backward(self, x, ldx, K0, extra, outs, dout, M, impl, accumulate, want_dextra=False, tag="a"):
+        """dout: gradient w.r.t. the network output [M][out]. Writes weight/bias grads into the flat grad buffer.
+        Returns d(extra) [M][E] if requested."""
+        L, st = capi.lib(), capi.stream_ptr()
+        n = len(self.specs)
+        dz = dout
+        dextra = None
+        for li in range(n - 1, -1, -1):
+            wo, bo, o, i = self.specs[li]
+            W = self.flat[wo:wo + o * i]
+            gW, gb = self.grad[wo:wo + o * i], self.grad[bo:bo + o]
+            if li < n - 1:     # dz = dy * ELU'(y)
+                y = outs[li]
+                capi.check(L.go1_elu_backward(capi.ptr(y), o, capi.ptr(dz), o, capi.ptr(dz), o, M, o, st), "elu_bwd")
+            capi.check(L.go1_colsum(capi.ptr(dz), o, capi.ptr(gb), M, o, accumulate, st), "colsum")
+            if li == 0:
+                inp, ld_in, K = x, ldx, (K0 if extra is not None else i)
+            else:
+                inp, ld_in, K = outs[li - 1], self.specs[li - 1][2], i
+            # dW[o][K] = dz^T[o][M] inp[M][K]
+            capi.check(L.go1_gemm(1, 0, o, K, M, capi.ptr(dz), o, capi.ptr(inp), ld_in, capi.ptr(gW), i, None, 0, accumulate, impl, st), "wgrad")
+            if li == 0 and extra is not None:
+                E = i - K0
+                capi.check(L.go1_gemm(1, 0, o, E, M, capi.ptr(dz), o, capi.ptr(extra), extra.stride(0), gW.data_ptr() + 4 * K0, i, None, 0, accumulate, 0, st), "wgrad_extra")
+                if want_dextra:
+                    dextra = self._buf((tag, "dextra"), M, E)
+                    capi.check(L.go1_gemm(0, 0, M, E, o, capi.ptr(dz), o, W.data_ptr() + 4 * K0, i, capi.ptr(dextra), E, None, 0, 0, 0, st), "dgrad_extra")
+            if li > 0:
+                dprev = self._buf((tag, "d", li - 1), M, i)
+                capi.check(L.go1_gemm(0, 0, M, i, o, capi.ptr(dz), o, capi.ptr(W), i, capi.ptr(dprev), i, None, 0, 0, impl, st), "dgrad")
+                dz = dprev
+        return dextra
+
+
+class ActorCritic(nn.Module):
+    is_recurrent = False
+
+    def __init__(self, num_obs, num_privileged_obs, num_obs_history, num_actions, **kwargs):
+        if kwargs:
+            print("ActorCritic.__init__ got unexpected arguments, which will be ignored: " + str([key for key in kwargs.keys()]))
+        self.decoder = AC_Args.use_decoder
+        super().__init__()
+        if AC_Args.activation != 'elu':
+            raise NotImplementedError("the fused MLP kernels implement ELU (the reference's configured activation)")
+        self.num_obs_history, self.num_privileged_obs, self.num_actions = num_obs_history, num_privileged_obs, num_actions
+        self.adaptation_module = _mlp(num_obs_history, AC_Args.adaptation_module_branch_hidden_dims, num_privileged_obs)
+        self.actor_body = _mlp(num_privileged_obs + num_obs_history, AC_Args.actor_hidden_dims, num_actions)
+        self.critic_body = _mlp(num_privileged_obs + num_obs_history, AC_Args.critic_hidden_dims, 1)
+        self.std = nn.Parameter(AC_Args.init_noise_std * torch.ones(num_actions))
+        self.distribution = None
+        self._flat = self._grad = None
+        self._mean = self._value = self._logp = None
+        self._sample_counter = 0
+        self.sample_seed = 0
+        self.injected_eps = None      # parity tests inject the N(0,1) draws
+
+    # ------------------------------------------------------------------ flat storage
+    def _ordered_params(self):
+        ps = []
+        for seq in (self.adaptation_module, self.actor_body, self.critic_body):
+            for m in seq:
+                if isinstance(m, nn.Linear):
+                    ps += [m.weight, m.bias]
+        return ps + [self.std]
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._flat = None              # device / dtype changed: rebuild the flat views lazily
+        return r
+
+    def flatten(self):
+        """(Re)build the flat parameter/gradient buffers and re-point every parameter at its slice."""
+        ps = self._ordered_params()
+        dev = ps[0].device
+        if self._flat is not None and self._flat.device == dev and all(p.data.untyped_storage().data_ptr() == self._flat.untyped_storage().data_ptr() for p in ps):
+            return
+        total = sum(p.numel() for p in ps)
+        flat = torch.empty(total, device=dev, dtype=torch.float32)
+        off = 0
+        for p in ps:
+            n = p.numel()
+            flat[off:off + n].copy_(p.data.reshape(-1))
+            p.data = flat[off:off + n].view(p.shape)
+            off += n
+        self._flat = flat
+        self._grad = torch.zeros_like(flat)
+        self.n_params = total
+        self._nets = {}
+        off = 0
+        for name, seq in (("adapt", self.adaptation_module), ("actor", self.actor_body), ("critic", self.critic_body)):
+            net = _Net(seq, self._flat, self._grad, off)
+            self._nets[name] = net
+            off = net.end
+        self.n_adapt_params = self._nets["adapt"].end
+        self.std_offset = off
+
+    @property
+    def flat_params(self):
+        self.flatten()
+        return self._flat
+
+    @property
+    def flat_grads(self):
+        self.flatten()
+        return self._grad
+
+    def load_state_dict(self, *a, **k):
+        self.flatten()
+        return super().load_state_dict(*a, **k)
+
+    # ------------------------------------------------------------------ reference API
+    def reset(self, dones=None):
+        pass
+
+    def forward(self):
+        raise NotImplementedError
+
+    @property
+    def action_mean(self):
+        return self._mean
+
+    @property
+    def action_std(self):
+        return self.std.detach().unsqueeze(0).expand_as(self._mean)
+
+    @property
+    def entropy(self):
+        return (0.5 + 0.5 * torch.log(torch.tensor(2 * torch.pi)) + torch.log(self.std.detach())).sum().expand(self._mean.shape[0])
+
+    def _impl(self):
+        return int(AC_Args.gemm_impl)
+
+    def _check_input(self, h):
+        if not h.is_cuda:
+            raise capi.Go1Error("ActorCritic runs on CUDA kernels only (no CPU fallback)")
+        assert h.dtype == torch.float32 and h.stride(1) == 1
+
+    def update_distribution(self, observation_history, tag="act"):
+        self.flatten()
+        self._check_input(observation_history)
+        h = observation_history
+        M, K0 = h.shape[0], self.num_obs_history
+        self._a_out = self._nets["adapt"].forward(h, h.stride(0), K0, None, M, self._impl(), tag)
+        latent = self._a_out[-1]
+        self._p_out = self._nets["actor"].forward(h, h.stride(0), K0, latent, M, self._impl(), tag)
+        self._mean = self._p_out[-1]
+        self._latent = latent
+
+    # Normal-like accessors used through `self.distribution`
+    @property
+    def mean(self):
+        return self._mean
+
+    @property
+    def stddev(self):
+        return self.action_std
+
+    def act(self, observation_history, **kwargs):
+        self.update_distribution(observation_history)
+        M = observation_history.shape[0]
+        actions = torch.empty(M, self.num_actions, device=observation_history.device)
+        self._logp = torch.empty(M, device=observation_history.device)
+        eps = self.injected_eps
+        self._sample_counter += 1
+        capi.check(capi.lib().go1_ppo_sample_actions(capi.ptr(self._mean), self._mean.stride(0), capi.ptr(self.std.data),
+                                                     capi.ptr(eps) if eps is not None else None, self.sample_seed, self._sample_counter,
+                                                     capi.ptr(actions), capi.ptr(self._logp), M, self.num_actions, capi.stream_ptr()), "sample")
+        self._last_actions = actions
+        return actions
+
+    def get_actions_log_prob(self, actions):
+        if actions is getattr(self, "_last_actions", None):
+            return self._logp
+        d = actions - self._mean
+        sd = self.std.detach()
+        return (-(d * d) / (2 * sd * sd) - torch.log(sd) - 0.9189385332046727).sum(-1)
+
+    def act_expert(self, ob, policy_info={}):
+        return self.act_teacher(ob["obs_history"], ob["privileged_obs"])
+
+    def act_inference(self, ob, policy_info={}):
+        return self.act_student(ob["obs_history"], policy_info=policy_info)
+
+    def act_student(self, observation_history, policy_info={}):
+        if observation_history.shape[0] == 0:
+            return observation_history.new_zeros(0, self.num_actions)
+        self.update_distribution(observation_history, tag="student")
+        policy_info["latents"] = self._latent.detach().cpu().numpy()
+        return self._mean
+
+    def act_teacher(self, observation_history, privileged_info, policy_info={}):
+        if observation_history.shape[0] == 0:
+            return observation_history.new_zeros(0, self.num_actions)
+        self.flatten()
+        h = observation_history
+        out = self._nets["actor"].forward(h, h.stride(0), self.num_obs_history, privileged_info.contiguous(), h.shape[0], self._impl(), "teacher")
+        policy_info["latents"] = privileged_info
+        return out[-1]
+
+    def evaluate(self, observation_history, privileged_observations, tag="act", **kwargs):
+        self.flatten()
+        self._check_input(observation_history)
+        h = observation_history
+        self._c_out = self._nets["critic"].forward(h, h.stride(0), self.num_obs_history, privileged_observations.contiguous(), h.shape[0], self._impl(), tag)
+        self._value = self._c_out[-1]
+        return self._value
+
+    def get_student_latent(self, observation_history):
+        self.flatten()
+        h = observation_history
+        return self._nets["adapt"].forward(h, h.stride(0), self.num_obs_history, None, h.shape[0], self._impl(), "latent")[-1]
+
+    # ------------------------------------------------------------------ explicit backward passes (ppo.py:154-189)
+    def backward_ppo(self, h, priv, dmean, dvalue, dstd):
+        """Gradients of the PPO loss into flat_grads (overwrites). h/priv are the minibatch inputs of the forward
+        pass just run with tag='train'; dmean [M,A], dvalue [M,1], dstd [A]."""
+        M, K0, impl = h.shape[0], self.num_obs_history, self._impl()
+        dlat = self._nets["actor"].backward(h, h.stride(0), K0, self._latent, self._p_out, dmean, M, impl, 0, want_dextra=True, tag="train")
+        self._nets["critic"].backward(h, h.stride(0), K0, priv, self._c_out, dvalue, M, impl, 0, tag="train")
+        self._nets["adapt"].backward(h, h.stride(0), K0, None, self._a_out, dlat, M, impl, 0, tag="train")
+        self._grad[self.std_offset:self.std_offset + self.num_actions].copy_(dstd)
+
+    def backward_adaptation(self, h, outs, dpred):
+        M, K0 = h.shape[0], self.num_obs_history
+        self._nets["adapt"].backward(h, h.stride(0), K0, None, outs, dpred, M, self._impl(), 0, tag="adapt")
+
+    def adaptation_forward(self, h):
+        self.flatten()
+        return self._nets["adapt"].forward(h, h.stride(0), self.num_obs_history, None, h.shape[0], self._impl(), "adapt")
+
+
+def get_activation(act_name):
+    table = {"elu": nn.ELU, "selu": nn.SELU, "relu": nn.ReLU, "crelu": nn.ReLU, "lrelu": nn.LeakyReLU, "tanh": nn.Tanh, "sigmoid": nn.Sigmoid}
+    if act_name not in table:
+        print("invalid activation function!")
+        return None
+    return table[act_name]()

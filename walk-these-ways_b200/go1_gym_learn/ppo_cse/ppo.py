@@ -1,0 +1,179 @@
+"""PPO of ppo_cse (reference go1_gym_learn/ppo_cse/ppo.py:13-205) on explicit kernels: fused loss+gradient
+kernel, hand-written MLP backward, one global grad-norm + clip + Adam launch over the flat parameter buffer,
+device-side adaptive-KL learning rate (no per-minibatch host sync), optional NCCL gradient all-reduce."""
+import torch
+
+from go1_b200 import capi
+from go1_gym_learn.ppo_cse import ActorCritic
+from go1_gym_learn.ppo_cse import RolloutStorage
+from go1_gym_learn.ppo_cse import caches
+from params_proto import PrefixProto
+
+
+class PPO_Args(PrefixProto):
+    # algorithm
+    value_loss_coef = 1.0
+    use_clipped_value_loss = True
+    clip_param = 0.2
+    entropy_coef = 0.01
+    num_learning_epochs = 5
+    num_mini_batches = 4  # mini batch size = num_envs*nsteps / nminibatches
+    learning_rate = 1.e-3  # 5.e-4
+    adaptation_module_learning_rate = 1.e-3
+    num_adaptation_module_substeps = 1
+    schedule = 'adaptive'  # could be adaptive, fixed
+    gamma = 0.99
+    lam = 0.95
+    desired_kl = 0.01
+    max_grad_norm = 1.
+
+    selective_adaptation_module_loss = False
+
+
+class _FlatAdam:
+    """torch.optim.Adam semantics (betas .9/.999, eps 1e-8) over a slice of the flat buffer."""
+
+    def __init__(self, ac, start, end, lr):
+        self.ac, self.start, self.end, self.lr = ac, start, end, lr
+        n = end - start
+        dev = ac.flat_params.device
+        self.exp_avg = torch.zeros(n, device=dev)
+        self.exp_avg_sq = torch.zeros(n, device=dev)
+        self.t = 0
+        self.param_groups = [{"lr": lr}]
+
+    def step(self, grad_sq=None, max_norm=0.0, lr_dev=None):
+        self.t += 1
+        p = self.ac.flat_params[self.start:self.end]
+        g = self.ac.flat_grads[self.start:self.end]
+        capi.check(capi.lib().go1_ppo_adam_step(capi.ptr(p), capi.ptr(g), capi.ptr(self.exp_avg), capi.ptr(self.exp_avg_sq), self.end - self.start,
+                                                capi.ptr(grad_sq) if grad_sq is not None else None, float(max_norm), float(self.param_groups[0]["lr"]),
+                                                capi.ptr(lr_dev) if lr_dev is not None else None, 0.9, 0.999, 1e-8, self.t, capi.stream_ptr()), "adam")
+
+
+class PPO:
+    actor_critic: ActorCritic
+
+    def __init__(self, actor_critic, device='cpu'):
+        self.device = device
+        self.actor_critic = actor_critic
+        self.actor_critic.to(device)
+        self.actor_critic.flatten()
+        self.storage = None  # initialized later
+        ac = self.actor_critic
+        self.optimizer = _FlatAdam(ac, 0, ac.n_params, PPO_Args.learning_rate)
+        # the reference builds a second Adam over ALL parameters (ppo.py:45-46); only the adaptation module ever
+        # receives a non-zero gradient from it, so its state is kept for that slice only (identical updates).
+        self.adaptation_module_optimizer = _FlatAdam(ac, 0, ac.n_adapt_params, PPO_Args.adaptation_module_learning_rate)
+        self.transition = RolloutStorage.Transition()
+        self.learning_rate = PPO_Args.learning_rate
+        dev = ac.flat_params.device
+        self._lr_dev = torch.full((1,), PPO_Args.learning_rate, device=dev)
+        self._scalars = torch.zeros(8, device=dev)
+        self._mse_scalars = torch.zeros(2, device=dev)
+        self._grad_sq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._dstd = torch.zeros(ac.num_actions, device=dev)
+        self._acc = torch.zeros(6, device=dev)
+        self.process_group = None          # set by the multi-GPU runner
+        self.fixed_minibatch_indices = None  # parity tests inject the permutation
+
+    def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, privileged_obs_shape, obs_history_shape, action_shape):
+        self.storage = RolloutStorage(num_envs, num_transitions_per_env, actor_obs_shape, privileged_obs_shape, obs_history_shape, action_shape, self.device)
+
+    def test_mode(self):
+        self.actor_critic.eval()
+
+    def train_mode(self):
+        self.actor_critic.train()
+
+    def act(self, obs, privileged_obs, obs_history):
+        tr = self.transition
+        tr.actions = self.actor_critic.act(obs_history).detach()
+        tr.values = self.actor_critic.evaluate(obs_history, privileged_obs).detach()
+        tr.actions_log_prob = self.actor_critic.get_actions_log_prob(tr.actions).detach()
+        tr.action_mean = self.actor_critic.action_mean.detach()
+        tr.action_sigma = self.actor_critic.action_std.detach()
+        tr.observations = obs
+        tr.critic_observations = obs
+        tr.privileged_observations = privileged_obs
+        tr.observation_histories = obs_history
+        return tr.actions
+
+    def process_env_step(self, rewards, dones, infos):
+        tr = self.transition
+        tr.rewards = rewards.clone()
+        tr.dones = dones
+        tr.env_bins = infos["env_bins"]
+        if 'time_outs' in infos:   # bootstrapping on time outs (ppo.py:84-86)
+            tr.rewards += PPO_Args.gamma * torch.squeeze(tr.values * infos['time_outs'].unsqueeze(1).to(self.device), 1)
+        self.storage.add_transitions(tr)
+        tr.clear()
+        self.actor_critic.reset(dones)
+
+    def compute_returns(self, last_critic_obs, last_critic_privileged_obs):
+        last_values = self.actor_critic.evaluate(last_critic_obs, last_critic_privileged_obs, tag="last").detach()
+        self.storage.compute_returns(last_values, PPO_Args.gamma, PPO_Args.lam)
+
+    def _allreduce(self, t):
+        if self.process_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(t, group=self.process_group)
+
+    def update(self):
+        ac, L, st = self.actor_critic, capi.lib(), capi.stream_ptr
+        world = 1
+        if self.process_group is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(self.process_group)
+        self._acc.zero_()
+        self._lr_dev.fill_(self.learning_rate)
+        n_updates = 0
+        gen = self.storage.mini_batch_generator(PPO_Args.num_mini_batches, PPO_Args.num_learning_epochs, indices=self.fixed_minibatch_indices)
+        for (obs_b, critic_obs_b, priv_b, hist_b, actions_b, target_values_b, adv_b, returns_b, old_logp_b, old_mu_b, old_sigma_b, masks_b, env_bins_b) in gen:
+            M = hist_b.shape[0]
+            ac.update_distribution(hist_b, tag="train")
+            value_b = ac.evaluate(hist_b, priv_b, tag="train")
+            mean_b = ac.action_mean
+            dmean = ac._nets["actor"]._buf(("train", "dmean"), M, ac.num_actions)
+            dvalue = ac._nets["critic"]._buf(("train", "dvalue"), M, 1)
+            capi.check(L.go1_ppo_loss(capi.ptr(mean_b), mean_b.stride(0), capi.ptr(ac.std.data), capi.ptr(value_b), capi.ptr(actions_b), capi.ptr(old_logp_b),
+                                      capi.ptr(old_mu_b), capi.ptr(old_sigma_b), capi.ptr(adv_b), capi.ptr(returns_b), capi.ptr(target_values_b),
+                                      capi.ptr(dmean), ac.num_actions, capi.ptr(dvalue), capi.ptr(self._dstd), capi.ptr(self._scalars), M, ac.num_actions,
+                                      PPO_Args.clip_param, PPO_Args.value_loss_coef, PPO_Args.entropy_coef, int(PPO_Args.use_clipped_value_loss),
+                                      1.0 / (M * world), st()), "ppo_loss")
+            self._allreduce(self._scalars)
+            if PPO_Args.desired_kl is not None and PPO_Args.schedule == 'adaptive':   # ppo.py:118-132, on the device
+                capi.check(L.go1_ppo_adaptive_lr(capi.ptr(self._scalars), capi.ptr(self._lr_dev), PPO_Args.desired_kl, 1e-5, 1e-2, st()), "adaptive_lr")
+            ac.backward_ppo(hist_b, priv_b, dmean, dvalue, self._dstd)
+            self._allreduce(ac.flat_grads)
+            capi.check(L.go1_ppo_grad_sqnorm(capi.ptr(ac.flat_grads), ac.n_params, capi.ptr(self._grad_sq), st()), "sqnorm")
+            self.optimizer.step(self._grad_sq, PPO_Args.max_grad_norm, self._lr_dev)
+            self._acc[0:2] += self._scalars[0:2]
+
+            num_train = int(M // 5 * 4)
+            for epoch in range(PPO_Args.num_adaptation_module_substeps):
+                outs = ac.adaptation_forward(hist_b)
+                pred = outs[-1]
+                dpred = ac._nets["adapt"]._buf(("adapt", "dpred"), M, pred.shape[1])
+                capi.check(L.go1_ppo_mse(capi.ptr(pred), pred.stride(0), capi.ptr(priv_b), priv_b.stride(0), capi.ptr(dpred), dpred.stride(0),
+                                         capi.ptr(self._mse_scalars), M, num_train, pred.shape[1], st()), "mse")
+                ac.backward_adaptation(hist_b, outs, dpred)
+                if self.process_group is not None:
+                    self._allreduce(ac.flat_grads[:ac.n_adapt_params])
+                    ac.flat_grads[:ac.n_adapt_params].div_(world)
+                    self._allreduce(self._mse_scalars); self._mse_scalars.div_(world)
+                self.adaptation_module_optimizer.step()
+                self._acc[2:4] += self._mse_scalars
+            n_updates += 1
+
+        acc = self._acc.tolist()                      # the only host sync of the update
+        self.learning_rate = float(self._lr_dev.item())
+        self.optimizer.param_groups[0]["lr"] = self.learning_rate
+        num_updates = PPO_Args.num_learning_epochs * PPO_Args.num_mini_batches
+        sub = num_updates * PPO_Args.num_adaptation_module_substeps
+        mean_value_loss = acc[1] / num_updates
+        mean_surrogate_loss = acc[0] / num_updates
+        mean_adaptation_module_loss = acc[2] / sub
+        mean_adaptation_module_test_loss = acc[3] / sub
+        self.storage.clear()
+        return mean_value_loss, mean_surrogate_loss, mean_adaptation_module_loss, 0.0, 0.0, mean_adaptation_module_test_loss, 0.0, 0.0

@@ -1,0 +1,115 @@
+"""RolloutStorage of ppo_cse (reference go1_gym_learn/ppo_cse/rollout_storage.py:5-178): [T, N, .] slabs,
+GAE through the warp-scan kernel, minibatches through the row-gather kernel."""
+import torch
+
+from go1_b200 import capi
+
+
+class RolloutStorage:
+    class Transition:
+        def __init__(self):
+            self.observations = None
+            self.privileged_observations = None
+            self.observation_histories = None
+            self.critic_observations = None
+            self.actions = None
+            self.rewards = None
+            self.dones = None
+            self.values = None
+            self.actions_log_prob = None
+            self.action_mean = None
+            self.action_sigma = None
+            self.env_bins = None
+
+        def clear(self):
+            self.__init__()
+
+    def __init__(self, num_envs, num_transitions_per_env, obs_shape, privileged_obs_shape, obs_history_shape, actions_shape, device='cpu'):
+        self.device = device
+        self.obs_shape, self.privileged_obs_shape = obs_shape, privileged_obs_shape
+        self.obs_history_shape, self.actions_shape = obs_history_shape, actions_shape
+        T, N = num_transitions_per_env, num_envs
+        z = lambda *s, **k: torch.zeros(T, N, *s, device=self.device, **k)
+        self.observations = z(*obs_shape)
+        self.privileged_observations = z(*privileged_obs_shape)
+        self.observation_histories = z(*obs_history_shape)
+        self.rewards = z(1)
+        self.actions = z(*actions_shape)
+        self.dones = z(1).byte()
+        self.actions_log_prob = z(1)
+        self.values = z(1)
+        self.returns = z(1)
+        self.advantages = z(1)
+        self.mu = z(*actions_shape)
+        self.sigma = z(*actions_shape)
+        self.env_bins = z(1)
+        self.num_transitions_per_env, self.num_envs = T, N
+        self.step = 0
+        self._stats = torch.zeros(2, dtype=torch.float64, device=self.device)
+        self.process_group = None          # set by the multi-GPU runner: advantage statistics are global
+
+    def add_transitions(self, transition: Transition):
+        if self.step >= self.num_transitions_per_env:
+            raise AssertionError("Rollout buffer overflow")
+        t = self.step
+        self.observations[t].copy_(transition.observations)
+        self.privileged_observations[t].copy_(transition.privileged_observations)
+        self.observation_histories[t].copy_(transition.observation_histories)
+        self.actions[t].copy_(transition.actions)
+        self.rewards[t].copy_(transition.rewards.view(-1, 1))
+        self.dones[t].copy_(transition.dones.view(-1, 1))
+        self.values[t].copy_(transition.values)
+        self.actions_log_prob[t].copy_(transition.actions_log_prob.view(-1, 1))
+        self.mu[t].copy_(transition.action_mean)
+        self.sigma[t].copy_(transition.action_sigma)
+        self.env_bins[t].copy_(transition.env_bins.view(-1, 1))
+        self.step += 1
+
+    def clear(self):
+        self.step = 0
+
+    def compute_returns(self, last_values, gamma, lam):
+        T, N = self.num_transitions_per_env, self.num_envs
+        L, st = capi.lib(), capi.stream_ptr()
+        last_values = last_values.contiguous()
+        capi.check(L.go1_ppo_gae(capi.ptr(self.rewards), capi.ptr(self.dones), capi.ptr(self.values), capi.ptr(last_values),
+                                 capi.ptr(self.returns), capi.ptr(self.advantages), capi.ptr(self._stats), T, N, float(gamma), float(lam), st), "gae")
+        count = T * N
+        if self.process_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(self._stats, group=self.process_group)
+            count = T * N * dist.get_world_size(self.process_group)
+        capi.check(L.go1_ppo_normalize_advantages(capi.ptr(self.advantages), capi.ptr(self._stats), count, T * N, st), "normalize")
+
+    def get_statistics(self):
+        done = self.dones
+        done[-1] = 1
+        flat_dones = done.permute(1, 0, 2).reshape(-1, 1)
+        done_indices = torch.cat((flat_dones.new_tensor([-1], dtype=torch.int64), flat_dones.nonzero(as_tuple=False)[:, 0]))
+        trajectory_lengths = (done_indices[1:] - done_indices[:-1])
+        return trajectory_lengths.float().mean(), self.rewards.mean()
+
+    def gather(self, src, idx, out=None, ldd=None):
+        """out[i] = src.flatten(0,1)[idx[i]] through go1_gather_rows."""
+        flat = src.flatten(0, 1)
+        w = flat.shape[1]
+        ldd = ldd or w
+        if out is None:
+            out = torch.empty(idx.shape[0], ldd, device=flat.device)
+        capi.check(capi.lib().go1_gather_rows(capi.ptr(flat), capi.ptr(idx), capi.ptr(out), idx.shape[0], w, ldd, capi.stream_ptr()), "gather")
+        return out
+
+    def mini_batch_generator(self, num_mini_batches, num_epochs=8, indices=None):
+        batch_size = self.num_envs * self.num_transitions_per_env
+        mini_batch_size = batch_size // num_mini_batches
+        if indices is None:
+            indices = torch.randperm(num_mini_batches * mini_batch_size, requires_grad=False, device=self.device)
+        dones8 = None
+        for epoch in range(num_epochs):
+            for i in range(num_mini_batches):
+                idx = indices[i * mini_batch_size:(i + 1) * mini_batch_size].contiguous()
+                obs = self.gather(self.observations, idx)
+                yield (obs, obs, self.gather(self.privileged_observations, idx), self.gather(self.observation_histories, idx),
+                       self.gather(self.actions, idx), self.gather(self.values, idx), self.gather(self.advantages, idx),
+                       self.gather(self.returns, idx), self.gather(self.actions_log_prob, idx), self.gather(self.mu, idx),
+                       self.gather(self.sigma, idx), dones8, self.gather(self.env_bins, idx))
