@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py — Go1 env-steps/s at 4096 envs per GPU (BASELINE.json metric), one JSON line on rank 0.
+
+A "step" is one training iteration of scripts/train.py's configuration: a 24-step rollout of 4096 envs
+(policy inference + fused sim step + host curriculum) followed by compute_returns and the full PPO update
+(5 epochs x 4 minibatches + adaptation steps).  value = env-steps of all ranks / device time (CUDA events,
+max over ranks); e2e = the same through the public API by host wall clock, including every host<->device
+copy of the path (event lists down, new commands up, loss read-back).
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference        # the CPU port of the reference path on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "walk-these-ways_b200")
+for p in (ROOT, PKG, os.path.join(PKG, "compat"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "env_steps_per_s"
+UNIT = "env-steps/s"
+T_ROLLOUT = 24
+
+# fp32 words the fused step kernel reads / writes per env-step in its SoA layout: every row it
+# touches, counted once.  reads: root 13, q/qd 24, motor_offsets 12, actions 12, DR 9, prev foot vel 12, action FIFO 72,
+# actuator lags 48, ep_len 1, commands 15, gait 1, last_* 60, last_contacts 4, episode/command sums (RMW) 44
+# writes: FIFO 72, lags 48, torques+target 24, q/qd 24, root 13, foot pos/vel/prev 36, contact forces 60, gait outputs 20,
+# base-frame 9, actions 12, gait 1, rew pos/neg 2, rew/reset/timeout/ep_len 4, obs 70, priv 2, last_* 60, sums 44, contacts 4
+SIM_READ_WORDS = 13 + 24 + 12 + 12 + 9 + 12 + 72 + 48 + 1 + 15 + 1 + 60 + 4 + 44
+SIM_WRITE_WORDS = 72 + 48 + 24 + 24 + 13 + 36 + 60 + 20 + 9 + 12 + 1 + 2 + 4 + 70 + 2 + 60 + 44 + 4
+SIM_BYTES_PER_ENV_STEP = 4 * (SIM_READ_WORDS + SIM_WRITE_WORDS)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p["hbm_gbs"], p.get("bf16_tflops_sustained", p["bf16_tflops"]), "measured"
+    except Exception:
+        return 6650.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index=0):
+        self.lines, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_training(num_envs, device, gemm_impl):
+    import torch
+    from go1_gym.envs.base.legged_robot_config import Cfg
+    from go1_b200.train_config import apply_train_config
+    from go1_gym.envs.go1.velocity_tracking import VelocityTrackingEasyEnv
+    from go1_gym.envs.wrappers.history_wrapper import HistoryWrapper
+    from go1_gym_learn.ppo_cse import Runner, RunnerArgs
+    from go1_gym_learn.ppo_cse.actor_critic import AC_Args
+    from ml_logger import logger
+    apply_train_config(Cfg)
+    Cfg.env.num_envs = num_envs
+    AC_Args.gemm_impl = gemm_impl
+    RunnerArgs.num_steps_per_env = T_ROLLOUT
+    logger.configure(prefix="bench", root=os.path.join(ROOT, "gpurun_out", "bench_runs"))
+    env = HistoryWrapper(VelocityTrackingEasyEnv(sim_device=device, headless=True, cfg=Cfg))
+    runner = Runner(env, device=device)
+    env.episode_length_buf = torch.randint_like(env.episode_length_buf, high=int(env.max_episode_length))   # learn(init_at_random_ep_len=True)
+    return env, runner
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from go1_b200 import capi
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback; use --impl reference for the CPU port)")
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun for N>1"
+    env, runner = build_training(args.envs, device, args.gemm)
+    L = capi.lib()
+    od = env.get_observations()
+    state = [od["obs"], od["privileged_obs"], od["obs_history"]]
+
+    def iteration():
+        obs, priv, hist, infos = runner.rollout(*state)
+        state[:] = [obs, priv, hist]
+        with torch.inference_mode():
+            runner.alg.compute_returns(hist[:env.num_train_envs], priv[:env.num_train_envs])
+        return runner.alg.update()          # returns host floats: one D2H sync per iteration
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        iteration()
+    sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    core = env.env.core
+    core.h2d_bytes = core.d2h_bytes = 0
+    core.iters_counted = args.steps
+    l0 = L.go1_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        losses = iteration()
+    e1.record()
+    sync()
+    wall = time.perf_counter() - t0
+    dev_ms = e0.elapsed_time(e1)
+    launches = L.go1_kernel_launch_count() - l0
+    t = torch.tensor([dev_ms, wall * 1e3], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms = t.tolist()
+    clocks = sampler.stop() if rank == 0 else None
+    env_steps = args.steps * T_ROLLOUT * args.envs * world
+
+    out = None
+    if rank == 0:
+        hbm, tf, src = peaks()
+        roof = sim_roofline(env, args.envs, hbm, src)
+        out = {
+            "metric": METRIC, "value": env_steps / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.gemm == 0 else "tf32", "data": "synthetic (random-init policy, randomised flat terrain, device RNG)",
+            "config": {"workload": "Go1 flat terrain, 4096 envs/GPU, 24-step rollout + ppo_cse update (scripts/train.py config)",
+                       "envs_per_gpu": args.envs, "rollout_steps": T_ROLLOUT, "parallelism": f"dp{world}",
+                       "l2_policy": "roofline kernel timed alone with a 512 MiB L2 flush between launches; iteration timing uses the live working set (rollout slab 0.87 GB > L2)",
+                       "gemm_impl": "fp32 CUDA cores" if args.gemm == 0 else "tcgen05 tf32"},
+            "e2e": {"value": env_steps / (wall_ms / 1e3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(runner_h2d_bytes(env)), "d2h_bytes_per_step": int(runner_d2h_bytes(env)) + 28},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "losses": [float(x) for x in losses[:3]],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(sample_envs=args.cpu_envs)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+def runner_h2d_bytes(env):
+    """Per training iteration: new commands + ids for reset/resampled envs (measured from the env's counters), env_bins."""
+    c = env.env.core
+    return getattr(c, "h2d_bytes", 0) / max(1, getattr(c, "iters_counted", 1))
+
+
+def runner_d2h_bytes(env):
+    c = env.env.core
+    return getattr(c, "d2h_bytes", 0) / max(1, getattr(c, "iters_counted", 1))
+
+
+def sim_roofline(env, n_envs, hbm_peak, src):
+    """Fused step kernel timed alone (CUDA events on the launch stream), L2 flushed between launches."""
+    import torch
+    core = env.env.core
+    actions = torch.zeros(n_envs, 12, device=core.device)
+    flush = torch.empty(512 * 1024 * 1024 // 4, device=core.device)
+    saved = [core.env_f32.clone(), core.leg_f32.clone(), core.env_i32.clone()]
+    times = []
+    for i in range(13):
+        flush.fill_(float(i))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        core.step(actions, common_step=10_000 + i, mode=0)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            times.append(e0.elapsed_time(e1))
+    core.env_f32.copy_(saved[0]); core.leg_f32.copy_(saved[1]); core.env_i32.copy_(saved[2])
+    ms = sum(times) / len(times)
+    achieved = SIM_BYTES_PER_ENV_STEP * n_envs / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "go1_step_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "traffic": None, "peak_source": src, "kernel_ms": ms, "bytes_per_env_step": SIM_BYTES_PER_ENV_STEP,
+            "sim_only_env_steps_per_s": n_envs / (ms * 1e-3)}
+
+
+def cpu_port_iteration(n_envs, T, threads):
+    """One bounded sample of the hot path on the CPU oracle port: T-step rollout of n_envs (policy + env step) + PPO update."""
+    import torch
+    from env_golden_util import train_sim_config
+    from oracle.env_step_oracle import OracleEnv
+    from oracle.ppo_oracle import ActorCriticOracle, PPOOracle, gae
+    torch.set_num_threads(threads)
+    Cfg, c, info = train_sim_config(n_envs)
+    env = OracleEnv(c, info["active_reward_scales"], info["dt"], n_envs)
+    ac = ActorCriticOracle()
+    ppo = PPOOracle(ac)
+    hist = torch.zeros(n_envs, 2100)
+    t0 = time.perf_counter()
+    H, P, A, V, LP, MU, R, D = [], [], [], [], [], [], [], []
+    with torch.no_grad():
+        priv = torch.zeros(n_envs, 2)
+        for t in range(T):
+            d = ac.dist(hist)
+            a = d.sample()
+            H.append(hist); P.append(priv); A.append(a); V.append(ac.value(hist, priv)); LP.append(d.log_prob(a).sum(-1, keepdim=True)); MU.append(d.mean)
+            obs, priv, rew, reset = env.step(a)
+            hist = torch.cat((hist[:, 70:], obs), -1)
+            R.append(rew.unsqueeze(-1)); D.append(reset.unsqueeze(-1))
+        values = torch.stack(V)
+        returns, adv = gae(torch.stack(R), torch.stack(D), values, ac.value(hist, priv))
+    f = lambda x: torch.stack(x).flatten(0, 1) if isinstance(x, list) else x.flatten(0, 1)
+    ppo.update(f(H), f(P), f(A), f(values), f(returns), f(adv), f(LP), f(MU), torch.ones_like(f(MU)), torch.randperm(n_envs * T))
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(sample_envs=32):
+    import torch
+    threads = torch.get_num_threads()
+    dt = cpu_port_iteration(sample_envs, T_ROLLOUT, threads)
+    return {"value": sample_envs * T_ROLLOUT / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{sample_envs} envs x {T_ROLLOUT}-step rollout (oracle policy + fp64 C physics + torch env logic) + full ppo_cse update on that batch, {dt:.1f} s"}
+
+
+def run_reference(args):
+    """CPU port of the reference path (the reference itself needs Isaac Gym, which is not installable): rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    times = []
+    for i in range(args.warmup_ref + args.steps):
+        dt = cpu_port_iteration(args.cpu_envs, T_ROLLOUT, threads)
+        if i >= args.warmup_ref:
+            times.append(dt)
+    per = sum(times) / len(times)
+    v = args.cpu_envs * T_ROLLOUT / per
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup_ref,
+        "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+        "config": {"workload": "Go1 flat terrain, 4096 envs/GPU, 24-step rollout + ppo_cse update (scripts/train.py config)",
+                   "sample": f"{args.cpu_envs} envs x {T_ROLLOUT} steps per timed step (bounded sample of the 4096-env workload)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.cpu_envs} envs x {T_ROLLOUT}-step rollout + ppo_cse update, oracle port (Isaac Gym is not installable: no 'reference' kind)"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
+    ap.add_argument("--gemm", type=int, default=int(os.environ.get("GO1_GEMM_IMPL", "0")), help="0 fp32 CUDA cores, 1 tcgen05 tf32")
+    ap.add_argument("--cpu-envs", type=int, default=32)
+    ap.add_argument("--warmup-ref", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

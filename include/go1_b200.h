@@ -119,6 +119,8 @@ int go1_device_count(void);
 /* sizeof(Go1SimConfig) / sizeof(Go1SimBuffers) as compiled, so FFI bindings can verify their struct mirrors */
 int go1_sizeof_config(void);
 int go1_sizeof_buffers(void);
+/* number of CUDA kernels this library has launched in this process (bench.py reports it as gpu_launches) */
+long long go1_kernel_launch_count(void);
 
 /* Layout queries: kind 0 = env_f32, 1 = leg_f32, 2 = env_i32. go1_sim_row returns the first row of the
  * named field or -1. */

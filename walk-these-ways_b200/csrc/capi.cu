@@ -19,6 +19,10 @@ static int cuda_fail(const char* what, int e) {
     return e ? e : 1;
 }
 int go1_set_error(const char* m) { return fail(m); }
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void go1_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" long long go1_kernel_launch_count(void) { return g_launches.load(); }
 
 struct Go1Sim {
     Go1SimConfig cfg;

@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include "../../include/go1_b200.h"
 #include "sim_math.cuh"
+void go1_count_launch(int n);
 
 extern int go1_set_error(const char* m);
 static int cuda_rc(const char* what) {
@@ -104,12 +105,12 @@ extern "C" int go1_ppo_gae(const float* rewards, const uint8_t* dones, const flo
     if (!rewards || !dones || !values || !last_values || !returns || !advantages || !stats || T <= 0 || n <= 0) return go1_set_error("go1_ppo_gae: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(stats, 0, 2 * sizeof(double), st);
-    gae_kernel<<<(n + 31) / 32, dim3(32, 32), 0, st>>>(rewards, dones, values, last_values, returns, advantages, stats, T, n, gamma, lam);
+    gae_kernel<<<(n + 31) / 32, dim3(32, 32), 0, st>>>(rewards, dones, values, last_values, returns, advantages, stats, T, n, gamma, lam); go1_count_launch(1);
     return cuda_rc("go1_ppo_gae");
 }
 extern "C" int go1_ppo_normalize_advantages(float* advantages, const double* stats, int64_t global_count, int64_t local_count, void* stream) {
     if (!advantages || !stats || global_count < 2 || local_count <= 0) return go1_set_error("go1_ppo_normalize_advantages: bad arguments");
-    normalize_adv_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(advantages, stats, global_count, local_count);
+    normalize_adv_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(advantages, stats, global_count, local_count); go1_count_launch(1);
     return cuda_rc("go1_ppo_normalize_advantages");
 }
 
@@ -249,14 +250,15 @@ extern "C" int go1_gemm(int transA, int transB, int M, int N, int K, const float
     dim3 grid((N + 127) / 128, (M + 127) / 128, splitk);
     if (splitk > 1 && !accumulate) {
         const size_t tot = (size_t)M * N;
-        zero_strided_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cm, ldc, M, N);
+        zero_strided_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cm, ldc, M, N); go1_count_launch(1);
     }
 #define LAUNCH(TA, TB) sgemm_kernel<TA, TB><<<grid, 256, 0, st>>>(A, lda, B, ldb, Cm, ldc, bias, M, N, K, act, accumulate, kchunk)
     if (!transA && !transB) LAUNCH(0, 0); else if (!transA && transB) LAUNCH(0, 1); else if (transA && !transB) LAUNCH(1, 0); else LAUNCH(1, 1);
+    go1_count_launch(1);
 #undef LAUNCH
     if (splitk > 1 && (bias || act)) {
         const size_t tot = (size_t)M * N;
-        bias_act_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cm, ldc, bias, M, N, act);
+        bias_act_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cm, ldc, bias, M, N, act); go1_count_launch(1);
     }
     return cuda_rc("go1_gemm");
 }
@@ -272,7 +274,7 @@ __global__ void elu_bwd_kernel(const float* __restrict__ y, int ldy, const float
 extern "C" int go1_elu_backward(const float* y, int ldy, const float* dy, int lddy, float* dz, int lddz, int M, int N, void* stream) {
     if (!y || !dy || !dz || M <= 0 || N <= 0) return go1_set_error("go1_elu_backward: bad arguments");
     const size_t tot = (size_t)M * N;
-    elu_bwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(y, ldy, dy, lddy, dz, lddz, M, N);
+    elu_bwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(y, ldy, dy, lddy, dz, lddz, M, N); go1_count_launch(1);
     return cuda_rc("go1_elu_backward");
 }
 
@@ -299,7 +301,7 @@ extern "C" int go1_colsum(const float* x, int ldx, float* out, int M, int N, int
     if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * N, st);
     const int rpb = 512;
     dim3 grid((N + 31) / 32, (M + rpb - 1) / rpb);
-    colsum_kernel<<<grid, 256, 0, st>>>(x, ldx, out, M, N, rpb);
+    colsum_kernel<<<grid, 256, 0, st>>>(x, ldx, out, M, N, rpb); go1_count_launch(1);
     return cuda_rc("go1_colsum");
 }
 
@@ -330,7 +332,7 @@ __global__ void sample_actions_kernel(const float* __restrict__ mean, int ldm, c
 extern "C" int go1_ppo_sample_actions(const float* mean, int ldm, const float* std, const float* eps, uint64_t seed, uint64_t counter,
                                       float* actions, float* logp, int n, int num_actions, void* stream) {
     if (!mean || !std || !actions || !logp || n <= 0 || num_actions <= 0) return go1_set_error("go1_ppo_sample_actions: bad arguments");
-    sample_actions_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean, ldm, std, eps, seed, counter, actions, logp, n, num_actions);
+    sample_actions_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean, ldm, std, eps, seed, counter, actions, logp, n, num_actions); go1_count_launch(1);
     return cuda_rc("go1_ppo_sample_actions");
 }
 
@@ -427,8 +429,8 @@ extern "C" int go1_ppo_loss(const float* mean, int ldm, const float* std, const 
     cudaMemsetAsync(scalars, 0, sizeof(float) * 8, st);
     ppo_loss_kernel<<<(n + 255) / 256, 256, 0, st>>>(mean, ldm, std, value, actions, old_logp, old_mean, old_std, advantages, returns, old_values,
                                                     dmean, lddm, dvalue, dstd, scalars, n, num_actions, clip_param, value_loss_coef, entropy_coef,
-                                                    use_clipped_value_loss, inv_count);
-    ppo_entropy_kernel<<<1, 32, 0, st>>>(std, dstd, scalars, num_actions, entropy_coef, (float)n * inv_count);
+                                                    use_clipped_value_loss, inv_count); go1_count_launch(1);
+    ppo_entropy_kernel<<<1, 32, 0, st>>>(std, dstd, scalars, num_actions, entropy_coef, (float)n * inv_count); go1_count_launch(1);
     return cuda_rc("go1_ppo_loss");
 }
 
@@ -463,7 +465,7 @@ extern "C" int go1_ppo_mse(const float* pred, int ldp, const float* target, int 
     if (!pred || !target || !dpred || !scalars || n <= 0 || dim <= 0 || num_train < 0 || num_train > n) return go1_set_error("go1_ppo_mse: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(scalars, 0, sizeof(float) * 2, st);
-    mse_kernel<<<(n + 255) / 256, 256, 0, st>>>(pred, ldp, target, ldt, dpred, lddp, scalars, n, num_train, dim);
+    mse_kernel<<<(n + 255) / 256, 256, 0, st>>>(pred, ldp, target, ldt, dpred, lddp, scalars, n, num_train, dim); go1_count_launch(1);
     return cuda_rc("go1_ppo_mse");
 }
 
@@ -484,7 +486,7 @@ extern "C" int go1_ppo_grad_sqnorm(const float* grad, int64_t count, double* gra
     if (!grad || !grad_sq || count <= 0) return go1_set_error("go1_ppo_grad_sqnorm: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(grad_sq, 0, sizeof(double), st);
-    sqnorm_kernel<<<296, 256, 0, st>>>(grad, count, grad_sq);
+    sqnorm_kernel<<<296, 256, 0, st>>>(grad, count, grad_sq); go1_count_launch(1);
     return cuda_rc("go1_ppo_grad_sqnorm");
 }
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long count,
@@ -514,14 +516,14 @@ __global__ void adaptive_lr_kernel(const float* __restrict__ scalars, float* __r
 }
 extern "C" int go1_ppo_adaptive_lr(const float* scalars, float* lr_dev, float desired_kl, float lr_min, float lr_max, void* stream) {
     if (!scalars || !lr_dev) return go1_set_error("go1_ppo_adaptive_lr: bad arguments");
-    adaptive_lr_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(scalars, lr_dev, desired_kl, lr_min, lr_max);
+    adaptive_lr_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(scalars, lr_dev, desired_kl, lr_min, lr_max); go1_count_launch(1);
     return cuda_rc("go1_ppo_adaptive_lr");
 }
 extern "C" int go1_ppo_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count, const double* grad_sq,
                                  float max_grad_norm, float lr, const float* lr_dev, float beta1, float beta2, float eps, int step, void* stream) {
     if (!param || !grad || !exp_avg || !exp_avg_sq || count <= 0 || step <= 0) return go1_set_error("go1_ppo_adam_step: bad arguments");
     const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
-    adam_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, count, grad_sq, max_grad_norm, lr, lr_dev, beta1, beta2, eps, bc1, sqrtf(bc2));
+    adam_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, count, grad_sq, max_grad_norm, lr, lr_dev, beta1, beta2, eps, bc1, sqrtf(bc2)); go1_count_launch(1);
     return cuda_rc("go1_ppo_adam_step");
 }
 
@@ -542,6 +544,6 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const long lon
 extern "C" int go1_gather_rows(const float* src, const int64_t* idx, float* dst, int64_t rows, int width, int ldd, void* stream) {
     if (!src || !idx || !dst || rows <= 0 || width <= 0 || ldd < width) return go1_set_error("go1_gather_rows: bad arguments");
     const int threads = width >= 1024 ? 256 : (width >= 128 ? 64 : 32);
-    gather_rows_kernel<<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(src, (const long long*)idx, dst, rows, width, ldd);
+    gather_rows_kernel<<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(src, (const long long*)idx, dst, rows, width, ldd); go1_count_launch(1);
     return cuda_rc("go1_gather_rows");
 }

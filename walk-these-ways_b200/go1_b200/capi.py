@@ -98,6 +98,7 @@ def lib():
     vp, ip, i64 = C.c_void_p, C.c_int, C.c_int64
     sig = {
         "go1_version": ([], ip), "go1_device_count": ([], ip), "go1_sizeof_config": ([], ip), "go1_sizeof_buffers": ([], ip),
+        "go1_kernel_launch_count": ([], C.c_longlong),
         "go1_sim_num_rows": ([ip], ip), "go1_sim_row": ([ip, C.c_char_p], ip),
         "go1_sim_create": ([C.POINTER(Go1SimConfig), vp, ip, C.POINTER(vp)], ip),
         "go1_sim_destroy": ([vp], ip), "go1_sim_bind": ([vp, C.POINTER(Go1SimBuffers)], ip),

@@ -48,6 +48,8 @@ class SimCore:
         self.d_cmds = torch.zeros(N, capi.NUM_COMMANDS, device=dev)
         self.h_ids = torch.zeros(N, dtype=torch.int32).pin_memory()
         self.h_cmds = torch.zeros(N, capi.NUM_COMMANDS).pin_memory()
+        self.h2d_bytes = self.d2h_bytes = 0            # host<->device traffic of the step path (bench.py reports it)
+        self.iters_counted = 1
         self.gravity = (C.c_float * 3)(0.0, 0.0, -9.8)
         self.gravity_vec = (C.c_float * 3)(0.0, 0.0, -1.0)
 
@@ -150,6 +152,7 @@ class SimCore:
         Returns (reset_ids, reset_sums[k,4], interval_ids, interval_sums[k,4]) sorted by env id."""
         self.h_count.copy_(self.event_count, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        self.d2h_bytes += 8
         out = []
         for lst in range(2):
             k = int(self.h_count[lst])
@@ -158,6 +161,7 @@ class SimCore:
                 continue
             self.h_events[lst, :k].copy_(self.events[lst, :k], non_blocking=True)
             torch.cuda.current_stream().synchronize()
+            self.d2h_bytes += k * capi.EVENT_STRIDE * 4
             ev = self.h_events[lst, :k].numpy()
             ids = ev[:, 0].astype(np.int64)
             order = np.argsort(ids, kind="stable")
@@ -170,6 +174,7 @@ class SimCore:
         self.h_cmds[:k] = torch.as_tensor(np.asarray(cmds, dtype=np.float32)).reshape(k, capi.NUM_COMMANDS)
         self.d_ids[:k].copy_(self.h_ids[:k], non_blocking=True)
         self.d_cmds[:k].copy_(self.h_cmds[:k], non_blocking=True)
+        self.h2d_bytes += k * 4 * (1 + capi.NUM_COMMANDS)
         return k
 
     def reset_idx(self, ids, new_commands, actions=None, post_step=False, common_step=0):

@@ -1,0 +1,518 @@
+"""LeggedRobot — the reference's vectorised Go1 env (go1_gym/envs/base/legged_robot.py:19-1806) with the
+simulator, torque model, rewards, observations, termination and resets running in the fused CUDA kernels of
+libgo1b200.so.  What stays on the host is exactly what the reference keeps on the host: the numpy command
+curriculum (legged_robot.py:710-824) and the global gravity randomisation (:546-561, 701-705).
+
+Per step:   [commands of envs due for the periodic resample -> go1_sim_set_commands]
+            go1_sim_step (one fused launch: control x4, physics x4, post-physics, rewards, obs)
+            one D2H read of the event list (reset envs + next step's resample envs, with their command sums)
+            host curriculum update/sample for the reset envs
+            go1_sim_reset_idx (sparse: re-initialise those envs and write their observations)
+
+Public attributes keep the reference's names and AoS shapes; they are views/copies of the SoA device state."""
+import numpy as np
+import torch
+
+from go1_b200 import capi
+from go1_b200.config import build_sim_config, cfg_dict
+from go1_b200.sim import SimCore
+from go1_gym.envs.base.base_task import BaseTask
+from go1_gym.utils.terrain import Terrain
+from .legged_robot_config import Cfg
+
+_TASK_KEYS = ["tracking_lin_vel", "tracking_ang_vel", "tracking_contacts_shaped_force", "tracking_contacts_shaped_vel"]
+_LOCAL_RANGE = np.array([0.55, 0.55, 0.55, 0.55, 0.35, 0.25, 0.25, 0.25, 0.25, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0])
+
+
+class LazyExtras(dict):
+    """dict whose expensive entries (device->host copies) are produced on first access."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self._lazy = {}
+
+    def lazy(self, key, thunk):
+        self._lazy[key] = thunk
+        dict.pop(self, key, None)
+
+    def __missing__(self, key):
+        if key in self._lazy:
+            v = self._lazy[key]()
+            return v
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._lazy
+
+    def get(self, key, default=None):
+        try:
+            return self[key]
+        except KeyError:
+            return default
+
+
+class LeggedRobot(BaseTask):
+    def __init__(self, cfg: Cfg, sim_params, physics_engine, sim_device, headless, eval_cfg=None, initial_dynamics_dict=None):
+        if eval_cfg is not None:
+            raise NotImplementedError("eval_cfg / num_eval_envs split (SURVEY.md §8f row 3) is not built yet")
+        self.cfg = cfg
+        self.eval_cfg = eval_cfg
+        self.sim_params = sim_params
+        self.height_samples = None
+        self.debug_viz = False
+        self.init_done = False
+        self.initial_dynamics_dict = initial_dynamics_dict
+        super().__init__(self.cfg, sim_params, physics_engine, sim_device, headless, self.eval_cfg)
+
+        self._init_command_distribution(np.arange(self.num_envs))
+        self._init_buffers()
+        self._prepare_reward_function()
+        self.init_done = True
+        self.record_now = False
+        self.record_eval_now = False
+        self.collecting_evaluation = False
+        self.num_still_evaluating = 0
+
+    # ------------------------------------------------------------------ construction
+    def create_sim(self):
+        """Replaces create_sim/_create_envs (legged_robot.py:493-515, 1481-1609): build the resolved kernel
+        configuration, allocate the SoA state, place the env origins, draw the creation-time randomisation."""
+        cfg = self.cfg
+        seed = int(getattr(cfg, "seed", 0)) if hasattr(cfg, "seed") else 0
+        self.sim_cfg, info = build_sim_config(cfg, num_envs=self.num_envs, num_train_envs=self.num_train_envs, seed=seed)
+        self.dt = info["dt"]
+        self.reward_scales = dict(info["active_reward_scales"])
+        self.obs_scales = cfg.obs_scales
+        self.curriculum_thresholds = cfg_dict(cfg.curriculum_thresholds)
+        cfg.command_ranges = cfg_dict(cfg.commands)
+        self.max_episode_length = cfg.env.max_episode_length
+        self.up_axis_idx = 2
+        mesh_type = cfg.terrain.mesh_type
+        if mesh_type in ['heightfield', 'trimesh']:
+            self.terrain = Terrain(cfg.terrain, self.num_train_envs)
+        elif mesh_type not in (None, 'plane'):
+            raise ValueError("Terrain mesh type not recognised. Allowed types are [None, plane, heightfield, trimesh]")
+        self.core = SimCore(self.sim_cfg, device=self.device)
+        self.num_dof = self.num_dofs = self.num_actuated_dof = 12
+        self.num_bodies = 17
+        self.dof_names = [f"{l}_{p}_joint" for l in ("FL", "FR", "RL", "RR") for p in ("hip", "thigh", "calf")]
+        self.feet_indices = torch.tensor([4, 8, 12, 16], device=self.device)
+        self.penalised_contact_indices = torch.tensor([2, 6, 10, 14, 3, 7, 11, 15], device=self.device)
+        self.termination_contact_indices = torch.tensor([0], device=self.device)
+        self._get_env_origins()
+        self._init_custom_buffers__()
+        self._randomize_rigid_body_props(torch.arange(self.num_envs, device=self.device), cfg)
+        self.common_step_counter = 0
+        self._randomize_gravity()
+
+    def _get_env_origins(self):
+        """legged_robot.py:1675-1714."""
+        cfg, N, dev = self.cfg, self.num_envs, self.device
+        self.env_origins = torch.zeros(N, 3, device=dev)
+        self.terrain_levels = torch.zeros(N, device=dev, dtype=torch.long)
+        self.terrain_types = torch.zeros(N, device=dev, dtype=torch.long)
+        if cfg.terrain.mesh_type in ["heightfield", "trimesh"]:
+            self.custom_origins = True
+            t = cfg.terrain
+            max_init, min_init = t.max_init_terrain_level, t.min_init_terrain_level
+            if not t.curriculum:
+                max_init, min_init = t.num_rows - 1, 0
+            if t.center_robots:
+                lo_l, hi_l = t.num_rows // 2 - t.center_span, t.num_rows // 2 + t.center_span - 1
+                lo_t, hi_t = t.num_cols // 2 - t.center_span, t.num_cols // 2 + t.center_span - 1
+                self.terrain_levels = torch.randint(lo_l, hi_l + 1, (N,), device=dev)
+                self.terrain_types = torch.randint(lo_t, hi_t + 1, (N,), device=dev)
+            else:
+                self.terrain_levels = torch.randint(min_init, max_init + 1, (N,), device=dev)
+                self.terrain_types = torch.div(torch.arange(N, device=dev), (N / t.num_cols), rounding_mode='floor').to(torch.long)
+            t.max_terrain_level = t.num_rows
+            t.terrain_origins = torch.from_numpy(t.env_origins).to(dev).to(torch.float)
+            self.env_origins = t.terrain_origins[self.terrain_levels, self.terrain_types]
+        else:
+            self.custom_origins = False
+            num_cols = np.floor(np.sqrt(N))
+            num_rows = np.ceil(N / num_cols)
+            xx, yy = torch.meshgrid(torch.arange(num_rows), torch.arange(num_cols), indexing="ij")
+            sp = cfg.env.env_spacing
+            self.env_origins[:, 0] = sp * xx.flatten()[:N].to(dev)
+            self.env_origins[:, 1] = sp * yy.flatten()[:N].to(dev)
+        self.core.env("env_origins").copy_(self.env_origins.t())
+
+    def _init_custom_buffers__(self):
+        """legged_robot.py:1260-1297: DR defaults (the SimCore constructor already set 1.0 where needed)."""
+        c = self.core
+        c.env("friction_coeffs").fill_(1.0)       # default asset friction
+        c.env("restitutions").fill_(0.0)
+        if self.initial_dynamics_dict is not None:
+            for k, v in self.initial_dynamics_dict.items():
+                if k in ("friction_coeffs", "restitutions"):
+                    c.env(k)[0].copy_(v.to(self.device).reshape(self.num_envs, -1)[:, 0])
+                elif k == "payloads":
+                    c.env(k)[0].copy_(v.to(self.device))
+                elif k == "com_displacements":
+                    c.env(k).copy_(v.to(self.device).t())
+                elif k in ("motor_strengths", "Kp_factors", "Kd_factors"):
+                    c.env(k)[0].copy_(v.to(self.device).reshape(self.num_envs, -1)[:, 0])
+        self.gravities = torch.zeros(self.num_envs, 3, dtype=torch.float, device=self.device)
+        self.gravity_vec = torch.tensor([0., 0., -1.], device=self.device).repeat((self.num_envs, 1))
+
+    def _randomize_rigid_body_props(self, env_ids, cfg):
+        """legged_robot.py:611-633 (creation-time draw; randomize_rigids_after_start is False in train.py)."""
+        dr, c, n, dev = cfg.domain_rand, self.core, len(env_ids), self.device
+        U = lambda lo, hi, *s: torch.rand(*s, dtype=torch.float, device=dev) * (hi - lo) + lo
+        if dr.randomize_base_mass:
+            c.env("payloads")[0, env_ids] = U(*dr.added_mass_range, n)
+        if dr.randomize_com_displacement:
+            c.env("com_displacements")[:, env_ids] = U(*dr.com_displacement_range, n, 3).t()
+        if dr.randomize_friction:
+            c.env("friction_coeffs")[0, env_ids] = U(*dr.friction_range, n)
+        if dr.randomize_restitution:
+            c.env("restitutions")[0, env_ids] = U(*dr.restitution_range, n)
+
+    def _randomize_gravity(self, external_force=None):
+        """legged_robot.py:546-561: one global gravity offset for all envs (kept on the host: it is a kernel argument)."""
+        if external_force is not None:
+            g0 = torch.as_tensor(external_force, dtype=torch.float).cpu()
+        elif self.cfg.domain_rand.randomize_gravity:
+            lo, hi = self.cfg.domain_rand.gravity_range
+            g0 = torch.rand(3, dtype=torch.float) * (hi - lo) + lo
+        else:
+            g0 = getattr(self, "_gravity_host", torch.zeros(3))
+        self._gravity_host = g0
+        self.gravities[:, :] = g0.to(self.device).unsqueeze(0)
+        gravity = g0 + torch.tensor([0., 0., -9.8])
+        gv = gravity / torch.norm(gravity)
+        self.gravity_vec[:, :] = gv.to(self.device).unsqueeze(0)
+        self.core.set_gravity(gravity.tolist(), gv.tolist())
+
+    def _init_command_distribution(self, env_ids):
+        """legged_robot.py:1299-1383."""
+        from .curriculum import RewardThresholdCurriculum
+        c = self.cfg.commands
+        self.category_names = ['pronk', 'trot', 'pace', 'bound'] if c.gaitwise_curricula else ['nominal']
+        if c.curriculum_type != "RewardThresholdCurriculum":
+            raise NotImplementedError(c.curriculum_type)
+        dims = [("x_vel", "vel_x"), ("y_vel", "vel_y"), ("yaw_vel", "vel_yaw"), ("body_height", "body_height"),
+                ("gait_frequency", "gait_frequency"), ("gait_phase", "gait_phase"), ("gait_offset", "gait_offset"),
+                ("gait_bounds", "gait_bound"), ("gait_duration", "gait_duration"), ("footswing_height", "footswing_height"),
+                ("body_pitch", "body_pitch"), ("body_roll", "body_roll"), ("stance_width", "stance_width"),
+                ("stance_length", "stance_length"), ("aux_reward_coef", "aux_reward_coef")]
+        kw = {name: (getattr(c, f"limit_{key}")[0], getattr(c, f"limit_{key}")[1], getattr(c, f"num_bins_{key}")) for name, key in dims}
+        self.curricula = [RewardThresholdCurriculum(seed=c.curriculum_seed, **kw) for _ in self.category_names]
+        self.env_command_bins = np.zeros(len(env_ids), dtype=int)
+        self.env_command_categories = np.zeros(len(env_ids), dtype=int)
+        rng_keys = ["lin_vel_x", "lin_vel_y", "ang_vel_yaw", "body_height_cmd", "gait_frequency_cmd_range", "gait_phase_cmd_range",
+                    "gait_offset_cmd_range", "gait_bound_cmd_range", "gait_duration_cmd_range", "footswing_height_range",
+                    "body_pitch_range", "body_roll_range", "stance_width_range", "stance_length_range", "aux_reward_coef_range"]
+        low = np.array([getattr(c, k)[0] for k in rng_keys])
+        high = np.array([getattr(c, k)[1] for k in rng_keys])
+        for cur in self.curricula:
+            cur.set_to(low=low, high=high)
+
+    def _init_buffers(self):
+        """legged_robot.py:1123-1258 — everything is a view of (or lives in) the SoA device state."""
+        self.extras = LazyExtras()
+        self.noise_scale_vec = torch.tensor(list(self.sim_cfg.noise_scale_vec)[:self.num_obs], device=self.device)
+        self.add_noise = self.cfg.noise.add_noise
+        self.default_dof_pos = torch.tensor(list(self.sim_cfg.default_dof_pos), device=self.device).unsqueeze(0)
+        self.commands_scale = torch.tensor(list(self.sim_cfg.commands_scale)[:self.cfg.commands.num_commands], device=self.device)
+        self.torque_limits = torch.full((12,), self.sim_cfg.torque_limit, device=self.device)
+        self.dof_pos_limits = torch.stack((torch.tensor(list(self.sim_cfg.soft_limit_lo)), torch.tensor(list(self.sim_cfg.soft_limit_hi))), 1).to(self.device)
+        self._pending_interval = (np.zeros(0, dtype=np.int64), np.zeros((0, 4), dtype=np.float32))
+        self._ep_len_dirty = False
+        self._time_outs = torch.zeros(self.num_train_envs, dtype=torch.bool, device=self.device)
+        self._env_bins_dev = torch.zeros(self.num_train_envs, device=self.device)
+        self._env_bins_dirty = True
+        self.actions = torch.zeros(self.num_envs, self.num_actions, device=self.device)
+        self.measured_heights = 0
+        self.lag_timesteps = self.cfg.domain_rand.lag_timesteps
+
+    def _prepare_reward_function(self):
+        """legged_robot.py:1385-1429: names of the active terms (the kernel owns the arithmetic)."""
+        self.reward_names = [n for n in self.reward_scales if n != "termination" and n in capi.REWARD_TERMS]
+
+    # ------------------------------------------------------------------ reference attribute surface (views / copies)
+    obs_buf = property(lambda s: s.core.obs)
+    privileged_obs_buf = property(lambda s: s.core.priv_obs)
+    rew_buf = property(lambda s: s.core.rew)
+    reset_buf = property(lambda s: s.core.reset_u8.bool())
+    time_out_buf = property(lambda s: s.core.timeout_u8.bool())
+    rew_buf_pos = property(lambda s: s.core.env("rew_buf_pos")[0])
+    rew_buf_neg = property(lambda s: s.core.env("rew_buf_neg")[0])
+    commands = property(lambda s: s.core.env_aos("commands")[:, :s.cfg.commands.num_commands])      # writable view [N, num_commands]
+    gait_indices = property(lambda s: s.core.env("gait_indices")[0])
+    base_lin_vel = property(lambda s: s.core.env_aos("base_lin_vel"))
+    base_ang_vel = property(lambda s: s.core.env_aos("base_ang_vel"))
+    projected_gravity = property(lambda s: s.core.env_aos("projected_gravity"))
+    base_pos = property(lambda s: s.core.env_aos("root_pos"))
+    base_quat = property(lambda s: s.core.env_aos("root_quat"))
+    dof_pos = property(lambda s: s.core.joint_aos("dof_pos"))
+    dof_vel = property(lambda s: s.core.joint_aos("dof_vel"))
+    torques = property(lambda s: s.core.joint_aos("torques"))
+    joint_pos_target = property(lambda s: s.core.joint_aos("joint_pos_target"))
+    last_actions = property(lambda s: s.core.joint_aos("last_actions"))
+    last_last_actions = property(lambda s: s.core.joint_aos("last_last_actions"))
+    last_dof_vel = property(lambda s: s.core.joint_aos("last_dof_vel"))
+    foot_positions = property(lambda s: s.core.foot_aos("foot_positions"))
+    foot_velocities = property(lambda s: s.core.foot_aos("foot_velocities"))
+    clock_inputs = property(lambda s: s.core.leg("clock_inputs")[0])
+    desired_contact_states = property(lambda s: s.core.leg("desired_contact_states")[0])
+    foot_indices = property(lambda s: s.core.leg("foot_indices")[0])
+    friction_coeffs = property(lambda s: s.core.env("friction_coeffs")[0].unsqueeze(1).repeat(1, 4))
+    restitutions = property(lambda s: s.core.env("restitutions")[0].unsqueeze(1).repeat(1, 4))
+    payloads = property(lambda s: s.core.env("payloads")[0])
+    com_displacements = property(lambda s: s.core.env_aos("com_displacements"))
+    motor_strengths = property(lambda s: s.core.env("motor_strengths")[0].unsqueeze(1).repeat(1, 12))
+    motor_offsets = property(lambda s: s.core.joint_aos("motor_offsets"))
+
+    @property
+    def root_states(self):
+        c = self.core
+        return torch.cat((c.env_aos("root_pos"), c.env_aos("root_quat"), c.env_aos("root_lin_vel"), c.env_aos("root_ang_vel")), 1)
+
+    @property
+    def contact_forces(self):
+        """[N, 17, 3] in Isaac Gym body order (base; per leg hip, thigh, calf, foot)."""
+        c = self.core
+        out = torch.zeros(self.num_envs, 17, 3, device=self.device)
+        out[:, 0] = c.foot_aos("base_contact_forces_part").sum(1)
+        for k, name in enumerate(("hip_contact_forces", "thigh_contact_forces", "calf_contact_forces", "foot_contact_forces")):
+            out[:, [1 + k, 5 + k, 9 + k, 13 + k]] = c.foot_aos(name)
+        return out
+
+    @property
+    def episode_sums(self):
+        es = self.core.env("episode_sums")
+        d = {n: es[capi.REWARD_TERMS.index(n)] for n in self.reward_scales if n in capi.REWARD_TERMS}
+        d["total"] = es[capi.NUM_REWARD_TERMS]
+        return d
+
+    @property
+    def command_sums(self):
+        cs = self.core.env("command_sums")
+        d = {n: cs[capi.REWARD_TERMS.index(n)] for n in self.reward_scales if n in capi.REWARD_TERMS}
+        for i, k in enumerate(capi.COMMAND_SUM_EXTRAS):
+            d[k] = cs[capi.NUM_REWARD_TERMS + i]
+        return d
+
+    @property
+    def episode_length_buf(self):
+        return self.core.episode_length_buf
+
+    @episode_length_buf.setter
+    def episode_length_buf(self, value):
+        """The Runner overwrites this with random episode lengths (ppo_cse/__init__.py:114-116)."""
+        self.core.episode_length_buf.copy_(value.to(self.device).to(torch.int32))
+        self._ep_len_dirty = True
+
+    # ------------------------------------------------------------------ stepping
+    def step(self, actions):
+        """legged_robot.py:60-88."""
+        core = self.core
+        actions = actions.to(self.device, dtype=torch.float32).contiguous()
+        self.actions = torch.clip(actions, -self.cfg.normalization.clip_actions, self.cfg.normalization.clip_actions)
+        self.common_step_counter += 1
+        self._apply_pending_interval_resample()
+        core.step(actions, common_step=self.common_step_counter, mode=0)
+        rid, rsum, iid, isum = core.fetch_events()
+        self._pending_interval = (iid, isum)
+        self._post_physics_step_callback_host()
+        if len(rid):
+            self.reset_idx(torch.from_numpy(rid), _sums=rsum, _post_step=True, _actions=actions)
+        return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    def _apply_pending_interval_resample(self):
+        """legged_robot.py:683-686: envs whose episode length hits a multiple of resampling_time/dt."""
+        if self._ep_len_dirty:          # episode lengths were overwritten from outside: rebuild the pending list
+            ep = self.core.episode_length_buf.cpu().numpy()
+            interval = int(self.sim_cfg.resampling_interval)
+            ids = np.nonzero((ep + 1) % interval == 0)[0] if interval > 0 else np.zeros(0, dtype=np.int64)
+            cs = self.core.env("command_sums")[[capi.REWARD_TERMS.index(k) for k in _TASK_KEYS]][:, torch.as_tensor(ids, device=self.device, dtype=torch.long)]
+            self._pending_interval = (ids, cs.t().cpu().numpy())
+            self._ep_len_dirty = False
+        ids, sums = self._pending_interval
+        if len(ids) == 0:
+            return
+        cmds = self._resample_commands_host(ids, sums)
+        self.core.set_commands(ids, cmds)
+        self._env_bins_dirty = True
+        self._pending_interval = (np.zeros(0, dtype=np.int64), np.zeros((0, 4), dtype=np.float32))
+
+    def _post_physics_step_callback_host(self):
+        """The host part of legged_robot.py:701-705 (global gravity impulses)."""
+        dr = self.cfg.domain_rand
+        if self.common_step_counter % int(dr.gravity_rand_interval) == 0:
+            self._randomize_gravity()
+        if int(self.common_step_counter - dr.gravity_rand_duration) % int(dr.gravity_rand_interval) == 0:
+            self._randomize_gravity(torch.tensor([0., 0., 0.]))
+
+    def post_physics_step(self):
+        raise NotImplementedError("fused into go1_sim_step; see step()")
+
+    # ------------------------------------------------------------------ commands / resets
+    def _resample_commands_host(self, env_ids, task_sums):
+        """legged_robot.py:710-824 for env ids (numpy, ascending) whose 4 task command sums are `task_sums`.
+        Returns the new commands [k, 15]; updates curricula, env_command_bins/categories."""
+        cfg = self.cfg
+        k = len(env_ids)
+        timesteps = int(cfg.commands.resampling_time / self.dt)
+        ep_len = min(cfg.env.max_episode_length, timesteps)
+        present = [key for key in _TASK_KEYS if key in self.reward_scales]
+        col = {key: i for i, key in enumerate(_TASK_KEYS)}
+        for i, (category, curriculum) in enumerate(zip(self.category_names, self.curricula)):
+            in_cat = self.env_command_categories[env_ids] == i
+            if not in_cat.any():
+                continue
+            task_rewards = [task_sums[in_cat, col[key]].astype(np.float32) / np.float32(ep_len) for key in present]
+            thresholds = [self.curriculum_thresholds[key] * self.reward_scales[key] for key in present]
+            old_bins = self.env_command_bins[env_ids[in_cat]]
+            if len(thresholds) > 0:
+                curriculum.update(old_bins, task_rewards, thresholds, local_range=_LOCAL_RANGE)
+        # new categories: host RNG (the reference draws torch.rand on the device; only the distribution matters)
+        r = torch.rand(k).numpy()
+        p = 1. / len(self.category_names)
+        new_cmds = np.zeros((k, capi.NUM_COMMANDS), dtype=np.float32)
+        cat_masks = [np.logical_and(p * i <= r, r < p * (i + 1)) for i in range(len(self.category_names))]
+        for i, (category, mask, curriculum) in enumerate(zip(self.category_names, cat_masks, self.curricula)):
+            n = int(mask.sum())
+            if n == 0:
+                continue
+            cmds, bins = curriculum.sample(batch_size=n)
+            ids = env_ids[mask]
+            self.env_command_bins[ids] = bins
+            self.env_command_categories[ids] = i
+            new_cmds[mask, :cfg.commands.num_commands] = cmds[:, :cfg.commands.num_commands].astype(np.float32)
+        c = new_cmds
+        if cfg.commands.num_commands > 5:
+            if cfg.commands.gaitwise_curricula:
+                for category, m in zip(self.category_names, cat_masks):
+                    if category == "pronk":
+                        for j in (5, 6, 7):
+                            c[m, j] = np.mod(c[m, j] / 2 - np.float32(0.25), 1)
+                    elif category == "trot":
+                        c[m, 5] = c[m, 5] / 2 + np.float32(0.25); c[m, 6] = 0; c[m, 7] = 0
+                    elif category == "pace":
+                        c[m, 5] = 0; c[m, 6] = c[m, 6] / 2 + np.float32(0.25); c[m, 7] = 0
+                    elif category == "bound":
+                        c[m, 5] = 0; c[m, 6] = 0; c[m, 7] = c[m, 7] / 2 + np.float32(0.25)
+            elif cfg.commands.exclusive_phase_offset:
+                r2 = torch.rand(k).numpy()
+                trot, pace, bound = r2 < 0.34, np.logical_and(0.34 <= r2, r2 < 0.67), 0.67 <= r2
+                c[pace, 5] = 0; c[bound, 5] = 0; c[trot, 6] = 0; c[bound, 6] = 0; c[trot, 7] = 0; c[pace, 7] = 0
+            elif cfg.commands.balance_gait_distribution:
+                r2 = torch.rand(k).numpy()
+                pronk, trot = r2 <= 0.25, np.logical_and(0.25 <= r2, r2 < 0.50)
+                pace, bound = np.logical_and(0.50 <= r2, r2 < 0.75), 0.75 <= r2
+                for j in (5, 6, 7):
+                    c[pronk, j] = np.mod(c[pronk, j] / 2 - np.float32(0.25), 1)
+                c[trot, 6] = 0; c[trot, 7] = 0; c[pace, 5] = 0; c[pace, 7] = 0; c[bound, 5] = 0; c[bound, 6] = 0
+                c[trot, 5] = c[trot, 5] / 2 + np.float32(0.25); c[pace, 6] = c[pace, 6] / 2 + np.float32(0.25)
+                c[bound, 7] = c[bound, 7] / 2 + np.float32(0.25)
+            if cfg.commands.binary_phases:
+                for j in (5, 6, 7):
+                    c[:, j] = np.mod(np.round(2 * c[:, j]) / np.float32(2.0), 1)     # torch.round == np.round (half to even)
+        small = np.linalg.norm(c[:, :2], axis=1) > 0.2
+        c[:, :2] *= small[:, None]
+        return c
+
+    def _resample_commands(self, env_ids):
+        """Reference-shaped entry point (legged_robot.py:710): env_ids is a tensor."""
+        ids = np.sort(np.asarray(env_ids.cpu() if hasattr(env_ids, "cpu") else env_ids, dtype=np.int64))
+        if len(ids) == 0:
+            return
+        idx = torch.as_tensor(ids, device=self.device)
+        cs = self.core.env("command_sums")[[capi.REWARD_TERMS.index(k) for k in _TASK_KEYS]][:, idx].t().cpu().numpy()
+        self.core.set_commands(ids, self._resample_commands_host(ids, cs))
+        self._env_bins_dirty = True
+
+    def reset_idx(self, env_ids, _sums=None, _post_step=False, _actions=None):
+        """legged_robot.py:150-239."""
+        if len(env_ids) == 0:
+            return
+        ids = np.sort(np.asarray(env_ids.cpu() if hasattr(env_ids, "cpu") else env_ids, dtype=np.int64))
+        core = self.core
+        if _sums is None:
+            idx = torch.as_tensor(ids, device=self.device)
+            _sums = core.env("command_sums")[[capi.REWARD_TERMS.index(k) for k in _TASK_KEYS]][:, idx].t().cpu().numpy()
+        cmds = self._resample_commands_host(ids, _sums)
+        core.episode_acc.zero_()
+        core.reset_idx(ids, cmds, actions=_actions, post_step=_post_step, common_step=self.common_step_counter)
+        self._env_bins_dirty = True
+        self._fill_extras(ids)
+
+    def _fill_extras(self, ids):
+        """legged_robot.py:180-234 — device scalars (no host sync); consumed lazily by the logger."""
+        core, ex = self.core, self.extras
+        train_ids = ids[ids < self.num_train_envs]
+        if len(train_ids) > 0:
+            acc = core.episode_acc.clone()
+            means = acc[:capi.NUM_EPISODE_SUMS] / acc[capi.NUM_EPISODE_SUMS].clamp(min=1.0)
+            ep = {}
+            for name in list(self.reward_scales) + ["total"]:
+                if name == "total":
+                    ep["rew_total"] = means[capi.NUM_REWARD_TERMS]
+                elif name in capi.REWARD_TERMS:
+                    ep["rew_" + name] = means[capi.REWARD_TERMS.index(name)]
+            ex["train/episode"] = ep
+        if self.cfg.terrain.curriculum:
+            ex["train/episode"]["terrain_level"] = torch.mean(self.terrain_levels[:self.num_train_envs].float())
+        if self.cfg.commands.command_curriculum:
+            if self._env_bins_dirty:
+                self._env_bins_dev = torch.as_tensor(self.env_command_bins[:self.num_train_envs], dtype=torch.float32).to(self.device, non_blocking=True)
+                self._env_bins_dirty = False
+                core.h2d_bytes += 4 * self.num_train_envs
+            ex["env_bins"] = self._env_bins_dev
+            cmd = core.env("commands")
+            mins, maxs = cmd.min(dim=1).values, cmd.max(dim=1).values
+            ep = ex.setdefault("train/episode", {})
+            for idx, nm in ((8, "duration"), (7, "bound"), (6, "offset"), (5, "phase"), (4, "freq"), (0, "x_vel"), (1, "y_vel"), (2, "yaw_vel")):
+                ep[f"min_command_{nm}"] = mins[idx]
+                ep[f"max_command_{nm}"] = maxs[idx]
+            if self.cfg.commands.num_commands > 9:
+                ep["min_command_swing_height"] = mins[9]
+                ep["max_command_swing_height"] = maxs[9]
+            for curriculum, category in zip(self.curricula, self.category_names):
+                ep[f"command_area_{category}"] = np.sum(curriculum.weights) / curriculum.weights.shape[0]
+            ep["min_action"] = torch.min(self.actions)
+            ep["max_action"] = torch.max(self.actions)
+            ex["curriculum/distribution"] = {}
+            for curriculum, category in zip(self.curricula, self.category_names):
+                ex["curriculum/distribution"][f"weights_{category}"] = curriculum.weights
+                ex["curriculum/distribution"][f"grid_{category}"] = curriculum.grid
+        if self.cfg.env.send_timeouts:
+            self._time_outs = core.timeout_u8[:self.num_train_envs].bool()      # a copy taken at reset time (legged_robot.py:234)
+            ex["time_outs"] = self._time_outs
+
+    def set_idx_pose(self, env_ids, dof_pos, base_state):
+        """legged_robot.py:241-261."""
+        if len(env_ids) == 0:
+            return
+        c, ids = self.core, env_ids.to(self.device).long()
+        if dof_pos is not None:
+            q = c.joint_aos("dof_pos"); q[ids] = dof_pos.to(self.device); c.set_joint_aos("dof_pos", q)
+            v = c.joint_aos("dof_vel"); v[ids] = 0.; c.set_joint_aos("dof_vel", v)
+        b = base_state.to(self.device).reshape(-1, 13)
+        c.env("root_pos")[:, ids] = b[:, 0:3].t(); c.env("root_quat")[:, ids] = b[:, 3:7].t()
+        c.env("root_lin_vel")[:, ids] = b[:, 7:10].t(); c.env("root_ang_vel")[:, ids] = b[:, 10:13].t()
+
+    # ------------------------------------------------------------------ recording API (rendering is out of scope)
+    def start_recording(self):
+        self.record_now = True
+
+    def start_recording_eval(self):
+        self.record_eval_now = True
+
+    def pause_recording(self):
+        self.record_now = False
+
+    def pause_recording_eval(self):
+        self.record_eval_now = False
+
+    def get_complete_frames(self):
+        return []
+
+    def get_complete_frames_eval(self):
+        return []
+
+    def render(self, mode="rgb_array"):
+        raise NotImplementedError("no renderer: SURVEY.md §2 row 1 marks rendering out of scope")
