@@ -188,6 +188,9 @@ int go1_ppo_normalize_advantages(float* advantages, const double* stats, int64_t
  * impl: 0 = fp32 CUDA cores (exact-fp32 path), 1 = tcgen05 TF32 tensor cores with fp32 accumulation. */
 int go1_gemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
              float* C, int ldc, const float* bias, int act, int accumulate, int impl, void* stream);
+/* dst[c][r] = src[r][c] (rows x cols fp32, row strides lds/ldd): brings the dgrad (W^T) and wgrad (dz^T, x^T) operands into
+ * the K-major form the tcgen05 kernel reads (impl=1 supports transA=0, transB=1 only). */
+int go1_transpose(const float* src, int lds, float* dst, int ldd, int rows, int cols, void* stream);
 /* dz = dy * ELU'(z) computed from the saved layer output y (autograd of nn.ELU). dz may alias dy. */
 int go1_elu_backward(const float* y, int ldy, const float* dy, int lddy, float* dz, int lddz, int M, int N, void* stream);
 /* out[n] (+)= sum_m x[m][n]: bias gradient of nn.Linear. */

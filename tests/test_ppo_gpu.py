@@ -130,12 +130,17 @@ def test_clip_adam_matches_torch_optim():
         assert torch.allclose(p, ref.detach(), rtol=1e-5, atol=1e-7)
 
 
-def test_full_ppo_cycle_matches_reference_golden():
+@pytest.mark.parametrize("impl", [0, 1])
+def test_full_ppo_cycle_matches_reference_golden(impl):
     """BASELINE config 1: act x24 -> process_env_step -> compute_returns -> update (5 epochs x 4 minibatches + adaptation
-    steps) on the reference's own vectors.  fp32 CUDA-core GEMMs; tolerances stated per quantity."""
+    steps) on the reference's own vectors.  impl 0: fp32 CUDA-core GEMMs (tolerances ~1e-4); impl 1: tcgen05 TF32 GEMMs
+    (10-bit mantissa products: tolerances x20, stated as `k`)."""
     from ppo_golden_util import seeded_weights, sample_tensor
     from go1_gym_learn.ppo_cse import ActorCritic
     from go1_gym_learn.ppo_cse.ppo import PPO
+    from go1_gym_learn.ppo_cse.actor_critic import AC_Args
+    AC_Args.gemm_impl = impl
+    k = 1.0 if impl == 0 else 20.0
     g = np.load(os.path.join(HERE, "golden", "ppo.npz"))
     N, T, NOBS, NH, NP, NA = 4, 24, 70, 2100, 2, 12
     ac = ActorCritic(NOBS, NP, NH, NA)
@@ -153,17 +158,64 @@ def test_full_ppo_cycle_matches_reference_golden():
     st = alg.storage
     for name, tol in (("actions", 2e-5), ("values", 2e-5), ("actions_log_prob", 1e-4), ("mu", 2e-5), ("returns", 5e-5), ("advantages", 2e-4)):
         got, want = getattr(st, name).cpu().numpy(), g[f"storage/{name}"]
-        assert np.allclose(got, want, rtol=1e-4, atol=tol), (name, np.abs(got - want).max())
+        assert np.allclose(got, want, rtol=1e-4 * k, atol=tol * k), (name, np.abs(got - want).max())
     assert np.array_equal(st.dones.cpu().numpy(), g["storage/dones"])
     alg.fixed_minibatch_indices = C(g["in/perm"])
     losses = alg.update()
     ref = g["update/losses"]
-    assert abs(losses[0] - ref[0]) < 2e-3 * abs(ref[0]) and abs(losses[1] - ref[1]) < 2e-3 and abs(losses[2] - ref[2]) < 2e-3 * abs(ref[2])
-    assert abs(losses[5] - ref[5]) < 2e-3 * abs(ref[5])
+    AC_Args.gemm_impl = 0
+    assert abs(losses[0] - ref[0]) < 2e-3 * k * abs(ref[0]) and abs(losses[1] - ref[1]) < 2e-3 * k and abs(losses[2] - ref[2]) < 2e-3 * k * abs(ref[2])
+    assert abs(losses[5] - ref[5]) < 2e-3 * k * abs(ref[5])
     assert abs(alg.learning_rate - float(g["update/learning_rate"])) < 1e-12
     sd = ac.state_dict()
-    for k, v in sd.items():
-        got, want = sample_tensor(v.cpu().numpy()), g[f"final/{k}"]
+    for name_k, v in sd.items():
+        got, want = sample_tensor(v.cpu().numpy()), g[f"final/{name_k}"]
         # 20 PPO + 20 adaptation Adam steps; lr <= 1e-3 so each weight moves <= ~0.02: compare the MOVED weights tightly
-        assert np.allclose(got[:-2], want[:-2], rtol=0, atol=3e-4), (k, np.abs(got[:-2] - want[:-2]).max())
-        assert abs(got[-1] - want[-1]) <= 2e-4 * max(1.0, abs(want[-1])), k
+        assert np.allclose(got[:-2], want[:-2], rtol=0, atol=3e-4 * (1 if impl == 0 else 10)), (name_k, np.abs(got[:-2] - want[:-2]).max())
+        assert abs(got[-1] - want[-1]) <= 2e-4 * (1 if impl == 0 else 10) * max(1.0, abs(want[-1])), name_k
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# tcgen05 TF32 tensor-core GEMM (impl=1).  TF32 keeps 10 mantissa bits: |err| <= ~2^-10 * sum|a||b| per product, so the
+# tolerance is stated relative to the fp64 reference of |A| |B|^T (torch 1.10, the reference's version, also ran its
+# matmuls in TF32 by default on Ampere+).
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 64, 64), (4096, 256, 2100), (300, 200, 70), (4, 512, 2100), (1000, 1280, 2100),
+                                   (24576, 128, 256), (256, 128, 24576), (2100, 1280, 4096)])
+def test_gemm_tcgen05_tf32(M, N, K):
+    torch.manual_seed(M * 7 + N * 3 + K)
+    ldk = (K + 3) // 4 * 4                               # TMA: row strides must be multiples of 16 bytes
+    A = torch.randn(M, ldk, device="cuda")[:, :K]
+    B = torch.randn(N, ldk, device="cuda")[:, :K]
+    bias = torch.randn(N, device="cuda")
+    ref = A.double() @ B.double().t()
+    bound = (A.abs().double() @ B.abs().double().t()) * 2.0 ** -10 + 1e-6
+    C = torch.full((M, N + 5), 3.0, device="cuda")
+    _gemm(0, 1, M, N, K, A, ldk, B, ldk, C, N + 5, impl=1)
+    torch.cuda.synchronize()
+    err = (C[:, :N].double() - ref).abs()
+    assert (err <= bound).all(), (float(err.max()), float((err / bound).max()))
+    assert (C[:, N:] == 3.0).all()
+    # must actually be TF32-accurate, not garbage-within-bound: relative Frobenius error ~1e-4..1e-3
+    assert float(err.norm() / ref.norm()) < 2e-3
+    C2 = torch.randn(M, N, device="cuda"); C0 = C2.clone()
+    _gemm(0, 1, M, N, K, A, ldk, B, ldk, C2, N, bias=bias, act=1, acc=1, impl=1)
+    want = torch.nn.functional.elu(C0.double() + ref + bias.double())
+    assert ((C2.double() - want).abs() <= bound + 1e-5).all()
+
+
+def test_transpose_kernel():
+    from go1_b200 import capi
+    src = torch.randn(1000, 300, device="cuda")[:, :257]
+    dst = torch.zeros(257, 1004, device="cuda")
+    capi.check(capi.lib().go1_transpose(capi.ptr(src), 300, capi.ptr(dst), 1004, 1000, 257, capi.stream_ptr()), "transpose")
+    assert torch.equal(dst[:, :1000], src.t()) and (dst[:, 1000:] == 0).all()
+
+
+def test_gemm_tcgen05_rejects_unsupported_layouts():
+    from go1_b200 import capi
+    A = torch.randn(64, 70, device="cuda"); B = torch.randn(70, 64, device="cuda"); C = torch.zeros(64, 64, device="cuda")
+    with pytest.raises(capi.Go1Error):
+        _gemm(0, 0, 64, 64, 70, A, 70, B, 64, C, 64, impl=1)      # transB=0: not K-major
+    with pytest.raises(capi.Go1Error):
+        _gemm(0, 1, 64, 64, 70, A, 70, A, 70, C, 64, impl=1)      # ld=70 floats: not a multiple of 16 bytes

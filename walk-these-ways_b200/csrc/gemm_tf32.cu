@@ -1,6 +1,323 @@
-// gemm_tf32.cu — tcgen05 TF32 GEMM (placeholder until the tensor-core kernel lands; impl=1 fails loudly).
+// gemm_tf32.cu — hand-written tcgen05 TF32 GEMM for sm_100a (the dense layers of ppo_cse's ActorCritic).
+//
+//   C[M][N] (+)= A[M][K] * B[N][K]^T (+ bias[n]) (ELU)          fp32 in HBM, TF32 multiply, fp32 accumulate
+//
+// Both operands are K-major (A = activations row-major, B = torch.nn.Linear weight [out][in]); the dgrad / wgrad
+// products are brought into this form by go1_transpose on the host side.  Structure (one 128 x BN output tile per
+// CTA, 192 threads):
+//   warp 0   TMA producer: cp.async.bulk.tensor 2D loads of 128x32 (A) and BNx32 (B) fp32 boxes, 128B swizzle,
+//            S-stage ring guarded by full/empty mbarriers
+//   warp 1   TMEM allocator + single-thread tcgen05.mma.cta_group::1.kind::tf32 issuer (M=128, N=BN, K=8 per
+//            instruction, 4 per k-block), tcgen05.commit to release smem stages and to publish the accumulator
+//   warps 2-5 epilogue: tcgen05.ld 32x32b from TMEM -> registers -> bias / ELU / accumulate -> global
+//            (red.global.add when split-K partitions the reduction)
+// Accumulators live in TMEM (BN fp32 columns x 128 lanes); 2 CTAs fit per SM so one CTA's epilogue overlaps the
+// other's main loop.
 #include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <mutex>
+
 extern int go1_set_error(const char* m);
-extern "C" int go1_gemm_tf32(int, int, int, int, int, const float*, int, const float*, int, float*, int, const float*, int, int, cudaStream_t) {
-    return go1_set_error("go1_gemm impl=1 (tcgen05 TF32) not built yet");
+void go1_count_launch(int n);
+
+namespace {
+
+constexpr int BM = 128, BK = 32;          // BK fp32 = 128 bytes = one swizzle-128B row
+constexpr int UMMA_K = 8;                 // tf32: 32 bytes per instruction along K
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    const uint32_t a = smem_u32(bar);
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// K-major, 128B-swizzled operand tile: 8-row groups 1024 B apart (SBO), rows 128 B apart inside a group
+__device__ __forceinline__ uint64_t make_desc(const void* smem) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(smem) >> 4) & 0x3FFF);        // start address
+    d |= (uint64_t)1 << 16;                                  // leading byte offset (unused for swizzled K-major) = 1
+    d |= (uint64_t)(1024 >> 4) << 32;                        // stride byte offset
+    d |= (uint64_t)1 << 46;                                  // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                                  // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                   "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                   "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct GemmArgs {
+    float* C; const float* bias;
+    int M, N, K, ldc, act, accumulate, kb_per_split;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1) gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [A stages][B stages][barriers]
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    float* sA = (float*)base;                                   // STAGES x 128 x 32
+    float* sB = (float*)(base + (size_t)STAGES * BM * BK * 4);  // STAGES x BN x 32
+    uint64_t* full = (uint64_t*)(base + (size_t)STAGES * (BM + BN) * BK * 4);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int num_kb_total = (g.K + BK - 1) / BK;
+    const int kb0 = blockIdx.z * g.kb_per_split;
+    const int num_kb = min(g.kb_per_split, num_kb_total - kb0);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM allocation: BN fp32 accumulator columns (power of two >= 32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            for (int i = 0; i < num_kb; i++) {
+                const int s = i % STAGES, ph = (i / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], (BM + BN) * BK * 4);
+                tma_load_2d(&mapA, &full[s], sA + (size_t)s * BM * BK, (kb0 + i) * BK, m0);
+                tma_load_2d(&mapB, &full[s], sB + (size_t)s * BN * BK, (kb0 + i) * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        // instruction descriptor: D=F32 (bits 4-5 = 1), A/B = TF32 (2 at bits 7-9 / 10-12), K-major both, N>>3 at 17, M>>4 at 24
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        for (int i = 0; i < num_kb; i++) {
+            const int s = i % STAGES, ph = (i / STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                const uint64_t da = make_desc(sA + (size_t)s * BM * BK), db = make_desc(sB + (size_t)s * BN * BK);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; k++)      // advance 32 B along K inside the 128 B swizzle row: +2 in 16-byte units
+                    umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&empty[s]);                    // stage reusable once these MMAs have read it
+                if (i == num_kb - 1) umma_commit(tmem_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        const int row = m0 + 32 * q + lane;
+        if (num_kb > 0) {
+            mbar_wait(tmem_full, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const bool split = gridDim.z > 1;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; c++) {
+            uint32_t r[32];
+            if (num_kb > 0) tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), r);
+            else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) r[j] = 0u;
+            }
+            const int col0 = n0 + 32 * c;
+            if (row < g.M && col0 < g.N) {
+                float* crow = g.C + (size_t)row * g.ldc + col0;
+                const int ncols = min(32, g.N - col0);
+                if (split) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) if (j < ncols) atomicAdd(crow + j, __uint_as_float(r[j]));
+                } else {
+                    const bool vec = (ncols == 32) && ((g.ldc & 3) == 0) && ((((uintptr_t)g.C) & 15) == 0) && ((col0 & 3) == 0);
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+                    if (g.accumulate) {
+                        if (vec) {
+#pragma unroll
+                            for (int j = 0; j < 8; j++) { const float4 o = reinterpret_cast<const float4*>(crow)[j]; v[4 * j] += o.x; v[4 * j + 1] += o.y; v[4 * j + 2] += o.z; v[4 * j + 3] += o.w; }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) if (j < ncols) v[j] += crow[j];
+                        }
+                    }
+                    if (g.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) if (j < ncols) v[j] += __ldg(g.bias + col0 + j);
+                    }
+                    if (g.act == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
+                    }
+                    if (vec) {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) reinterpret_cast<float4*>(crow)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) if (j < ncols) crow[j] = v[j];
+                    }
+                }
+            }
+        }
+    }
+    // ===== teardown =====
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)BN) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::once_flag g_once;
+
+int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_rows) {
+    std::call_once(g_once, [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) g_encode = (EncodeTiledFn)fn;
+    });
+    if (!g_encode) return go1_set_error("cuTensorMapEncodeTiled unavailable");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { char b[96]; snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed (%d)", (int)r); return go1_set_error(b); }
+    return 0;
+}
+
+__global__ void zero_strided(float* C, int ldc, int M, int N) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)M * N) return;
+    C[(i / N) * ldc + (i % N)] = 0.f;
+}
+__global__ void bias_act_strided(float* C, int ldc, const float* bias, int M, int N, int act) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)M * N) return;
+    float* c = C + (i / N) * ldc + (i % N);
+    float v = *c;
+    if (bias) v += bias[i % N];
+    if (act == 1) v = v > 0.f ? v : expm1f(v);
+    *c = v;
+}
+
+template <int BN, int STAGES>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, int splits, cudaStream_t st) {
+    const size_t smem = (size_t)STAGES * (BM + BN) * BK * 4 + (2 * STAGES + 1) * 8 + 16 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return go1_set_error(cudaGetErrorString(e));
+        configured = true;
+    }
+    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, splits);
+    gemm_tf32_kernel<BN, STAGES><<<grid, 192, smem, st>>>(ma, mb, g);
+    go1_count_launch(1);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                             float* Cm, int ldc, const float* bias, int act, int accumulate, cudaStream_t st) {
+    if (transA != 0 || transB != 1)
+        return go1_set_error("go1_gemm impl=1 (tcgen05 TF32) takes K-major operands only: transA=0, transB=1 (use go1_transpose for dgrad/wgrad)");
+    if ((lda & 3) || (ldb & 3) || (((uintptr_t)A | (uintptr_t)B) & 15))
+        return go1_set_error("go1_gemm impl=1: A/B must be 16-byte aligned with row strides that are multiples of 4 floats (TMA)");
+    GemmArgs g;
+    g.C = Cm; g.bias = bias; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.act = act; g.accumulate = accumulate;
+    const int num_kb = (K + BK - 1) / BK;
+    const int BN = (N > 64) ? 128 : 64;
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    int splits = 1;
+    if (tiles < 148 && num_kb >= 16) { splits = (2 * 148 + tiles - 1) / tiles; if (splits > num_kb / 4) splits = num_kb / 4; if (splits < 1) splits = 1; }
+    g.kb_per_split = (num_kb + splits - 1) / splits;
+    splits = (num_kb + g.kb_per_split - 1) / g.kb_per_split;
+    CUtensorMap ma, mb;
+    if (int e = make_map(&ma, A, M, K, lda, BM)) return e;
+    if (int e = make_map(&mb, B, N, K, ldb, BN)) return e;
+    if (splits > 1) {
+        if (!accumulate) { const size_t tot = (size_t)M * N; zero_strided<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cm, ldc, M, N); go1_count_launch(1); }
+        g.bias = nullptr; g.act = 0;
+    }
+    int e = (BN == 128) ? launch<128, 3>(ma, mb, g, splits, st) : launch<64, 4>(ma, mb, g, splits, st);
+    if (e) return e;
+    if (splits > 1 && (bias || act)) { const size_t tot = (size_t)M * N; bias_act_strided<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cm, ldc, bias, M, N, act); go1_count_launch(1); }
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return go1_set_error(cudaGetErrorString(ce));
+    return 0;
+}
+
+// dst[c][r] = src[r][c]  (32x32 smem tiles): brings dgrad/wgrad operands into the K-major form the tcgen05 kernel reads
+__global__ void transpose_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int rows, int cols) {
+    __shared__ float t[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        t[i][threadIdx.x] = (r < rows && c < cols) ? src[(size_t)r * lds + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (c < cols && r < rows) dst[(size_t)c * ldd + r] = t[threadIdx.x][i];
+    }
+}
+extern "C" int go1_transpose(const float* src, int lds, float* dst, int ldd, int rows, int cols, void* stream) {
+    if (!src || !dst || rows <= 0 || cols <= 0 || lds < cols || ldd < rows) return go1_set_error("go1_transpose: bad arguments");
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+    transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, rows, cols);
+    go1_count_launch(1);
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return go1_set_error(cudaGetErrorString(ce));
+    return 0;
 }

@@ -110,6 +110,7 @@ def lib():
         "go1_ppo_gae": ([vp, vp, vp, vp, vp, vp, vp, ip, ip, _f, _f, vp], ip),
         "go1_ppo_normalize_advantages": ([vp, vp, i64, i64, vp], ip),
         "go1_gemm": ([ip, ip, ip, ip, ip, vp, ip, vp, ip, vp, ip, vp, ip, ip, ip, vp], ip),
+        "go1_transpose": ([vp, ip, vp, ip, ip, ip, vp], ip),
         "go1_elu_backward": ([vp, ip, vp, ip, vp, ip, ip, ip, vp], ip),
         "go1_colsum": ([vp, ip, vp, ip, ip, ip, vp], ip),
         "go1_ppo_sample_actions": ([vp, ip, vp, vp, C.c_uint64, C.c_uint64, vp, vp, ip, ip, vp], ip),

@@ -38,10 +38,22 @@ def _mlp(in_dim, hidden, out_dim):
     return nn.Sequential(*layers)
 
 
-class _Net:
-    """Forward/backward of one MLP whose first layer reads [x (K0 columns) | extra (E columns)]."""
+def _aligned(t_or_ptr, ld):
+    p = t_or_ptr if isinstance(t_or_ptr, int) else t_or_ptr.data_ptr()
+    return (p & 15) == 0 and (ld & 3) == 0
 
-    def __init__(self, seq, flat, grad, offset):
+
+class _Net:
+    """Forward/backward of one MLP whose first layer reads [x (K0 columns) | extra (E columns)].
+
+    impl 0: every product is one fp32 CUDA-core go1_gemm.  impl 1: the large products run on the tcgen05 TF32 kernel,
+    which reads K-major operands through TMA (16-byte aligned rows): the first-layer weight block W[:, :K0] is packed
+    to a contiguous copy, dgrad reads a transposed weight copy and wgrad transposed activations/gradients
+    (go1_transpose); copies are cached per weight version."""
+
+    MIN_TC = 32      # products with an output or reduction dimension below this stay on the fp32 kernel
+
+    def __init__(self, seq, flat, grad, offset, owner):
         self.linears = [m for m in seq if isinstance(m, nn.Linear)]
         self.specs = []                       # (w_off, b_off, out, in)
         off = offset
@@ -50,8 +62,9 @@ class _Net:
             self.specs.append((off, off + o * i, o, i))
             off += o * i + o
         self.end = off
-        self.flat, self.grad = flat, grad
+        self.flat, self.grad, self.owner = flat, grad, owner
         self.acts = {}
+        self._cache = {}
 
     def _buf(self, key, M, width):
         t = self.acts.get(key)
@@ -60,9 +73,31 @@ class _Net:
             self.acts[key] = t
         return t[:M]
 
+    def _cached(self, key, build):
+        ver = self.owner.weights_version
+        hit = self._cache.get(key)
+        if hit is None or hit[0] != ver:
+            hit = (ver, build(hit[1] if hit else None))
+            self._cache[key] = hit
+        return hit[1]
+
+    def _gemm(self, ta, tb, M, N, K, A, lda, B, ldb, Cm, ldc, bias, act, acc, impl):
+        capi.check(capi.lib().go1_gemm(ta, tb, M, N, K, capi.ptr(A) if torch.is_tensor(A) else A, lda, capi.ptr(B) if torch.is_tensor(B) else B, ldb,
+                                       capi.ptr(Cm) if torch.is_tensor(Cm) else Cm, ldc, capi.ptr(bias) if bias is not None else None, act, acc, impl,
+                                       capi.stream_ptr()), "go1_gemm")
+
+    def _transpose(self, src, lds, rows, cols, out=None):
+        ldd = (rows + 3) // 4 * 4
+        if out is None or out.shape != (cols, ldd):
+            out = torch.empty(cols, ldd, device=self.flat.device)
+        capi.check(capi.lib().go1_transpose(capi.ptr(src) if torch.is_tensor(src) else src, lds, capi.ptr(out), ldd, rows, cols, capi.stream_ptr()), "go1_transpose")
+        return out
+
+    def _tc_ok(self, impl, *dims):
+        return impl == 1 and min(dims) >= self.MIN_TC
+
     def forward(self, x, ldx, K0, extra, M, impl, tag="a"):
         """x: [M][K0] rows with stride ldx; extra: [M][E] contiguous or None. Returns list of layer outputs."""
-        L, st = capi.lib(), capi.stream_ptr()
         outs, inp, ld_in = [], x, ldx
         n = len(self.specs)
         for li, (wo, bo, o, i) in enumerate(self.specs):
@@ -70,19 +105,28 @@ class _Net:
             W = self.flat[wo:wo + o * i]
             b = self.flat[bo:bo + o]
             act = 1 if li < n - 1 else 0
+            K = K0 if (li == 0 and extra is not None) else i
+            Wm, ldw = W, i
+            tc = self._tc_ok(impl, o, K) and _aligned(inp, ld_in)
+            if tc and not _aligned(W, i):      # pack W[:, :K] into a TMA-readable copy (rows of K floats, K % 4 == 0)
+                if K % 4 == 0:
+                    Wm = self._cached(("pack", li), lambda old: (old if old is not None else torch.empty(o, K, device=W.device)).copy_(W.view(o, i)[:, :K]))
+                    ldw = K
+                else:
+                    tc = False
             if li == 0 and extra is not None:
                 E = i - K0
-                capi.check(L.go1_gemm(0, 1, M, o, K0, capi.ptr(inp), ld_in, capi.ptr(W), i, capi.ptr(y), o, None, 0, 0, impl, st), "gemm")
-                capi.check(L.go1_gemm(0, 1, M, o, E, capi.ptr(extra), extra.stride(0), W.data_ptr() + 4 * K0, i, capi.ptr(y), o, capi.ptr(b), act, 1, 0, st), "gemm")
+                self._gemm(0, 1, M, o, K0, inp, ld_in, Wm, ldw, y, o, None, 0, 0, 1 if tc else 0)
+                self._gemm(0, 1, M, o, E, extra, extra.stride(0), W.data_ptr() + 4 * K0, i, y, o, b, act, 1, 0)
             else:
-                K = i
-                capi.check(L.go1_gemm(0, 1, M, o, K, capi.ptr(inp), ld_in, capi.ptr(W), i, capi.ptr(y), o, capi.ptr(b), act, 0, impl, st), "gemm")
+                self._gemm(0, 1, M, o, K, inp, ld_in, Wm, ldw, y, o, b, act, 0, 1 if tc else 0)
             outs.append(y)
             inp, ld_in = y, o
         return outs
 
-    def backward(self, x, ldx, K0, extra, outs, dout, M, impl, accumulate, want_dextra=False, tag="a"):
+    def backward(self, x, ldx, K0, extra, outs, dout, M, impl, accumulate, want_dextra=False, tag="a", xT=None):
         """dout: gradient w.r.t. the network output [M][out]. Writes weight/bias grads into the flat grad buffer.
+        xT: optional precomputed transpose of the first-layer input ([K0][ld>=M]) for the tensor-core wgrad.
         Returns d(extra) [M][E] if requested."""
         L, st = capi.lib(), capi.stream_ptr()
         n = len(self.specs)
@@ -100,17 +144,32 @@ class _Net:
                 inp, ld_in, K = x, ldx, (K0 if extra is not None else i)
             else:
                 inp, ld_in, K = outs[li - 1], self.specs[li - 1][2], i
-            # dW[o][K] = dz^T[o][M] inp[M][K]
-            capi.check(L.go1_gemm(1, 0, o, K, M, capi.ptr(dz), o, capi.ptr(inp), ld_in, capi.ptr(gW), i, None, 0, accumulate, impl, st), "wgrad")
+            # ---- wgrad: dW[o][K] = dz^T[o][M] inp[M][K]
+            if self._tc_ok(impl, o, K, M):
+                dzT = self._transpose(dz, o, M, o, self.acts.get((tag, "dzT", li)))
+                self.acts[(tag, "dzT", li)] = dzT
+                if li == 0 and xT is not None:
+                    inT = xT
+                else:
+                    inT = self._transpose(inp, ld_in, M, K, self.acts.get((tag, "inT", li)))
+                    self.acts[(tag, "inT", li)] = inT
+                self._gemm(0, 1, o, K, M, dzT, dzT.stride(0), inT, inT.stride(0), gW, i, None, 0, accumulate, 1)
+            else:
+                self._gemm(1, 0, o, K, M, dz, o, inp, ld_in, gW, i, None, 0, accumulate, 0)
             if li == 0 and extra is not None:
                 E = i - K0
-                capi.check(L.go1_gemm(1, 0, o, E, M, capi.ptr(dz), o, capi.ptr(extra), extra.stride(0), gW.data_ptr() + 4 * K0, i, None, 0, accumulate, 0, st), "wgrad_extra")
+                self._gemm(1, 0, o, E, M, dz, o, extra, extra.stride(0), gW.data_ptr() + 4 * K0, i, None, 0, accumulate, 0)
                 if want_dextra:
                     dextra = self._buf((tag, "dextra"), M, E)
-                    capi.check(L.go1_gemm(0, 0, M, E, o, capi.ptr(dz), o, W.data_ptr() + 4 * K0, i, capi.ptr(dextra), E, None, 0, 0, 0, st), "dgrad_extra")
+                    self._gemm(0, 0, M, E, o, dz, o, W.data_ptr() + 4 * K0, i, dextra, E, None, 0, 0, 0)
+            # ---- dgrad: dprev[M][i] = dz[M][o] W[o][i]
             if li > 0:
                 dprev = self._buf((tag, "d", li - 1), M, i)
-                capi.check(L.go1_gemm(0, 0, M, i, o, capi.ptr(dz), o, capi.ptr(W), i, capi.ptr(dprev), i, None, 0, 0, impl, st), "dgrad")
+                if self._tc_ok(impl, i, o):
+                    WT = self._cached(("WT", li), lambda old: self._transpose(W, i, o, i, old))
+                    self._gemm(0, 1, M, i, o, dz, o, WT, WT.stride(0), dprev, i, None, 0, 0, 1)
+                else:
+                    self._gemm(0, 0, M, i, o, dz, o, W, i, dprev, i, None, 0, 0, 0)
                 dz = dprev
         return dextra
 
@@ -136,6 +195,7 @@ class ActorCritic(nn.Module):
         self._sample_counter = 0
         self.sample_seed = 0
         self.injected_eps = None      # parity tests inject the N(0,1) draws
+        self.weights_version = 0      # bumped by every optimizer step / load: invalidates packed + transposed weight copies
 
     # ------------------------------------------------------------------ flat storage
     def _ordered_params(self):
@@ -171,7 +231,7 @@ class ActorCritic(nn.Module):
         self._nets = {}
         off = 0
         for name, seq in (("adapt", self.adaptation_module), ("actor", self.actor_body), ("critic", self.critic_body)):
-            net = _Net(seq, self._flat, self._grad, off)
+            net = _Net(seq, self._flat, self._grad, off, self)
             self._nets[name] = net
             off = net.end
         self.n_adapt_params = self._nets["adapt"].end
@@ -189,6 +249,7 @@ class ActorCritic(nn.Module):
 
     def load_state_dict(self, *a, **k):
         self.flatten()
+        self.weights_version += 1
         return super().load_state_dict(*a, **k)
 
     # ------------------------------------------------------------------ reference API
@@ -294,18 +355,22 @@ class ActorCritic(nn.Module):
         return self._nets["adapt"].forward(h, h.stride(0), self.num_obs_history, None, h.shape[0], self._impl(), "latent")[-1]
 
     # ------------------------------------------------------------------ explicit backward passes (ppo.py:154-189)
-    def backward_ppo(self, h, priv, dmean, dvalue, dstd):
+    def backward_ppo(self, h, priv, dmean, dvalue, dstd, hT=None):
         """Gradients of the PPO loss into flat_grads (overwrites). h/priv are the minibatch inputs of the forward
         pass just run with tag='train'; dmean [M,A], dvalue [M,1], dstd [A]."""
         M, K0, impl = h.shape[0], self.num_obs_history, self._impl()
-        dlat = self._nets["actor"].backward(h, h.stride(0), K0, self._latent, self._p_out, dmean, M, impl, 0, want_dextra=True, tag="train")
-        self._nets["critic"].backward(h, h.stride(0), K0, priv, self._c_out, dvalue, M, impl, 0, tag="train")
-        self._nets["adapt"].backward(h, h.stride(0), K0, None, self._a_out, dlat, M, impl, 0, tag="train")
+        dlat = self._nets["actor"].backward(h, h.stride(0), K0, self._latent, self._p_out, dmean, M, impl, 0, want_dextra=True, tag="train", xT=hT)
+        self._nets["critic"].backward(h, h.stride(0), K0, priv, self._c_out, dvalue, M, impl, 0, tag="train", xT=hT)
+        self._nets["adapt"].backward(h, h.stride(0), K0, None, self._a_out, dlat, M, impl, 0, tag="train", xT=hT)
         self._grad[self.std_offset:self.std_offset + self.num_actions].copy_(dstd)
 
-    def backward_adaptation(self, h, outs, dpred):
+    def backward_adaptation(self, h, outs, dpred, hT=None):
         M, K0 = h.shape[0], self.num_obs_history
-        self._nets["adapt"].backward(h, h.stride(0), K0, None, outs, dpred, M, self._impl(), 0, tag="adapt")
+        self._nets["adapt"].backward(h, h.stride(0), K0, None, outs, dpred, M, self._impl(), 0, tag="adapt", xT=hT)
+
+    def transpose_input(self, h, out=None):
+        """[M][K0] -> [K0][ld>=M] for the tensor-core wgrad of the three first layers (computed once per minibatch)."""
+        return self._nets["adapt"]._transpose(h, h.stride(0), h.shape[0], self.num_obs_history, out)
 
     def adaptation_forward(self, h):
         self.flatten()

@@ -89,11 +89,16 @@ class RolloutStorage:
         trajectory_lengths = (done_indices[1:] - done_indices[:-1])
         return trajectory_lengths.float().mean(), self.rewards.mean()
 
-    def gather(self, src, idx, out=None, ldd=None):
-        """out[i] = src.flatten(0,1)[idx[i]] through go1_gather_rows."""
+    def gather(self, src, idx, out=None, ldd=None, key=None):
+        """out[i] = src.flatten(0,1)[idx[i]] through go1_gather_rows (destination buffers are reused across updates)."""
         flat = src.flatten(0, 1)
         w = flat.shape[1]
         ldd = ldd or w
+        if out is None and key is not None:
+            cache = self.__dict__.setdefault("_gather_bufs", {})
+            out = cache.get(key)
+            if out is None or out.shape != (idx.shape[0], ldd):
+                out = cache[key] = torch.empty(idx.shape[0], ldd, device=flat.device)
         if out is None:
             out = torch.empty(idx.shape[0], ldd, device=flat.device)
         capi.check(capi.lib().go1_gather_rows(capi.ptr(flat), capi.ptr(idx), capi.ptr(out), idx.shape[0], w, ldd, capi.stream_ptr()), "gather")
@@ -109,7 +114,7 @@ class RolloutStorage:
             for i in range(num_mini_batches):
                 idx = indices[i * mini_batch_size:(i + 1) * mini_batch_size].contiguous()
                 obs = self.gather(self.observations, idx)
-                yield (obs, obs, self.gather(self.privileged_observations, idx), self.gather(self.observation_histories, idx),
+                yield (obs, obs, self.gather(self.privileged_observations, idx), self.gather(self.observation_histories, idx, key=("hist", i)),
                        self.gather(self.actions, idx), self.gather(self.values, idx), self.gather(self.advantages, idx),
                        self.gather(self.returns, idx), self.gather(self.actions_log_prob, idx), self.gather(self.mu, idx),
                        self.gather(self.sigma, idx), dones8, self.gather(self.env_bins, idx))
