@@ -38,6 +38,13 @@ def _mlp(in_dim, hidden, out_dim):
     return nn.Sequential(*layers)
 
 
+def _empty(*shape, device):
+    """Scratch buffers outlive the Runner's torch.inference_mode() rollout block and are written again by the update,
+    so they must be ordinary (non-inference) tensors whichever mode they are first needed in."""
+    with torch.inference_mode(False):
+        return torch.empty(*shape, device=device)
+
+
 def _aligned(t_or_ptr, ld):
     p = t_or_ptr if isinstance(t_or_ptr, int) else t_or_ptr.data_ptr()
     return (p & 15) == 0 and (ld & 3) == 0
@@ -69,7 +76,7 @@ class _Net:
     def _buf(self, key, M, width):
         t = self.acts.get(key)
         if t is None or t.shape[0] < M or t.shape[1] != width:
-            t = torch.empty(M, width, device=self.flat.device)
+            t = _empty(M, width, device=self.flat.device)
             self.acts[key] = t
         return t[:M]
 
@@ -89,7 +96,7 @@ class _Net:
     def _transpose(self, src, lds, rows, cols, out=None):
         ldd = (rows + 3) // 4 * 4
         if out is None or out.shape != (cols, ldd):
-            out = torch.empty(cols, ldd, device=self.flat.device)
+            out = _empty(cols, ldd, device=self.flat.device)
         capi.check(capi.lib().go1_transpose(capi.ptr(src) if torch.is_tensor(src) else src, lds, capi.ptr(out), ldd, rows, cols, capi.stream_ptr()), "go1_transpose")
         return out
 
@@ -110,7 +117,7 @@ class _Net:
             tc = self._tc_ok(impl, o, K) and _aligned(inp, ld_in)
             if tc and not _aligned(W, i):      # pack W[:, :K] into a TMA-readable copy (rows of K floats, K % 4 == 0)
                 if K % 4 == 0:
-                    Wm = self._cached(("pack", li), lambda old: (old if old is not None else torch.empty(o, K, device=W.device)).copy_(W.view(o, i)[:, :K]))
+                    Wm = self._cached(("pack", li), lambda old: (old if old is not None else _empty(o, K, device=W.device)).copy_(W.view(o, i)[:, :K]))
                     ldw = K
                 else:
                     tc = False
