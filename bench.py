@@ -128,12 +128,25 @@ def run_b200(args):
     od = env.get_observations()
     state = [od["obs"], od["privileged_obs"], od["obs_history"]]
 
+    phase_ms = [0.0, 0.0, 0.0, 0]
+
     def iteration():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if args.breakdown else None
+        if ev: ev[0].record()
         obs, priv, hist, infos = runner.rollout(*state)
         state[:] = [obs, priv, hist]
+        if ev: ev[1].record()
         with torch.inference_mode():
             runner.alg.compute_returns(hist[:env.num_train_envs], priv[:env.num_train_envs])
-        return runner.alg.update()          # returns host floats: one D2H sync per iteration
+        if ev: ev[2].record()
+        out = runner.alg.update()          # returns host floats: one D2H sync per iteration
+        if ev:
+            ev[3].record(); torch.cuda.synchronize()
+            if phase_ms[3] >= args.warmup:
+                for i in range(3):
+                    phase_ms[i] += ev[i].elapsed_time(ev[i + 1])
+            phase_ms[3] += 1
+        return out
 
     def sync():
         torch.cuda.synchronize()
@@ -155,8 +168,23 @@ def run_b200(args):
     sync()
     t0 = time.perf_counter()
     e0.record()
+    prof = cprof = None
+    if args.profile:
+        import cProfile
+        from torch.profiler import profile, ProfilerActivity
+        prof = profile(activities=[ProfilerActivity.CUDA]); prof.__enter__()
+        cprof = cProfile.Profile(); cprof.enable()
     for _ in range(args.steps):
         losses = iteration()
+    if args.profile:
+        cprof.disable(); torch.cuda.synchronize(); prof.__exit__(None, None, None)
+        import pstats, io
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "kernels_torchprof.txt"), "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70))
+        sio = io.StringIO(); pstats.Stats(cprof, stream=sio).sort_stats("cumulative").print_stats(45)
+        with open(os.path.join(ROOT, "gpurun_out", "host_cprofile.txt"), "w") as f:
+            f.write(sio.getvalue())
     e1.record()
     sync()
     wall = time.perf_counter() - t0
@@ -186,6 +214,9 @@ def run_b200(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "losses": [float(x) for x in losses[:3]],
         }
+        if args.breakdown:
+            n_it = args.steps
+            out["phase_ms"] = {"rollout": phase_ms[0] / n_it, "compute_returns": phase_ms[1] / n_it, "update": phase_ms[2] / n_it}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(sample_envs=args.cpu_envs)
     if world > 1:
@@ -300,10 +331,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
-    ap.add_argument("--gemm", type=int, default=int(os.environ.get("GO1_GEMM_IMPL", "0")), help="0 fp32 CUDA cores, 1 tcgen05 tf32")
+    ap.add_argument("--gemm", type=int, default=int(os.environ.get("GO1_GEMM_IMPL", "1")), help="0 fp32 CUDA cores, 1 tcgen05 tf32")
     ap.add_argument("--cpu-envs", type=int, default=32)
     ap.add_argument("--warmup-ref", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="torch.profiler (CUPTI) kernel table + cProfile of the host loop -> gpurun_out/")
+    ap.add_argument("--breakdown", action="store_true", help="per-phase CUDA-event timing (adds a sync per phase: not for headline numbers)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

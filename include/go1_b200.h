@@ -188,6 +188,18 @@ int go1_ppo_normalize_advantages(float* advantages, const double* stats, int64_t
  * impl: 0 = fp32 CUDA cores (exact-fp32 path), 1 = tcgen05 TF32 tensor cores with fp32 accumulation. */
 int go1_gemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
              float* C, int ldc, const float* bias, int act, int accumulate, int impl, void* stream);
+/* Same product with the full fused epilogue, applied in this order to each output element v = sum_k a*b:
+ *   v += C_old (accumulate);  v += sum_e extra[m][e] * w_extra[n][e]  (num_extra <= 4: the 2 trailing input columns of
+ *   the actor/critic first layer, i.e. cat(obs_history, latent) without the cat);  v += bias[n];
+ *   act 1: v = ELU(v);  act 2: v *= ELU'(z) computed from the saved activation dact_y[m][n] (the autograd of nn.ELU fused
+ *   into the dgrad GEMM). */
+typedef struct Go1GemmEpilogue {
+    const float* bias; int32_t act, accumulate;
+    const float* extra; int32_t ld_extra; const float* w_extra; int32_t ld_w_extra, num_extra;
+    const float* dact_y; int32_t ld_dact_y;
+} Go1GemmEpilogue;
+int go1_gemm_ex(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                float* C, int ldc, const Go1GemmEpilogue* ep, int impl, void* stream);
 /* dst[c][r] = src[r][c] (rows x cols fp32, row strides lds/ldd): brings the dgrad (W^T) and wgrad (dz^T, x^T) operands into
  * the K-major form the tcgen05 kernel reads (impl=1 supports transA=0, transB=1 only). */
 int go1_transpose(const float* src, int lds, float* dst, int ldd, int rows, int cols, void* stream);

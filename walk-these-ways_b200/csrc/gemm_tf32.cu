@@ -18,6 +18,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <mutex>
+#include "../../include/go1_b200.h"
 
 extern int go1_set_error(const char* m);
 void go1_count_launch(int n);
@@ -84,6 +85,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 struct GemmArgs {
     float* C; const float* bias;
     int M, N, K, ldc, act, accumulate, kb_per_split;
+    const float* ex; const float* wex; const float* aux;      // fused epilogue operands (see Go1GemmEpilogue)
+    int ldex, ldwex, nex, ldaux;
 };
 
 template <int BN, int STAGES>
@@ -187,6 +190,17 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_kernel(const __grid_constant
                             for (int j = 0; j < 32; j++) if (j < ncols) v[j] += crow[j];
                         }
                     }
+                    if (g.nex > 0) {        // rank-nex update from the trailing input columns (cat(obs_history, latent))
+                        float e[4] = {0.f, 0.f, 0.f, 0.f};
+                        for (int t = 0; t < g.nex; t++) e[t] = __ldg(g.ex + (size_t)row * g.ldex + t);
+#pragma unroll
+                        for (int j = 0; j < 32; j++) if (j < ncols) {
+                            const float* w = g.wex + (size_t)(col0 + j) * g.ldwex;
+                            float acc = 0.f;
+                            for (int t = 0; t < g.nex; t++) acc = fmaf(e[t], __ldg(w + t), acc);
+                            v[j] += acc;
+                        }
+                    }
                     if (g.bias) {
 #pragma unroll
                         for (int j = 0; j < 32; j++) if (j < ncols) v[j] += __ldg(g.bias + col0 + j);
@@ -194,6 +208,10 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_kernel(const __grid_constant
                     if (g.act == 1) {
 #pragma unroll
                         for (int j = 0; j < 32; j++) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
+                    } else if (g.act == 2) {   // multiply by ELU'(z) from the saved activation y: 1 if y > 0 else y + 1
+                        const float* arow = g.aux + (size_t)row * g.ldaux + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j++) if (j < ncols) { const float y = __ldg(arow + j); v[j] *= (y > 0.f ? 1.0f : y + 1.0f); }
                     }
                     if (vec) {
 #pragma unroll
@@ -269,18 +287,23 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, int 
 }  // namespace
 
 extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
-                             float* Cm, int ldc, const float* bias, int act, int accumulate, cudaStream_t st) {
+                             float* Cm, int ldc, const Go1GemmEpilogue* ep, cudaStream_t st) {
+    const float* bias = ep->bias; const int act = ep->act, accumulate = ep->accumulate;
     if (transA != 0 || transB != 1)
         return go1_set_error("go1_gemm impl=1 (tcgen05 TF32) takes K-major operands only: transA=0, transB=1 (use go1_transpose for dgrad/wgrad)");
     if ((lda & 3) || (ldb & 3) || (((uintptr_t)A | (uintptr_t)B) & 15))
         return go1_set_error("go1_gemm impl=1: A/B must be 16-byte aligned with row strides that are multiples of 4 floats (TMA)");
     GemmArgs g;
     g.C = Cm; g.bias = bias; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.act = act; g.accumulate = accumulate;
+    g.ex = ep->extra; g.ldex = ep->ld_extra; g.wex = ep->w_extra; g.ldwex = ep->ld_w_extra; g.nex = ep->extra ? ep->num_extra : 0;
+    g.aux = ep->dact_y; g.ldaux = ep->ld_dact_y;
+    if (g.nex < 0 || g.nex > 4) return go1_set_error("go1_gemm_ex: num_extra must be 0..4");
+    if (act == 2 && !g.aux) return go1_set_error("go1_gemm_ex: act 2 needs dact_y");
     const int num_kb = (K + BK - 1) / BK;
-    const int BN = (N > 64) ? 128 : 64;
+    const int BN = (N > 64) ? 128 : (N > 32 ? 64 : 32);
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     int splits = 1;
-    if (tiles < 148 && num_kb >= 16) { splits = (2 * 148 + tiles - 1) / tiles; if (splits > num_kb / 4) splits = num_kb / 4; if (splits < 1) splits = 1; }
+    if (tiles < 148 && num_kb >= 16 && g.nex == 0 && act != 2) { splits = (2 * 148 + tiles - 1) / tiles; if (splits > num_kb / 4) splits = num_kb / 4; if (splits < 1) splits = 1; }
     g.kb_per_split = (num_kb + splits - 1) / splits;
     splits = (num_kb + g.kb_per_split - 1) / g.kb_per_split;
     CUtensorMap ma, mb;
@@ -290,7 +313,7 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
         if (!accumulate) { const size_t tot = (size_t)M * N; zero_strided<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cm, ldc, M, N); go1_count_launch(1); }
         g.bias = nullptr; g.act = 0;
     }
-    int e = (BN == 128) ? launch<128, 3>(ma, mb, g, splits, st) : launch<64, 4>(ma, mb, g, splits, st);
+    int e = (BN == 128) ? launch<128, 3>(ma, mb, g, splits, st) : (BN == 64 ? launch<64, 4>(ma, mb, g, splits, st) : launch<32, 4>(ma, mb, g, splits, st));
     if (e) return e;
     if (splits > 1 && (bias || act)) { const size_t tot = (size_t)M * N; bias_act_strided<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cm, ldc, bias, M, N, act); go1_count_launch(1); }
     cudaError_t ce = cudaGetLastError();

@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include "../../include/go1_b200.h"
 #include "sim_math.cuh"
 void go1_count_launch(int n);
@@ -121,10 +122,12 @@ extern "C" int go1_ppo_normalize_advantages(float* advantages, const double* sta
 // ---------------------------------------------------------------------------------------------
 DI float elu1(float x) { return x > 0.f ? x : expm1f(x); }
 
+struct SgemmEp { const float* ex; const float* wex; const float* aux; int ldex, ldwex, nex, ldaux; };
+
 template <int TA, int TB>
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                                                     float* __restrict__ Cm, int ldc, const float* __restrict__ bias,
-                                                    int M, int N, int K, int act, int accumulate, int kchunk) {
+                                                    int M, int N, int K, int act, int accumulate, int kchunk, const SgemmEp ep) {
     constexpr int BM = 128, BN = 128, BK = 8;
     __shared__ float As[2][BK][BM + 4], Bs[2][BK][BN + 4];
     const int tid = threadIdx.x;
@@ -210,8 +213,10 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
             float v = acc[i][j];
             if (split) { atomicAdd(c, v); continue; }      // caller pre-initialised C (zero or accumulate target)
             if (accumulate) v += *c;
+            for (int t = 0; t < ep.nex; t++) v = fmaf(ep.ex[(size_t)gm * ep.ldex + t], ep.wex[(size_t)gn * ep.ldwex + t], v);
             if (bias) v += bias[gn];
             if (act == 1) v = elu1(v);
+            else if (act == 2) { const float y = ep.aux[(size_t)gm * ep.ldaux + gn]; v *= (y > 0.f ? 1.0f : y + 1.0f); }
             *c = v;
         }
     }
@@ -234,17 +239,23 @@ __global__ void zero_strided_kernel(float* __restrict__ Cm, int ldc, int M, int 
 }
 
 extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
-                             float* Cm, int ldc, const float* bias, int act, int accumulate, cudaStream_t st);
+                             float* Cm, int ldc, const Go1GemmEpilogue* ep, cudaStream_t st);
 
-extern "C" int go1_gemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
-                        float* Cm, int ldc, const float* bias, int act, int accumulate, int impl, void* stream) {
-    if (!A || !B || !Cm || M <= 0 || N <= 0 || K <= 0) return go1_set_error("go1_gemm: bad arguments");
+extern "C" int go1_gemm_ex(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                           float* Cm, int ldc, const Go1GemmEpilogue* epi, int impl, void* stream) {
+    if (!A || !B || !Cm || !epi || M <= 0 || N <= 0 || K <= 0) return go1_set_error("go1_gemm: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    if (impl == 1) return go1_gemm_tf32(transA, transB, M, N, K, A, lda, B, ldb, Cm, ldc, bias, act, accumulate, st);
+    if (impl == 1) return go1_gemm_tf32(transA, transB, M, N, K, A, lda, B, ldb, Cm, ldc, epi, st);
     if (impl != 0) return go1_set_error("go1_gemm: unknown impl");
+    const float* bias = epi->bias; const int act = epi->act, accumulate = epi->accumulate;
+    SgemmEp ep; ep.ex = epi->extra; ep.wex = epi->w_extra; ep.aux = epi->dact_y; ep.ldex = epi->ld_extra; ep.ldwex = epi->ld_w_extra;
+    ep.nex = epi->extra ? epi->num_extra : 0; ep.ldaux = epi->ld_dact_y;
+    if (ep.nex < 0 || ep.nex > 4) return go1_set_error("go1_gemm_ex: num_extra must be 0..4");
+    if (act == 2 && !ep.aux) return go1_set_error("go1_gemm_ex: act 2 needs dact_y");
+    const bool fused = ep.nex > 0 || act == 2;
     const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
     int splitk = 1;
-    if (tiles < 148 && K >= 2048) { splitk = min((148 * 2 + tiles - 1) / tiles, (K + 255) / 256); if (splitk < 1) splitk = 1; }
+    if (tiles < 148 && K >= 2048 && !fused) { splitk = min((148 * 2 + tiles - 1) / tiles, (K + 255) / 256); if (splitk < 1) splitk = 1; }
     int kchunk = ((K + splitk - 1) / splitk + 7) / 8 * 8;
     splitk = (K + kchunk - 1) / kchunk;
     dim3 grid((N + 127) / 128, (M + 127) / 128, splitk);
@@ -252,7 +263,7 @@ extern "C" int go1_gemm(int transA, int transB, int M, int N, int K, const float
         const size_t tot = (size_t)M * N;
         zero_strided_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cm, ldc, M, N); go1_count_launch(1);
     }
-#define LAUNCH(TA, TB) sgemm_kernel<TA, TB><<<grid, 256, 0, st>>>(A, lda, B, ldb, Cm, ldc, bias, M, N, K, act, accumulate, kchunk)
+#define LAUNCH(TA, TB) sgemm_kernel<TA, TB><<<grid, 256, 0, st>>>(A, lda, B, ldb, Cm, ldc, bias, M, N, K, act, accumulate, kchunk, ep)
     if (!transA && !transB) LAUNCH(0, 0); else if (!transA && transB) LAUNCH(0, 1); else if (transA && !transB) LAUNCH(1, 0); else LAUNCH(1, 1);
     go1_count_launch(1);
 #undef LAUNCH
@@ -261,6 +272,13 @@ extern "C" int go1_gemm(int transA, int transB, int M, int N, int K, const float
         bias_act_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cm, ldc, bias, M, N, act); go1_count_launch(1);
     }
     return cuda_rc("go1_gemm");
+}
+extern "C" int go1_gemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                        float* Cm, int ldc, const float* bias, int act, int accumulate, int impl, void* stream) {
+    Go1GemmEpilogue ep;
+    memset(&ep, 0, sizeof ep);
+    ep.bias = bias; ep.act = act; ep.accumulate = accumulate;
+    return go1_gemm_ex(transA, transB, M, N, K, A, lda, B, ldb, Cm, ldc, &ep, impl, stream);
 }
 
 // dz = dy * ELU'(y) from the saved output y (alpha = 1: ELU' = 1 for y > 0 else y + 1)

@@ -51,7 +51,10 @@ class Curriculum:
 
     def sample(self, batch_size, low=None, high=None):
         centroids, inds = self.sample_bins(batch_size, low=low, high=high)
-        return np.stack([self.sample_uniform_from_cell(c) for c in centroids]), inds
+        # one vectorised draw: RandomState.uniform fills its output in C order, so a [batch, D] call consumes the stream
+        # exactly like the reference's `batch` sequential D-wide calls (curriculum.py:87-89) — bit-identical samples
+        bin_sizes = np.array([*self.bin_sizes.values()])
+        return self.rng.uniform(centroids + bin_sizes / 2, centroids - bin_sizes / 2), inds
 
 
 class SumCurriculum(Curriculum):

@@ -58,20 +58,18 @@ class _Net:
     to a contiguous copy, dgrad reads a transposed weight copy and wgrad transposed activations/gradients
     (go1_transpose); copies are cached per weight version."""
 
-    MIN_TC = 32      # products with an output or reduction dimension below this stay on the fp32 kernel
-
-    def __init__(self, seq, flat, grad, offset, owner):
+    def __init__(self, seq, flat, grad, offsets, owner):
         self.linears = [m for m in seq if isinstance(m, nn.Linear)]
         self.specs = []                       # (w_off, b_off, out, in)
-        off = offset
         for lin in self.linears:
             o, i = lin.weight.shape
-            self.specs.append((off, off + o * i, o, i))
-            off += o * i + o
-        self.end = off
+            self.specs.append((offsets[id(lin.weight)], offsets[id(lin.bias)], o, i))
+        last = self.linears[-1]
+        self.end = offsets[id(last.bias)] + last.bias.numel()
         self.flat, self.grad, self.owner = flat, grad, owner
         self.acts = {}
         self._cache = {}
+        self._ep = capi.Go1GemmEpilogue()
 
     def _buf(self, key, M, width):
         t = self.acts.get(key)
@@ -88,20 +86,36 @@ class _Net:
             self._cache[key] = hit
         return hit[1]
 
-    def _gemm(self, ta, tb, M, N, K, A, lda, B, ldb, Cm, ldc, bias, act, acc, impl):
-        capi.check(capi.lib().go1_gemm(ta, tb, M, N, K, capi.ptr(A) if torch.is_tensor(A) else A, lda, capi.ptr(B) if torch.is_tensor(B) else B, ldb,
-                                       capi.ptr(Cm) if torch.is_tensor(Cm) else Cm, ldc, capi.ptr(bias) if bias is not None else None, act, acc, impl,
-                                       capi.stream_ptr()), "go1_gemm")
+    @staticmethod
+    def _p(x):
+        return x.data_ptr() if torch.is_tensor(x) else x
+
+    def _gemm(self, ta, tb, M, N, K, A, lda, B, ldb, Cm, ldc, bias=None, act=0, acc=0, impl=0, extra=None, w_extra=0, ld_w_extra=0, dact_y=None):
+        ep = self._ep
+        ep.bias = self._p(bias) if bias is not None else None
+        ep.act, ep.accumulate = act, acc
+        if extra is not None:
+            ep.extra, ep.ld_extra, ep.w_extra, ep.ld_w_extra, ep.num_extra = extra.data_ptr(), extra.stride(0), w_extra, ld_w_extra, extra.shape[1]
+        else:
+            ep.extra, ep.num_extra = None, 0
+        if dact_y is not None:
+            ep.dact_y, ep.ld_dact_y = dact_y.data_ptr(), dact_y.stride(0)
+        else:
+            ep.dact_y = None
+        capi.check(capi.lib().go1_gemm_ex(ta, tb, M, N, K, self._p(A), lda, self._p(B), ldb, self._p(Cm), ldc, ep, impl, capi.stream_ptr()), "go1_gemm")
 
     def _transpose(self, src, lds, rows, cols, out=None):
         ldd = (rows + 3) // 4 * 4
         if out is None or out.shape != (cols, ldd):
             out = _empty(cols, ldd, device=self.flat.device)
-        capi.check(capi.lib().go1_transpose(capi.ptr(src) if torch.is_tensor(src) else src, lds, capi.ptr(out), ldd, rows, cols, capi.stream_ptr()), "go1_transpose")
+        capi.check(capi.lib().go1_transpose(self._p(src), lds, capi.ptr(out), ldd, rows, cols, capi.stream_ptr()), "go1_transpose")
         return out
 
-    def _tc_ok(self, impl, *dims):
-        return impl == 1 and min(dims) >= self.MIN_TC
+    @staticmethod
+    def _tma_ok(x, ld):
+        """TMA-readable K-major operand: 16-byte aligned base, row stride a multiple of 16 bytes."""
+        p = x.data_ptr() if torch.is_tensor(x) else x
+        return (p & 15) == 0 and (ld & 3) == 0
 
     def forward(self, x, ldx, K0, extra, M, impl, tag="a"):
         """x: [M][K0] rows with stride ldx; extra: [M][E] contiguous or None. Returns list of layer outputs."""
@@ -112,19 +126,18 @@ class _Net:
             W = self.flat[wo:wo + o * i]
             b = self.flat[bo:bo + o]
             act = 1 if li < n - 1 else 0
-            K = K0 if (li == 0 and extra is not None) else i
+            first_extra = li == 0 and extra is not None
+            K = K0 if first_extra else i
             Wm, ldw = W, i
-            tc = self._tc_ok(impl, o, K) and _aligned(inp, ld_in)
-            if tc and not _aligned(W, i):      # pack W[:, :K] into a TMA-readable copy (rows of K floats, K % 4 == 0)
+            tc = impl == 1 and self._tma_ok(inp, ld_in)
+            if tc and not self._tma_ok(W, i):      # pack W[:, :K] into a TMA-readable copy (rows of K floats, K % 4 == 0)
                 if K % 4 == 0:
                     Wm = self._cached(("pack", li), lambda old: (old if old is not None else _empty(o, K, device=W.device)).copy_(W.view(o, i)[:, :K]))
                     ldw = K
                 else:
                     tc = False
-            if li == 0 and extra is not None:
-                E = i - K0
-                self._gemm(0, 1, M, o, K0, inp, ld_in, Wm, ldw, y, o, None, 0, 0, 1 if tc else 0)
-                self._gemm(0, 1, M, o, E, extra, extra.stride(0), W.data_ptr() + 4 * K0, i, y, o, b, act, 1, 0)
+            if first_extra:     # y = act(x W[:, :K0]^T + extra W[:, K0:]^T + b): the 2 trailing columns ride in the epilogue
+                self._gemm(0, 1, M, o, K0, inp, ld_in, Wm, ldw, y, o, b, act, 0, 1 if tc else 0, extra=extra, w_extra=W.data_ptr() + 4 * K0, ld_w_extra=i)
             else:
                 self._gemm(0, 1, M, o, K, inp, ld_in, Wm, ldw, y, o, b, act, 0, 1 if tc else 0)
             outs.append(y)
@@ -132,9 +145,10 @@ class _Net:
         return outs
 
     def backward(self, x, ldx, K0, extra, outs, dout, M, impl, accumulate, want_dextra=False, tag="a", xT=None):
-        """dout: gradient w.r.t. the network output [M][out]. Writes weight/bias grads into the flat grad buffer.
-        xT: optional precomputed transpose of the first-layer input ([K0][ld>=M]) for the tensor-core wgrad.
-        Returns d(extra) [M][E] if requested."""
+        """dout: gradient w.r.t. the network output [M][out] (the last layer has no activation).  Writes weight/bias grads
+        into the flat grad buffer.  dz of every hidden layer comes out of the dgrad GEMM already multiplied by ELU'
+        (fused epilogue).  xT: optional precomputed transpose of the first-layer input ([K0][ld>=M]) for the tensor-core
+        wgrad.  Returns d(extra) [M][E] if requested."""
         L, st = capi.lib(), capi.stream_ptr()
         n = len(self.specs)
         dz = dout
@@ -143,17 +157,15 @@ class _Net:
             wo, bo, o, i = self.specs[li]
             W = self.flat[wo:wo + o * i]
             gW, gb = self.grad[wo:wo + o * i], self.grad[bo:bo + o]
-            if li < n - 1:     # dz = dy * ELU'(y)
-                y = outs[li]
-                capi.check(L.go1_elu_backward(capi.ptr(y), o, capi.ptr(dz), o, capi.ptr(dz), o, M, o, st), "elu_bwd")
-            capi.check(L.go1_colsum(capi.ptr(dz), o, capi.ptr(gb), M, o, accumulate, st), "colsum")
+            ldz = dz.stride(0)
+            capi.check(L.go1_colsum(capi.ptr(dz), ldz, capi.ptr(gb), M, o, accumulate, st), "colsum")
             if li == 0:
                 inp, ld_in, K = x, ldx, (K0 if extra is not None else i)
             else:
                 inp, ld_in, K = outs[li - 1], self.specs[li - 1][2], i
             # ---- wgrad: dW[o][K] = dz^T[o][M] inp[M][K]
-            if self._tc_ok(impl, o, K, M):
-                dzT = self._transpose(dz, o, M, o, self.acts.get((tag, "dzT", li)))
+            if impl == 1 and M >= 64 and K >= 8:
+                dzT = self._transpose(dz, ldz, M, o, self.acts.get((tag, "dzT", li)))
                 self.acts[(tag, "dzT", li)] = dzT
                 if li == 0 and xT is not None:
                     inT = xT
@@ -162,21 +174,22 @@ class _Net:
                     self.acts[(tag, "inT", li)] = inT
                 self._gemm(0, 1, o, K, M, dzT, dzT.stride(0), inT, inT.stride(0), gW, i, None, 0, accumulate, 1)
             else:
-                self._gemm(1, 0, o, K, M, dz, o, inp, ld_in, gW, i, None, 0, accumulate, 0)
+                self._gemm(1, 0, o, K, M, dz, ldz, inp, ld_in, gW, i, None, 0, accumulate, 0)
             if li == 0 and extra is not None:
                 E = i - K0
-                self._gemm(1, 0, o, E, M, dz, o, extra, extra.stride(0), gW.data_ptr() + 4 * K0, i, None, 0, accumulate, 0)
+                self._gemm(1, 0, o, E, M, dz, ldz, extra, extra.stride(0), gW.data_ptr() + 4 * K0, i, None, 0, accumulate, 0)
                 if want_dextra:
                     dextra = self._buf((tag, "dextra"), M, E)
-                    self._gemm(0, 0, M, E, o, dz, o, W.data_ptr() + 4 * K0, i, dextra, E, None, 0, 0, 0)
-            # ---- dgrad: dprev[M][i] = dz[M][o] W[o][i]
+                    self._gemm(0, 0, M, E, o, dz, ldz, W.data_ptr() + 4 * K0, i, dextra, E, None, 0, 0, 0)
+            # ---- dgrad (+ fused ELU'): dz_prev[M][i] = (dz[M][o] W[o][i]) * ELU'(y_prev)
             if li > 0:
                 dprev = self._buf((tag, "d", li - 1), M, i)
-                if self._tc_ok(impl, i, o):
+                yprev = outs[li - 1]
+                if impl == 1 and self._tma_ok(dz, ldz) and M >= 64:
                     WT = self._cached(("WT", li), lambda old: self._transpose(W, i, o, i, old))
-                    self._gemm(0, 1, M, i, o, dz, o, WT, WT.stride(0), dprev, i, None, 0, 0, 1)
+                    self._gemm(0, 1, M, i, o, dz, ldz, WT, WT.stride(0), dprev, i, None, 2, 0, 1, dact_y=yprev)
                 else:
-                    self._gemm(0, 0, M, i, o, dz, o, W, i, dprev, i, None, 0, 0, 0)
+                    self._gemm(0, 0, M, i, o, dz, ldz, W, i, dprev, i, None, 2, 0, 0, dact_y=yprev)
                 dz = dprev
         return dextra
 
@@ -220,29 +233,31 @@ class ActorCritic(nn.Module):
 
     def flatten(self):
         """(Re)build the flat parameter/gradient buffers and re-point every parameter at its slice."""
+        if self._flat is not None:          # _apply() (device/dtype moves) resets it to None
+            return
         ps = self._ordered_params()
         dev = ps[0].device
-        if self._flat is not None and self._flat.device == dev and all(p.data.untyped_storage().data_ptr() == self._flat.untyped_storage().data_ptr() for p in ps):
-            return
-        total = sum(p.numel() for p in ps)
-        flat = torch.empty(total, device=dev, dtype=torch.float32)
-        off = 0
+        # every tensor starts on a 16-byte boundary (zero padding in between: zero gradient, never moves) so that weights
+        # are TMA-readable in place wherever their row length allows it
+        offsets, off = {}, 0
         for p in ps:
-            n = p.numel()
-            flat[off:off + n].copy_(p.data.reshape(-1))
-            p.data = flat[off:off + n].view(p.shape)
-            off += n
+            off = (off + 3) // 4 * 4
+            offsets[id(p)] = off
+            off += p.numel()
+        total = (off + 3) // 4 * 4
+        flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        for p in ps:
+            o, n = offsets[id(p)], p.numel()
+            flat[o:o + n].copy_(p.data.reshape(-1))
+            p.data = flat[o:o + n].view(p.shape)
         self._flat = flat
         self._grad = torch.zeros_like(flat)
-        self.n_params = total
+        self.n_params = total                 # length of the flat buffers (3,054,619 parameters + alignment padding)
         self._nets = {}
-        off = 0
         for name, seq in (("adapt", self.adaptation_module), ("actor", self.actor_body), ("critic", self.critic_body)):
-            net = _Net(seq, self._flat, self._grad, off, self)
-            self._nets[name] = net
-            off = net.end
-        self.n_adapt_params = self._nets["adapt"].end
-        self.std_offset = off
+            self._nets[name] = _Net(seq, self._flat, self._grad, offsets, self)
+        self.n_adapt_params = (self._nets["adapt"].end + 3) // 4 * 4
+        self.std_offset = offsets[id(self.std)]
 
     @property
     def flat_params(self):
