@@ -205,6 +205,15 @@ int go1_gemm_ex(int transA, int transB, int M, int N, int K, const float* A, int
 int go1_transpose(const float* src, int lds, float* dst, int ldd, int rows, int cols, void* stream);
 /* dz = dy * ELU'(z) computed from the saved layer output y (autograd of nn.ELU). dz may alias dy. */
 int go1_elu_backward(const float* y, int ldy, const float* dy, int lddy, float* dz, int lddz, int M, int N, void* stream);
+/* Backward of the E (<= 4) trailing input columns of a first layer (the `latent` / privileged columns of
+ * cat(obs_history, .), actor_critic.py:115,143), one bandwidth-bound pass over dz [M][o]:
+ *   g_w_extra[j][t] (+)= sum_m dz[m][j] extra[m][t];   dextra[m][t] = sum_j dz[m][j] w_extra[j][t] (if dextra != NULL). */
+int go1_mlp_extra_backward(const float* dz, int lddz, const float* extra, int ldex, const float* w_extra, int ldw, float* g_w_extra, int ldgw,
+                           float* dextra, int ldde, int M, int o, int E, int accumulate, void* stream);
+/* dgrad through a narrow (o <= 16) output layer, with the previous layer's ELU' fused (y_prev may be NULL):
+ *   dprev[m][c] = (sum_t dz[m][t] W[t][c]) * ELU'(y_prev[m][c]),  W row-major [o][n]. */
+int go1_skinny_dgrad(const float* dz, int lddz, const float* W, int ldw, const float* y_prev, int ldy, float* dprev, int lddp,
+                     int M, int o, int n, void* stream);
 /* out[n] (+)= sum_m x[m][n]: bias gradient of nn.Linear. */
 int go1_colsum(const float* x, int ldx, float* out, int M, int N, int accumulate, void* stream);
 

@@ -14,6 +14,7 @@ class ML_Logger:
         self.root = str(root) if root is not None else os.path.abspath("./runs")
         self.prefix = prefix or "default"
         self._metrics = defaultdict(list)
+        self._lazy = []
         self._metric_prefix = ""
         self._timers = {}
         self._every = defaultdict(int)
@@ -72,6 +73,10 @@ class ML_Logger:
         for k, v in d.items():
             self._metrics[self._metric_prefix + k].append(v)
 
+    def store_metrics_lazy(self, prefix, mapping):
+        """Keep a reference to a (possibly lazily built) dict; it is expanded at summary time."""
+        self._lazy.append((prefix.rstrip("/") + "/", mapping))
+
     def every(self, n, key="default", start_on=0):
         self._every[key] += 1
         c = self._every[key]
@@ -92,6 +97,14 @@ class ML_Logger:
 
     def log_metrics_summary(self, key_values=None, **kw):
         row = dict(key_values or {})
+        seen = set()
+        for prefix, mapping in self._lazy:
+            if id(mapping) in seen:
+                continue
+            seen.add(id(mapping))
+            for k, v in mapping.items():
+                self._metrics[prefix + k].append(v)
+        self._lazy = []
         for k, vals in self._metrics.items():
             fs = [f for f in (self._to_float(v) for v in vals) if f is not None]
             if fs:

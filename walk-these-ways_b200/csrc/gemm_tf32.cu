@@ -303,7 +303,7 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
     const int BN = (N > 64) ? 128 : (N > 32 ? 64 : 32);
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     int splits = 1;
-    if (tiles < 148 && num_kb >= 16 && g.nex == 0 && act != 2) { splits = (2 * 148 + tiles - 1) / tiles; if (splits > num_kb / 4) splits = num_kb / 4; if (splits < 1) splits = 1; }
+    if (tiles < 148 && num_kb >= 16 && g.nex == 0 && act != 2) { splits = (2 * 148) / tiles; if (splits > num_kb / 16) splits = num_kb / 16; if (splits < 1) splits = 1; }   // one wave of 2 CTAs/SM, >= 16 k-blocks each
     g.kb_per_split = (num_kb + splits - 1) / splits;
     splits = (num_kb + g.kb_per_split - 1) / g.kb_per_split;
     CUtensorMap ma, mb;

@@ -565,3 +565,72 @@ extern "C" int go1_gather_rows(const float* src, const int64_t* idx, float* dst,
     gather_rows_kernel<<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(src, (const long long*)idx, dst, rows, width, ldd); go1_count_launch(1);
     return cuda_rc("go1_gather_rows");
 }
+
+// ---------------------------------------------------------------------------------------------
+// skinny pieces of the MLP backward that are pure bandwidth (one pass over dz), kept off the GEMM kernels:
+//   extra columns of a first layer:  dextra[m][t] = sum_j dz[m][j] We[j][t];   gWe[j][t] (+)= sum_m dz[m][j] extra[m][t]
+//   dgrad through a <=4-wide output: dprev[m][c] = (sum_t dz[m][t] W[t][c]) * ELU'(y_prev[m][c])
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) extra_dinput_kernel(const float* __restrict__ dz, int lddz, const float* __restrict__ We, int ldw,
+                                                           float* __restrict__ dextra, int ldde, int M, int o, int E) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= M) return;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* row = dz + (size_t)warp * lddz;
+    for (int j = lane; j < o; j += 32) {
+        const float d = row[j];
+        for (int t = 0; t < E; t++) acc[t] = fmaf(d, __ldg(We + (size_t)j * ldw + t), acc[t]);
+    }
+    for (int t = 0; t < E; t++) {
+        float v = acc[t];
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if (lane == 0) dextra[(size_t)warp * ldde + t] = v;
+    }
+}
+__global__ void __launch_bounds__(256) extra_wgrad_kernel(const float* __restrict__ dz, int lddz, const float* __restrict__ extra, int ldex,
+                                                          float* __restrict__ gWe, int ldgw, int M, int o, int E, int rows_per_block) {
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= o) return;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int m = r0; m < r1; m++) {
+        const float d = dz[(size_t)m * lddz + j];
+        for (int t = 0; t < E; t++) acc[t] = fmaf(d, __ldg(extra + (size_t)m * ldex + t), acc[t]);
+    }
+    for (int t = 0; t < E; t++) atomicAdd(gWe + (size_t)j * ldgw + t, acc[t]);
+}
+__global__ void zero_small_kernel(float* p, int ld, int rows, int cols) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows * cols) p[(size_t)(i / cols) * ld + (i % cols)] = 0.f;
+}
+extern "C" int go1_mlp_extra_backward(const float* dz, int lddz, const float* extra, int ldex, const float* w_extra, int ldw, float* g_w_extra, int ldgw,
+                                      float* dextra, int ldde, int M, int o, int E, int accumulate, void* stream) {
+    if (!dz || !extra || !g_w_extra || M <= 0 || o <= 0 || E <= 0 || E > 4) return go1_set_error("go1_mlp_extra_backward: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dextra) {
+        if (!w_extra) return go1_set_error("go1_mlp_extra_backward: dextra needs w_extra");
+        extra_dinput_kernel<<<(M * 32 + 255) / 256, 256, 0, st>>>(dz, lddz, w_extra, ldw, dextra, ldde, M, o, E); go1_count_launch(1);
+    }
+    if (!accumulate) { zero_small_kernel<<<(o * E + 255) / 256, 256, 0, st>>>(g_w_extra, ldgw, o, E); go1_count_launch(1); }
+    const int rpb = 32;
+    dim3 grid((o + 255) / 256, (M + rpb - 1) / rpb);
+    extra_wgrad_kernel<<<grid, 256, 0, st>>>(dz, lddz, extra, ldex, g_w_extra, ldgw, M, o, E, rpb); go1_count_launch(1);
+    return cuda_rc("go1_mlp_extra_backward");
+}
+__global__ void skinny_dgrad_kernel(const float* __restrict__ dz, int lddz, const float* __restrict__ W, int ldw, const float* __restrict__ y, int ldy,
+                                    float* __restrict__ dprev, int lddp, int M, int o, int n) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)M * n) return;
+    const int m = (int)(idx / n), c = (int)(idx - (size_t)m * n);
+    float v = 0.f;
+    for (int t = 0; t < o; t++) v = fmaf(dz[(size_t)m * lddz + t], __ldg(W + (size_t)t * ldw + c), v);
+    if (y) { const float yy = y[(size_t)m * ldy + c]; v *= (yy > 0.f ? 1.0f : yy + 1.0f); }
+    dprev[(size_t)m * lddp + c] = v;
+}
+extern "C" int go1_skinny_dgrad(const float* dz, int lddz, const float* W, int ldw, const float* y_prev, int ldy, float* dprev, int lddp,
+                                int M, int o, int n, void* stream) {
+    if (!dz || !W || !dprev || M <= 0 || o <= 0 || o > 16 || n <= 0) return go1_set_error("go1_skinny_dgrad: bad arguments");
+    const size_t tot = (size_t)M * n;
+    skinny_dgrad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dz, lddz, W, ldw, y_prev, ldy, dprev, lddp, M, o, n); go1_count_launch(1);
+    return cuda_rc("go1_skinny_dgrad");
+}

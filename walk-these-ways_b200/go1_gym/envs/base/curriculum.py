@@ -35,14 +35,26 @@ class Curriculum:
     def update(self, **kwargs):
         pass
 
+    def _cdf(self):
+        """cdf of the bin weights exactly as RandomState.choice(p=w/sum) builds it, cached until the weights change."""
+        key = self.weights.tobytes()
+        if getattr(self, "_cdf_key", None) != key:
+            p = self.weights / self.weights.sum()
+            cdf = p.cumsum()
+            cdf /= cdf[-1]
+            self._cdf_key, self._cdf_val = key, cdf
+        return self._cdf_val
+
     def sample_bins(self, batch_size, low=None, high=None):
         if low is not None and high is not None:
             valid = np.logical_and(self.grid >= low[:, None], self.grid <= high[:, None]).all(axis=0)
             w = np.zeros_like(self.weights)
             w[valid] = self.weights[valid]
+            inds = self.rng.choice(self.indices, batch_size, p=w / w.sum())
         else:
-            w = self.weights
-        inds = self.rng.choice(self.indices, batch_size, p=w / w.sum())
+            # RandomState.choice(a, n, p=p) == cdf.searchsorted(random_sample(n), side='right') (numpy legacy generator):
+            # same draws from the same stream, without rebuilding the cdf on every call
+            inds = self._cdf().searchsorted(self.rng.random_sample(batch_size), side='right')
         return self.grid.T[inds], inds
 
     def sample_uniform_from_cell(self, centroids):
@@ -99,8 +111,14 @@ class RewardThresholdCurriculum(Curriculum):
             for rew, thr in zip(task_rewards, success_thresholds):
                 rew = rew.cpu().numpy() if hasattr(rew, "cpu") else np.asarray(rew)
                 ok &= rew.astype(np.float32) > np.float32(thr)
-        self.weights[bin_inds[ok]] = np.clip(self.weights[bin_inds[ok]] + 0.2, 0, 1)
-        for adjacent in self.get_local_bins(bin_inds[ok], ranges=local_range):
+        self.apply_successes(bin_inds[ok], local_range)
+
+    def apply_successes(self, ok_bins, local_range):
+        """Weight update for the bins of successful envs (curriculum.py:141-154)."""
+        if len(ok_bins) == 0:
+            return
+        self.weights[ok_bins] = np.clip(self.weights[ok_bins] + 0.2, 0, 1)
+        for adjacent in self.get_local_bins(ok_bins, ranges=local_range):
             adj = np.array(adjacent.nonzero()[0])
             self.weights[adj] = np.clip(self.weights[adj] + 0.2, 0, 1)
 

@@ -51,6 +51,46 @@ class LazyExtras(dict):
             return default
 
 
+class _LazyDict(dict):
+    """A dict that fills itself from `build()` the first time it is read (keys(), items(), [], **, len, in)."""
+
+    def __init__(self, build):
+        super().__init__()
+        self._build = build
+
+    def _fill(self):
+        if self._build is not None:
+            b, self._build = self._build, None
+            dict.update(self, b())
+
+    def keys(self):
+        self._fill(); return dict.keys(self)
+
+    def items(self):
+        self._fill(); return dict.items(self)
+
+    def values(self):
+        self._fill(); return dict.values(self)
+
+    def __getitem__(self, k):
+        self._fill(); return dict.__getitem__(self, k)
+
+    def __iter__(self):
+        self._fill(); return dict.__iter__(self)
+
+    def __len__(self):
+        self._fill(); return dict.__len__(self)
+
+    def __contains__(self, k):
+        self._fill(); return dict.__contains__(self, k)
+
+    def setdefault(self, k, d=None):
+        self._fill(); return dict.setdefault(self, k, d)
+
+    def __setitem__(self, k, v):
+        self._fill(); dict.__setitem__(self, k, v)
+
+
 class LeggedRobot(BaseTask):
     def __init__(self, cfg: Cfg, sim_params, physics_engine, sim_device, headless, eval_cfg=None, initial_dynamics_dict=None):
         if eval_cfg is not None:
@@ -201,6 +241,7 @@ class LeggedRobot(BaseTask):
         self.curricula = [RewardThresholdCurriculum(seed=c.curriculum_seed, **kw) for _ in self.category_names]
         self.env_command_bins = np.zeros(len(env_ids), dtype=int)
         self.env_command_categories = np.zeros(len(env_ids), dtype=int)
+        self._cat_rng = np.random.default_rng(c.curriculum_seed + 1)      # category draws (torch.rand on the device in the reference)
         rng_keys = ["lin_vel_x", "lin_vel_y", "ang_vel_yaw", "body_height_cmd", "gait_frequency_cmd_range", "gait_phase_cmd_range",
                     "gait_offset_cmd_range", "gait_bound_cmd_range", "gait_duration_cmd_range", "footswing_height_range",
                     "body_pitch_range", "body_roll_range", "stance_width_range", "stance_length_range", "aux_reward_coef_range"]
@@ -355,21 +396,27 @@ class LeggedRobot(BaseTask):
         Returns the new commands [k, 15]; updates curricula, env_command_bins/categories."""
         cfg = self.cfg
         k = len(env_ids)
-        timesteps = int(cfg.commands.resampling_time / self.dt)
-        ep_len = min(cfg.env.max_episode_length, timesteps)
-        present = [key for key in _TASK_KEYS if key in self.reward_scales]
-        col = {key: i for i, key in enumerate(_TASK_KEYS)}
-        for i, (category, curriculum) in enumerate(zip(self.category_names, self.curricula)):
-            in_cat = self.env_command_categories[env_ids] == i
-            if not in_cat.any():
-                continue
-            task_rewards = [task_sums[in_cat, col[key]].astype(np.float32) / np.float32(ep_len) for key in present]
-            thresholds = [self.curriculum_thresholds[key] * self.reward_scales[key] for key in present]
-            old_bins = self.env_command_bins[env_ids[in_cat]]
-            if len(thresholds) > 0:
-                curriculum.update(old_bins, task_rewards, thresholds, local_range=_LOCAL_RANGE)
+        hc = self.__dict__.get("_resample_consts")
+        if hc is None:
+            timesteps = int(cfg.commands.resampling_time / self.dt)
+            ep_len = min(cfg.env.max_episode_length, timesteps)
+            present = [key for key in _TASK_KEYS if key in self.reward_scales]
+            cols = [_TASK_KEYS.index(key) for key in present]
+            thr = np.array([self.curriculum_thresholds[key] * self.reward_scales[key] for key in present], dtype=np.float32)
+            hc = self._resample_consts = (np.float32(ep_len), cols, thr)
+        ep_len, cols, thr = hc
+        cats_old = self.env_command_categories[env_ids]
+        if len(cols) > 0:
+            # success = every task reward above its threshold, in float32 like the reference's torch comparison
+            ok = (task_sums[:, cols].astype(np.float32) / ep_len > thr).all(axis=1)
+            if ok.any():
+                old_bins = self.env_command_bins[env_ids]
+                for i, curriculum in enumerate(self.curricula):
+                    m = ok & (cats_old == i)
+                    if m.any():
+                        curriculum.apply_successes(old_bins[m], _LOCAL_RANGE)
         # new categories: host RNG (the reference draws torch.rand on the device; only the distribution matters)
-        r = torch.rand(k).numpy()
+        r = self._cat_rng.random(k)
         p = 1. / len(self.category_names)
         new_cmds = np.zeros((k, capi.NUM_COMMANDS), dtype=np.float32)
         cat_masks = [np.logical_and(p * i <= r, r < p * (i + 1)) for i in range(len(self.category_names))]
@@ -396,11 +443,11 @@ class LeggedRobot(BaseTask):
                     elif category == "bound":
                         c[m, 5] = 0; c[m, 6] = 0; c[m, 7] = c[m, 7] / 2 + np.float32(0.25)
             elif cfg.commands.exclusive_phase_offset:
-                r2 = torch.rand(k).numpy()
+                r2 = self._cat_rng.random(k)
                 trot, pace, bound = r2 < 0.34, np.logical_and(0.34 <= r2, r2 < 0.67), 0.67 <= r2
                 c[pace, 5] = 0; c[bound, 5] = 0; c[trot, 6] = 0; c[bound, 6] = 0; c[trot, 7] = 0; c[pace, 7] = 0
             elif cfg.commands.balance_gait_distribution:
-                r2 = torch.rand(k).numpy()
+                r2 = self._cat_rng.random(k)
                 pronk, trot = r2 <= 0.25, np.logical_and(0.25 <= r2, r2 < 0.50)
                 pace, bound = np.logical_and(0.50 <= r2, r2 < 0.75), 0.75 <= r2
                 for j in (5, 6, 7):
@@ -441,44 +488,47 @@ class LeggedRobot(BaseTask):
         self._fill_extras(ids)
 
     def _fill_extras(self, ids):
-        """legged_robot.py:180-234 — device scalars (no host sync); consumed lazily by the logger."""
+        """legged_robot.py:180-234.  Everything the logger consumes is produced lazily from ONE snapshot of the device
+        accumulators taken here (a clone, no host sync); the dict values are materialised when somebody reads them."""
         core, ex = self.core, self.extras
-        train_ids = ids[ids < self.num_train_envs]
-        if len(train_ids) > 0:
+        if (ids < self.num_train_envs).any():
             acc = core.episode_acc.clone()
-            means = acc[:capi.NUM_EPISODE_SUMS] / acc[capi.NUM_EPISODE_SUMS].clamp(min=1.0)
-            ep = {}
-            for name in list(self.reward_scales) + ["total"]:
-                if name == "total":
-                    ep["rew_total"] = means[capi.NUM_REWARD_TERMS]
-                elif name in capi.REWARD_TERMS:
-                    ep["rew_" + name] = means[capi.REWARD_TERMS.index(name)]
-            ex["train/episode"] = ep
-        if self.cfg.terrain.curriculum:
-            ex["train/episode"]["terrain_level"] = torch.mean(self.terrain_levels[:self.num_train_envs].float())
+            cmd_snapshot = None
+            env = self
+
+            def build_episode():
+                means = acc[:capi.NUM_EPISODE_SUMS] / acc[capi.NUM_EPISODE_SUMS].clamp(min=1.0)
+                ep = {}
+                for name in list(env.reward_scales) + ["total"]:
+                    if name == "total":
+                        ep["rew_total"] = means[capi.NUM_REWARD_TERMS]
+                    elif name in capi.REWARD_TERMS:
+                        ep["rew_" + name] = means[capi.REWARD_TERMS.index(name)]
+                if env.cfg.terrain.curriculum:
+                    ep["terrain_level"] = torch.mean(env.terrain_levels[:env.num_train_envs].float())
+                if env.cfg.commands.command_curriculum:
+                    cmd = core.env("commands")
+                    mins, maxs = cmd.min(dim=1).values, cmd.max(dim=1).values
+                    for idx, nm in ((8, "duration"), (7, "bound"), (6, "offset"), (5, "phase"), (4, "freq"), (0, "x_vel"), (1, "y_vel"), (2, "yaw_vel")):
+                        ep[f"min_command_{nm}"] = mins[idx]
+                        ep[f"max_command_{nm}"] = maxs[idx]
+                    if env.cfg.commands.num_commands > 9:
+                        ep["min_command_swing_height"] = mins[9]
+                        ep["max_command_swing_height"] = maxs[9]
+                    for curriculum, category in zip(env.curricula, env.category_names):
+                        ep[f"command_area_{category}"] = np.sum(curriculum.weights) / curriculum.weights.shape[0]
+                    ep["min_action"] = torch.min(env.actions)
+                    ep["max_action"] = torch.max(env.actions)
+                return ep
+            ex["train/episode"] = _LazyDict(build_episode)
         if self.cfg.commands.command_curriculum:
             if self._env_bins_dirty:
                 self._env_bins_dev = torch.as_tensor(self.env_command_bins[:self.num_train_envs], dtype=torch.float32).to(self.device, non_blocking=True)
                 self._env_bins_dirty = False
                 core.h2d_bytes += 4 * self.num_train_envs
             ex["env_bins"] = self._env_bins_dev
-            cmd = core.env("commands")
-            mins, maxs = cmd.min(dim=1).values, cmd.max(dim=1).values
-            ep = ex.setdefault("train/episode", {})
-            for idx, nm in ((8, "duration"), (7, "bound"), (6, "offset"), (5, "phase"), (4, "freq"), (0, "x_vel"), (1, "y_vel"), (2, "yaw_vel")):
-                ep[f"min_command_{nm}"] = mins[idx]
-                ep[f"max_command_{nm}"] = maxs[idx]
-            if self.cfg.commands.num_commands > 9:
-                ep["min_command_swing_height"] = mins[9]
-                ep["max_command_swing_height"] = maxs[9]
-            for curriculum, category in zip(self.curricula, self.category_names):
-                ep[f"command_area_{category}"] = np.sum(curriculum.weights) / curriculum.weights.shape[0]
-            ep["min_action"] = torch.min(self.actions)
-            ep["max_action"] = torch.max(self.actions)
-            ex["curriculum/distribution"] = {}
-            for curriculum, category in zip(self.curricula, self.category_names):
-                ex["curriculum/distribution"][f"weights_{category}"] = curriculum.weights
-                ex["curriculum/distribution"][f"grid_{category}"] = curriculum.grid
+            ex["curriculum/distribution"] = _LazyDict(lambda: {**{f"weights_{c}": cur.weights for cur, c in zip(self.curricula, self.category_names)},
+                                                               **{f"grid_{c}": cur.grid for cur, c in zip(self.curricula, self.category_names)}})
         if self.cfg.env.send_timeouts:
             self._time_outs = core.timeout_u8[:self.num_train_envs].bool()      # a copy taken at reset time (legged_robot.py:234)
             ex["time_outs"] = self._time_outs

@@ -129,12 +129,13 @@ class Runner:
                 obs_dict, rewards, dones, infos = self.env.step(actions)
                 obs, privileged_obs, obs_history = obs_dict["obs"], obs_dict["privileged_obs"], obs_dict["obs_history"]
                 self.alg.process_env_step(rewards[:num_train_envs], dones[:num_train_envs], infos)
-                if 'train/episode' in infos:
-                    with logger.Prefix(metrics="train/episode"):
-                        logger.store_metrics(**infos['train/episode'])
-                if 'eval/episode' in infos:
-                    with logger.Prefix(metrics="eval/episode"):
-                        logger.store_metrics(**infos['eval/episode'])
+                for key in ('train/episode', 'eval/episode'):
+                    if key in infos:
+                        if hasattr(logger, "store_metrics_lazy"):      # expanded once per log_metrics_summary, not per env step
+                            logger.store_metrics_lazy(key, infos[key])
+                        else:
+                            with logger.Prefix(metrics=key):
+                                logger.store_metrics(**infos[key])
         return obs, privileged_obs, obs_history, infos
 
     def learn(self, num_learning_iterations, init_at_random_ep_len=False, eval_freq=100, curriculum_dump_freq=500, eval_expert=False):

@@ -144,11 +144,12 @@ class _Net:
             inp, ld_in = y, o
         return outs
 
-    def backward(self, x, ldx, K0, extra, outs, dout, M, impl, accumulate, want_dextra=False, tag="a", xT=None):
+    def backward(self, x, ldx, K0, extra, outs, dout, M, impl, accumulate, want_dextra=False, tag="a", xT=None, dz1_out=None):
         """dout: gradient w.r.t. the network output [M][out] (the last layer has no activation).  Writes weight/bias grads
         into the flat grad buffer.  dz of every hidden layer comes out of the dgrad GEMM already multiplied by ELU'
         (fused epilogue).  xT: optional precomputed transpose of the first-layer input ([K0][ld>=M]) for the tensor-core
-        wgrad.  Returns d(extra) [M][E] if requested."""
+        wgrad.  dz1_out: optional [M][o1] strided view; when given the first layer's dz is written there and its wgrad is
+        left to the caller (ActorCritic fuses the three first-layer wgrads into one GEMM).  Returns d(extra) [M][E] if requested."""
         L, st = capi.lib(), capi.stream_ptr()
         n = len(self.specs)
         dz = dout
@@ -164,7 +165,9 @@ class _Net:
             else:
                 inp, ld_in, K = outs[li - 1], self.specs[li - 1][2], i
             # ---- wgrad: dW[o][K] = dz^T[o][M] inp[M][K]
-            if impl == 1 and M >= 64 and K >= 8:
+            if li == 0 and dz1_out is not None:
+                pass                                    # fused by the caller
+            elif impl == 1 and M >= 64 and K >= 8:
                 dzT = self._transpose(dz, ldz, M, o, self.acts.get((tag, "dzT", li)))
                 self.acts[(tag, "dzT", li)] = dzT
                 if li == 0 and xT is not None:
@@ -177,19 +180,22 @@ class _Net:
                 self._gemm(1, 0, o, K, M, dz, ldz, inp, ld_in, gW, i, None, 0, accumulate, 0)
             if li == 0 and extra is not None:
                 E = i - K0
-                self._gemm(1, 0, o, E, M, dz, ldz, extra, extra.stride(0), gW.data_ptr() + 4 * K0, i, None, 0, accumulate, 0)
                 if want_dextra:
                     dextra = self._buf((tag, "dextra"), M, E)
-                    self._gemm(0, 0, M, E, o, dz, ldz, W.data_ptr() + 4 * K0, i, dextra, E, None, 0, 0, 0)
+                capi.check(L.go1_mlp_extra_backward(capi.ptr(dz), ldz, capi.ptr(extra), extra.stride(0), W.data_ptr() + 4 * K0, i, gW.data_ptr() + 4 * K0, i,
+                                                    capi.ptr(dextra) if want_dextra else None, E, M, o, E, accumulate, st), "extra_backward")
             # ---- dgrad (+ fused ELU'): dz_prev[M][i] = (dz[M][o] W[o][i]) * ELU'(y_prev)
             if li > 0:
-                dprev = self._buf((tag, "d", li - 1), M, i)
+                dprev = dz1_out if (li == 1 and dz1_out is not None) else self._buf((tag, "d", li - 1), M, i)
+                ldp = dprev.stride(0)
                 yprev = outs[li - 1]
                 if impl == 1 and self._tma_ok(dz, ldz) and M >= 64:
                     WT = self._cached(("WT", li), lambda old: self._transpose(W, i, o, i, old))
-                    self._gemm(0, 1, M, i, o, dz, ldz, WT, WT.stride(0), dprev, i, None, 2, 0, 1, dact_y=yprev)
+                    self._gemm(0, 1, M, i, o, dz, ldz, WT, WT.stride(0), dprev, ldp, None, 2, 0, 1, dact_y=yprev)
+                elif o <= 16:
+                    capi.check(L.go1_skinny_dgrad(capi.ptr(dz), ldz, capi.ptr(W), i, capi.ptr(yprev), yprev.stride(0), capi.ptr(dprev), ldp, M, o, i, st), "skinny_dgrad")
                 else:
-                    self._gemm(0, 0, M, i, o, dz, ldz, W, i, dprev, i, None, 2, 0, 0, dact_y=yprev)
+                    self._gemm(0, 0, M, i, o, dz, ldz, W, i, dprev, ldp, None, 2, 0, 0, dact_y=yprev)
                 dz = dprev
         return dextra
 
@@ -381,9 +387,30 @@ class ActorCritic(nn.Module):
         """Gradients of the PPO loss into flat_grads (overwrites). h/priv are the minibatch inputs of the forward
         pass just run with tag='train'; dmean [M,A], dvalue [M,1], dstd [A]."""
         M, K0, impl = h.shape[0], self.num_obs_history, self._impl()
-        dlat = self._nets["actor"].backward(h, h.stride(0), K0, self._latent, self._p_out, dmean, M, impl, 0, want_dextra=True, tag="train", xT=hT)
-        self._nets["critic"].backward(h, h.stride(0), K0, priv, self._c_out, dvalue, M, impl, 0, tag="train", xT=hT)
-        self._nets["adapt"].backward(h, h.stride(0), K0, None, self._a_out, dlat, M, impl, 0, tag="train", xT=hT)
+        nets = self._nets
+        if impl == 1 and hT is not None and M >= 64:
+            # the three first layers share their input: ONE transposed dz [o_a+o_p+o_c][M] and ONE tensor-core wgrad
+            # dWcat[1280][2100] = dzcat^T h instead of three (the first-layer dz of each net is written straight into its
+            # column slice of `dz1` by that net's layer-2 dgrad)
+            oa, op, oc = nets["adapt"].specs[0][2], nets["actor"].specs[0][2], nets["critic"].specs[0][2]
+            dz1 = nets["adapt"]._buf(("train", "dz1cat"), M, oa + op + oc)
+            dlat = nets["actor"].backward(h, h.stride(0), K0, self._latent, self._p_out, dmean, M, impl, 0, want_dextra=True, tag="train", dz1_out=dz1[:, oa:oa + op])
+            nets["critic"].backward(h, h.stride(0), K0, priv, self._c_out, dvalue, M, impl, 0, tag="train", dz1_out=dz1[:, oa + op:])
+            nets["adapt"].backward(h, h.stride(0), K0, None, self._a_out, dlat, M, impl, 0, tag="train", dz1_out=dz1[:, :oa])
+            n0 = nets["adapt"]
+            dzT = n0._transpose(dz1, dz1.stride(0), M, oa + op + oc, n0.acts.get(("train", "dz1catT")))
+            n0.acts[("train", "dz1catT")] = dzT
+            gcat = n0._buf(("train", "gWcat"), oa + op + oc, K0)
+            n0._gemm(0, 1, oa + op + oc, K0, M, dzT, dzT.stride(0), hT, hT.stride(0), gcat, K0, None, 0, 0, 1)
+            row = 0
+            for name in ("adapt", "actor", "critic"):
+                wo, bo, o, i = nets[name].specs[0]
+                self._grad[wo:wo + o * i].view(o, i)[:, :K0].copy_(gcat[row:row + o])
+                row += o
+        else:
+            dlat = nets["actor"].backward(h, h.stride(0), K0, self._latent, self._p_out, dmean, M, impl, 0, want_dextra=True, tag="train", xT=hT)
+            nets["critic"].backward(h, h.stride(0), K0, priv, self._c_out, dvalue, M, impl, 0, tag="train", xT=hT)
+            nets["adapt"].backward(h, h.stride(0), K0, None, self._a_out, dlat, M, impl, 0, tag="train", xT=hT)
         self._grad[self.std_offset:self.std_offset + self.num_actions].copy_(dstd)
 
     def backward_adaptation(self, h, outs, dpred, hT=None):

@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""Per-shape timing of go1_gemm (impl 0/1) on the learner's GEMM shapes: TFLOP/s with CUDA events, L2 flushed between runs."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from go1_b200 import capi  # noqa: E402
+
+SHAPES = [  # (M, N, K, note)
+    (24576, 256, 2100, "adapt L1 fwd"), (24576, 512, 2100, "actor/critic L1 fwd"), (24576, 1280, 2100, "fused L1 fwd (3 nets)"),
+    (24576, 256, 512, "L2 fwd"), (24576, 128, 256, "L3 fwd"), (24576, 12, 128, "actor out"), (24576, 512, 256, "dgrad L2"),
+    (512, 2100, 24576, "wgrad L1 (actor)"), (256, 2100, 24576, "wgrad L1 (adapt)"), (1280, 2100, 24576, "fused wgrad L1"),
+    (256, 512, 24576, "wgrad L2"), (128, 256, 24576, "wgrad L3"), (12, 128, 24576, "wgrad out"),
+    (4096, 512, 2100, "rollout L1"), (4096, 1280, 2100, "rollout fused L1"), (4096, 256, 512, "rollout L2"),
+]
+
+
+def main():
+    L = capi.lib()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
+    print(f"{'shape':>24s} {'note':>26s} {'impl0 us':>10s} {'TF/s':>7s} {'impl1 us':>10s} {'TF/s':>7s}")
+    for M, N, K, note in SHAPES:
+        ld = (K + 3) // 4 * 4
+        A = torch.randn(M, ld, device="cuda"); B = torch.randn(N, ld, device="cuda"); Cm = torch.empty(M, N, device="cuda")
+        res = []
+        for impl in (0, 1):
+            ts = []
+            for it in range(6):
+                flush.fill_(it)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                capi.check(L.go1_gemm(0, 1, M, N, K, capi.ptr(A), ld, capi.ptr(B), ld, capi.ptr(Cm), N, None, 0, 0, impl, capi.stream_ptr()), "gemm")
+                e1.record(); torch.cuda.synchronize()
+                if it >= 2:
+                    ts.append(e0.elapsed_time(e1) * 1e3)
+            us = sum(ts) / len(ts)
+            res += [us, 2.0 * M * N * K / us / 1e6]
+        print(f"{str((M, N, K)):>24s} {note:>26s} {res[0]:10.1f} {res[1]:7.1f} {res[2]:10.1f} {res[3]:7.1f}")
+
+
+if __name__ == "__main__":
+    main()
