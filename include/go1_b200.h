@@ -219,9 +219,11 @@ int go1_colsum(const float* x, int ldx, float* out, int M, int N, int accumulate
 
 /* Replaces the Normal(mean,std) sample + log-prob of ActorCritic.act / get_actions_log_prob
  * (actor_critic.py:113-126): actions = mean + std*eps (eps ~ N(0,1) from Philox(seed,counter) or the
- * injected `eps` for parity tests), logp = sum_j log N(a_j). */
+ * injected `eps` for parity tests), logp = sum_j log N(a_j).  counter_dev (optional, device memory): added to `counter` and
+ * incremented by the call, so that a CUDA graph holding this call draws fresh noise on every replay. */
 int go1_ppo_sample_actions(const float* mean, int ldm, const float* std, const float* eps, uint64_t seed,
-                           uint64_t counter, float* actions, float* logp, int n, int num_actions, void* stream);
+                           uint64_t counter, uint64_t* counter_dev, float* actions, float* logp, int n, int num_actions,
+                           void* stream);
 
 /* Replaces the loss block of PPO.update (ppo.py:113-152): from the minibatch forward outputs computes the
  * clipped surrogate, clipped value loss, entropy bonus, their gradients w.r.t. mean / value / std, and the
@@ -251,6 +253,14 @@ int go1_ppo_adam_step(float* param, const float* grad, float* exp_avg, float* ex
  * kl = scalars[3] written by go1_ppo_loss (all-reduced first on multi-GPU).  go1_ppo_adam_step reads the
  * learning rate from lr_dev when it is non-NULL. */
 int go1_ppo_adaptive_lr(const float* scalars, float* lr_dev, float desired_kl, float lr_min, float lr_max, void* stream);
+
+/* Replaces RolloutStorage.add_transitions (rollout_storage.py:55-69) and the time-out bootstrap of
+ * PPO.process_env_step (ppo.py:84-86: rewards += gamma * values * time_outs) in one launch.
+ * in_f32[10]  = {obs[n][nobs], priv[n][npriv], obs_history[n][nhist], actions[n][nact], rewards[n], values[n], log_prob[n],
+ *                action_mean[n][nact], std[nact], env_bins[n] or NULL};  dones/time_outs: uint8 [n] (time_outs may be NULL)
+ * out_f32[10] = the slot `step` of the storage slabs in the same order (sigma[n][nact] for std);  s_dones: uint8 [n]. */
+int go1_store_transition(const float* const* in_f32, const uint8_t* dones, const uint8_t* time_outs, float* const* out_f32, uint8_t* s_dones,
+                         int n, int nobs, int npriv, int nhist, int nact, float gamma, void* stream);
 
 /* Replaces the fancy-index gathers of RolloutStorage.mini_batch_generator (rollout_storage.py:98-137):
  * dst[i][0:width] = src[idx[i]][0:width]; ldd = row stride of dst in floats (>= width). */

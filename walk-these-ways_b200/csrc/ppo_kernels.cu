@@ -327,9 +327,11 @@ extern "C" int go1_colsum(const float* x, int ldx, float* out, int M, int N, int
 // Normal(mean, std): sample + log-prob  (actor_critic.py:113-126)
 // ---------------------------------------------------------------------------------------------
 __global__ void sample_actions_kernel(const float* __restrict__ mean, int ldm, const float* __restrict__ std, const float* __restrict__ eps,
-                                      uint64_t seed, uint64_t counter, float* __restrict__ actions, float* __restrict__ logp, int n, int na) {
+                                      uint64_t seed, uint64_t counter, const unsigned long long* __restrict__ counter_dev,
+                                      float* __restrict__ actions, float* __restrict__ logp, int n, int na) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (counter_dev) counter += *counter_dev;
     float lp = 0.f;
     for (int j = 0; j < na; j++) {
         float e;
@@ -347,10 +349,12 @@ __global__ void sample_actions_kernel(const float* __restrict__ mean, int ldm, c
     }
     logp[i] = lp;
 }
+__global__ void bump_counter_kernel(unsigned long long* c) { *c += 1ull; }
 extern "C" int go1_ppo_sample_actions(const float* mean, int ldm, const float* std, const float* eps, uint64_t seed, uint64_t counter,
-                                      float* actions, float* logp, int n, int num_actions, void* stream) {
+                                      uint64_t* counter_dev, float* actions, float* logp, int n, int num_actions, void* stream) {
     if (!mean || !std || !actions || !logp || n <= 0 || num_actions <= 0) return go1_set_error("go1_ppo_sample_actions: bad arguments");
-    sample_actions_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean, ldm, std, eps, seed, counter, actions, logp, n, num_actions); go1_count_launch(1);
+    sample_actions_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean, ldm, std, eps, seed, counter, (const unsigned long long*)counter_dev, actions, logp, n, num_actions);
+    if (counter_dev) { bump_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)counter_dev); go1_count_launch(1); } go1_count_launch(1);
     return cuda_rc("go1_ppo_sample_actions");
 }
 
@@ -633,4 +637,57 @@ extern "C" int go1_skinny_dgrad(const float* dz, int lddz, const float* W, int l
     const size_t tot = (size_t)M * n;
     skinny_dgrad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dz, lddz, W, ldw, y_prev, ldy, dprev, lddp, M, o, n); go1_count_launch(1);
     return cuda_rc("go1_skinny_dgrad");
+}
+
+// ---------------------------------------------------------------------------------------------
+// RolloutStorage.add_transitions (rollout_storage.py:55-69) + the time-out bootstrap of PPO.process_env_step
+// (ppo.py:84-86) in one launch: the 2100-wide history row is the bulk (float4 copy), the small fields ride along.
+// ---------------------------------------------------------------------------------------------
+struct StoreArgs {
+    const float *obs, *priv, *hist, *actions, *rewards, *values, *logp, *mean, *std, *env_bins;
+    const uint8_t *dones, *time_outs;
+    float *s_obs, *s_priv, *s_hist, *s_actions, *s_rewards, *s_values, *s_logp, *s_mu, *s_sigma, *s_env_bins;
+    uint8_t* s_dones;
+    int n, nobs, npriv, nhist, nact; float gamma;
+};
+__global__ void __launch_bounds__(256) store_transition_kernel(const StoreArgs a) {
+    const int e = blockIdx.x;
+    if (e >= a.n) return;
+    const int t = threadIdx.x;
+    if ((a.nhist & 3) == 0) {
+        const float4* src = reinterpret_cast<const float4*>(a.hist + (size_t)e * a.nhist);
+        float4* dst = reinterpret_cast<float4*>(a.s_hist + (size_t)e * a.nhist);
+        for (int c = t; c < a.nhist / 4; c += blockDim.x) dst[c] = src[c];
+    } else {
+        for (int c = t; c < a.nhist; c += blockDim.x) a.s_hist[(size_t)e * a.nhist + c] = a.hist[(size_t)e * a.nhist + c];
+    }
+    for (int c = t; c < a.nobs; c += blockDim.x) a.s_obs[(size_t)e * a.nobs + c] = a.obs[(size_t)e * a.nobs + c];
+    if (t < a.npriv) a.s_priv[(size_t)e * a.npriv + t] = a.priv[(size_t)e * a.npriv + t];
+    if (t < a.nact) {
+        a.s_actions[(size_t)e * a.nact + t] = a.actions[(size_t)e * a.nact + t];
+        a.s_mu[(size_t)e * a.nact + t] = a.mean[(size_t)e * a.nact + t];
+        a.s_sigma[(size_t)e * a.nact + t] = a.std[t];
+    }
+    if (t == 0) {
+        const float v = a.values[e];
+        float r = a.rewards[e];
+        if (a.time_outs) r += a.gamma * v * (a.time_outs[e] ? 1.0f : 0.0f);
+        a.s_rewards[e] = r; a.s_values[e] = v; a.s_logp[e] = a.logp[e]; a.s_dones[e] = a.dones[e] ? 1 : 0;
+        a.s_env_bins[e] = a.env_bins ? a.env_bins[e] : 0.f;
+    }
+}
+extern "C" int go1_store_transition(const float* const* in_f32, const uint8_t* dones, const uint8_t* time_outs, float* const* out_f32, uint8_t* s_dones,
+                                    int n, int nobs, int npriv, int nhist, int nact, float gamma, void* stream) {
+    if (!in_f32 || !out_f32 || !dones || !s_dones || n <= 0 || nact > 256 || npriv > 256) return go1_set_error("go1_store_transition: bad arguments");
+    StoreArgs a;
+    a.obs = in_f32[0]; a.priv = in_f32[1]; a.hist = in_f32[2]; a.actions = in_f32[3]; a.rewards = in_f32[4]; a.values = in_f32[5];
+    a.logp = in_f32[6]; a.mean = in_f32[7]; a.std = in_f32[8]; a.env_bins = in_f32[9];
+    a.dones = dones; a.time_outs = time_outs;
+    a.s_obs = out_f32[0]; a.s_priv = out_f32[1]; a.s_hist = out_f32[2]; a.s_actions = out_f32[3]; a.s_rewards = out_f32[4]; a.s_values = out_f32[5];
+    a.s_logp = out_f32[6]; a.s_mu = out_f32[7]; a.s_sigma = out_f32[8]; a.s_env_bins = out_f32[9]; a.s_dones = s_dones;
+    a.n = n; a.nobs = nobs; a.npriv = npriv; a.nhist = nhist; a.nact = nact; a.gamma = gamma;
+    for (int i = 0; i < 9; i++) if (!in_f32[i] || !out_f32[i]) return go1_set_error("go1_store_transition: null tensor");
+    if (!out_f32[9]) return go1_set_error("go1_store_transition: null tensor");
+    store_transition_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(a); go1_count_launch(1);
+    return cuda_rc("go1_store_transition");
 }

@@ -121,12 +121,13 @@ def lib():
         "go1_mlp_extra_backward": ([vp, ip, vp, ip, vp, ip, vp, ip, vp, ip, ip, ip, ip, ip, vp], ip),
         "go1_skinny_dgrad": ([vp, ip, vp, ip, vp, ip, vp, ip, ip, ip, ip, vp], ip),
         "go1_colsum": ([vp, ip, vp, ip, ip, ip, vp], ip),
-        "go1_ppo_sample_actions": ([vp, ip, vp, vp, C.c_uint64, C.c_uint64, vp, vp, ip, ip, vp], ip),
+        "go1_ppo_sample_actions": ([vp, ip, vp, vp, C.c_uint64, C.c_uint64, vp, vp, vp, ip, ip, vp], ip),
         "go1_ppo_loss": ([vp, ip, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ip, vp, vp, vp, ip, ip, _f, _f, _f, ip, _f, vp], ip),
         "go1_ppo_mse": ([vp, ip, vp, ip, vp, ip, vp, ip, ip, ip, vp], ip),
         "go1_ppo_grad_sqnorm": ([vp, i64, vp, vp], ip),
         "go1_ppo_adam_step": ([vp, vp, vp, vp, i64, vp, _f, _f, vp, _f, _f, _f, ip, vp], ip),
         "go1_ppo_adaptive_lr": ([vp, vp, _f, _f, _f, vp], ip),
+        "go1_store_transition": ([vp, vp, vp, vp, vp, ip, ip, ip, ip, ip, _f, vp], ip),
         "go1_gather_rows": ([vp, vp, vp, i64, ip, ip, vp], ip),
     }
     for name, (args, res) in sig.items():

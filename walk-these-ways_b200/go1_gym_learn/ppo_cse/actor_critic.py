@@ -81,7 +81,7 @@ class _Net:
     def _cached(self, key, build):
         ver = self.owner.weights_version
         hit = self._cache.get(key)
-        if hit is None or hit[0] != ver:
+        if hit is None or hit[0] != ver or self.owner.force_repack:
             hit = (ver, build(hit[1] if hit else None))
             self._cache[key] = hit
         return hit[1]
@@ -219,6 +219,8 @@ class ActorCritic(nn.Module):
         self._flat = self._grad = None
         self._mean = self._value = self._logp = None
         self._sample_counter = 0
+        self._counter_dev = None
+        self.force_repack = False     # set while a CUDA graph of the forward pass is captured: weight packing must be IN the graph
         self.sample_seed = 0
         self.injected_eps = None      # parity tests inject the N(0,1) draws
         self.weights_version = 0      # bumped by every optimizer step / load: invalidates packed + transposed weight copies
@@ -333,9 +335,11 @@ class ActorCritic(nn.Module):
         actions = torch.empty(M, self.num_actions, device=observation_history.device)
         self._logp = torch.empty(M, device=observation_history.device)
         eps = self.injected_eps
-        self._sample_counter += 1
+        if self._counter_dev is None or self._counter_dev.device != observation_history.device:
+            with torch.inference_mode(False):
+                self._counter_dev = torch.zeros(1, dtype=torch.int64, device=observation_history.device)
         capi.check(capi.lib().go1_ppo_sample_actions(capi.ptr(self._mean), self._mean.stride(0), capi.ptr(self.std.data),
-                                                     capi.ptr(eps) if eps is not None else None, self.sample_seed, self._sample_counter,
+                                                     capi.ptr(eps) if eps is not None else None, self.sample_seed, 0, capi.ptr(self._counter_dev),
                                                      capi.ptr(actions), capi.ptr(self._logp), M, self.num_actions, capi.stream_ptr()), "sample")
         self._last_actions = actions
         return actions

@@ -87,10 +87,55 @@ class PPO:
     def train_mode(self):
         self.actor_critic.train()
 
+    use_cuda_graph = True      # rollout policy evaluation (11 GEMMs + sampling) replayed as one CUDA graph
+
+    def _act_eager(self, obs_history, privileged_obs):
+        actions = self.actor_critic.act(obs_history).detach()
+        values = self.actor_critic.evaluate(obs_history, privileged_obs).detach()
+        return actions, values
+
+    def _act_graphed(self, obs_history, privileged_obs):
+        """Same computation through a captured CUDA graph: static input copies, static outputs, device-side RNG counter."""
+        ac = self.actor_critic
+        key = (obs_history.shape[0], ac._impl())
+        st = self.__dict__.setdefault("_graph_state", {})
+        g = st.get(key)
+        if g is None:
+            with torch.inference_mode(False):
+                h_in = torch.empty_like(obs_history); p_in = torch.empty_like(privileged_obs)
+            h_in.copy_(obs_history); p_in.copy_(privileged_obs)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._act_eager(h_in, p_in)             # allocates every scratch buffer, configures kernels
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            ac.force_repack = True
+            try:
+                with torch.cuda.graph(graph):
+                    outs = self._act_eager(h_in, p_in)
+            finally:
+                ac.force_repack = False
+            g = st[key] = (graph, h_in, p_in, outs, (ac._mean, ac._logp, ac._last_actions, ac._value, ac._latent))
+        graph, h_in, p_in, outs, attrs = g
+        h_in.copy_(obs_history); p_in.copy_(privileged_obs)
+        graph.replay()
+        ac._mean, ac._logp, ac._last_actions, ac._value, ac._latent = attrs     # the graph's static outputs
+        return outs
+
     def act(self, obs, privileged_obs, obs_history):
         tr = self.transition
-        tr.actions = self.actor_critic.act(obs_history).detach()
-        tr.values = self.actor_critic.evaluate(obs_history, privileged_obs).detach()
+        ac = self.actor_critic
+        if self.use_cuda_graph and obs_history.is_cuda and ac.injected_eps is None and self.use_cuda_graph != "failed":
+            try:
+                tr.actions, tr.values = self._act_graphed(obs_history, privileged_obs)
+            except Exception as e:      # capture not possible in this context: fall back to eager launches of the same kernels
+                print(f"[go1_b200] CUDA graph capture of PPO.act disabled: {type(e).__name__}: {e}")
+                PPO.use_cuda_graph = "failed"
+                tr.actions, tr.values = self._act_eager(obs_history, privileged_obs)
+        else:
+            tr.actions, tr.values = self._act_eager(obs_history, privileged_obs)
         tr.actions_log_prob = self.actor_critic.get_actions_log_prob(tr.actions).detach()
         tr.action_mean = self.actor_critic.action_mean.detach()
         tr.action_sigma = self.actor_critic.action_std.detach()
@@ -102,12 +147,18 @@ class PPO:
 
     def process_env_step(self, rewards, dones, infos):
         tr = self.transition
-        tr.rewards = rewards.clone()
         tr.dones = dones
         tr.env_bins = infos["env_bins"]
-        if 'time_outs' in infos:   # bootstrapping on time outs (ppo.py:84-86)
-            tr.rewards += PPO_Args.gamma * torch.squeeze(tr.values * infos['time_outs'].unsqueeze(1).to(self.device), 1)
-        self.storage.add_transitions(tr)
+        fused = rewards.is_cuda and rewards.is_contiguous() and tr.observation_histories.is_contiguous() and tr.env_bins.is_cuda
+        if fused:   # rewards += gamma * values * time_outs (ppo.py:84-86) happens inside the store kernel
+            tr.rewards = rewards
+            tr.action_sigma_vec = self.actor_critic.std.data
+            self.storage.add_transitions_fused(tr, infos.get('time_outs'), PPO_Args.gamma)
+        else:
+            tr.rewards = rewards.clone()
+            if 'time_outs' in infos:
+                tr.rewards += PPO_Args.gamma * torch.squeeze(tr.values * infos['time_outs'].unsqueeze(1).to(self.device), 1)
+            self.storage.add_transitions(tr)
         tr.clear()
         self.actor_critic.reset(dones)
 

@@ -65,6 +65,27 @@ class RolloutStorage:
         self.env_bins[t].copy_(transition.env_bins.view(-1, 1))
         self.step += 1
 
+    def add_transitions_fused(self, tr, time_outs, gamma):
+        """add_transitions + the time-out bootstrap in ONE kernel (go1_store_transition)."""
+        import ctypes as C
+        if self.step >= self.num_transitions_per_env:
+            raise AssertionError("Rollout buffer overflow")
+        t = self.step
+        u8 = lambda x: x if x.dtype == torch.uint8 else (x.view(torch.uint8) if x.dtype == torch.bool else x.to(torch.uint8))
+        dones, touts = u8(tr.dones), (u8(time_outs) if time_outs is not None else None)
+        ins = [tr.observations, tr.privileged_observations, tr.observation_histories, tr.actions, tr.rewards, tr.values, tr.actions_log_prob,
+               tr.action_mean, tr.action_sigma_vec, tr.env_bins]
+        outs = [self.observations[t], self.privileged_observations[t], self.observation_histories[t], self.actions[t], self.rewards[t], self.values[t],
+                self.actions_log_prob[t], self.mu[t], self.sigma[t], self.env_bins[t]]
+        for x in ins[:9]:
+            assert x.is_contiguous(), "transition tensors must be contiguous"
+        arr_in = (C.c_void_p * 10)(*[x.data_ptr() if x is not None else None for x in ins])
+        arr_out = (C.c_void_p * 10)(*[x.data_ptr() for x in outs])
+        capi.check(capi.lib().go1_store_transition(arr_in, capi.ptr(dones), capi.ptr(touts), arr_out, capi.ptr(self.dones[t]), self.num_envs,
+                                                   self.observations.shape[-1], self.privileged_observations.shape[-1], self.observation_histories.shape[-1],
+                                                   self.actions.shape[-1], float(gamma), capi.stream_ptr()), "go1_store_transition")
+        self.step += 1
+
     def clear(self):
         self.step = 0
 
