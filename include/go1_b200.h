@@ -188,6 +188,8 @@ int go1_ppo_normalize_advantages(float* advantages, const double* stats, int64_t
  * impl: 0 = fp32 CUDA cores (exact-fp32 path), 1 = tcgen05 TF32 tensor cores with fp32 accumulation. */
 int go1_gemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
              float* C, int ldc, const float* bias, int act, int accumulate, int impl, void* stream);
+/* impl=1 kernel selection: 1 (default) = persistent tile loop with double-buffered TMEM accumulators, 0 = one tile per CTA. */
+void go1_gemm_tf32_set_persistent(int on);
 /* Same product with the full fused epilogue, applied in this order to each output element v = sum_k a*b:
  *   v += C_old (accumulate);  v += sum_e extra[m][e] * w_extra[n][e]  (num_extra <= 4: the 2 trailing input columns of
  *   the actor/critic first layer, i.e. cat(obs_history, latent) without the cat);  v += bias[n];

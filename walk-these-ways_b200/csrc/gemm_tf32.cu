@@ -44,6 +44,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                      : "=r"(done) : "r"(a), "r"(parity) : "memory");
     }
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -232,6 +235,170 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_kernel(const __grid_constant
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent variant: grid = min(#tiles, 2 x #SMs); every CTA walks tiles t = blockIdx.x + i * gridDim.x (n fastest, so the
+// CTAs of one wave share A tiles through L2).  The accumulator is double-buffered in TMEM (2 x BN columns): while the
+// epilogue warps drain tile i from buffer i&1, the MMA warp already accumulates tile i+1 into the other buffer, and the
+// per-CTA set-up (TMEM allocation, barrier init, tensormap prefetch) is paid once instead of once per tile.
+// ---------------------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1) gemm_tf32_persistent(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmArgs g,
+                                                                const int tiles_m, const int tiles_n, const int total_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    float* sA = (float*)base;
+    float* sB = (float*)(base + (size_t)STAGES * BM * BK * 4);
+    uint64_t* full = (uint64_t*)(base + (size_t)STAGES * (BM + BN) * BK * 4);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;        // [2]
+    uint64_t* tmem_empty = tmem_full + 2;        // [2]
+    uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb_total = (g.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile -> (m0, n0, k-block range)
+    auto tile_coords = [&](int t, int& m0, int& n0, int& kb0, int& nkb) {
+        const int tn = t % tiles_n; t /= tiles_n;
+        const int tm = t % tiles_m; const int z = t / tiles_m;
+        m0 = tm * BM; n0 = tn * BN; kb0 = z * g.kb_per_split; nkb = min(g.kb_per_split, num_kb_total - kb0);
+    };
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int it = 0;      // global k-block counter of this CTA: stage = it % STAGES, phase = (it / STAGES) & 1
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                int m0, n0, kb0, nkb; tile_coords(t, m0, n0, kb0, nkb);
+                for (int i = 0; i < nkb; i++, it++) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], (BM + BN) * BK * 4);
+                    tma_load_2d(&mapA, &full[s], sA + (size_t)s * BM * BK, (kb0 + i) * BK, m0);
+                    tma_load_2d(&mapB, &full[s], sB + (size_t)s * BN * BK, (kb0 + i) * BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        int it = 0, j = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, j++) {
+            int m0, n0, kb0, nkb; tile_coords(t, m0, n0, kb0, nkb);
+            const int buf = j & 1;
+            mbar_wait(&tmem_empty[buf], ((j >> 1) & 1) ^ 1);          // epilogue has drained this accumulator buffer
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+            for (int i = 0; i < nkb; i++, it++) {
+                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint64_t da = make_desc(sA + (size_t)s * BM * BK), db = make_desc(sB + (size_t)s * BN * BK);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; k++) umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&empty[s]);
+                    if (i == nkb - 1) umma_commit(&tmem_full[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const bool split = g.kb_per_split < num_kb_total;
+        int j = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, j++) {
+            int m0, n0, kb0, nkb; tile_coords(t, m0, n0, kb0, nkb);
+            const int buf = j & 1;
+            const int row = m0 + 32 * q + lane;
+            mbar_wait(&tmem_full[buf], (j >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; c++) {
+                uint32_t r[32];
+                tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), r);
+                const int col0 = n0 + 32 * c;
+                if (row < g.M && col0 < g.N) {
+                    float* crow = g.C + (size_t)row * g.ldc + col0;
+                    const int ncols = min(32, g.N - col0);
+                    if (split) {
+#pragma unroll
+                        for (int jj = 0; jj < 32; jj++) if (jj < ncols) atomicAdd(crow + jj, __uint_as_float(r[jj]));
+                    } else {
+                        const bool vec = (ncols == 32) && ((g.ldc & 3) == 0) && ((((uintptr_t)g.C) & 15) == 0) && ((col0 & 3) == 0);
+                        float v[32];
+#pragma unroll
+                        for (int jj = 0; jj < 32; jj++) v[jj] = __uint_as_float(r[jj]);
+                        if (g.accumulate) {
+                            if (vec) {
+#pragma unroll
+                                for (int jj = 0; jj < 8; jj++) { const float4 o = reinterpret_cast<const float4*>(crow)[jj]; v[4 * jj] += o.x; v[4 * jj + 1] += o.y; v[4 * jj + 2] += o.z; v[4 * jj + 3] += o.w; }
+                            } else {
+#pragma unroll
+                                for (int jj = 0; jj < 32; jj++) if (jj < ncols) v[jj] += crow[jj];
+                            }
+                        }
+                        if (g.nex > 0) {
+                            float e[4] = {0.f, 0.f, 0.f, 0.f};
+                            for (int tt = 0; tt < g.nex; tt++) e[tt] = __ldg(g.ex + (size_t)row * g.ldex + tt);
+#pragma unroll
+                            for (int jj = 0; jj < 32; jj++) if (jj < ncols) {
+                                const float* w = g.wex + (size_t)(col0 + jj) * g.ldwex;
+                                float acc = 0.f;
+                                for (int tt = 0; tt < g.nex; tt++) acc = fmaf(e[tt], __ldg(w + tt), acc);
+                                v[jj] += acc;
+                            }
+                        }
+                        if (g.bias) {
+#pragma unroll
+                            for (int jj = 0; jj < 32; jj++) if (jj < ncols) v[jj] += __ldg(g.bias + col0 + jj);
+                        }
+                        if (g.act == 1) {
+#pragma unroll
+                            for (int jj = 0; jj < 32; jj++) v[jj] = v[jj] > 0.f ? v[jj] : expm1f(v[jj]);
+                        } else if (g.act == 2) {
+                            const float* arow = g.aux + (size_t)row * g.ldaux + col0;
+#pragma unroll
+                            for (int jj = 0; jj < 32; jj++) if (jj < ncols) { const float y = __ldg(arow + jj); v[jj] *= (y > 0.f ? 1.0f : y + 1.0f); }
+                        }
+                        if (vec) {
+#pragma unroll
+                            for (int jj = 0; jj < 8; jj++) reinterpret_cast<float4*>(crow)[jj] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+                        } else {
+#pragma unroll
+                            for (int jj = 0; jj < 32; jj++) if (jj < ncols) crow[jj] = v[jj];
+                        }
+                    }
+                }
+            }
+            // this thread's TMEM reads of the buffer are complete (tcgen05.wait::ld inside tmem_ld32): hand it back
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&tmem_empty[buf]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
@@ -284,7 +451,28 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, int 
     return 0;
 }
 
+template <int BN, int STAGES>
+int launch_persistent(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, int splits, cudaStream_t st) {
+    const size_t smem = (size_t)STAGES * (BM + BN) * BK * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_persistent<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return go1_set_error(cudaGetErrorString(e));
+        configured = true;
+    }
+    const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN, total = tiles_m * tiles_n * splits;
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    const int grid = total < 2 * sms ? total : 2 * sms;
+    gemm_tf32_persistent<BN, STAGES><<<grid, 192, smem, st>>>(ma, mb, g, tiles_m, tiles_n, total);
+    go1_count_launch(1);
+    return 0;
+}
+
 }  // namespace
+
+static int g_tf32_persistent = 1;
+extern "C" void go1_gemm_tf32_set_persistent(int on) { g_tf32_persistent = on; }
 
 extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                              float* Cm, int ldc, const Go1GemmEpilogue* ep, cudaStream_t st) {
@@ -313,7 +501,9 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
         if (!accumulate) { const size_t tot = (size_t)M * N; zero_strided<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cm, ldc, M, N); go1_count_launch(1); }
         g.bias = nullptr; g.act = 0;
     }
-    int e = (BN == 128) ? launch<128, 3>(ma, mb, g, splits, st) : (BN == 64 ? launch<64, 4>(ma, mb, g, splits, st) : launch<32, 4>(ma, mb, g, splits, st));
+    int e;
+    if (g_tf32_persistent) e = (BN == 128) ? launch_persistent<128, 3>(ma, mb, g, splits, st) : (BN == 64 ? launch_persistent<64, 4>(ma, mb, g, splits, st) : launch_persistent<32, 4>(ma, mb, g, splits, st));
+    else e = (BN == 128) ? launch<128, 3>(ma, mb, g, splits, st) : (BN == 64 ? launch<64, 4>(ma, mb, g, splits, st) : launch<32, 4>(ma, mb, g, splits, st));
     if (e) return e;
     if (splits > 1 && (bias || act)) { const size_t tot = (size_t)M * N; bias_act_strided<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cm, ldc, bias, M, N, act); go1_count_launch(1); }
     cudaError_t ce = cudaGetLastError();
