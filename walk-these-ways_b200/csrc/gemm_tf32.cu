@@ -463,7 +463,8 @@ int launch_persistent(const CUtensorMap& ma, const CUtensorMap& mb, const GemmAr
     const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN, total = tiles_m * tiles_n * splits;
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-    const int grid = total < 2 * sms ? total : 2 * sms;
+    const int per_sm = (smem > 113 * 1024) ? 1 : 2;      // CTAs that fit one SM (shared memory bound)
+    const int grid = total < per_sm * sms ? total : per_sm * sms;
     gemm_tf32_persistent<BN, STAGES><<<grid, 192, smem, st>>>(ma, mb, g, tiles_m, tiles_n, total);
     go1_count_launch(1);
     return 0;
@@ -471,7 +472,8 @@ int launch_persistent(const CUtensorMap& ma, const CUtensorMap& mb, const GemmAr
 
 }  // namespace
 
-static int g_tf32_persistent = 1;
+static int g_tf32_persistent = 1, g_tf32_wide = 0;   // wide (128x256, 1 CTA/SM) tiles: +25% on isolated big products, -8% on the whole update (no co-residency) -> opt-in
+extern "C" void go1_gemm_tf32_set_wide(int on) { g_tf32_wide = on; }
 extern "C" void go1_gemm_tf32_set_persistent(int on) { g_tf32_persistent = on; }
 
 extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
@@ -488,7 +490,9 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
     if (g.nex < 0 || g.nex > 4) return go1_set_error("go1_gemm_ex: num_extra must be 0..4");
     if (act == 2 && !g.aux) return go1_set_error("go1_gemm_ex: act 2 needs dact_y");
     const int num_kb = (K + BK - 1) / BK;
-    const int BN = (N > 64) ? 128 : (N > 32 ? 64 : 32);
+    // 128 x 256 tiles (one CTA per SM, 4-stage ring of 48 KB) raise the flop/byte ratio of the L2-bound big products by 1.33x
+    const bool wide = g_tf32_persistent && g_tf32_wide && N >= 512 && (N % 256 == 0 || N >= 1024) && ((M + BM - 1) / BM) * ((N + 255) / 256) >= 120;
+    const int BN = wide ? 256 : ((N > 64) ? 128 : (N > 32 ? 64 : 32));
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     int splits = 1;
     if (tiles < 148 && num_kb >= 16 && g.nex == 0 && act != 2) { splits = (2 * 148) / tiles; if (splits > num_kb / 16) splits = num_kb / 16; if (splits < 1) splits = 1; }   // one wave of 2 CTAs/SM, >= 16 k-blocks each
@@ -502,7 +506,8 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
         g.bias = nullptr; g.act = 0;
     }
     int e;
-    if (g_tf32_persistent) e = (BN == 128) ? launch_persistent<128, 3>(ma, mb, g, splits, st) : (BN == 64 ? launch_persistent<64, 4>(ma, mb, g, splits, st) : launch_persistent<32, 4>(ma, mb, g, splits, st));
+    if (BN == 256) e = launch_persistent<256, 4>(ma, mb, g, splits, st);
+    else if (g_tf32_persistent) e = (BN == 128) ? launch_persistent<128, 3>(ma, mb, g, splits, st) : (BN == 64 ? launch_persistent<64, 4>(ma, mb, g, splits, st) : launch_persistent<32, 4>(ma, mb, g, splits, st));
     else e = (BN == 128) ? launch<128, 3>(ma, mb, g, splits, st) : (BN == 64 ? launch<64, 4>(ma, mb, g, splits, st) : launch<32, 4>(ma, mb, g, splits, st));
     if (e) return e;
     if (splits > 1 && (bias || act)) { const size_t tot = (size_t)M * N; bias_act_strided<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cm, ldc, bias, M, N, act); go1_count_launch(1); }
