@@ -332,7 +332,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
     ap.add_argument("--gemm", type=int, default=int(os.environ.get("GO1_GEMM_IMPL", "1")), help="0 fp32 CUDA cores, 1 tcgen05 tf32")
-    ap.add_argument("--cpu-envs", type=int, default=32)
+    ap.add_argument("--cpu-envs", type=int, default=256)
     ap.add_argument("--warmup-ref", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="torch.profiler (CUPTI) kernel table + cProfile of the host loop -> gpurun_out/")

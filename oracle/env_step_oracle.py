@@ -30,13 +30,16 @@ class OracleEnv:
                       gravity_vec=torch.tensor([0., 0., -1.]).repeat(n, 1))
         self.s["commands"][:, 4] = 3.0; self.s["commands"][:, 5] = 0.5; self.s["commands"][:, 8] = 0.5
         self.s["commands"][:, 9] = 0.08; self.s["commands"][:, 12] = 0.25; self.s["commands"][:, 13] = 0.4
-        self.states = [ph.make_state([0, 0, 0.34], [0, 0, 0, 1], [0, 0, 0], [0, 0, 0], ph.DEFAULT_DOF_POS, np.zeros(12)) for _ in range(n)]
-        self.drs = [ph.make_dr(1.0, 0.0, 0.0) for _ in range(n)]
+        self.states = ph.state_array(n)
+        self.drs = ph.dr_array(n)
+        for i in range(n):
+            self.states[i] = ph.make_state([0, 0, 0.34], [0, 0, 0, 1], [0, 0, 0], [0, 0, 0], ph.DEFAULT_DOF_POS, np.zeros(12))
+            self.drs[i] = ph.make_dr(1.0, 0.0, 0.0)
+        self._sview = np.frombuffer(self.states, dtype=np.float64).reshape(n, 37)      # pos3 quat4 lin3 ang3 q12 qd12
         self.s["episode_sums"], self.s["command_sums"] = None, None
 
     def _sync_from_physics(self):
-        q = np.array([np.array(x.q) for x in self.states]); qd = np.array([np.array(x.qd) for x in self.states])
-        self.s["dof_pos"] = torch.tensor(q, dtype=torch.float32); self.s["dof_vel"] = torch.tensor(qd, dtype=torch.float32)
+        self.s["dof_pos"] = torch.tensor(self._sview[:, 13:25], dtype=torch.float32); self.s["dof_vel"] = torch.tensor(self._sview[:, 25:37], dtype=torch.float32)
 
     def step(self, actions):
         s, P, n = self.s, self.P, self.n
@@ -45,14 +48,13 @@ class OracleEnv:
         for _ in range(self.c.decimation):
             tau = eo.compute_torques(s, P, self.net)
             tq = tau.numpy().astype(np.float64)
-            cf = np.stack([ph.substep(self.pp, self.drs[i], self.states[i], tq[i]) for i in range(n)])
+            cf = ph.substep_batch(self.pp, self.drs, self.states, tq)
             self._sync_from_physics()
         s["torques"] = tau
-        root = np.array([np.concatenate([np.array(x.pos), np.array(x.quat), np.array(x.linvel), np.array(x.angvel)]) for x in self.states])
-        s["root_states"] = torch.tensor(root, dtype=torch.float32)
-        feet = [ph.feet(x) for x in self.states]
-        s["foot_positions"] = torch.tensor(np.array([f[0] for f in feet]), dtype=torch.float32)
-        s["foot_velocities"] = torch.tensor(np.array([f[1] for f in feet]), dtype=torch.float32)
+        s["root_states"] = torch.tensor(self._sview[:, :13], dtype=torch.float32)
+        fp, fv = ph.feet_batch(self.states)
+        s["foot_positions"] = torch.tensor(fp, dtype=torch.float32)
+        s["foot_velocities"] = torch.tensor(fv, dtype=torch.float32)
         s["contact_forces"] = torch.tensor(cf, dtype=torch.float32)
         s["episode_length_buf"] = s["episode_length_buf"] + 1
         quat = s["root_states"][:, 3:7]

@@ -20,6 +20,8 @@
 #include <math.h>
 #include <string.h>
 #include <stdlib.h>
+#include <pthread.h>
+#include <unistd.h>
 #include "../walk-these-ways_b200/csrc/go1_model_generated.h"
 #include "go1_physics_oracle.h"
 
@@ -457,7 +459,44 @@ void go1_oracle_aba(const Go1PhysParams* P, const Go1PhysDR* dr, const Go1PhysSt
     for (int i=0;i<12;i++) qdd_out[i]=(t.qd[i]-s->qd[i])/Q.dt;
 }
 
+typedef struct { const Go1PhysParams* P; const Go1PhysDR* dr; Go1PhysState* s; const double* tau; Go1PhysOut* out; double* fp; double* fv; int e0, e1; } BatchJob;
+static int n_threads(int n) {
+    long c = sysconf(_SC_NPROCESSORS_ONLN);
+    int T = (int)(c > 0 ? c : 1);
+    if (T > 256) T = 256;
+    if (T > n / 4) T = n / 4;
+    return T < 1 ? 1 : T;
+}
+static void* substep_job(void* a) {
+    BatchJob* j = (BatchJob*)a;
+    for (int e=j->e0;e<j->e1;e++) go1_oracle_substep(j->P, j->dr+e, j->s+e, j->tau+12*e, j->out+e);
+    return NULL;
+}
+static void* feet_job(void* a) {
+    BatchJob* j = (BatchJob*)a;
+    for (int e=j->e0;e<j->e1;e++) go1_oracle_feet(j->s+e, (double(*)[3])(j->fp+12*e), (double(*)[3])(j->fv+12*e));
+    return NULL;
+}
+void go1_oracle_feet_batch(int n, const Go1PhysState* s, double* foot_pos, double* foot_vel) {
+    BatchJob jobs[256]; pthread_t th[256];
+    int T = n_threads(n);
+    for (int t=0;t<T;t++) {
+        jobs[t] = (BatchJob){NULL, NULL, (Go1PhysState*)s, NULL, NULL, foot_pos, foot_vel, t*n/T, (t+1)*n/T};
+        if (t < T-1) pthread_create(&th[t], NULL, feet_job, &jobs[t]);
+    }
+    feet_job(&jobs[T-1]);
+    for (int t=0;t<T-1;t++) pthread_join(th[t], NULL);
+}
+
 void go1_oracle_substep_batch(const Go1PhysParams* P, int n, const Go1PhysDR* dr, Go1PhysState* s,
                               const double* tau, Go1PhysOut* out) {
-    for (int e=0;e<n;e++) go1_oracle_substep(P, dr+e, s+e, tau+12*e, out+e);
+    /* envs are independent: split the batch over all host cores (pthreads; this image has no OpenMP runtime) */
+    BatchJob jobs[256]; pthread_t th[256];
+    int T = n_threads(n);
+    for (int t=0;t<T;t++) {
+        jobs[t] = (BatchJob){P, dr, s, tau, out, NULL, NULL, t*n/T, (t+1)*n/T};
+        if (t < T-1) pthread_create(&th[t], NULL, substep_job, &jobs[t]);
+    }
+    substep_job(&jobs[T-1]);
+    for (int t=0;t<T-1;t++) pthread_join(th[t], NULL);
 }

@@ -55,9 +55,36 @@ def lib():
         _lib.go1_oracle_substep.argtypes = [C.POINTER(PhysParams), C.POINTER(PhysDR), C.POINTER(PhysState),
                                             C.POINTER(C.c_double), C.POINTER(PhysOut)]
         _lib.go1_oracle_feet.argtypes = [C.POINTER(PhysState), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        _lib.go1_oracle_substep_batch.argtypes = [C.POINTER(PhysParams), C.c_int, C.POINTER(PhysDR), C.POINTER(PhysState), C.POINTER(C.c_double), C.POINTER(PhysOut)]
+        _lib.go1_oracle_feet_batch.argtypes = [C.c_int, C.POINTER(PhysState), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         _lib.go1_oracle_aba.argtypes = [C.POINTER(PhysParams), C.POINTER(PhysDR), C.POINTER(PhysState),
                                         C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     return _lib
+
+
+def substep_batch(p, drs, states, tau):
+    """All envs in one C call (OpenMP over envs). drs/states: ctypes arrays; tau: float64 [n,12]. Returns contact forces [n,17,3]."""
+    n = len(states)
+    L = lib()
+    out = (PhysOut * n)()
+    t = np.ascontiguousarray(tau, dtype=np.float64)
+    L.go1_oracle_substep_batch(C.byref(p), n, drs, states, t.ctypes.data_as(C.POINTER(C.c_double)), out)
+    return np.ctypeslib.as_array(out).view(np.float64).reshape(n, 17, 3).copy() if False else np.frombuffer(out, dtype=np.float64).reshape(n, 17, 3).copy()
+
+
+def feet_batch(states):
+    n = len(states)
+    fp = np.zeros((n, 4, 3)); fv = np.zeros((n, 4, 3))
+    lib().go1_oracle_feet_batch(n, states, fp.ctypes.data_as(C.POINTER(C.c_double)), fv.ctypes.data_as(C.POINTER(C.c_double)))
+    return fp, fv
+
+
+def state_array(n):
+    return (PhysState * n)()
+
+
+def dr_array(n):
+    return (PhysDR * n)()
 
 
 def default_params():

@@ -20,13 +20,18 @@ SHAPES = [  # (M, N, K, note)
 
 def main():
     L = capi.lib()
+    only = os.environ.get("GEMM_BENCH_ONLY")
+    global SHAPES
+    if only:
+        SHAPES = [sh for sh in SHAPES if sh[3] in only.split(";")]
+    impls = (1,) if os.environ.get("GEMM_BENCH_TC_ONLY") else (0, 1)
     flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
     print(f"{'shape':>24s} {'note':>26s} {'impl0 us':>10s} {'TF/s':>7s} {'impl1 us':>10s} {'TF/s':>7s}")
     for M, N, K, note in SHAPES:
         ld = (K + 3) // 4 * 4
         A = torch.randn(M, ld, device="cuda"); B = torch.randn(N, ld, device="cuda"); Cm = torch.empty(M, N, device="cuda")
         res = []
-        for impl in (0, 1):
+        for impl in impls:
             ts = []
             for it in range(6):
                 flush.fill_(it)
@@ -38,6 +43,7 @@ def main():
                     ts.append(e0.elapsed_time(e1) * 1e3)
             us = sum(ts) / len(ts)
             res += [us, 2.0 * M * N * K / us / 1e6]
+        res = ([0.0, 0.0] + res) if len(res) == 2 else res
         print(f"{str((M, N, K)):>24s} {note:>26s} {res[0]:10.1f} {res[1]:7.1f} {res[2]:10.1f} {res[3]:7.1f}")
 
 
