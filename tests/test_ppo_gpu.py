@@ -210,6 +210,37 @@ def test_gemm_tcgen05_tf32(M, N, K):
     assert ((C2.double() - want).abs() <= bound + 1e-5).all()
 
 
+# MN-major operands (dgrad: B = W as [K][N]; wgrad: A = dz as [K][M], B = activations as [K][N]) read straight from HBM
+@pytest.mark.parametrize("ta,tb", [(0, 0), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 32, 64), (300, 200, 72), (24576, 128, 12), (12, 128, 24576), (1280, 2100, 4096),
+                                   (512, 256, 24576), (4096, 512, 256)])
+def test_gemm_tcgen05_tf32_mn_major(ta, tb, M, N, K):
+    torch.manual_seed(M * 7 + N * 3 + K + ta * 2 + tb)
+    pad = lambda n: (n + 3) // 4 * 4 + 4
+    if ta:
+        As = torch.randn(K, pad(M), device="cuda"); A = As[:, :M].t(); lda = As.stride(0)
+    else:
+        As = torch.randn(M, pad(K), device="cuda"); A = As[:, :K]; lda = As.stride(0)
+    if tb:
+        Bs = torch.randn(N, pad(K), device="cuda"); B = Bs[:, :K]; ldb = Bs.stride(0)
+    else:
+        Bs = torch.randn(K, pad(N), device="cuda"); B = Bs[:, :N].t(); ldb = Bs.stride(0)
+    ref = A.double() @ B.double().t()
+    # worst case per product: both operands truncated to 10 mantissa bits (2^-10 each); with K = 12 and 3M outputs the
+    # tail of the distribution reaches ~1.4 * 2^-10 * sum|a||b|, so the hard bound is the two-operand one
+    bound = (A.abs().double() @ B.abs().double().t()) * 2.0 ** -9 + 1e-6
+    C = torch.full((M, N + 3), 3.0, device="cuda")
+    _gemm(ta, tb, M, N, K, As, lda, Bs, ldb, C, N + 3, impl=1)
+    torch.cuda.synchronize()
+    err = (C[:, :N].double() - ref).abs()
+    assert (err <= bound).all(), (float(err.max()), float((err / bound).max()))
+    assert (C[:, N:] == 3.0).all()
+    assert float(err.norm() / ref.norm()) < 2e-3
+    C2 = torch.randn(M, N, device="cuda"); C0 = C2.clone()
+    _gemm(ta, tb, M, N, K, As, lda, Bs, ldb, C2, N, acc=1, impl=1)
+    assert ((C2.double() - (C0.double() + ref)).abs() <= bound + 1e-5).all()
+
+
 def test_transpose_kernel():
     from go1_b200 import capi
     src = torch.randn(1000, 300, device="cuda")[:, :257]
@@ -220,8 +251,6 @@ def test_transpose_kernel():
 
 def test_gemm_tcgen05_rejects_unsupported_layouts():
     from go1_b200 import capi
-    A = torch.randn(64, 70, device="cuda"); B = torch.randn(70, 64, device="cuda"); C = torch.zeros(64, 64, device="cuda")
-    with pytest.raises(capi.Go1Error):
-        _gemm(0, 0, 64, 64, 70, A, 70, B, 64, C, 64, impl=1)      # transB=0: not K-major
+    A = torch.randn(64, 70, device="cuda"); C = torch.zeros(64, 64, device="cuda")
     with pytest.raises(capi.Go1Error):
         _gemm(0, 1, 64, 64, 70, A, 70, A, 70, C, 64, impl=1)      # ld=70 floats: not a multiple of 16 bytes

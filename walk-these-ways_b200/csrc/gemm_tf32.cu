@@ -2,8 +2,10 @@
 //
 //   C[M][N] (+)= A[M][K] * B[N][K]^T (+ bias[n]) (ELU)          fp32 in HBM, TF32 multiply, fp32 accumulate
 //
-// Both operands are K-major (A = activations row-major, B = torch.nn.Linear weight [out][in]); the dgrad / wgrad
-// products are brought into this form by go1_transpose on the host side.  Structure (one 128 x BN output tile per
+// The forward products read both operands K-major (A = activations row-major, B = torch.nn.Linear weight [out][in]);
+// dgrad (B = W as [K][N]) and wgrad (A = dz as [K][M], B = activations as [K][N]) read MN-major operands straight from
+// HBM: the TMA boxes become [32 k-rows][32 mn-floats] and the UMMA descriptors / instruction descriptor switch to the
+// MN-major canonical layout, so no transposed copies exist anywhere.  Structure (one 128 x BN output tile per
 // CTA, 192 threads):
 //   warp 0   TMA producer: cp.async.bulk.tensor 2D loads of 128x32 (A) and BNx32 (B) fp32 boxes, 128B swizzle,
 //            S-stage ring guarded by full/empty mbarriers
@@ -66,6 +68,21 @@ __device__ __forceinline__ uint64_t make_desc(const void* smem) {
     d |= (uint64_t)2 << 61;                                  // SWIZZLE_128B
     return d;
 }
+// MN-major TF32 operand tile.  32-bit MN-major operands have exactly one legal shared-memory layout on tcgen05: 128-byte
+// swizzle with 32-byte atoms (descriptor layout type 1, SWIZZLE_128B_BASE32B; TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) --
+// the ordinary 16-byte-atom SWIZZLE_128B descriptor is accepted but multiplies by zero (measured, tools/gemm_bench.py
+// history in DESIGN.md).  The TMA box is [32 k-rows][32 mn-floats] = 4 KB: rows of 128 B, the swizzle pattern repeats
+// every 4 k-rows (512 B = SBO), one instruction (K = 8) consumes 8 rows = 1024 B, and the 32-wide MN blocks of the
+// tile sit 4 KB apart (LBO).  Canonical layout ((8,n),(4,k)):((1,LBO),(8,SBO)) in 16-byte units.
+__device__ __forceinline__ uint64_t make_desc_mn(const void* smem) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(smem) >> 4) & 0x3FFF);
+    d |= (uint64_t)(4096 >> 4) << 16;                        // leading byte offset: next 32-float MN block
+    d |= (uint64_t)(512 >> 4) << 32;                         // stride byte offset: next 4 k-rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                                  // SWIZZLE_128B_BASE32B
+    return d;
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
@@ -90,6 +107,7 @@ struct GemmArgs {
     int M, N, K, ldc, act, accumulate, kb_per_split;
     const float* ex; const float* wex; const float* aux;      // fused epilogue operands (see Go1GemmEpilogue)
     int ldex, ldwex, nex, ldaux;
+    int amn, bmn;            // operand is MN-major in HBM (A given as [K][M], B given as [K][N]); persistent kernel only
 };
 
 template <int BN, int STAGES>
@@ -290,13 +308,24 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_persistent(const __grid_cons
                     const int s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
                     mbar_expect_tx(&full[s], (BM + BN) * BK * 4);
-                    tma_load_2d(&mapA, &full[s], sA + (size_t)s * BM * BK, (kb0 + i) * BK, m0);
-                    tma_load_2d(&mapB, &full[s], sB + (size_t)s * BN * BK, (kb0 + i) * BK, n0);
+                    float* a = sA + (size_t)s * BM * BK;
+                    float* b = sB + (size_t)s * BN * BK;
+                    if (g.amn) {
+#pragma unroll
+                        for (int x = 0; x < BM / 32; x++) tma_load_2d(&mapA, &full[s], a + x * 32 * BK, m0 + 32 * x, (kb0 + i) * BK);
+                    } else tma_load_2d(&mapA, &full[s], a, (kb0 + i) * BK, m0);
+                    if (g.bmn) {
+#pragma unroll
+                        for (int x = 0; x < BN / 32; x++) tma_load_2d(&mapB, &full[s], b + x * 32 * BK, n0 + 32 * x, (kb0 + i) * BK);
+                    } else tma_load_2d(&mapB, &full[s], b, (kb0 + i) * BK, n0);
                 }
             }
         }
     } else if (warp == 1) {
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        // bits 15 / 16: A / B operand is MN-major
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.amn ? 1 : 0) << 15) | ((uint32_t)(g.bmn ? 1 : 0) << 16) |
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const uint32_t ka = g.amn ? (1024 >> 4) : 2, kb = g.bmn ? (1024 >> 4) : 2;     // per-instruction K advance of the descriptors
         int it = 0, j = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, j++) {
             int m0, n0, kb0, nkb; tile_coords(t, m0, n0, kb0, nkb);
@@ -309,9 +338,10 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_persistent(const __grid_cons
                 mbar_wait(&full[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
-                    const uint64_t da = make_desc(sA + (size_t)s * BM * BK), db = make_desc(sB + (size_t)s * BN * BK);
+                    const uint64_t da = g.amn ? make_desc_mn(sA + (size_t)s * BM * BK) : make_desc(sA + (size_t)s * BM * BK);
+                    const uint64_t db = g.bmn ? make_desc_mn(sB + (size_t)s * BN * BK) : make_desc(sB + (size_t)s * BN * BK);
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; k++) umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < BK / UMMA_K; k++) umma_tf32(tmem_d, da + ka * k, db + kb * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
                     umma_commit(&empty[s]);
                     if (i == nkb - 1) umma_commit(&tmem_full[buf]);
                 }
@@ -404,7 +434,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode = nullptr;
 std::once_flag g_once;
 
-int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_rows) {
+int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_rows, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     std::call_once(g_once, [] {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult q;
@@ -416,7 +446,7 @@ int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { char b[96]; snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed (%d)", (int)r); return go1_set_error(b); }
     return 0;
 }
@@ -479,14 +509,16 @@ extern "C" void go1_gemm_tf32_set_persistent(int on) { g_tf32_persistent = on; }
 extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                              float* Cm, int ldc, const Go1GemmEpilogue* ep, cudaStream_t st) {
     const float* bias = ep->bias; const int act = ep->act, accumulate = ep->accumulate;
-    if (transA != 0 || transB != 1)
-        return go1_set_error("go1_gemm impl=1 (tcgen05 TF32) takes K-major operands only: transA=0, transB=1 (use go1_transpose for dgrad/wgrad)");
+    const int amn = transA ? 1 : 0, bmn = transB ? 0 : 1;     // A given as [K][M] / B given as [K][N]: MN-major operands
+    if ((amn || bmn) && !g_tf32_persistent)
+        return go1_set_error("go1_gemm impl=1: MN-major operands (transA=1 / transB=0) need the persistent kernel");
     if ((lda & 3) || (ldb & 3) || (((uintptr_t)A | (uintptr_t)B) & 15))
         return go1_set_error("go1_gemm impl=1: A/B must be 16-byte aligned with row strides that are multiples of 4 floats (TMA)");
     GemmArgs g;
     g.C = Cm; g.bias = bias; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.act = act; g.accumulate = accumulate;
     g.ex = ep->extra; g.ldex = ep->ld_extra; g.wex = ep->w_extra; g.ldwex = ep->ld_w_extra; g.nex = ep->extra ? ep->num_extra : 0;
     g.aux = ep->dact_y; g.ldaux = ep->ld_dact_y;
+    g.amn = amn; g.bmn = bmn;
     if (g.nex < 0 || g.nex > 4) return go1_set_error("go1_gemm_ex: num_extra must be 0..4");
     if (act == 2 && !g.aux) return go1_set_error("go1_gemm_ex: act 2 needs dact_y");
     const int num_kb = (K + BK - 1) / BK;
@@ -499,8 +531,9 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
     g.kb_per_split = (num_kb + splits - 1) / splits;
     splits = (num_kb + g.kb_per_split - 1) / g.kb_per_split;
     CUtensorMap ma, mb;
-    if (int e = make_map(&ma, A, M, K, lda, BM)) return e;
-    if (int e = make_map(&mb, B, N, K, ldb, BN)) return e;
+    // K-major: rows = M (or N), cols = K, box BK x tile rows.  MN-major: rows = K, cols = M (or N), box 32 mn x BK k-rows.
+    if (int e = amn ? make_map(&ma, A, K, M, lda, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) : make_map(&ma, A, M, K, lda, BM)) return e;
+    if (int e = bmn ? make_map(&mb, B, K, N, ldb, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) : make_map(&mb, B, N, K, ldb, BN)) return e;
     if (splits > 1) {
         if (!accumulate) { const size_t tot = (size_t)M * N; zero_strided<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cm, ldc, M, N); go1_count_launch(1); }
         g.bias = nullptr; g.act = 0;

@@ -54,9 +54,10 @@ class _Net:
     """Forward/backward of one MLP whose first layer reads [x (K0 columns) | extra (E columns)].
 
     impl 0: every product is one fp32 CUDA-core go1_gemm.  impl 1: the large products run on the tcgen05 TF32 kernel,
-    which reads K-major operands through TMA (16-byte aligned rows): the first-layer weight block W[:, :K0] is packed
-    to a contiguous copy, dgrad reads a transposed weight copy and wgrad transposed activations/gradients
-    (go1_transpose); copies are cached per weight version."""
+    which reads its operands through TMA (16-byte aligned rows) in either major: forward K-major, dgrad with W as an
+    MN-major B operand, wgrad with dz and the layer input as MN-major A and B operands -- no transposed copies.  Only
+    the first-layer weight block W[:, :K0] (row stride 2102 floats) is packed to a TMA-readable copy, cached per
+    weight version."""
 
     def __init__(self, seq, flat, grad, offsets, owner):
         self.linears = [m for m in seq if isinstance(m, nn.Linear)]
@@ -144,11 +145,10 @@ class _Net:
             inp, ld_in = y, o
         return outs
 
-    def backward(self, x, ldx, K0, extra, outs, dout, M, impl, accumulate, want_dextra=False, tag="a", xT=None, dz1_out=None):
+    def backward(self, x, ldx, K0, extra, outs, dout, M, impl, accumulate, want_dextra=False, tag="a", dz1_out=None):
         """dout: gradient w.r.t. the network output [M][out] (the last layer has no activation).  Writes weight/bias grads
         into the flat grad buffer.  dz of every hidden layer comes out of the dgrad GEMM already multiplied by ELU'
-        (fused epilogue).  xT: optional precomputed transpose of the first-layer input ([K0][ld>=M]) for the tensor-core
-        wgrad.  dz1_out: optional [M][o1] strided view; when given the first layer's dz is written there and its wgrad is
+        (fused epilogue).  dz1_out: optional [M][o1] strided view; when given the first layer's dz is written there and its wgrad is
         left to the caller (ActorCritic fuses the three first-layer wgrads into one GEMM).  Returns d(extra) [M][E] if requested."""
         L, st = capi.lib(), capi.stream_ptr()
         n = len(self.specs)
@@ -167,17 +167,9 @@ class _Net:
             # ---- wgrad: dW[o][K] = dz^T[o][M] inp[M][K]
             if li == 0 and dz1_out is not None:
                 pass                                    # fused by the caller
-            elif impl == 1 and M >= 64 and K >= 8:
-                dzT = self._transpose(dz, ldz, M, o, self.acts.get((tag, "dzT", li)))
-                self.acts[(tag, "dzT", li)] = dzT
-                if li == 0 and xT is not None:
-                    inT = xT
-                else:
-                    inT = self._transpose(inp, ld_in, M, K, self.acts.get((tag, "inT", li)))
-                    self.acts[(tag, "inT", li)] = inT
-                self._gemm(0, 1, o, K, M, dzT, dzT.stride(0), inT, inT.stride(0), gW, i, None, 0, accumulate, 1)
-            else:
-                self._gemm(1, 0, o, K, M, dz, ldz, inp, ld_in, gW, i, None, 0, accumulate, 0)
+            else:       # impl 1: both operands MN-major, read in place by the tcgen05 kernel
+                tc = impl == 1 and M >= 64 and K >= 8 and self._tma_ok(dz, ldz) and self._tma_ok(inp, ld_in)
+                self._gemm(1, 0, o, K, M, dz, ldz, inp, ld_in, gW, i, None, 0, accumulate, 1 if tc else 0)
             if li == 0 and extra is not None:
                 E = i - K0
                 if want_dextra:
@@ -189,9 +181,8 @@ class _Net:
                 dprev = dz1_out if (li == 1 and dz1_out is not None) else self._buf((tag, "d", li - 1), M, i)
                 ldp = dprev.stride(0)
                 yprev = outs[li - 1]
-                if impl == 1 and self._tma_ok(dz, ldz) and M >= 64:
-                    WT = self._cached(("WT", li), lambda old: self._transpose(W, i, o, i, old))
-                    self._gemm(0, 1, M, i, o, dz, ldz, WT, WT.stride(0), dprev, ldp, None, 2, 0, 1, dact_y=yprev)
+                if impl == 1 and self._tma_ok(dz, ldz) and self._tma_ok(W, i) and M >= 64:
+                    self._gemm(0, 0, M, i, o, dz, ldz, W, i, dprev, ldp, None, 2, 0, 1, dact_y=yprev)      # W read MN-major in place
                 elif o <= 16:
                     capi.check(L.go1_skinny_dgrad(capi.ptr(dz), ldz, capi.ptr(W), i, capi.ptr(yprev), yprev.stride(0), capi.ptr(dprev), ldp, M, o, i, st), "skinny_dgrad")
                 else:
@@ -387,13 +378,13 @@ class ActorCritic(nn.Module):
         return self._nets["adapt"].forward(h, h.stride(0), self.num_obs_history, None, h.shape[0], self._impl(), "latent")[-1]
 
     # ------------------------------------------------------------------ explicit backward passes (ppo.py:154-189)
-    def backward_ppo(self, h, priv, dmean, dvalue, dstd, hT=None):
+    def backward_ppo(self, h, priv, dmean, dvalue, dstd):
         """Gradients of the PPO loss into flat_grads (overwrites). h/priv are the minibatch inputs of the forward
         pass just run with tag='train'; dmean [M,A], dvalue [M,1], dstd [A]."""
         M, K0, impl = h.shape[0], self.num_obs_history, self._impl()
         nets = self._nets
-        if impl == 1 and hT is not None and M >= 64:
-            # the three first layers share their input: ONE transposed dz [o_a+o_p+o_c][M] and ONE tensor-core wgrad
+        if impl == 1 and M >= 64 and _Net._tma_ok(h, h.stride(0)):
+            # the three first layers share their input: ONE dz [M][o_a+o_p+o_c] and ONE tensor-core wgrad
             # dWcat[1280][2100] = dzcat^T h instead of three (the first-layer dz of each net is written straight into its
             # column slice of `dz1` by that net's layer-2 dgrad)
             oa, op, oc = nets["adapt"].specs[0][2], nets["actor"].specs[0][2], nets["critic"].specs[0][2]
@@ -402,28 +393,22 @@ class ActorCritic(nn.Module):
             nets["critic"].backward(h, h.stride(0), K0, priv, self._c_out, dvalue, M, impl, 0, tag="train", dz1_out=dz1[:, oa + op:])
             nets["adapt"].backward(h, h.stride(0), K0, None, self._a_out, dlat, M, impl, 0, tag="train", dz1_out=dz1[:, :oa])
             n0 = nets["adapt"]
-            dzT = n0._transpose(dz1, dz1.stride(0), M, oa + op + oc, n0.acts.get(("train", "dz1catT")))
-            n0.acts[("train", "dz1catT")] = dzT
             gcat = n0._buf(("train", "gWcat"), oa + op + oc, K0)
-            n0._gemm(0, 1, oa + op + oc, K0, M, dzT, dzT.stride(0), hT, hT.stride(0), gcat, K0, None, 0, 0, 1)
+            n0._gemm(1, 0, oa + op + oc, K0, M, dz1, dz1.stride(0), h, h.stride(0), gcat, K0, None, 0, 0, 1)
             row = 0
             for name in ("adapt", "actor", "critic"):
                 wo, bo, o, i = nets[name].specs[0]
                 self._grad[wo:wo + o * i].view(o, i)[:, :K0].copy_(gcat[row:row + o])
                 row += o
         else:
-            dlat = nets["actor"].backward(h, h.stride(0), K0, self._latent, self._p_out, dmean, M, impl, 0, want_dextra=True, tag="train", xT=hT)
-            nets["critic"].backward(h, h.stride(0), K0, priv, self._c_out, dvalue, M, impl, 0, tag="train", xT=hT)
-            nets["adapt"].backward(h, h.stride(0), K0, None, self._a_out, dlat, M, impl, 0, tag="train", xT=hT)
+            dlat = nets["actor"].backward(h, h.stride(0), K0, self._latent, self._p_out, dmean, M, impl, 0, want_dextra=True, tag="train")
+            nets["critic"].backward(h, h.stride(0), K0, priv, self._c_out, dvalue, M, impl, 0, tag="train")
+            nets["adapt"].backward(h, h.stride(0), K0, None, self._a_out, dlat, M, impl, 0, tag="train")
         self._grad[self.std_offset:self.std_offset + self.num_actions].copy_(dstd)
 
-    def backward_adaptation(self, h, outs, dpred, hT=None):
+    def backward_adaptation(self, h, outs, dpred):
         M, K0 = h.shape[0], self.num_obs_history
-        self._nets["adapt"].backward(h, h.stride(0), K0, None, outs, dpred, M, self._impl(), 0, tag="adapt", xT=hT)
-
-    def transpose_input(self, h, out=None):
-        """[M][K0] -> [K0][ld>=M] for the tensor-core wgrad of the three first layers (computed once per minibatch)."""
-        return self._nets["adapt"]._transpose(h, h.stride(0), h.shape[0], self.num_obs_history, out)
+        self._nets["adapt"].backward(h, h.stride(0), K0, None, outs, dpred, M, self._impl(), 0, tag="adapt")
 
     def adaptation_forward(self, h):
         self.flatten()

@@ -181,18 +181,11 @@ class PPO:
         self._lr_dev.fill_(self.learning_rate)
         n_updates = 0
         # The reference draws ONE permutation per update and reuses it for all epochs (rollout_storage.py:101), so the
-        # gathered minibatches (and, for the tensor-core wgrad, their transposed histories) are built once and reused.
+        # gathered minibatches are built once and reused.
         batches = list(self.storage.mini_batch_generator(PPO_Args.num_mini_batches, 1, indices=self.fixed_minibatch_indices))
-        use_tc = ac._impl() == 1
-        if use_tc:
-            if getattr(self, "_hT", None) is None or len(self._hT) != len(batches):
-                self._hT = [None] * len(batches)
-            for bi, bt in enumerate(batches):
-                self._hT[bi] = ac.transpose_input(bt[3], self._hT[bi])
         for it_mb in range(PPO_Args.num_learning_epochs * len(batches)):
             bi = it_mb % len(batches)
             (obs_b, critic_obs_b, priv_b, hist_b, actions_b, target_values_b, adv_b, returns_b, old_logp_b, old_mu_b, old_sigma_b, masks_b, env_bins_b) = batches[bi]
-            hT = self._hT[bi] if use_tc else None
             M = hist_b.shape[0]
             ac.update_distribution(hist_b, tag="train")
             value_b = ac.evaluate(hist_b, priv_b, tag="train")
@@ -207,7 +200,7 @@ class PPO:
             self._allreduce(self._scalars)
             if PPO_Args.desired_kl is not None and PPO_Args.schedule == 'adaptive':   # ppo.py:118-132, on the device
                 capi.check(L.go1_ppo_adaptive_lr(capi.ptr(self._scalars), capi.ptr(self._lr_dev), PPO_Args.desired_kl, 1e-5, 1e-2, st()), "adaptive_lr")
-            ac.backward_ppo(hist_b, priv_b, dmean, dvalue, self._dstd, hT)
+            ac.backward_ppo(hist_b, priv_b, dmean, dvalue, self._dstd)
             self._allreduce(ac.flat_grads)
             capi.check(L.go1_ppo_grad_sqnorm(capi.ptr(ac.flat_grads), ac.n_params, capi.ptr(self._grad_sq), st()), "sqnorm")
             self.optimizer.step(self._grad_sq, PPO_Args.max_grad_norm, self._lr_dev)
@@ -220,7 +213,7 @@ class PPO:
                 dpred = ac._nets["adapt"]._buf(("adapt", "dpred"), M, pred.shape[1])
                 capi.check(L.go1_ppo_mse(capi.ptr(pred), pred.stride(0), capi.ptr(priv_b), priv_b.stride(0), capi.ptr(dpred), dpred.stride(0),
                                          capi.ptr(self._mse_scalars), M, num_train, pred.shape[1], st()), "mse")
-                ac.backward_adaptation(hist_b, outs, dpred, hT)
+                ac.backward_adaptation(hist_b, outs, dpred)
                 if self.process_group is not None:
                     self._allreduce(ac.flat_grads[:ac.n_adapt_params])
                     ac.flat_grads[:ac.n_adapt_params].div_(world)

@@ -28,8 +28,14 @@ def main():
     flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
     print(f"{'shape':>24s} {'note':>26s} {'impl0 us':>10s} {'TF/s':>7s} {'impl1 us':>10s} {'TF/s':>7s}")
     for M, N, K, note in SHAPES:
-        ld = (K + 3) // 4 * 4
-        A = torch.randn(M, ld, device="cuda"); B = torch.randn(N, ld, device="cuda"); Cm = torch.empty(M, N, device="cuda")
+        # operand majors as the learner issues them: wgrad reads dz / activations as [K][M] / [K][N], dgrad reads W as [K][N]
+        ta, tb = (1, 0) if "wgrad" in note else ((0, 0) if "dgrad" in note else (0, 1))
+        if os.environ.get("GEMM_BENCH_KMAJOR"):
+            ta, tb = 0, 1
+        pad = lambda n: (n + 3) // 4 * 4
+        A = torch.randn(K, pad(M), device="cuda") if ta else torch.randn(M, pad(K), device="cuda")
+        B = torch.randn(N, pad(K), device="cuda") if tb else torch.randn(K, pad(N), device="cuda")
+        Cm = torch.empty(M, N, device="cuda")
         res = []
         for impl in impls:
             ts = []
@@ -37,7 +43,7 @@ def main():
                 flush.fill_(it)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                capi.check(L.go1_gemm(0, 1, M, N, K, capi.ptr(A), ld, capi.ptr(B), ld, capi.ptr(Cm), N, None, 0, 0, impl, capi.stream_ptr()), "gemm")
+                capi.check(L.go1_gemm(ta, tb, M, N, K, capi.ptr(A), A.stride(0), capi.ptr(B), B.stride(0), capi.ptr(Cm), N, None, 0, 0, impl, capi.stream_ptr()), "gemm")
                 e1.record(); torch.cuda.synchronize()
                 if it >= 2:
                     ts.append(e0.elapsed_time(e1) * 1e3)
