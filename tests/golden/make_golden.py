@@ -10,6 +10,8 @@ Outputs (committed):
                      check_termination, compute_reward, compute_observations on a mock env (N=64)
   kats.npz           known-answer tests of SURVEY.md §8c: actuator net, gait clock, curriculum, policy MLPs
   ppo.npz            one full ppo_cse act->process_env_step->compute_returns->update cycle (BASELINE config 1)
+  resample.npz       14 rounds of LeggedRobot._resample_commands (curriculum update + sampling + gait remap) on a mock
+                     env with scripts/train.py's config (N=64), incl. the torch.rand category draws of every round
 """
 import io
 import json
@@ -376,6 +378,46 @@ def make_ppo():
     print("ppo.npz:", len(out), "arrays; losses", losses[:3], "lr", alg.learning_rate)
 
 
+def make_resample(Cfg):
+    """the host side of reset_idx / the 500-step resample, through the reference's own code."""
+    import math
+    from go1_gym.envs.base.legged_robot import LeggedRobot
+    N, dt = 64, 4 * float(np.float32(0.005))
+    Cfg.env.max_episode_length = math.ceil(Cfg.env.episode_length_s / dt)
+    keys = ["tracking_lin_vel", "tracking_ang_vel", "tracking_contacts_shaped_force", "tracking_contacts_shaped_vel"]
+    env = types.SimpleNamespace(cfg=Cfg, dt=dt, device="cpu")
+    env.reward_scales = {k: float(getattr(Cfg.reward_scales, k)) * dt for k in keys}        # legged_robot.py:1396-1400
+    env.curriculum_thresholds = {k: v for k, v in clean(vars(Cfg.curriculum_thresholds)).items()}
+    LeggedRobot._init_command_distribution(env, torch.arange(N))
+    env.commands = torch.zeros(N, Cfg.commands.num_commands)
+    env.command_sums = {k: torch.zeros(N) for k in keys + ["lin_vel_raw", "ang_vel_raw"]}
+    ep_len = min(Cfg.env.max_episode_length, int(Cfg.commands.resampling_time / dt))
+    out = {"meta/dt": np.float64(dt), "meta/ep_len": np.int64(ep_len), "meta/max_episode_length": np.int64(Cfg.env.max_episode_length)}
+    rs = np.random.RandomState(7)
+    rounds = 14
+    for r in range(rounds):
+        k = [N, 1, 5, 9, 2, 17, 6, 3, 12, 1, 8, 30, 4, 11][r]
+        ids = torch.from_numpy(np.sort(rs.choice(N, k, replace=False)).astype(np.int64))
+        sums = np.zeros((k, 4), dtype=np.float32)
+        for j, key in enumerate(keys):      # around the success threshold so that both outcomes occur (more successes later)
+            thr = env.curriculum_thresholds[key] * env.reward_scales[key] * ep_len
+            sums[:, j] = (thr * (1.0 + rs.uniform(-0.25, 0.6 + 0.1 * r, size=k))).astype(np.float32)
+            env.command_sums[key][ids] = torch.from_numpy(sums[:, j])
+        torch.manual_seed(1000 + r)
+        floats = torch.rand(k)
+        torch.manual_seed(1000 + r)
+        LeggedRobot._resample_commands(env, ids)
+        out[f"r{r}/ids"] = ids.numpy(); out[f"r{r}/sums"] = sums; out[f"r{r}/rand"] = floats.numpy()
+        out[f"r{r}/commands"] = env.commands[ids].numpy().copy()
+        out[f"r{r}/bins"] = env.env_command_bins.copy(); out[f"r{r}/categories"] = env.env_command_categories.copy()
+        for i, c in enumerate(env.curricula):
+            out[f"r{r}/weights{i}"] = np.packbits(np.round(c.weights * 5).astype(np.uint8) > 0) if False else c.weights.astype(np.float32)
+        assert all((env.command_sums[key][ids] == 0).all() for key in keys)
+    out["meta/rounds"] = np.int64(rounds)
+    np.savez_compressed(os.path.join(HERE, "resample.npz"), **out)
+    print("resample.npz:", len(out), "arrays; successes per round:", [int((out[f"r{r}/weights0"] > 0).sum()) for r in range(rounds)])
+
+
 if __name__ == "__main__":
     Cfg, trees = reference_train_cfg()
     with open(os.path.join(HERE, "cfg_trees.json"), "w") as f:
@@ -383,3 +425,4 @@ if __name__ == "__main__":
     make_env_logic(Cfg)
     make_kats(Cfg)
     make_ppo()
+    make_resample(Cfg)
