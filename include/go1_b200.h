@@ -158,6 +158,60 @@ int go1_sim_reset_idx(Go1Sim* sim, const int32_t* env_ids, int k, const float* n
  * (legged_robot.py:684-686, 756-824): write new commands, zero command_sums. */
 int go1_sim_set_commands(Go1Sim* sim, const int32_t* env_ids, int k, const float* new_commands, void* stream);
 
+/* ---- device-resident command curriculum ---------------------------------------------------------------------
+ * Replaces the HOST work of LeggedRobot._resample_commands (legged_robot.py:710-824) and of
+ * RewardThresholdCurriculum.update / Curriculum.sample (go1_gym/envs/base/curriculum.py:67-89, 135-154): success
+ * test on the 4 task command sums, bin-weight updates with neighbour bumps, category draw, numpy
+ * RandomState(MT19937)-exact bin + in-cell sampling (cdf, searchsorted, uniform), gait-category remap of commands
+ * 5-7, binary phases, zeroing of small xy commands.  One CTA consumes the event list the step kernel wrote
+ * (`events[list]`, ids sorted ascending like the reference's env_ids) so the rollout needs no host round trip. */
+#define GO1_CUR_MAX_CATEGORIES 8
+typedef struct Go1CurriculumConfig {
+    int32_t num_categories;                          /* 1 ('nominal') or 4 (gaitwise_curricula) */
+    int32_t category_kind[GO1_CUR_MAX_CATEGORIES];   /* 0 nominal, 1 pronk, 2 trot, 3 pace, 4 bound */
+    int32_t num_bins, num_dims;                      /* bins per curriculum, command dimensions of the grid (15) */
+    int32_t num_commands;                            /* Cfg.commands.num_commands */
+    int32_t num_task_keys, task_col[4];              /* active task rewards: column of the 4 event sums */
+    float threshold[4];                              /* curriculum_thresholds[key] * reward_scales[key], float32 */
+    float ep_len;                                    /* min(max_episode_length, resampling_time / dt) */
+    int32_t gaitwise_curricula, exclusive_phase_offset, balance_gait_distribution, binary_phases;
+    int32_t num_train_envs, snapshot_time_outs;
+} Go1CurriculumConfig;
+
+typedef struct Go1CurriculumBuffers {
+    double* weights;             /* [num_categories][num_bins]   Curriculum.weights */
+    const double* grid;          /* [num_bins][num_dims]         bin centroids (Curriculum.grid.T) */
+    const double* half_bins;     /* [num_dims]                   bin_sizes / 2 */
+    const double* local_range;   /* [num_dims]                   neighbour range of the weight update */
+    uint32_t* mt;                /* [num_categories][625]        RandomState key[624] + pos, one per curriculum */
+    uint64_t* cat_rng;           /* [1]                          splitmix64 state of the category draws */
+    int32_t* env_bins;           /* [N]                          LeggedRobot.env_command_bins */
+    int32_t* env_categories;     /* [N]                          LeggedRobot.env_command_categories */
+    float* env_bins_f32;         /* [num_train_envs]             extras["env_bins"] */
+    uint8_t* time_outs_snapshot; /* [num_train_envs]             extras["time_outs"] (copied when list 0 is not empty) */
+    double* cdf;                 /* [num_categories][num_bins]   cached sampling cdf */
+    int32_t* cdf_valid;          /* [num_categories]             0 after a weight change */
+    int32_t* scratch_i32;        /* [8N + 64], zero on first use */
+    uint32_t* scratch_u32;       /* [2 (num_dims + 1) N] */
+    double* scratch_f64;         /* [(num_dims + 2) N] */
+    int32_t* out_count;          /* [1]   number of envs processed (k for go1_sim_reset_idx_dev) */
+    int32_t* out_ids;            /* [N]   their ids, ascending */
+    float* out_commands;         /* [N][15] their new commands */
+} Go1CurriculumBuffers;
+
+/* sizeof(Go1CurriculumConfig) (which = 0) / sizeof(Go1CurriculumBuffers) (which = 1) as compiled */
+int go1_sizeof_curriculum(int which);
+
+/* list 0: envs that terminated this step -> out_ids / out_commands / out_count feed go1_sim_reset_idx_dev.
+ * list 1: envs due for the periodic resample -> commands written and command_sums zeroed in place
+ *         (go1_sim_set_commands semantics). */
+int go1_curriculum_resample(Go1Sim* sim, const Go1CurriculumConfig* cfg, const Go1CurriculumBuffers* bufs, int list, void* stream);
+
+/* go1_sim_reset_idx with the env count read from device memory (*k_dev <= num_envs) and an optional per-call
+ * accumulator for extras["train/episode"] (NULL = the bound episode_acc). */
+int go1_sim_reset_idx_dev(Go1Sim* sim, const int32_t* env_ids, const int32_t* k_dev, const float* new_commands,
+                          const float* actions, int post_step, int64_t common_step, float* episode_acc, void* stream);
+
 /* Replaces HistoryWrapper.step's torch.cat roll (go1_gym/envs/wrappers/history_wrapper.py:23):
  * hist_out[n] = concat(hist_in[n][num_obs:], obs[n]). */
 int go1_history_roll(const float* hist_in, const float* obs, float* hist_out, int n, int num_obs,

@@ -10,6 +10,8 @@
 extern "C" int go1_launch_step(const Go1SimBuffers*, const Go1DevTable*, const float*, const float*, const float*, long long, int, int, cudaStream_t);
 extern "C" int go1_launch_reset(const Go1SimBuffers*, const Go1DevTable*, const int*, int, const float*, const float*, int, long long, const float*, int, cudaStream_t);
 extern "C" int go1_launch_set_commands(const Go1SimBuffers*, const int*, int, const float*, int, cudaStream_t);
+extern "C" int go1_launch_reset_dev(const Go1SimBuffers*, const Go1DevTable*, const int*, const int*, const float*, const float*, int, long long, const float*, float*, int, cudaStream_t);
+extern "C" int go1_launch_curriculum(const Go1SimBuffers*, const Go1CurriculumConfig*, const Go1CurriculumBuffers*, int, int, cudaStream_t);
 extern "C" int go1_launch_history_roll(const float*, const float*, float*, int, int, int, cudaStream_t);
 
 static thread_local std::string g_err;
@@ -220,6 +222,31 @@ extern "C" int go1_sim_set_commands(Go1Sim* s, const int32_t* env_ids, int k, co
     if (k < 0 || !env_ids || !new_commands) return fail("go1_sim_set_commands: bad arguments");
     int e = go1_launch_set_commands(&s->bufs, env_ids, k, new_commands, s->cfg.num_envs, (cudaStream_t)stream);
     return e ? cuda_fail("go1_sim_set_commands launch", e) : 0;
+}
+
+extern "C" int go1_sizeof_curriculum(int which) { return which == 0 ? (int)sizeof(Go1CurriculumConfig) : (int)sizeof(Go1CurriculumBuffers); }
+
+extern "C" int go1_curriculum_resample(Go1Sim* s, const Go1CurriculumConfig* cfg, const Go1CurriculumBuffers* cb, int list, void* stream) {
+    if (!s || !s->bound) return fail("go1_curriculum_resample: sim not bound");
+    if (!cfg || !cb || list < 0 || list > 1) return fail("go1_curriculum_resample: bad arguments");
+    if (cfg->num_categories < 1 || cfg->num_categories > GO1_CUR_MAX_CATEGORIES || cfg->num_bins < 1 || cfg->num_dims < 1 ||
+        cfg->num_task_keys < 0 || cfg->num_task_keys > 4 || cfg->num_commands < 1 || cfg->num_commands > GO1_NUM_COMMANDS)
+        return fail("go1_curriculum_resample: bad curriculum config");
+    if (!cb->weights || !cb->grid || !cb->half_bins || !cb->local_range || !cb->mt || !cb->cat_rng || !cb->env_bins || !cb->env_categories ||
+        !cb->env_bins_f32 || !cb->cdf || !cb->cdf_valid || !cb->scratch_i32 || !cb->scratch_u32 || !cb->scratch_f64 || !cb->out_count ||
+        !cb->out_ids || !cb->out_commands || (cfg->snapshot_time_outs && !cb->time_outs_snapshot))
+        return fail("go1_curriculum_resample: null buffer");
+    int e = go1_launch_curriculum(&s->bufs, cfg, cb, list, s->cfg.num_envs, (cudaStream_t)stream);
+    return e ? cuda_fail("go1_curriculum_resample launch", e) : 0;
+}
+
+extern "C" int go1_sim_reset_idx_dev(Go1Sim* s, const int32_t* env_ids, const int32_t* k_dev, const float* new_commands, const float* actions,
+                                     int post_step, int64_t common_step, float* episode_acc, void* stream) {
+    if (!s || !s->bound) return fail("go1_sim_reset_idx_dev: sim not bound");
+    if (!env_ids || !k_dev || !new_commands) return fail("go1_sim_reset_idx_dev: null ids/count/commands");
+    int e = go1_launch_reset_dev(&s->bufs, s->d_tab, env_ids, k_dev, new_commands, actions, post_step, (long long)common_step, s->gravity,
+                                 episode_acc, s->cfg.num_envs, (cudaStream_t)stream);
+    return e ? cuda_fail("go1_sim_reset_idx_dev launch", e) : 0;
 }
 
 extern "C" int go1_history_roll(const float* hist_in, const float* obs, float* hist_out, int n, int num_obs, int history_len, void* stream) {

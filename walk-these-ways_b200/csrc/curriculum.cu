@@ -1,0 +1,397 @@
+// curriculum.cu — the command curriculum of LeggedRobot._resample_commands on the device (one CTA per call).
+//
+// What the reference does on the host for every env that resets or hits the 10 s resample mark
+// (legged_robot.py:710-824 + curriculum.py:67-89,135-154) is sequential by construction: a numpy RandomState
+// (MT19937) stream per curriculum, weight updates applied success by success, cdf = cumsum(w / w.sum()).  This kernel
+// reproduces that arithmetic bit for bit (fp64, numpy's pairwise summation, genrand_res53 doubles, separate mul/add
+// instead of fma) so that the rollout never has to stop for a host round trip:
+//   A  sort the event list by env id (counting sort through a mark array: ids are unique)
+//   B  success test per env (float32 division + compare, as torch does it)
+//   C  per category: +0.2 on the successful bins (from the old values), then one neighbour bump per successful env
+//   D  category draw per env (splitmix64 stream shared with the host implementation)
+//   E  per category: (re)build the cdf if the weights changed, pull 2(1+D) n_i MT words collectively (parallel
+//      tempering, 3-phase parallel twist), searchsorted + in-cell uniform
+//   F  gait-category remap, binary phases, small-command zeroing, bookkeeping, output
+// Host twin: go1_gym/envs/base/legged_robot.py::_resample_commands_host (pinned to the reference by
+// tests/test_resample_host.py); tests/test_curriculum_gpu.py pins this kernel to the host twin.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "go1_layout.h"
+
+void go1_count_launch(int n);
+
+namespace {
+
+constexpr int CT = 1024;
+constexpr int S = GO1_EVENT_STRIDE;
+
+struct CurArgs {
+    Go1SimBuffers b;
+    Go1CurriculumConfig c;
+    Go1CurriculumBuffers cb;
+    int list, N;
+};
+
+// numpy's DOUBLE_pairwise_sum (contiguous): <8 plain loop, <=128 eight partial sums, else split at n/2 rounded down to
+// a multiple of 8 and add the two halves.  The recursion is unrolled over an explicit frame stack (depth log2(n/128)).
+__device__ double pairwise_leaf(const double* a, int n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; i++) r = __dadd_rn(r, a[i]);
+        return r;
+    }
+    double r[8];
+    for (int j = 0; j < 8; j++) r[j] = a[j];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8)
+        for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], a[i + j]);
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; i++) res = __dadd_rn(res, a[i]);
+    return res;
+}
+__device__ double pairwise_sum(const double* a, int n) {
+    struct Frame { int off, n, stage; double left; };
+    Frame st[28];
+    int sp = 0;
+    st[sp++] = {0, n, 0, 0.0};
+    double ret = 0.0;
+    while (sp > 0) {
+        Frame& f = st[sp - 1];
+        if (f.n <= 128) { ret = pairwise_leaf(a + f.off, f.n); sp--; continue; }
+        int n2 = f.n / 2;
+        n2 -= n2 % 8;
+        if (f.stage == 0) { f.stage = 1; st[sp++] = {f.off, n2, 0, 0.0}; }
+        else if (f.stage == 1) { f.left = ret; f.stage = 2; st[sp++] = {f.off + n2, f.n - n2, 0, 0.0}; }
+        else { ret = __dadd_rn(f.left, ret); sp--; }
+    }
+    return ret;
+}
+
+__device__ __forceinline__ double clip01(double x) { return fmin(fmax(x, 0.0), 1.0); }
+
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+__device__ __forceinline__ uint32_t mt_mix(uint32_t u, uint32_t v) {
+    const uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu);
+    return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+// mt19937_gen over key[624] in shared memory, by the whole CTA.  The sequential recurrence
+//   key[i] = key[(i + 397) % 624] ^ mix(key[i], key[i + 1])
+// only looks 397 ahead / 227 behind, so it splits into three parallel sweeps ([0,227) reads old words only,
+// [227,454) reads the new [0,227), [454,623) reads the new [227,396)) plus the last word.
+__device__ void mt_twist(uint32_t* key) {
+    const int t = threadIdx.x;
+    uint32_t v = 0;
+    if (t < 227) v = key[t + 397] ^ mt_mix(key[t], key[t + 1]);
+    __syncthreads();
+    if (t < 227) key[t] = v;
+    __syncthreads();
+    if (t >= 227 && t < 454) v = key[t - 227] ^ mt_mix(key[t], key[t + 1]);
+    __syncthreads();
+    if (t >= 227 && t < 454) key[t] = v;
+    __syncthreads();
+    if (t >= 454 && t < 623) v = key[t - 227] ^ mt_mix(key[t], key[t + 1]);
+    __syncthreads();
+    if (t >= 454 && t < 623) key[t] = v;
+    __syncthreads();
+    if (t == 0) key[623] = key[396] ^ mt_mix(key[623], key[0]);
+    __syncthreads();
+}
+// out[0..need) = the next `need` tempered words of the stream (uniform control flow across the CTA)
+__device__ void mt_draw(uint32_t* key, int* pos_sh, uint32_t* out, int need) {
+    const int t = threadIdx.x;
+    int done = 0;
+    while (done < need) {
+        int pos = *pos_sh;
+        __syncthreads();
+        if (pos >= 624) {
+            mt_twist(key);
+            pos = 0;
+        }
+        const int take = min(624 - pos, need - done);
+        for (int i = t; i < take; i += CT) out[done + i] = mt_temper(key[pos + i]);
+        __syncthreads();
+        if (t == 0) *pos_sh = pos + take;
+        __syncthreads();
+        done += take;
+    }
+}
+
+__device__ __forceinline__ double splitmix_next(uint64_t& st) {
+    st += 0x9E3779B97F4A7C15ull;
+    uint64_t z = st;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// numpy remainder for float32 with divisor 1 (npy_divmodf): fmod, then the sign of the result follows the divisor
+__device__ __forceinline__ float mod1(float a) {
+    float m = fmodf(a, 1.0f);
+    if (m != 0.0f) { if (m < 0.0f) m = __fadd_rn(m, 1.0f); }
+    else m = 0.0f;
+    return m;
+}
+__device__ __forceinline__ float half_plus_quarter(float x) { return __fadd_rn(__fdiv_rn(x, 2.0f), 0.25f); }
+__device__ __forceinline__ float half_minus_quarter_mod1(float x) { return mod1(__fsub_rn(__fdiv_rn(x, 2.0f), 0.25f)); }
+
+__global__ void __launch_bounds__(CT, 1) go1_curriculum_kernel(const CurArgs A) {
+    __shared__ uint32_t s_key[624];
+    __shared__ int s_pos;
+    __shared__ int s_scan[CT];
+    __shared__ int s_n;
+    __shared__ double s_d[2];
+    const int t = threadIdx.x;
+    const int N = A.N;
+    const Go1CurriculumConfig& c = A.c;
+    const Go1CurriculumBuffers& cb = A.cb;
+    const int L = c.num_bins, D = c.num_dims, ncat = c.num_categories, nc = c.num_commands;
+    const int n = A.b.event_count[A.list];
+    if (t == 0 && A.list == 0) cb.out_count[0] = n;
+    if (n <= 0) return;
+    const float* ev = A.b.events + (size_t)A.list * N * S;
+
+    int* mark = cb.scratch_i32;          // [N], all zero between calls
+    int* order = mark + N;               // [N] event slot of the p-th smallest env id
+    int* a_cat_old = order + N;
+    int* a_bin_old = a_cat_old + N;
+    int* a_ok = a_bin_old + N;
+    int* a_cat_new = a_ok + N;
+    int* a_bin_new = a_cat_new + N;
+    int* a_list = a_bin_new + N;         // [N] per-phase index list (successful bins / category members)
+    double* dd = cb.scratch_f64;         // [(D + 1) N] doubles of the current category
+    double* r2 = dd + (size_t)(D + 1) * N;   // [N] second category draw (exclusive / balanced gait modes)
+
+    // ---- A: ascending env order --------------------------------------------------------------------------------
+    for (int i = t; i < n; i += CT) mark[(int)ev[(size_t)i * S]] = i + 1;
+    __syncthreads();
+    {
+        const int chunk = (N + CT - 1) / CT;
+        const int lo = min(t * chunk, N), hi = min(lo + chunk, N);
+        int cnt = 0;
+        for (int e = lo; e < hi; e++) cnt += mark[e] != 0;
+        s_scan[t] = cnt;
+        __syncthreads();
+        for (int off = 1; off < CT; off <<= 1) {        // inclusive Hillis-Steele scan
+            const int v = (t >= off) ? s_scan[t - off] : 0;
+            __syncthreads();
+            s_scan[t] += v;
+            __syncthreads();
+        }
+        int base = s_scan[t] - cnt;
+        for (int e = lo; e < hi; e++)
+            if (mark[e]) { order[base++] = mark[e] - 1; mark[e] = 0; }
+    }
+    __syncthreads();
+
+    // ---- B: success test (legged_robot.py:727-732; curriculum.py:136-139), old bin / category ---------------------
+    for (int p = t; p < n; p += CT) {
+        const float* e = ev + (size_t)order[p] * S;
+        const int id = (int)e[0];
+        bool ok = c.num_task_keys > 0;
+        for (int q = 0; q < c.num_task_keys; q++) ok = ok && (__fdiv_rn(e[1 + c.task_col[q]], c.ep_len) > c.threshold[q]);
+        cb.out_ids[p] = id;
+        a_ok[p] = ok ? 1 : 0;
+        a_cat_old[p] = cb.env_categories[id];
+        a_bin_old[p] = cb.env_bins[id];
+    }
+    __syncthreads();
+
+    // ---- C: curriculum update, category by category (curriculum.py:141-154) --------------------------------------
+    for (int i = 0; i < ncat; i++) {
+        if (t == 0) {
+            int ns = 0;
+            for (int p = 0; p < n; p++)
+                if (a_ok[p] && a_cat_old[p] == i) a_list[ns++] = a_bin_old[p];
+            s_n = ns;
+        }
+        __syncthreads();
+        const int ns = s_n;
+        if (ns > 0) {
+            double* w = cb.weights + (size_t)i * L;
+            for (int s = t; s < ns; s += CT) dd[s] = clip01(__dadd_rn(w[a_list[s]], 0.2));     // from the OLD weights
+            __syncthreads();
+            for (int s = t; s < ns; s += CT) w[a_list[s]] = dd[s];
+            __syncthreads();
+            for (int s = 0; s < ns; s++) {
+                const int bsel = a_list[s];
+                for (int j = t; j < L; j += CT) {
+                    bool adj = true;
+                    for (int d = 0; d < D; d++) {
+                        const double g = cb.grid[(size_t)j * D + d], ce = cb.grid[(size_t)bsel * D + d], r = cb.local_range[d];
+                        adj = adj && (g >= __dsub_rn(ce, r)) && (g <= __dadd_rn(ce, r));
+                    }
+                    if (adj) w[j] = clip01(__dadd_rn(w[j], 0.2));
+                }
+                __syncthreads();
+            }
+            if (t == 0) cb.cdf_valid[i] = 0;
+        }
+        __syncthreads();
+    }
+
+    // ---- D: new categories (legged_robot.py:742-746) -----------------------------------------------------------------
+    if (t == 0) {
+        uint64_t st = cb.cat_rng[0];
+        const bool pow2 = (ncat & (ncat - 1)) == 0;
+        const double pc = 1.0 / (double)ncat;
+        for (int p = 0; p < n; p++) {
+            const double r = splitmix_next(st);
+            int cat = -1;
+            if (pow2) cat = (int)(r * (double)ncat);
+            else
+                for (int i = 0; i < ncat; i++)
+                    if (pc * i <= r && r < pc * (i + 1)) cat = i;
+            a_cat_new[p] = cat;
+            a_bin_new[p] = a_bin_old[p];
+        }
+        cb.cat_rng[0] = st;
+    }
+    __syncthreads();
+    for (int p = t; p < n; p += CT)
+        for (int d = 0; d < GO1_NUM_COMMANDS; d++) cb.out_commands[(size_t)p * GO1_NUM_COMMANDS + d] = 0.0f;
+    __syncthreads();
+
+    // ---- E: sample each category's members from its curriculum (curriculum.py:67-89) ---------------------------------
+    for (int i = 0; i < ncat; i++) {
+        if (t == 0) {
+            int ni = 0;
+            for (int p = 0; p < n; p++)
+                if (a_cat_new[p] == i) a_list[ni++] = p;
+            s_n = ni;
+        }
+        __syncthreads();
+        const int ni = s_n;
+        if (ni == 0) { __syncthreads(); continue; }
+        double* w = cb.weights + (size_t)i * L;
+        double* cdf = cb.cdf + (size_t)i * L;
+        if (!cb.cdf_valid[i]) {                 // p = w / w.sum(); cdf = p.cumsum(); cdf /= cdf[-1]
+            if (t == 0) s_d[0] = __dadd_rn(0.0, pairwise_sum(w, L));
+            __syncthreads();
+            const double tot = s_d[0];
+            for (int j = t; j < L; j += CT) cdf[j] = __ddiv_rn(w[j], tot);
+            __syncthreads();
+            if (t == 0) {
+                double acc = cdf[0];
+                for (int j = 1; j < L; j++) { acc = __dadd_rn(acc, cdf[j]); cdf[j] = acc; }
+                s_d[1] = acc;
+            }
+            __syncthreads();
+            const double last = s_d[1];
+            for (int j = t; j < L; j += CT) cdf[j] = __ddiv_rn(cdf[j], last);
+            __syncthreads();
+            if (t == 0) cb.cdf_valid[i] = 1;
+        }
+        // the RandomState stream: ni doubles for the bins, then ni x D for the in-cell positions (C order)
+        uint32_t* mt = cb.mt + (size_t)i * 625;
+        for (int j = t; j < 624; j += CT) s_key[j] = mt[j];
+        if (t == 0) s_pos = (int)mt[624];
+        __syncthreads();
+        const int nd = (D + 1) * ni;
+        mt_draw(s_key, &s_pos, cb.scratch_u32, 2 * nd);
+        for (int j = t; j < 624; j += CT) mt[j] = s_key[j];
+        if (t == 0) mt[624] = (uint32_t)s_pos;
+        for (int q = t; q < nd; q += CT) {
+            const uint32_t a = cb.scratch_u32[2 * q] >> 5, bb = cb.scratch_u32[2 * q + 1] >> 6;
+            dd[q] = __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)bb), 9007199254740992.0);
+        }
+        __syncthreads();
+        for (int m = t; m < ni; m += CT) {
+            const int p = a_list[m];
+            const double u = dd[m];
+            int lo = 0, hi = L;                 // searchsorted(cdf, u, side='right')
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+            }
+            const int idx = min(lo, L - 1);
+            a_bin_new[p] = idx;
+            for (int d = 0; d < D; d++) {
+                const double ce = cb.grid[(size_t)idx * D + d];
+                const double lo_ = __dadd_rn(ce, cb.half_bins[d]), hi_ = __dsub_rn(ce, cb.half_bins[d]);
+                const double val = __dadd_rn(lo_, __dmul_rn(__dsub_rn(hi_, lo_), dd[ni + (size_t)m * D + d]));
+                if (d < nc && d < GO1_NUM_COMMANDS) cb.out_commands[(size_t)p * GO1_NUM_COMMANDS + d] = __double2float_rn(val);
+            }
+        }
+        __syncthreads();
+    }
+
+    // second category draw of the two non-gaitwise gait modes (legged_robot.py:783, 795)
+    const bool need_r2 = nc > 5 && !c.gaitwise_curricula && (c.exclusive_phase_offset || c.balance_gait_distribution);
+    if (need_r2) {
+        if (t == 0) {
+            uint64_t st = cb.cat_rng[0];
+            for (int p = 0; p < n; p++) r2[p] = splitmix_next(st);
+            cb.cat_rng[0] = st;
+        }
+        __syncthreads();
+    }
+
+    // ---- F: gait remap (legged_robot.py:762-817), small-command zeroing (:820), bookkeeping, output ---------------------
+    for (int p = t; p < n; p += CT) {
+        float* cm = cb.out_commands + (size_t)p * GO1_NUM_COMMANDS;
+        const int id = cb.out_ids[p];
+        const int cat = a_cat_new[p];
+        if (nc > 5) {
+            if (c.gaitwise_curricula) {
+                const int kind = cat >= 0 ? c.category_kind[cat] : 0;
+                if (kind == 1) { for (int j = 5; j < 8; j++) cm[j] = half_minus_quarter_mod1(cm[j]); }
+                else if (kind == 2) { cm[5] = half_plus_quarter(cm[5]); cm[6] = 0.f; cm[7] = 0.f; }
+                else if (kind == 3) { cm[6] = half_plus_quarter(cm[6]); cm[5] = 0.f; cm[7] = 0.f; }
+                else if (kind == 4) { cm[7] = half_plus_quarter(cm[7]); cm[5] = 0.f; cm[6] = 0.f; }
+            } else if (c.exclusive_phase_offset) {
+                const double r = r2[p];
+                const bool trot = r < 0.34, pace = 0.34 <= r && r < 0.67, bound = 0.67 <= r;
+                if (pace || bound) cm[5] = 0.f;
+                if (trot || bound) cm[6] = 0.f;
+                if (trot || pace) cm[7] = 0.f;
+            } else if (c.balance_gait_distribution) {
+                const double r = r2[p];
+                const bool pronk = r <= 0.25, trot = 0.25 <= r && r < 0.50, pace = 0.50 <= r && r < 0.75, bound = 0.75 <= r;
+                if (pronk) for (int j = 5; j < 8; j++) cm[j] = half_minus_quarter_mod1(cm[j]);
+                if (trot) { cm[6] = 0.f; cm[7] = 0.f; }
+                if (pace) { cm[5] = 0.f; cm[7] = 0.f; }
+                if (bound) { cm[5] = 0.f; cm[6] = 0.f; }
+                if (trot) cm[5] = half_plus_quarter(cm[5]);
+                if (pace) cm[6] = half_plus_quarter(cm[6]);
+                if (bound) cm[7] = half_plus_quarter(cm[7]);
+            }
+            if (c.binary_phases)
+                for (int j = 5; j < 8; j++) cm[j] = mod1(__fdiv_rn(rintf(__fmul_rn(2.0f, cm[j])), 2.0f));
+        }
+        const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(cm[0], cm[0]), __fmul_rn(cm[1], cm[1])));
+        const float keep = nrm > 0.2f ? 1.0f : 0.0f;
+        cm[0] = __fmul_rn(cm[0], keep); cm[1] = __fmul_rn(cm[1], keep);
+        if (cat >= 0) { cb.env_bins[id] = a_bin_new[p]; cb.env_categories[id] = cat; }
+        if (A.list == 1) {              // periodic resample: commands take effect here (go1_sim_set_commands)
+            for (int d = 0; d < GO1_NUM_COMMANDS; d++) A.b.env_f32[(size_t)(EROW(commands) + d) * N + id] = cm[d];
+            for (int d = 0; d < GO1_NUM_COMMAND_SUMS; d++) A.b.env_f32[(size_t)(EROW(command_sums) + d) * N + id] = 0.f;
+        }
+    }
+    // extras["env_bins"] / extras["time_outs"] are snapshots taken inside reset_idx (legged_robot.py:231-234): refreshed
+    // only by a step in which some env reset, and then for ALL train envs
+    if (A.list == 0) {
+        __syncthreads();
+        for (int e = t; e < c.num_train_envs; e += CT) {
+            cb.env_bins_f32[e] = (float)cb.env_bins[e];
+            if (c.snapshot_time_outs) cb.time_outs_snapshot[e] = A.b.time_out[e];
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int go1_launch_curriculum(const Go1SimBuffers* b, const Go1CurriculumConfig* cfg, const Go1CurriculumBuffers* cb, int list, int N,
+                                     cudaStream_t st) {
+    CurArgs a;
+    a.b = *b; a.c = *cfg; a.cb = *cb; a.list = list; a.N = N;
+    go1_curriculum_kernel<<<1, CT, 0, st>>>(a);
+    go1_count_launch(1);
+    return (int)cudaGetLastError();
+}

@@ -78,6 +78,22 @@ class Go1SimBuffers(C.Structure):
         "episode_acc", "noise", "reset_rand")]
 
 
+CUR_MAX_CATEGORIES = 8
+
+
+class Go1CurriculumConfig(C.Structure):
+    _fields_ = [("num_categories", _i), ("category_kind", _i * CUR_MAX_CATEGORIES), ("num_bins", _i), ("num_dims", _i), ("num_commands", _i),
+                ("num_task_keys", _i), ("task_col", _i * 4), ("threshold", _f * 4), ("ep_len", _f),
+                ("gaitwise_curricula", _i), ("exclusive_phase_offset", _i), ("balance_gait_distribution", _i), ("binary_phases", _i),
+                ("num_train_envs", _i), ("snapshot_time_outs", _i)]
+
+
+class Go1CurriculumBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "weights", "grid", "half_bins", "local_range", "mt", "cat_rng", "env_bins", "env_categories", "env_bins_f32", "time_outs_snapshot",
+        "cdf", "cdf_valid", "scratch_i32", "scratch_u32", "scratch_f64", "out_count", "out_ids", "out_commands")]
+
+
 class Go1GemmEpilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("act", _i), ("accumulate", _i), ("extra", C.c_void_p), ("ld_extra", _i), ("w_extra", C.c_void_p),
                 ("ld_w_extra", _i), ("num_extra", _i), ("dact_y", C.c_void_p), ("ld_dact_y", _i)]
@@ -111,6 +127,9 @@ def lib():
         "go1_sim_step": ([vp, vp, C.POINTER(_f * 3), C.POINTER(_f * 3), i64, ip, vp], ip),
         "go1_sim_reset_idx": ([vp, vp, ip, vp, vp, ip, i64, vp], ip),
         "go1_sim_set_commands": ([vp, vp, ip, vp, vp], ip),
+        "go1_sizeof_curriculum": ([ip], ip),
+        "go1_curriculum_resample": ([vp, C.POINTER(Go1CurriculumConfig), C.POINTER(Go1CurriculumBuffers), ip, vp], ip),
+        "go1_sim_reset_idx_dev": ([vp, vp, vp, vp, vp, ip, i64, vp, vp], ip),
         "go1_history_roll": ([vp, vp, vp, ip, ip, ip, vp], ip),
         "go1_ppo_gae": ([vp, vp, vp, vp, vp, vp, vp, ip, ip, _f, _f, vp], ip),
         "go1_ppo_normalize_advantages": ([vp, vp, i64, i64, vp], ip),
@@ -140,6 +159,8 @@ def lib():
         raise Go1Error(f"Go1SimConfig mirror out of date: C {L.go1_sizeof_config()} vs ctypes {C.sizeof(Go1SimConfig)}")
     if L.go1_sizeof_buffers() != C.sizeof(Go1SimBuffers):
         raise Go1Error("Go1SimBuffers mirror out of date")
+    if L.go1_sizeof_curriculum(0) != C.sizeof(Go1CurriculumConfig) or L.go1_sizeof_curriculum(1) != C.sizeof(Go1CurriculumBuffers):
+        raise Go1Error("Go1Curriculum* mirrors out of date")
     _lib = L
     return L
 

@@ -23,6 +23,8 @@ class Curriculum:
         self.ls = {key: len(self.cfg[key]) for key in self.cfg}
         self.weights = np.zeros(self._l)
         self.indices = np.arange(self._l)
+        self._grid_rows = np.ascontiguousarray(self.grid.T)               # [L][D] bin centroids
+        self._half_bins = np.array([*self.bin_sizes.values()]) / 2
 
     def __len__(self):
         return self._l
@@ -55,7 +57,7 @@ class Curriculum:
             # RandomState.choice(a, n, p=p) == cdf.searchsorted(random_sample(n), side='right') (numpy legacy generator):
             # same draws from the same stream, without rebuilding the cdf on every call
             inds = self._cdf().searchsorted(self.rng.random_sample(batch_size), side='right')
-        return self.grid.T[inds], inds
+        return self._grid_rows[inds], inds
 
     def sample_uniform_from_cell(self, centroids):
         bin_sizes = np.array([*self.bin_sizes.values()])
@@ -65,8 +67,7 @@ class Curriculum:
         centroids, inds = self.sample_bins(batch_size, low=low, high=high)
         # one vectorised draw: RandomState.uniform fills its output in C order, so a [batch, D] call consumes the stream
         # exactly like the reference's `batch` sequential D-wide calls (curriculum.py:87-89) — bit-identical samples
-        bin_sizes = np.array([*self.bin_sizes.values()])
-        return self.rng.uniform(centroids + bin_sizes / 2, centroids - bin_sizes / 2), inds
+        return self.rng.uniform(centroids + self._half_bins, centroids - self._half_bins), inds
 
 
 class SumCurriculum(Curriculum):
@@ -114,13 +115,20 @@ class RewardThresholdCurriculum(Curriculum):
         self.apply_successes(bin_inds[ok], local_range)
 
     def apply_successes(self, ok_bins, local_range):
-        """Weight update for the bins of successful envs (curriculum.py:141-154)."""
+        """Weight update for the bins of successful envs (curriculum.py:141-154): +0.2 on the bins themselves (once per
+        distinct bin), then +0.2 on every bin within local_range of each successful env's bin, one env after another.
+        The neighbour lists depend only on the constant grid, so they are built once per (bin, range) and cached."""
         if len(ok_bins) == 0:
             return
-        self.weights[ok_bins] = np.clip(self.weights[ok_bins] + 0.2, 0, 1)
-        for adjacent in self.get_local_bins(ok_bins, ranges=local_range):
-            adj = np.array(adjacent.nonzero()[0])
-            self.weights[adj] = np.clip(self.weights[adj] + 0.2, 0, 1)
+        w = self.weights
+        w[ok_bins] = np.clip(w[ok_bins] + 0.2, 0, 1)
+        cache = self.__dict__.setdefault("_adjacent", {})
+        rkey = local_range if isinstance(local_range, float) else np.asarray(local_range).tobytes()
+        for b in ok_bins.reshape(-1).tolist():
+            adj = cache.get((b, rkey))
+            if adj is None:
+                adj = cache[(b, rkey)] = np.flatnonzero(self.get_local_bins(np.array([b]), ranges=local_range)[0])
+            w[adj] = np.clip(w[adj] + 0.2, 0, 1)
 
     def log(self, bin_inds, lin_vel_raw=None, ang_vel_raw=None, episode_duration=None):
         self.episode_lin_vel_raw[bin_inds] = lin_vel_raw.cpu().numpy()

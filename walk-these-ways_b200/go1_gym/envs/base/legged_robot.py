@@ -241,7 +241,8 @@ class LeggedRobot(BaseTask):
         self.curricula = [RewardThresholdCurriculum(seed=c.curriculum_seed, **kw) for _ in self.category_names]
         self.env_command_bins = np.zeros(len(env_ids), dtype=int)
         self.env_command_categories = np.zeros(len(env_ids), dtype=int)
-        self._cat_rng = np.random.default_rng(c.curriculum_seed + 1)      # category draws (torch.rand on the device in the reference)
+        from go1_b200.curriculum_dev import SplitMix64
+        self._cat_rng = SplitMix64(c.curriculum_seed + 1)      # category draws (torch.rand on the device in the reference)
         rng_keys = ["lin_vel_x", "lin_vel_y", "ang_vel_yaw", "body_height_cmd", "gait_frequency_cmd_range", "gait_phase_cmd_range",
                     "gait_offset_cmd_range", "gait_bound_cmd_range", "gait_duration_cmd_range", "footswing_height_range",
                     "body_pitch_range", "body_roll_range", "stance_width_range", "stance_length_range", "aux_reward_coef_range"]
@@ -263,6 +264,9 @@ class LeggedRobot(BaseTask):
         self._ep_len_dirty = False
         self._time_outs = torch.zeros(self.num_train_envs, dtype=torch.bool, device=self.device)
         self._env_bins_dev = torch.zeros(self.num_train_envs, device=self.device)
+        self._env_bins_host = [torch.zeros(self.num_train_envs).pin_memory() for _ in range(2)]      # ping-pong upload staging
+        self._env_bins_host_np = [t.numpy() for t in self._env_bins_host]
+        self._env_bins_flip = 0
         self._env_bins_dirty = True
         self.actions = torch.zeros(self.num_envs, self.num_actions, device=self.device)
         self.measured_heights = 0
@@ -346,20 +350,89 @@ class LeggedRobot(BaseTask):
         self.core.episode_length_buf.copy_(value.to(self.device).to(torch.int32))
         self._ep_len_dirty = True
 
+    @property
+    def actions(self):
+        """The last actions clipped to +-clip_actions (legged_robot.py:64-65); the kernel clips its own copy."""
+        a = self.__dict__.get("_raw_actions")
+        clip = self.cfg.normalization.clip_actions
+        return None if a is None else torch.clip(a, -clip, clip)
+
+    @actions.setter
+    def actions(self, value):
+        self._raw_actions = value
+
     # ------------------------------------------------------------------ stepping
     def step(self, actions):
         """legged_robot.py:60-88."""
         core = self.core
         actions = actions.to(self.device, dtype=torch.float32).contiguous()
-        self.actions = torch.clip(actions, -self.cfg.normalization.clip_actions, self.cfg.normalization.clip_actions)
+        self._raw_actions = actions                 # `self.actions` (the clipped copy, legged_robot.py:64-65) is produced on read
         self.common_step_counter += 1
+        dc = self._device_curriculum()
+        if dc is not None:
+            return self._step_device(dc, actions)
         self._apply_pending_interval_resample()
         core.step(actions, common_step=self.common_step_counter, mode=0)
         rid, rsum, iid, isum = core.fetch_events()
         self._pending_interval = (iid, isum)
         self._post_physics_step_callback_host()
         if len(rid):
-            self.reset_idx(torch.from_numpy(rid), _sums=rsum, _post_step=True, _actions=actions)
+            self._reset_sorted(rid, rsum, True, actions)
+        return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    # ------------------------------------------------------------------ device-resident curriculum (no host round trip)
+    device_curriculum = True        # class switch; GO1_HOST_CURRICULUM=1 in the environment forces the host path
+
+    def _device_curriculum(self):
+        dc = self.__dict__.get("_dev_cur", False)
+        if dc is False:
+            import os
+            dc = None
+            if self.device_curriculum and not os.environ.get("GO1_HOST_CURRICULUM") and self.core.noise is None and self.core.reset_rand is None:
+                from go1_b200.curriculum_dev import DeviceCurriculum
+                dc = DeviceCurriculum(self, _LOCAL_RANGE, _TASK_KEYS)
+            self._dev_cur = dc
+        return dc
+
+    def _curriculum_to_host(self, keep_device=False):
+        dc = self.__dict__.get("_dev_cur")
+        if dc:
+            dc.to_host(keep_device=keep_device)
+
+    def _step_device(self, dc, actions):
+        """step() with the curriculum on the device: five stream-ordered launches, no synchronisation.
+        [resample list 1 (envs marked last step)] -> [step kernel] -> [resample list 0] -> [reset kernel]."""
+        core = self.core
+        if self._ep_len_dirty:          # episode lengths were overwritten from outside: rebuild the pending interval list
+            interval = int(self.sim_cfg.resampling_interval)
+            ep = core.episode_length_buf
+            ids = torch.nonzero((ep + 1) % interval == 0).squeeze(1) if interval > 0 else ep.new_zeros(0, dtype=torch.long)
+            k = int(ids.numel())
+            if k:
+                rows = [capi.REWARD_TERMS.index(key) for key in _TASK_KEYS]
+                core.events[1, :k, 0] = ids.float()
+                core.events[1, :k, 1:5] = core.env("command_sums")[rows][:, ids].t()
+            core.event_count[1] = k
+            self._ep_len_dirty = False
+        dc.to_device()
+        dc.resample(1)
+        core.step(actions, common_step=self.common_step_counter, mode=0)
+        self._post_physics_step_callback_host()
+        acc = torch.zeros(capi.NUM_EPISODE_SUMS + 1, device=self.device)
+        dc.resample(0)
+        dc.reset_envs(actions, True, self.common_step_counter, acc)
+        # a step without a reset carries the last non-empty sums forward (the reference's extras entry just stays in place)
+        prev = self.__dict__.get("_episode_acc_prev")
+        if prev is not None:
+            torch.where(acc[capi.NUM_EPISODE_SUMS:] > 0, acc, prev, out=acc)
+        self._episode_acc_prev = acc
+        ex = self.extras
+        ex["train/episode"] = _LazyDict(self._episode_builder(acc, may_be_empty=True))
+        if self.cfg.commands.command_curriculum:
+            ex["env_bins"] = dc.env_bins_f32
+            ex["curriculum/distribution"] = _LazyDict(self._distribution_builder())
+        if self.cfg.env.send_timeouts:
+            ex["time_outs"] = dc.time_outs
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
 
     def _apply_pending_interval_resample(self):
@@ -391,57 +464,77 @@ class LeggedRobot(BaseTask):
         raise NotImplementedError("fused into go1_sim_step; see step()")
 
     # ------------------------------------------------------------------ commands / resets
-    def _resample_commands_host(self, env_ids, task_sums):
-        """legged_robot.py:710-824 for env ids (numpy, ascending) whose 4 task command sums are `task_sums`.
-        Returns the new commands [k, 15]; updates curricula, env_command_bins/categories."""
-        cfg = self.cfg
-        k = len(env_ids)
+    def _resample_constants(self):
+        """(ep_len float32, columns of the 4 task sums that have an active reward, their float32 success thresholds)."""
         hc = self.__dict__.get("_resample_consts")
         if hc is None:
+            cfg = self.cfg
             timesteps = int(cfg.commands.resampling_time / self.dt)
             ep_len = min(cfg.env.max_episode_length, timesteps)
             present = [key for key in _TASK_KEYS if key in self.reward_scales]
             cols = [_TASK_KEYS.index(key) for key in present]
             thr = np.array([self.curriculum_thresholds[key] * self.reward_scales[key] for key in present], dtype=np.float32)
             hc = self._resample_consts = (np.float32(ep_len), cols, thr)
-        ep_len, cols, thr = hc
-        cats_old = self.env_command_categories[env_ids]
+        return hc
+
+    def _resample_commands_host(self, env_ids, task_sums):
+        """legged_robot.py:710-824 for env ids (numpy, ascending) whose 4 task command sums are `task_sums`.
+        Returns the new commands [k, 15]; updates curricula, env_command_bins/categories.  Runs on the critical path
+        between the event D2H and the reset launch, so it is written for few numpy calls at k ~ 5; bit-exactness
+        against the reference is pinned by tests/test_resample_host.py."""
+        cfg = self.cfg
+        k = len(env_ids)
+        ep_len, cols, thr = self._resample_constants()
+        ncat = len(self.category_names)
+        nc = cfg.commands.num_commands
         if len(cols) > 0:
             # success = every task reward above its threshold, in float32 like the reference's torch comparison
-            ok = (task_sums[:, cols].astype(np.float32) / ep_len > thr).all(axis=1)
+            ok = (task_sums[:, cols].astype(np.float32, copy=False) / ep_len > thr).all(axis=1)
             if ok.any():
-                old_bins = self.env_command_bins[env_ids]
-                for i, curriculum in enumerate(self.curricula):
-                    m = ok & (cats_old == i)
+                ok_ids = env_ids[ok]
+                ok_bins, ok_cats = self.env_command_bins[ok_ids], self.env_command_categories[ok_ids]
+                for i in (range(ncat) if ncat > 1 else (0,)):
+                    m = ok_cats == i
                     if m.any():
-                        curriculum.apply_successes(old_bins[m], _LOCAL_RANGE)
+                        self.curricula[i].apply_successes(ok_bins[m], _LOCAL_RANGE)
         # new categories: host RNG (the reference draws torch.rand on the device; only the distribution matters)
         r = self._cat_rng.random(k)
-        p = 1. / len(self.category_names)
-        new_cmds = np.zeros((k, capi.NUM_COMMANDS), dtype=np.float32)
-        cat_masks = [np.logical_and(p * i <= r, r < p * (i + 1)) for i in range(len(self.category_names))]
-        for i, (category, mask, curriculum) in enumerate(zip(self.category_names, cat_masks, self.curricula)):
-            n = int(mask.sum())
-            if n == 0:
+        if ncat in (1, 2, 4, 8):       # p = 1/ncat is exact: p*i <= r < p*(i+1)  <=>  floor(r * ncat) == i
+            cat = (r * ncat).astype(np.intp)
+        else:
+            p = 1. / ncat
+            cat = np.full(k, -1, dtype=np.intp)
+            for i in range(ncat):
+                cat[np.logical_and(p * i <= r, r < p * (i + 1))] = i
+        c = np.zeros((k, capi.NUM_COMMANDS), dtype=np.float32)
+        new_bins = self.env_command_bins[env_ids]
+        new_cats = self.env_command_categories[env_ids]
+        members = [None] * ncat
+        for i in range(ncat):
+            m = np.flatnonzero(cat == i) if ncat > 1 else np.arange(k)
+            members[i] = m
+            if len(m) == 0:
                 continue
-            cmds, bins = curriculum.sample(batch_size=n)
-            ids = env_ids[mask]
-            self.env_command_bins[ids] = bins
-            self.env_command_categories[ids] = i
-            new_cmds[mask, :cfg.commands.num_commands] = cmds[:, :cfg.commands.num_commands].astype(np.float32)
-        c = new_cmds
-        if cfg.commands.num_commands > 5:
+            cmds, bins = self.curricula[i].sample(batch_size=len(m))
+            new_bins[m] = bins
+            new_cats[m] = i
+            c[m, :nc] = cmds[:, :nc]            # float64 -> float32 on assignment, like torch.Tensor(new_commands)
+        self.env_command_bins[env_ids] = new_bins
+        self.env_command_categories[env_ids] = new_cats
+        q = np.float32(0.25)
+        if nc > 5:
             if cfg.commands.gaitwise_curricula:
-                for category, m in zip(self.category_names, cat_masks):
+                for category, m in zip(self.category_names, members):
+                    if len(m) == 0:
+                        continue
                     if category == "pronk":
-                        for j in (5, 6, 7):
-                            c[m, j] = np.mod(c[m, j] / 2 - np.float32(0.25), 1)
+                        c[m, 5:8] = np.mod(c[m, 5:8] / 2 - q, 1)
                     elif category == "trot":
-                        c[m, 5] = c[m, 5] / 2 + np.float32(0.25); c[m, 6] = 0; c[m, 7] = 0
+                        c[m, 5] = c[m, 5] / 2 + q; c[m, 6:8] = 0
                     elif category == "pace":
-                        c[m, 5] = 0; c[m, 6] = c[m, 6] / 2 + np.float32(0.25); c[m, 7] = 0
+                        c[m, 6] = c[m, 6] / 2 + q; c[m, 5] = 0; c[m, 7] = 0
                     elif category == "bound":
-                        c[m, 5] = 0; c[m, 6] = 0; c[m, 7] = c[m, 7] / 2 + np.float32(0.25)
+                        c[m, 7] = c[m, 7] / 2 + q; c[m, 5:7] = 0
             elif cfg.commands.exclusive_phase_offset:
                 r2 = self._cat_rng.random(k)
                 trot, pace, bound = r2 < 0.34, np.logical_and(0.34 <= r2, r2 < 0.67), 0.67 <= r2
@@ -451,15 +544,14 @@ class LeggedRobot(BaseTask):
                 pronk, trot = r2 <= 0.25, np.logical_and(0.25 <= r2, r2 < 0.50)
                 pace, bound = np.logical_and(0.50 <= r2, r2 < 0.75), 0.75 <= r2
                 for j in (5, 6, 7):
-                    c[pronk, j] = np.mod(c[pronk, j] / 2 - np.float32(0.25), 1)
+                    c[pronk, j] = np.mod(c[pronk, j] / 2 - q, 1)
                 c[trot, 6] = 0; c[trot, 7] = 0; c[pace, 5] = 0; c[pace, 7] = 0; c[bound, 5] = 0; c[bound, 6] = 0
-                c[trot, 5] = c[trot, 5] / 2 + np.float32(0.25); c[pace, 6] = c[pace, 6] / 2 + np.float32(0.25)
-                c[bound, 7] = c[bound, 7] / 2 + np.float32(0.25)
+                c[trot, 5] = c[trot, 5] / 2 + q; c[pace, 6] = c[pace, 6] / 2 + q
+                c[bound, 7] = c[bound, 7] / 2 + q
             if cfg.commands.binary_phases:
-                for j in (5, 6, 7):
-                    c[:, j] = np.mod(np.round(2 * c[:, j]) / np.float32(2.0), 1)     # torch.round == np.round (half to even)
-        small = np.linalg.norm(c[:, :2], axis=1) > 0.2
-        c[:, :2] *= small[:, None]
+                c[:, 5:8] = np.mod(np.round(2 * c[:, 5:8]) / np.float32(2.0), 1)     # torch.round == np.round (half to even)
+        x, y = c[:, 0], c[:, 1]
+        c[:, :2] *= (np.sqrt(x * x + y * y) > np.float32(0.2))[:, None]          # torch.norm(...) > 0.2 in float32
         return c
 
     def _resample_commands(self, env_ids):
@@ -467,6 +559,7 @@ class LeggedRobot(BaseTask):
         ids = np.sort(np.asarray(env_ids.cpu() if hasattr(env_ids, "cpu") else env_ids, dtype=np.int64))
         if len(ids) == 0:
             return
+        self._curriculum_to_host()
         idx = torch.as_tensor(ids, device=self.device)
         cs = self.core.env("command_sums")[[capi.REWARD_TERMS.index(k) for k in _TASK_KEYS]][:, idx].t().cpu().numpy()
         self.core.set_commands(ids, self._resample_commands_host(ids, cs))
@@ -477,58 +570,77 @@ class LeggedRobot(BaseTask):
         if len(env_ids) == 0:
             return
         ids = np.sort(np.asarray(env_ids.cpu() if hasattr(env_ids, "cpu") else env_ids, dtype=np.int64))
-        core = self.core
+        self._curriculum_to_host()
         if _sums is None:
             idx = torch.as_tensor(ids, device=self.device)
-            _sums = core.env("command_sums")[[capi.REWARD_TERMS.index(k) for k in _TASK_KEYS]][:, idx].t().cpu().numpy()
-        cmds = self._resample_commands_host(ids, _sums)
+            _sums = self.core.env("command_sums")[[capi.REWARD_TERMS.index(k) for k in _TASK_KEYS]][:, idx].t().cpu().numpy()
+        self._reset_sorted(ids, _sums, _post_step, _actions)
+
+    def _reset_sorted(self, ids, sums, post_step, actions):
+        """reset_idx for ascending numpy ids whose task command sums are already on the host (the step() path)."""
+        core = self.core
+        cmds = self._resample_commands_host(ids, sums)
         core.episode_acc.zero_()
-        core.reset_idx(ids, cmds, actions=_actions, post_step=_post_step, common_step=self.common_step_counter)
+        core.reset_idx(ids, cmds, actions=actions, post_step=post_step, common_step=self.common_step_counter)
         self._env_bins_dirty = True
         self._fill_extras(ids)
+
+    def _episode_builder(self, acc, may_be_empty=False):
+        """extras["train/episode"] of legged_robot.py:180-229 from one snapshot `acc` of the device accumulators
+        (episode sums of the envs reset in that step + their count).  may_be_empty: no env has reset yet -> no entries."""
+        core, env = self.core, self
+
+        def build_episode():
+            if may_be_empty and float(acc[capi.NUM_EPISODE_SUMS]) == 0.0:
+                return {}
+            means = acc[:capi.NUM_EPISODE_SUMS] / acc[capi.NUM_EPISODE_SUMS].clamp(min=1.0)
+            ep = {}
+            for name in list(env.reward_scales) + ["total"]:
+                if name == "total":
+                    ep["rew_total"] = means[capi.NUM_REWARD_TERMS]
+                elif name in capi.REWARD_TERMS:
+                    ep["rew_" + name] = means[capi.REWARD_TERMS.index(name)]
+            if env.cfg.terrain.curriculum:
+                ep["terrain_level"] = torch.mean(env.terrain_levels[:env.num_train_envs].float())
+            if env.cfg.commands.command_curriculum:
+                env._curriculum_to_host(keep_device=True)
+                cmd = core.env("commands")
+                mins, maxs = cmd.min(dim=1).values, cmd.max(dim=1).values
+                for idx, nm in ((8, "duration"), (7, "bound"), (6, "offset"), (5, "phase"), (4, "freq"), (0, "x_vel"), (1, "y_vel"), (2, "yaw_vel")):
+                    ep[f"min_command_{nm}"] = mins[idx]
+                    ep[f"max_command_{nm}"] = maxs[idx]
+                if env.cfg.commands.num_commands > 9:
+                    ep["min_command_swing_height"] = mins[9]
+                    ep["max_command_swing_height"] = maxs[9]
+                for curriculum, category in zip(env.curricula, env.category_names):
+                    ep[f"command_area_{category}"] = np.sum(curriculum.weights) / curriculum.weights.shape[0]
+                ep["min_action"] = torch.min(env.actions)
+                ep["max_action"] = torch.max(env.actions)
+            return ep
+        return build_episode
+
+    def _distribution_builder(self):
+        def build():
+            self._curriculum_to_host(keep_device=True)
+            return {**{f"weights_{c}": cur.weights for cur, c in zip(self.curricula, self.category_names)},
+                    **{f"grid_{c}": cur.grid for cur, c in zip(self.curricula, self.category_names)}}
+        return build
 
     def _fill_extras(self, ids):
         """legged_robot.py:180-234.  Everything the logger consumes is produced lazily from ONE snapshot of the device
         accumulators taken here (a clone, no host sync); the dict values are materialised when somebody reads them."""
         core, ex = self.core, self.extras
         if (ids < self.num_train_envs).any():
-            acc = core.episode_acc.clone()
-            cmd_snapshot = None
-            env = self
-
-            def build_episode():
-                means = acc[:capi.NUM_EPISODE_SUMS] / acc[capi.NUM_EPISODE_SUMS].clamp(min=1.0)
-                ep = {}
-                for name in list(env.reward_scales) + ["total"]:
-                    if name == "total":
-                        ep["rew_total"] = means[capi.NUM_REWARD_TERMS]
-                    elif name in capi.REWARD_TERMS:
-                        ep["rew_" + name] = means[capi.REWARD_TERMS.index(name)]
-                if env.cfg.terrain.curriculum:
-                    ep["terrain_level"] = torch.mean(env.terrain_levels[:env.num_train_envs].float())
-                if env.cfg.commands.command_curriculum:
-                    cmd = core.env("commands")
-                    mins, maxs = cmd.min(dim=1).values, cmd.max(dim=1).values
-                    for idx, nm in ((8, "duration"), (7, "bound"), (6, "offset"), (5, "phase"), (4, "freq"), (0, "x_vel"), (1, "y_vel"), (2, "yaw_vel")):
-                        ep[f"min_command_{nm}"] = mins[idx]
-                        ep[f"max_command_{nm}"] = maxs[idx]
-                    if env.cfg.commands.num_commands > 9:
-                        ep["min_command_swing_height"] = mins[9]
-                        ep["max_command_swing_height"] = maxs[9]
-                    for curriculum, category in zip(env.curricula, env.category_names):
-                        ep[f"command_area_{category}"] = np.sum(curriculum.weights) / curriculum.weights.shape[0]
-                    ep["min_action"] = torch.min(env.actions)
-                    ep["max_action"] = torch.max(env.actions)
-                return ep
-            ex["train/episode"] = _LazyDict(build_episode)
+            ex["train/episode"] = _LazyDict(self._episode_builder(core.episode_acc.clone()))
         if self.cfg.commands.command_curriculum:
             if self._env_bins_dirty:
-                self._env_bins_dev = torch.as_tensor(self.env_command_bins[:self.num_train_envs], dtype=torch.float32).to(self.device, non_blocking=True)
+                f = self._env_bins_flip = self._env_bins_flip ^ 1
+                self._env_bins_host_np[f][:] = self.env_command_bins[:self.num_train_envs]
+                self._env_bins_dev.copy_(self._env_bins_host[f], non_blocking=True)
                 self._env_bins_dirty = False
                 core.h2d_bytes += 4 * self.num_train_envs
             ex["env_bins"] = self._env_bins_dev
-            ex["curriculum/distribution"] = _LazyDict(lambda: {**{f"weights_{c}": cur.weights for cur, c in zip(self.curricula, self.category_names)},
-                                                               **{f"grid_{c}": cur.grid for cur, c in zip(self.curricula, self.category_names)}})
+            ex["curriculum/distribution"] = _LazyDict(self._distribution_builder())
         if self.cfg.env.send_timeouts:
             self._time_outs = core.timeout_u8[:self.num_train_envs].bool()      # a copy taken at reset time (legged_robot.py:234)
             ex["time_outs"] = self._time_outs

@@ -17,11 +17,11 @@ class VelocityTrackingEasyEnv(LeggedRobot):
         sim_params = types.SimpleNamespace(**{k: v for k, v in vars(cfg.sim).items() if not k.startswith("_")})
         super().__init__(cfg, sim_params, physics_engine, sim_device, headless, eval_cfg, initial_dynamics_dict)
 
-    def step(self, actions):
-        obs, priv, rew, reset, extras = super().step(actions)
-        extras["privileged_obs"] = priv
+    def _register_lazy_extras(self):
+        """The 12 per-step numpy extras of the reference (velocity_tracking/__init__.py:27-42): registered once; each
+        one reads the live device state when (and only when) a consumer looks it up."""
         np_ = lambda t: t.detach().cpu().numpy()
-        c = self
+        c, extras = self, self.extras
         extras.lazy("joint_pos", lambda: np_(c.dof_pos))
         extras.lazy("joint_vel", lambda: np_(c.dof_vel))
         extras.lazy("joint_pos_target", lambda: np_(c.joint_pos_target))
@@ -34,6 +34,13 @@ class VelocityTrackingEasyEnv(LeggedRobot):
         extras.lazy("foot_positions", lambda: np_(c.foot_positions).copy())
         extras.lazy("body_pos", lambda: np_(c.root_states[:, 0:3]))
         extras.lazy("torques", lambda: np_(c.torques))
+        self._lazy_extras_of = id(extras)
+
+    def step(self, actions):
+        obs, priv, rew, reset, extras = super().step(actions)
+        extras["privileged_obs"] = priv
+        if self.__dict__.get("_lazy_extras_of") != id(extras):
+            self._register_lazy_extras()
         return obs, rew, reset, extras
 
     def reset(self):
