@@ -256,6 +256,8 @@ typedef struct Go1GemmEpilogue {
     const float* bias; int32_t act, accumulate;
     const float* extra; int32_t ld_extra; const float* w_extra; int32_t ld_w_extra, num_extra;
     const float* dact_y; int32_t ld_dact_y;
+    int32_t lead_cols;   /* > 0: the extra columns and the activation apply to output columns < lead_cols only (the rest gets
+                          * bias only): lets several first layers that share their input run as ONE product (impl 1) */
 } Go1GemmEpilogue;
 int go1_gemm_ex(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                 float* C, int ldc, const Go1GemmEpilogue* ep, int impl, void* stream);
@@ -264,6 +266,10 @@ int go1_gemm_ex(int transA, int transB, int M, int N, int K, const float* A, int
 int go1_transpose(const float* src, int lds, float* dst, int ldd, int rows, int cols, void* stream);
 /* dz = dy * ELU'(z) computed from the saved layer output y (autograd of nn.ELU). dz may alias dy. */
 int go1_elu_backward(const float* y, int ldy, const float* dy, int lddy, float* dz, int lddz, int M, int N, void* stream);
+/* Finishes a first layer whose trailing-input term was left out of the product: y = act(y + extra[m][:E] . w_extra[n][:E])
+ * in place (E <= 4; act 0/1). */
+int go1_mlp_extra_forward(float* y, int ldy, const float* extra, int ldex, const float* w_extra, int ldw, int M, int o, int E, int act,
+                          void* stream);
 /* Backward of the E (<= 4) trailing input columns of a first layer (the `latent` / privileged columns of
  * cat(obs_history, .), actor_critic.py:115,143), one bandwidth-bound pass over dz [M][o]:
  *   g_w_extra[j][t] (+)= sum_m dz[m][j] extra[m][t];   dextra[m][t] = sum_j dz[m][j] w_extra[j][t] (if dextra != NULL). */

@@ -107,6 +107,7 @@ struct GemmArgs {
     int M, N, K, ldc, act, accumulate, kb_per_split;
     const float* ex; const float* wex; const float* aux;      // fused epilogue operands (see Go1GemmEpilogue)
     int ldex, ldwex, nex, ldaux;
+    int lead;                // > 0: extra columns + activation only for output columns < lead
     int amn, bmn;            // operand is MN-major in HBM (A given as [K][M], B given as [K][N]); persistent kernel only
 };
 
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_kernel(const __grid_constant
                         float e[4] = {0.f, 0.f, 0.f, 0.f};
                         for (int t = 0; t < g.nex; t++) e[t] = __ldg(g.ex + (size_t)row * g.ldex + t);
 #pragma unroll
-                        for (int j = 0; j < 32; j++) if (j < ncols) {
+                        for (int j = 0; j < 32; j++) if (j < ncols && (g.lead <= 0 || col0 + j < g.lead)) {
                             const float* w = g.wex + (size_t)(col0 + j) * g.ldwex;
                             float acc = 0.f;
                             for (int t = 0; t < g.nex; t++) acc = fmaf(e[t], __ldg(w + t), acc);
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_kernel(const __grid_constant
                     }
                     if (g.act == 1) {
 #pragma unroll
-                        for (int j = 0; j < 32; j++) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
+                        for (int j = 0; j < 32; j++) if (g.lead <= 0 || col0 + j < g.lead) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
                     } else if (g.act == 2) {   // multiply by ELU'(z) from the saved activation y: 1 if y > 0 else y + 1
                         const float* arow = g.aux + (size_t)row * g.ldaux + col0;
 #pragma unroll
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_persistent(const __grid_cons
                             float e[4] = {0.f, 0.f, 0.f, 0.f};
                             for (int tt = 0; tt < g.nex; tt++) e[tt] = __ldg(g.ex + (size_t)row * g.ldex + tt);
 #pragma unroll
-                            for (int jj = 0; jj < 32; jj++) if (jj < ncols) {
+                            for (int jj = 0; jj < 32; jj++) if (jj < ncols && (g.lead <= 0 || col0 + jj < g.lead)) {
                                 const float* w = g.wex + (size_t)(col0 + jj) * g.ldwex;
                                 float acc = 0.f;
                                 for (int tt = 0; tt < g.nex; tt++) acc = fmaf(e[tt], __ldg(w + tt), acc);
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_persistent(const __grid_cons
                         }
                         if (g.act == 1) {
 #pragma unroll
-                            for (int jj = 0; jj < 32; jj++) v[jj] = v[jj] > 0.f ? v[jj] : expm1f(v[jj]);
+                            for (int jj = 0; jj < 32; jj++) if (g.lead <= 0 || col0 + jj < g.lead) v[jj] = v[jj] > 0.f ? v[jj] : expm1f(v[jj]);
                         } else if (g.act == 2) {
                             const float* arow = g.aux + (size_t)row * g.ldaux + col0;
 #pragma unroll
@@ -518,7 +519,7 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
     g.C = Cm; g.bias = bias; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.act = act; g.accumulate = accumulate;
     g.ex = ep->extra; g.ldex = ep->ld_extra; g.wex = ep->w_extra; g.ldwex = ep->ld_w_extra; g.nex = ep->extra ? ep->num_extra : 0;
     g.aux = ep->dact_y; g.ldaux = ep->ld_dact_y;
-    g.amn = amn; g.bmn = bmn;
+    g.amn = amn; g.bmn = bmn; g.lead = ep->lead_cols;
     if (g.nex < 0 || g.nex > 4) return go1_set_error("go1_gemm_ex: num_extra must be 0..4");
     if (act == 2 && !g.aux) return go1_set_error("go1_gemm_ex: act 2 needs dact_y");
     const int num_kb = (K + BK - 1) / BK;
@@ -527,7 +528,7 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
     const int BN = wide ? 256 : ((N > 64) ? 128 : (N > 32 ? 64 : 32));
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     int splits = 1;
-    if (tiles < 148 && num_kb >= 16 && g.nex == 0 && act != 2) { splits = (2 * 148) / tiles; if (splits > num_kb / 16) splits = num_kb / 16; if (splits < 1) splits = 1; }   // one wave of 2 CTAs/SM, >= 16 k-blocks each
+    if (tiles < 148 && num_kb >= 16 && g.nex == 0 && act != 2 && g.lead <= 0) { splits = (2 * 148) / tiles; if (splits > num_kb / 16) splits = num_kb / 16; if (splits < 1) splits = 1; }   // one wave of 2 CTAs/SM, >= 16 k-blocks each
     g.kb_per_split = (num_kb + splits - 1) / splits;
     splits = (num_kb + g.kb_per_split - 1) / g.kb_per_split;
     CUtensorMap ma, mb;

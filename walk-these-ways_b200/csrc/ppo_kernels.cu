@@ -247,6 +247,7 @@ extern "C" int go1_gemm_ex(int transA, int transB, int M, int N, int K, const fl
     cudaStream_t st = (cudaStream_t)stream;
     if (impl == 1) return go1_gemm_tf32(transA, transB, M, N, K, A, lda, B, ldb, Cm, ldc, epi, st);
     if (impl != 0) return go1_set_error("go1_gemm: unknown impl");
+    if (epi->lead_cols > 0) return go1_set_error("go1_gemm_ex: lead_cols is implemented by impl 1 only");
     const float* bias = epi->bias; const int act = epi->act, accumulate = epi->accumulate;
     SgemmEp ep; ep.ex = epi->extra; ep.wex = epi->w_extra; ep.aux = epi->dact_y; ep.ldex = epi->ld_extra; ep.ldwex = epi->ld_w_extra;
     ep.nex = epi->extra ? epi->num_extra : 0; ep.ldaux = epi->ld_dact_y;
@@ -279,6 +280,27 @@ extern "C" int go1_gemm(int transA, int transB, int M, int N, int K, const float
     memset(&ep, 0, sizeof ep);
     ep.bias = bias; ep.act = act; ep.accumulate = accumulate;
     return go1_gemm_ex(transA, transB, M, N, K, A, lda, B, ldb, Cm, ldc, &ep, impl, stream);
+}
+
+// y = act(y + extra . w_extra^T) in place: the deferred trailing-input term + activation of a first layer
+__global__ void extra_fwd_kernel(float* __restrict__ y, int ldy, const float* __restrict__ ex, int ldex, const float* __restrict__ wex, int ldw,
+                                 int M, int o, int E, int act) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)M * o) return;
+    const int m = (int)(i / o), n = (int)(i - (size_t)m * o);
+    float v = y[(size_t)m * ldy + n];
+    float acc = 0.f;
+    for (int t = 0; t < E; t++) acc = fmaf(__ldg(ex + (size_t)m * ldex + t), __ldg(wex + (size_t)n * ldw + t), acc);
+    v += acc;
+    if (act == 1) v = v > 0.f ? v : expm1f(v);
+    y[(size_t)m * ldy + n] = v;
+}
+extern "C" int go1_mlp_extra_forward(float* y, int ldy, const float* extra, int ldex, const float* w_extra, int ldw, int M, int o, int E, int act,
+                                     void* stream) {
+    if (!y || !extra || !w_extra || M <= 0 || o <= 0 || E < 1 || E > 4 || act < 0 || act > 1) return go1_set_error("go1_mlp_extra_forward: bad arguments");
+    const size_t tot = (size_t)M * o;
+    extra_fwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(y, ldy, extra, ldex, w_extra, ldw, M, o, E, act); go1_count_launch(1);
+    return cuda_rc("go1_mlp_extra_forward");
 }
 
 // dz = dy * ELU'(y) from the saved output y (alpha = 1: ELU' = 1 for y > 0 else y + 1)

@@ -96,7 +96,7 @@ class Go1CurriculumBuffers(C.Structure):
 
 class Go1GemmEpilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("act", _i), ("accumulate", _i), ("extra", C.c_void_p), ("ld_extra", _i), ("w_extra", C.c_void_p),
-                ("ld_w_extra", _i), ("num_extra", _i), ("dact_y", C.c_void_p), ("ld_dact_y", _i)]
+                ("ld_w_extra", _i), ("num_extra", _i), ("dact_y", C.c_void_p), ("ld_dact_y", _i), ("lead_cols", _i)]
 
 
 class Go1Error(RuntimeError):
@@ -139,6 +139,7 @@ def lib():
         "go1_gemm_tf32_set_wide": ([ip], None),
         "go1_transpose": ([vp, ip, vp, ip, ip, ip, vp], ip),
         "go1_elu_backward": ([vp, ip, vp, ip, vp, ip, ip, ip, vp], ip),
+        "go1_mlp_extra_forward": ([vp, ip, vp, ip, vp, ip, ip, ip, ip, ip, vp], ip),
         "go1_mlp_extra_backward": ([vp, ip, vp, ip, vp, ip, vp, ip, vp, ip, ip, ip, ip, ip, vp], ip),
         "go1_skinny_dgrad": ([vp, ip, vp, ip, vp, ip, vp, ip, ip, ip, ip, vp], ip),
         "go1_colsum": ([vp, ip, vp, ip, ip, ip, vp], ip),

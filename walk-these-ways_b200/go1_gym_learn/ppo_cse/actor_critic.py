@@ -91,8 +91,9 @@ class _Net:
     def _p(x):
         return x.data_ptr() if torch.is_tensor(x) else x
 
-    def _gemm(self, ta, tb, M, N, K, A, lda, B, ldb, Cm, ldc, bias=None, act=0, acc=0, impl=0, extra=None, w_extra=0, ld_w_extra=0, dact_y=None):
+    def _gemm(self, ta, tb, M, N, K, A, lda, B, ldb, Cm, ldc, bias=None, act=0, acc=0, impl=0, extra=None, w_extra=0, ld_w_extra=0, dact_y=None, lead_cols=0):
         ep = self._ep
+        ep.lead_cols = lead_cols
         ep.bias = self._p(bias) if bias is not None else None
         ep.act, ep.accumulate = act, acc
         if extra is not None:
@@ -118,11 +119,16 @@ class _Net:
         p = x.data_ptr() if torch.is_tensor(x) else x
         return (p & 15) == 0 and (ld & 3) == 0
 
-    def forward(self, x, ldx, K0, extra, M, impl, tag="a"):
-        """x: [M][K0] rows with stride ldx; extra: [M][E] contiguous or None. Returns list of layer outputs."""
+    def forward(self, x, ldx, K0, extra, M, impl, tag="a", first_out=None):
+        """x: [M][K0] rows with stride ldx; extra: [M][E] contiguous or None. Returns list of layer outputs.
+        first_out: the first layer's activated output if the caller already produced it (ActorCritic.forward_all)."""
         outs, inp, ld_in = [], x, ldx
         n = len(self.specs)
         for li, (wo, bo, o, i) in enumerate(self.specs):
+            if li == 0 and first_out is not None:
+                outs.append(first_out)
+                inp, ld_in = first_out, first_out.stride(0)
+                continue
             y = self._buf((tag, li), M, o)
             W = self.flat[wo:wo + o * i]
             b = self.flat[bo:bo + o]
@@ -142,7 +148,7 @@ class _Net:
             else:
                 self._gemm(0, 1, M, o, K, inp, ld_in, Wm, ldw, y, o, b, act, 0, 1 if tc else 0)
             outs.append(y)
-            inp, ld_in = y, o
+            inp, ld_in = y, y.stride(0)
         return outs
 
     def backward(self, x, ldx, K0, extra, outs, dout, M, impl, accumulate, want_dextra=False, tag="a", dz1_out=None):
@@ -163,7 +169,7 @@ class _Net:
             if li == 0:
                 inp, ld_in, K = x, ldx, (K0 if extra is not None else i)
             else:
-                inp, ld_in, K = outs[li - 1], self.specs[li - 1][2], i
+                inp, ld_in, K = outs[li - 1], outs[li - 1].stride(0), i
             # ---- wgrad: dW[o][K] = dz^T[o][M] inp[M][K]
             if li == 0 and dz1_out is not None:
                 pass                                    # fused by the caller
@@ -311,6 +317,67 @@ class ActorCritic(nn.Module):
         self._mean = self._p_out[-1]
         self._latent = latent
 
+    def forward_all(self, observation_history, privileged_observations, tag="act"):
+        """update_distribution + evaluate in one pass.  With the tensor-core path the first layers of the three MLPs --
+        which all read obs_history -- run as ONE product [M][256+512+512] = h Wcat^T: bias + ELU (+ the critic's two
+        privileged columns) ride in its epilogue for the adaptation/critic slices; the actor slice is finished
+        (latent columns + ELU) by go1_mlp_extra_forward once the adaptation module has produced the latent."""
+        self.flatten()
+        self._check_input(observation_history)
+        h, priv = observation_history, privileged_observations.contiguous()
+        M, K0, impl = h.shape[0], self.num_obs_history, self._impl()
+        nets = self._nets
+        na, npol, ncr = nets["adapt"], nets["actor"], nets["critic"]
+        E = self.num_privileged_obs
+        fused = impl == 1 and _Net._tma_ok(h, h.stride(0)) and K0 % 4 == 0 and 1 <= E <= 4 and \
+            npol.specs[0][3] == K0 + E and ncr.specs[0][3] == K0 + E and na.specs[0][3] == K0
+        if not fused:
+            self.update_distribution(h, tag)
+            return self._mean, self.evaluate(h, priv, tag)
+        oa, op, oc = na.specs[0][2], npol.specs[0][2], ncr.specs[0][2]
+        flat = self._flat
+
+        def w1(net):
+            wo, bo, o, i = net.specs[0]
+            return flat[wo:wo + o * i].view(o, i), flat[bo:bo + o]
+
+        (Wa, ba), (Wp, bp), (Wc, bc) = w1(na), w1(npol), w1(ncr)
+
+        def build_w(old):
+            W = old if old is not None else _empty(oa + oc + op, K0, device=flat.device)
+            W[:oa].copy_(Wa); W[oa:oa + oc].copy_(Wc[:, :K0]); W[oa + oc:].copy_(Wp[:, :K0])
+            return W
+
+        def build_b(old):
+            b = old if old is not None else _empty(1, oa + oc + op, device=flat.device)
+            b[0, :oa].copy_(ba); b[0, oa:oa + oc].copy_(bc); b[0, oa + oc:].copy_(bp)
+            return b
+
+        def build_x(old):       # trailing-input weights of the leading (adaptation | critic) columns: zeros | Wc[:, K0:]
+            x = old if old is not None else _empty(oa + oc, E, device=flat.device).zero_()
+            x[oa:].copy_(Wc[:, K0:])
+            return x
+
+        Wcat, bcat, xcat = na._cached(("l1cat", "W"), build_w), na._cached(("l1cat", "b"), build_b), na._cached(("l1cat", "x"), build_x)
+        y = na._buf((tag, "y1cat"), M, oa + oc + op)
+        na._gemm(0, 1, M, oa + oc + op, K0, h, h.stride(0), Wcat, K0, y, y.stride(0), bcat, 1, 0, 1,
+                 extra=priv, w_extra=xcat.data_ptr(), ld_w_extra=E, lead_cols=oa + oc)
+        ya, yc, yp = y[:, :oa], y[:, oa:oa + oc], y[:, oa + oc:]
+        self._a_out = na.forward(h, h.stride(0), K0, None, M, impl, tag, first_out=ya)
+        latent = self._latent = self._a_out[-1]
+        capi.check(capi.lib().go1_mlp_extra_forward(capi.ptr(yp), yp.stride(0), capi.ptr(latent), latent.stride(0), Wp.data_ptr() + 4 * K0, K0 + E,
+                                                    M, op, E, 1, capi.stream_ptr()), "go1_mlp_extra_forward")
+        self._p_out = npol.forward(h, h.stride(0), K0, latent, M, impl, tag, first_out=yp)
+        self._mean = self._p_out[-1]
+        self._c_out = ncr.forward(h, h.stride(0), K0, priv, M, impl, tag, first_out=yc)
+        self._value = self._c_out[-1]
+        return self._mean, self._value
+
+    def act_and_evaluate(self, observation_history, privileged_observations):
+        """PPO.act's two calls (actor_critic.act + evaluate, ppo.py:67-68) on one fused forward pass."""
+        self.forward_all(observation_history, privileged_observations, "act")
+        return self._sample(observation_history), self._value
+
     # Normal-like accessors used through `self.distribution`
     @property
     def mean(self):
@@ -322,6 +389,9 @@ class ActorCritic(nn.Module):
 
     def act(self, observation_history, **kwargs):
         self.update_distribution(observation_history)
+        return self._sample(observation_history)
+
+    def _sample(self, observation_history):
         M = observation_history.shape[0]
         actions = torch.empty(M, self.num_actions, device=observation_history.device)
         self._logp = torch.empty(M, device=observation_history.device)

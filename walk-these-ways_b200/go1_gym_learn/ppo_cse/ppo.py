@@ -90,9 +90,8 @@ class PPO:
     use_cuda_graph = True      # rollout policy evaluation (11 GEMMs + sampling) replayed as one CUDA graph
 
     def _act_eager(self, obs_history, privileged_obs):
-        actions = self.actor_critic.act(obs_history).detach()
-        values = self.actor_critic.evaluate(obs_history, privileged_obs).detach()
-        return actions, values
+        actions, values = self.actor_critic.act_and_evaluate(obs_history, privileged_obs)
+        return actions.detach(), values.detach()
 
     _MAX_INPLACE_GRAPHS = 4
 
@@ -202,9 +201,7 @@ class PPO:
             bi = it_mb % len(batches)
             (obs_b, critic_obs_b, priv_b, hist_b, actions_b, target_values_b, adv_b, returns_b, old_logp_b, old_mu_b, old_sigma_b, masks_b, env_bins_b) = batches[bi]
             M = hist_b.shape[0]
-            ac.update_distribution(hist_b, tag="train")
-            value_b = ac.evaluate(hist_b, priv_b, tag="train")
-            mean_b = ac.action_mean
+            mean_b, value_b = ac.forward_all(hist_b, priv_b, tag="train")
             dmean = ac._nets["actor"]._buf(("train", "dmean"), M, ac.num_actions)
             dvalue = ac._nets["critic"]._buf(("train", "dvalue"), M, 1)
             capi.check(L.go1_ppo_loss(capi.ptr(mean_b), mean_b.stride(0), capi.ptr(ac.std.data), capi.ptr(value_b), capi.ptr(actions_b), capi.ptr(old_logp_b),

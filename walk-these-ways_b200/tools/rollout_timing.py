@@ -44,6 +44,7 @@ def main():
     wrap(runner.alg, "act", "alg.act")
     wrap(runner.alg, "process_env_step", "alg.process_env_step")
     wrap(env, "step", "wrapper.step (total)")
+    wrap(base, "_step_device", "  _step_device")
     wrap(base, "_apply_pending_interval_resample", "  interval resample")
     wrap(core, "step", "  core.step launch")
     wrap(core, "fetch_events", "  fetch_events (sync)")
@@ -65,6 +66,19 @@ def main():
     print(f"rollout wall {tot / n * 1e3:.2f} ms  ({tot / steps * 1e6:.0f} us/step)")
     for k, v in acc.items():
         print(f"{k:34s} {v / steps * 1e6:8.1f} us/step   calls/step {cnt[k] / steps:.2f}")
+    # GPU side of the same loop: kernel time per env step (CUPTI)
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(2):
+            o, p, h, _ = runner.rollout(*st)
+            st[:] = [o, p, h]
+            torch.cuda.synchronize()
+            runner.alg.storage.clear()
+    rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
+    tot_us = sum(e.device_time_total for e in rows)
+    print(f"GPU busy {tot_us / 48:.0f} us/step")
+    for e in rows[:14]:
+        print(f"  {e.key[:70]:70s} {e.device_time_total / 48:8.1f} us/step  x{e.count / 48:.1f}")
 
 
 if __name__ == "__main__":
