@@ -125,6 +125,8 @@ def run_b200(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun for N>1"
     env, runner = build_training(args.envs, device, args.gemm)
     L = capi.lib()
+    if os.environ.get("GO1_TF32_WIDE"):
+        L.go1_gemm_tf32_set_wide(int(os.environ["GO1_TF32_WIDE"]))
     od = env.get_observations()
     state = [od["obs"], od["privileged_obs"], od["obs_history"]]
 

@@ -279,6 +279,8 @@ int go1_mlp_extra_backward(const float* dz, int lddz, const float* extra, int ld
  *   dprev[m][c] = (sum_t dz[m][t] W[t][c]) * ELU'(y_prev[m][c]),  W row-major [o][n]. */
 int go1_skinny_dgrad(const float* dz, int lddz, const float* W, int ldw, const float* y_prev, int ldy, float* dprev, int lddp,
                      int M, int o, int n, void* stream);
+/* wgrad of a narrow (o <= 16) output layer (the 12 / 2 / 1-wide heads): gW[j][k] (+)= sum_m dz[m][j] x[m][k]. */
+int go1_skinny_wgrad(const float* dz, int lddz, const float* x, int ldx, float* gW, int ldg, int M, int o, int K, int accumulate, void* stream);
 /* out[n] (+)= sum_m x[m][n]: bias gradient of nn.Linear. */
 int go1_colsum(const float* x, int ldx, float* out, int M, int N, int accumulate, void* stream);
 

@@ -254,3 +254,63 @@ def test_gemm_tcgen05_rejects_unsupported_layouts():
     A = torch.randn(64, 70, device="cuda"); C = torch.zeros(64, 64, device="cuda")
     with pytest.raises(capi.Go1Error):
         _gemm(0, 1, 64, 64, 70, A, 70, A, 70, C, 64, impl=1)      # ld=70 floats: not a multiple of 16 bytes
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# pieces of the fused first-layer forward and of the narrow-head backward
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,o,K", [(24576, 1, 128), (24576, 2, 128), (4097, 12, 128), (300, 16, 257)])
+def test_skinny_wgrad_matches_fp64(M, o, K):
+    from go1_b200 import capi
+    torch.manual_seed(M + o + K)
+    dz = torch.randn(M, o + 3, device="cuda")[:, :o]
+    x = torch.randn(M, K + 4, device="cuda")[:, :K]
+    g = torch.full((o, K + 2), 5.0, device="cuda")
+    L = capi.lib()
+    capi.check(L.go1_skinny_wgrad(capi.ptr(dz), dz.stride(0), capi.ptr(x), x.stride(0), capi.ptr(g), K + 2, M, o, K, 0, capi.stream_ptr()), "skinny_wgrad")
+    ref = dz.double().t() @ x.double()
+    tol = 1e-5 * (dz.abs().double().t() @ x.abs().double()) + 1e-6
+    assert ((g[:, :K].double() - ref).abs() <= tol).all() and (g[:, K:] == 5.0).all()
+    capi.check(L.go1_skinny_wgrad(capi.ptr(dz), dz.stride(0), capi.ptr(x), x.stride(0), capi.ptr(g), K + 2, M, o, K, 1, capi.stream_ptr()), "skinny_wgrad")
+    assert ((g[:, :K].double() - 2 * ref).abs() <= 2 * tol).all()
+
+
+def test_colsum_wide_and_narrow_paths():
+    from go1_b200 import capi
+    for M, N, ld in ((24576, 512, 1280), (1000, 256, 256), (777, 12, 12), (24576, 130, 132)):
+        x = torch.randn(M, ld, device="cuda")
+        out = torch.full((N,), 9.0, device="cuda")
+        capi.check(capi.lib().go1_colsum(capi.ptr(x), ld, capi.ptr(out), M, N, 0, capi.stream_ptr()), "colsum")
+        ref = x[:, :N].double().sum(0)
+        assert ((out.double() - ref).abs() <= 1e-5 * x[:, :N].abs().double().sum(0) + 1e-6).all(), (M, N)
+
+
+def test_fused_first_layer_epilogue_lead_cols_and_extra_forward():
+    """One product for [lead | tail] output columns: bias everywhere, extra columns + ELU only on the leading ones; the tail
+    is finished by go1_mlp_extra_forward (ActorCritic.forward_all)."""
+    from go1_b200 import capi
+    torch.manual_seed(5)
+    M, K, lead, tail, E = 1000, 2100, 768, 512, 2
+    A = torch.randn(M, K, device="cuda"); W = torch.randn(lead + tail, K, device="cuda") * 0.02
+    bias = torch.randn(lead + tail, device="cuda"); ex = torch.randn(M, E, device="cuda")
+    wx = torch.randn(lead, E, device="cuda"); wt = torch.randn(tail, E + 3, device="cuda"); lat = torch.randn(M, E, device="cuda")
+    y = torch.zeros(M, lead + tail, device="cuda")
+    ep = capi.Go1GemmEpilogue()
+    ep.bias, ep.act, ep.accumulate = bias.data_ptr(), 1, 0
+    ep.extra, ep.ld_extra, ep.w_extra, ep.ld_w_extra, ep.num_extra = ex.data_ptr(), E, wx.data_ptr(), E, E
+    ep.dact_y, ep.lead_cols = None, lead
+    L = capi.lib()
+    capi.check(L.go1_gemm_ex(0, 1, M, lead + tail, K, capi.ptr(A), K, capi.ptr(W), K, capi.ptr(y), lead + tail, ep, 1, capi.stream_ptr()), "gemm_ex")
+    pre = A.double() @ W.double().t() + bias.double()
+    want_lead = torch.nn.functional.elu(pre[:, :lead] + ex.double() @ wx.double().t())
+    tol = 2.0 ** -9 * (A.abs().double() @ W.abs().double().t()) + 1e-4
+    assert ((y[:, :lead].double() - want_lead).abs() <= tol[:, :lead]).all()
+    assert ((y[:, lead:].double() - pre[:, lead:]).abs() <= tol[:, lead:]).all()          # bias only, no activation
+    yt = y[:, lead:]
+    before = yt.clone()
+    capi.check(L.go1_mlp_extra_forward(capi.ptr(yt), yt.stride(0), capi.ptr(lat), E, capi.ptr(wt), E + 3, M, tail, E, 1, capi.stream_ptr()), "extra_fwd")
+    want_tail = torch.nn.functional.elu(before.double() + lat.double() @ wt[:, :E].double().t())
+    assert ((yt.double() - want_tail).abs() <= 1e-5 * (1 + want_tail.abs())).all()
+    with pytest.raises(capi.Go1Error):      # the fp32 CUDA-core path does not implement the split epilogue
+        ep.lead_cols = lead
+        capi.check(L.go1_gemm_ex(0, 1, M, lead + tail, K, capi.ptr(A), K, capi.ptr(W), K, capi.ptr(y), lead + tail, ep, 0, capi.stream_ptr()), "gemm_ex")

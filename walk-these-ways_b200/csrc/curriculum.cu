@@ -157,18 +157,35 @@ __global__ void __launch_bounds__(CT, 1) go1_curriculum_kernel(const CurArgs A) 
     if (n <= 0) return;
     const float* ev = A.b.events + (size_t)A.list * N * S;
 
+    // the usual call handles a handful of envs: then every per-env array lives in shared memory and the index lists are
+    // built by counting predecessors in parallel; the global-scratch path (n > SMALL) keeps the simple serial builders
+    constexpr int SMALL = 512;
+    __shared__ int s_arr[7][SMALL];
+    __shared__ double s_cdf[1024];       // cdf of the current category when it fits (searchsorted latency)
+    const bool small = n <= SMALL;
     int* mark = cb.scratch_i32;          // [N], all zero between calls
-    int* order = mark + N;               // [N] event slot of the p-th smallest env id
-    int* a_cat_old = order + N;
-    int* a_bin_old = a_cat_old + N;
-    int* a_ok = a_bin_old + N;
-    int* a_cat_new = a_ok + N;
-    int* a_bin_new = a_cat_new + N;
-    int* a_list = a_bin_new + N;         // [N] per-phase index list (successful bins / category members)
+    int* order = small ? s_arr[0] : mark + N;               // [n] event slot of the p-th smallest env id
+    int* a_cat_old = small ? s_arr[1] : mark + 2 * (size_t)N;
+    int* a_bin_old = small ? s_arr[2] : mark + 3 * (size_t)N;
+    int* a_ok = small ? s_arr[3] : mark + 4 * (size_t)N;
+    int* a_cat_new = small ? s_arr[4] : mark + 5 * (size_t)N;
+    int* a_bin_new = small ? s_arr[5] : mark + 6 * (size_t)N;
+    int* a_list = small ? s_arr[6] : mark + 7 * (size_t)N;  // [n] per-phase index list (successful bins / category members)
     double* dd = cb.scratch_f64;         // [(D + 1) N] doubles of the current category
     double* r2 = dd + (size_t)(D + 1) * N;   // [N] second category draw (exclusive / balanced gait modes)
 
     // ---- A: ascending env order --------------------------------------------------------------------------------
+    if (small) {             // rank of every id among the n ids (ids are unique)
+        int* ids = a_list;
+        for (int i = t; i < n; i += CT) ids[i] = (int)ev[(size_t)i * S];
+        __syncthreads();
+        for (int i = t; i < n; i += CT) {
+            const int me = ids[i];
+            int rank = 0;
+            for (int q = 0; q < n; q++) rank += ids[q] < me;
+            order[rank] = i;
+        }
+    } else {
     for (int i = t; i < n; i += CT) mark[(int)ev[(size_t)i * S]] = i + 1;
     __syncthreads();
     {
@@ -188,6 +205,7 @@ __global__ void __launch_bounds__(CT, 1) go1_curriculum_kernel(const CurArgs A) 
         for (int e = lo; e < hi; e++)
             if (mark[e]) { order[base++] = mark[e] - 1; mark[e] = 0; }
     }
+    }
     __syncthreads();
 
     // ---- B: success test (legged_robot.py:727-732; curriculum.py:136-139), old bin / category ---------------------
@@ -205,7 +223,17 @@ __global__ void __launch_bounds__(CT, 1) go1_curriculum_kernel(const CurArgs A) 
 
     // ---- C: curriculum update, category by category (curriculum.py:141-154) --------------------------------------
     for (int i = 0; i < ncat; i++) {
-        if (t == 0) {
+        if (small) {            // position = number of earlier successes of this category
+            if (t == 0) s_n = 0;
+            __syncthreads();
+            for (int p = t; p < n; p += CT)
+                if (a_ok[p] && a_cat_old[p] == i) {
+                    int pos = 0;
+                    for (int q = 0; q < p; q++) pos += (a_ok[q] && a_cat_old[q] == i);
+                    a_list[pos] = a_bin_old[p];
+                    atomicAdd(&s_n, 1);
+                }
+        } else if (t == 0) {
             int ns = 0;
             for (int p = 0; p < n; p++)
                 if (a_ok[p] && a_cat_old[p] == i) a_list[ns++] = a_bin_old[p];
@@ -260,7 +288,17 @@ __global__ void __launch_bounds__(CT, 1) go1_curriculum_kernel(const CurArgs A) 
 
     // ---- E: sample each category's members from its curriculum (curriculum.py:67-89) ---------------------------------
     for (int i = 0; i < ncat; i++) {
-        if (t == 0) {
+        if (small) {
+            if (t == 0) s_n = 0;
+            __syncthreads();
+            for (int p = t; p < n; p += CT)
+                if (a_cat_new[p] == i) {
+                    int pos = 0;
+                    for (int q = 0; q < p; q++) pos += a_cat_new[q] == i;
+                    a_list[pos] = p;
+                    atomicAdd(&s_n, 1);
+                }
+        } else if (t == 0) {
             int ni = 0;
             for (int p = 0; p < n; p++)
                 if (a_cat_new[p] == i) a_list[ni++] = p;
@@ -301,6 +339,11 @@ __global__ void __launch_bounds__(CT, 1) go1_curriculum_kernel(const CurArgs A) 
             const uint32_t a = cb.scratch_u32[2 * q] >> 5, bb = cb.scratch_u32[2 * q + 1] >> 6;
             dd[q] = __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)bb), 9007199254740992.0);
         }
+        const double* cdf_s = cdf;
+        if (L <= 1024) {
+            for (int j = t; j < L; j += CT) s_cdf[j] = cdf[j];
+            cdf_s = s_cdf;
+        }
         __syncthreads();
         for (int m = t; m < ni; m += CT) {
             const int p = a_list[m];
@@ -308,7 +351,7 @@ __global__ void __launch_bounds__(CT, 1) go1_curriculum_kernel(const CurArgs A) 
             int lo = 0, hi = L;                 // searchsorted(cdf, u, side='right')
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
-                if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+                if (cdf_s[mid] <= u) lo = mid + 1; else hi = mid;
             }
             const int idx = min(lo, L - 1);
             a_bin_new[p] = idx;

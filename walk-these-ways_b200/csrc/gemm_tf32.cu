@@ -20,6 +20,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <mutex>
+#include <stdlib.h>
 #include "../../include/go1_b200.h"
 
 extern int go1_set_error(const char* m);
@@ -524,11 +525,18 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
     if (act == 2 && !g.aux) return go1_set_error("go1_gemm_ex: act 2 needs dact_y");
     const int num_kb = (K + BK - 1) / BK;
     // 128 x 256 tiles (one CTA per SM, 4-stage ring of 48 KB) raise the flop/byte ratio of the L2-bound big products by 1.33x
-    const bool wide = g_tf32_persistent && g_tf32_wide && N >= 512 && (N % 256 == 0 || N >= 1024) && ((M + BM - 1) / BM) * ((N + 255) / 256) >= 120;
+    static const int wide_min_k = getenv("GO1_TF32_WIDE_MINK") ? atoi(getenv("GO1_TF32_WIDE_MINK")) : 1024;
+    static const int wide_min_tiles = getenv("GO1_TF32_WIDE_MINTILES") ? atoi(getenv("GO1_TF32_WIDE_MINTILES")) : 120;
+    static const int split_ctas = getenv("GO1_TF32_SPLIT_CTAS") ? atoi(getenv("GO1_TF32_SPLIT_CTAS")) : 2 * 148;
+    static const int split_min_kb = getenv("GO1_TF32_SPLIT_MINKB") ? atoi(getenv("GO1_TF32_SPLIT_MINKB")) : 16;
+    const bool wide = g_tf32_persistent && g_tf32_wide && K >= wide_min_k && N >= 256 && (N % 256 == 0 || N >= 1024) &&
+                      ((M + BM - 1) / BM) * ((N + 255) / 256) >= wide_min_tiles;
     const int BN = wide ? 256 : ((N > 64) ? 128 : (N > 32 ? 64 : 32));
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     int splits = 1;
-    if (tiles < 148 && num_kb >= 16 && g.nex == 0 && act != 2 && g.lead <= 0) { splits = (2 * 148) / tiles; if (splits > num_kb / 16) splits = num_kb / 16; if (splits < 1) splits = 1; }   // one wave of 2 CTAs/SM, >= 16 k-blocks each
+    if (tiles < 148 && num_kb >= split_min_kb && g.nex == 0 && act != 2 && g.lead <= 0) {      // one wave of 2 CTAs/SM, >= 16 k-blocks each
+        splits = split_ctas / tiles; if (splits > num_kb / split_min_kb) splits = num_kb / split_min_kb; if (splits < 1) splits = 1;
+    }
     g.kb_per_split = (num_kb + splits - 1) / splits;
     splits = (num_kb + g.kb_per_split - 1) / g.kb_per_split;
     CUtensorMap ma, mb;

@@ -283,23 +283,27 @@ extern "C" int go1_gemm(int transA, int transB, int M, int N, int K, const float
 }
 
 // y = act(y + extra . w_extra^T) in place: the deferred trailing-input term + activation of a first layer
-__global__ void extra_fwd_kernel(float* __restrict__ y, int ldy, const float* __restrict__ ex, int ldex, const float* __restrict__ wex, int ldw,
-                                 int M, int o, int E, int act) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)M * o) return;
-    const int m = (int)(i / o), n = (int)(i - (size_t)m * o);
-    float v = y[(size_t)m * ldy + n];
-    float acc = 0.f;
-    for (int t = 0; t < E; t++) acc = fmaf(__ldg(ex + (size_t)m * ldex + t), __ldg(wex + (size_t)n * ldw + t), acc);
-    v += acc;
-    if (act == 1) v = v > 0.f ? v : expm1f(v);
-    y[(size_t)m * ldy + n] = v;
+// grid (column blocks of 256, row blocks of 8): each thread keeps its column's E weights in registers and walks 8 rows
+__global__ void __launch_bounds__(256) extra_fwd_kernel(float* __restrict__ y, int ldy, const float* __restrict__ ex, int ldex, const float* __restrict__ wex, int ldw,
+                                                        int M, int o, int E, int act) {
+    const int n = blockIdx.x * 256 + threadIdx.x;
+    if (n >= o) return;
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < E; t++) w[t] = __ldg(wex + (size_t)n * ldw + t);
+    const int m0 = blockIdx.y * 8, m1 = min(M, m0 + 8);
+    for (int m = m0; m < m1; m++) {
+        float acc = 0.f;
+        for (int t = 0; t < E; t++) acc = fmaf(__ldg(ex + (size_t)m * ldex + t), w[t], acc);
+        float v = y[(size_t)m * ldy + n] + acc;
+        if (act == 1) v = v > 0.f ? v : expm1f(v);
+        y[(size_t)m * ldy + n] = v;
+    }
 }
 extern "C" int go1_mlp_extra_forward(float* y, int ldy, const float* extra, int ldex, const float* w_extra, int ldw, int M, int o, int E, int act,
                                      void* stream) {
     if (!y || !extra || !w_extra || M <= 0 || o <= 0 || E < 1 || E > 4 || act < 0 || act > 1) return go1_set_error("go1_mlp_extra_forward: bad arguments");
-    const size_t tot = (size_t)M * o;
-    extra_fwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(y, ldy, extra, ldex, w_extra, ldw, M, o, E, act); go1_count_launch(1);
+    dim3 grid((o + 255) / 256, (M + 7) / 8);
+    extra_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, ldy, extra, ldex, w_extra, ldw, M, o, E, act); go1_count_launch(1);
     return cuda_rc("go1_mlp_extra_forward");
 }
 
@@ -316,6 +320,42 @@ extern "C" int go1_elu_backward(const float* y, int ldy, const float* dy, int ld
     const size_t tot = (size_t)M * N;
     elu_bwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(y, ldy, dy, lddy, dz, lddz, M, N); go1_count_launch(1);
     return cuda_rc("go1_elu_backward");
+}
+
+// wgrad of a narrow (o <= 16) output layer: gW[j][k] (+)= sum_m dz[m][j] x[m][k].  One thread per input column k keeps the o
+// partial sums in registers over a 64-row slab (x read once, coalesced; dz rows broadcast), then o atomics.
+template <int O>
+__global__ void __launch_bounds__(128) skinny_wgrad_kernel(const float* __restrict__ dz, int lddz, const float* __restrict__ x, int ldx,
+                                                           float* __restrict__ gW, int ldg, int M, int o, int K, int rows_per_block) {
+    const int k = blockIdx.x * 128 + threadIdx.x;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    if (k >= K) return;
+    float acc[O];
+#pragma unroll
+    for (int j = 0; j < O; j++) acc[j] = 0.f;
+#pragma unroll 4
+    for (int m = r0; m < r1; m++) {
+        const float xv = x[(size_t)m * ldx + k];
+#pragma unroll
+        for (int j = 0; j < O; j++) if (j < o) acc[j] = fmaf(__ldg(dz + (size_t)m * lddz + j), xv, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < O; j++) if (j < o) atomicAdd(gW + (size_t)j * ldg + k, acc[j]);
+}
+extern "C" int go1_skinny_wgrad(const float* dz, int lddz, const float* x, int ldx, float* gW, int ldg, int M, int o, int K, int accumulate, void* stream) {
+    if (!dz || !x || !gW || M <= 0 || o < 1 || o > 16 || K <= 0 || ldg < K) return go1_set_error("go1_skinny_wgrad: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!accumulate) {
+        if (ldg == K) cudaMemsetAsync(gW, 0, sizeof(float) * (size_t)o * K, st);
+        else cudaMemset2DAsync(gW, sizeof(float) * ldg, 0, sizeof(float) * K, o, st);
+    }
+    const int rpb = 64;
+    dim3 grid((K + 127) / 128, (M + rpb - 1) / rpb);
+    if (o <= 2) skinny_wgrad_kernel<2><<<grid, 128, 0, st>>>(dz, lddz, x, ldx, gW, ldg, M, o, K, rpb);
+    else if (o <= 4) skinny_wgrad_kernel<4><<<grid, 128, 0, st>>>(dz, lddz, x, ldx, gW, ldg, M, o, K, rpb);
+    else skinny_wgrad_kernel<16><<<grid, 128, 0, st>>>(dz, lddz, x, ldx, gW, ldg, M, o, K, rpb);
+    go1_count_launch(1);
+    return cuda_rc("go1_skinny_wgrad");
 }
 
 // out[n] (+)= sum_m x[m][n]   (bias gradients)
@@ -335,10 +375,47 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
         atomicAdd(out + n, t);
     }
 }
+// wide variant: one float4 column group per lane (128 columns per warp row), 4 independent rows in flight per thread
+__global__ void __launch_bounds__(256) colsum4_kernel(const float* __restrict__ x, int ldx, float* __restrict__ out, int M, int N, int rows_per_block) {
+    __shared__ float4 s[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n = blockIdx.x * 128 + lane * 4;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < N) {
+        int m = r0 + w;
+        for (; m + 24 < r1; m += 32) {
+            const float4 a = *reinterpret_cast<const float4*>(x + (size_t)m * ldx + n);
+            const float4 b = *reinterpret_cast<const float4*>(x + (size_t)(m + 8) * ldx + n);
+            const float4 c = *reinterpret_cast<const float4*>(x + (size_t)(m + 16) * ldx + n);
+            const float4 d = *reinterpret_cast<const float4*>(x + (size_t)(m + 24) * ldx + n);
+            acc.x += (a.x + b.x) + (c.x + d.x); acc.y += (a.y + b.y) + (c.y + d.y);
+            acc.z += (a.z + b.z) + (c.z + d.z); acc.w += (a.w + b.w) + (c.w + d.w);
+        }
+        for (; m < r1; m += 8) {
+            const float4 a = *reinterpret_cast<const float4*>(x + (size_t)m * ldx + n);
+            acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+        }
+    }
+    s[w][lane] = acc;
+    __syncthreads();
+    if (w == 0 && n < N) {
+        float4 t = s[0][lane];
+#pragma unroll
+        for (int k = 1; k < 8; k++) { t.x += s[k][lane].x; t.y += s[k][lane].y; t.z += s[k][lane].z; t.w += s[k][lane].w; }
+        atomicAdd(out + n, t.x); atomicAdd(out + n + 1, t.y); atomicAdd(out + n + 2, t.z); atomicAdd(out + n + 3, t.w);
+    }
+}
 extern "C" int go1_colsum(const float* x, int ldx, float* out, int M, int N, int accumulate, void* stream) {
     if (!x || !out || M <= 0 || N <= 0) return go1_set_error("go1_colsum: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * N, st);
+    if (N >= 64 && (N & 3) == 0 && (ldx & 3) == 0 && (((uintptr_t)x) & 15) == 0) {
+        const int rpb4 = 128;
+        dim3 grid4((N + 127) / 128, (M + rpb4 - 1) / rpb4);
+        colsum4_kernel<<<grid4, 256, 0, st>>>(x, ldx, out, M, N, rpb4); go1_count_launch(1);
+        return cuda_rc("go1_colsum");
+    }
     const int rpb = 512;
     dim3 grid((N + 31) / 32, (M + rpb - 1) / rpb);
     colsum_kernel<<<grid, 256, 0, st>>>(x, ldx, out, M, N, rpb); go1_count_launch(1);
@@ -542,6 +619,25 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
         coef = fminf(max_norm / (total + 1e-6f), 1.0f);
     }
     const float step_size = lr / bc1;
+    if ((count & 3) == 0 && ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) == 0) {      // same arithmetic, 16-byte accesses
+        float4* p4 = reinterpret_cast<float4*>(p); const float4* g4 = reinterpret_cast<const float4*>(g);
+        float4* m4 = reinterpret_cast<float4*>(m); float4* v4 = reinterpret_cast<float4*>(v);
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count / 4; i += (long long)gridDim.x * blockDim.x) {
+            float4 pp = p4[i], mm = m4[i], vv = v4[i]; const float4 gg = g4[i];
+            float* pa = &pp.x; float* ma = &mm.x; float* va = &vv.x; const float* ga = &gg.x;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const float gi = ga[c] * coef;
+                const float mi = b1 * ma[c] + (1.0f - b1) * gi;
+                const float vi = b2 * va[c] + (1.0f - b2) * gi * gi;
+                ma[c] = mi; va[c] = vi;
+                const float denom = sqrtf(vi) / bc2_sqrt + eps;
+                pa[c] -= step_size * (mi / denom);
+            }
+            p4[i] = pp; m4[i] = mm; v4[i] = vv;
+        }
+        return;
+    }
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
         const float gi = g[i] * coef;
         const float mi = b1 * m[i] + (1.0f - b1) * gi;

@@ -173,6 +173,8 @@ class _Net:
             # ---- wgrad: dW[o][K] = dz^T[o][M] inp[M][K]
             if li == 0 and dz1_out is not None:
                 pass                                    # fused by the caller
+            elif o <= 16 and K >= 32:   # the narrow heads: one bandwidth-bound pass instead of a padded GEMM tile
+                capi.check(L.go1_skinny_wgrad(capi.ptr(dz), ldz, capi.ptr(inp), ld_in, gW.data_ptr(), i, M, o, K, accumulate, st), "skinny_wgrad")
             else:       # impl 1: both operands MN-major, read in place by the tcgen05 kernel
                 tc = impl == 1 and M >= 64 and K >= 8 and self._tma_ok(dz, ldz) and self._tma_ok(inp, ld_in)
                 self._gemm(1, 0, o, K, M, dz, ldz, inp, ld_in, gW, i, None, 0, accumulate, 1 if tc else 0)
