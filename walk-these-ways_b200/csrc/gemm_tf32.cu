@@ -112,6 +112,90 @@ struct GemmArgs {
     int amn, bmn;            // operand is MN-major in HBM (A given as [K][M], B given as [K][N]); persistent kernel only
 };
 
+// Epilogue of one 32-column chunk held in registers (thread = output row, r[j] = column col0 + j).  Called by all 32 lanes
+// of an epilogue warp (the per-column operands -- bias, extra-input weights -- are loaded once per lane and broadcast
+// with shuffles instead of 32 x per-thread global loads, which made the rank-2 term the slowest part of the kernel).
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, uint32_t (&r)[32], const int row, const int col0, const bool split, const int lane) {
+    if (col0 >= g.N) return;                                    // warp-uniform
+    const int ncols = min(32, g.N - col0);
+    const bool row_ok = row < g.M;
+    float* crow = g.C + (size_t)(row_ok ? row : 0) * g.ldc + col0;
+    if (split) {
+        if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) if (j < ncols) atomicAdd(crow + j, __uint_as_float(r[j]));
+        }
+        return;
+    }
+    const bool vec = (ncols == 32) && ((g.ldc & 3) == 0) && ((((uintptr_t)g.C) & 15) == 0) && ((col0 & 3) == 0);
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+    if (g.accumulate && row_ok) {
+        if (vec) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) { const float4 o = reinterpret_cast<const float4*>(crow)[j]; v[4 * j] += o.x; v[4 * j + 1] += o.y; v[4 * j + 2] += o.z; v[4 * j + 3] += o.w; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) if (j < ncols) v[j] += crow[j];
+        }
+    }
+    const int cj = col0 + lane;                                  // the column whose per-column operands this lane fetches
+    const bool lead_j = cj < g.N && (g.lead <= 0 || cj < g.lead);
+    if (g.nex > 0) {        // rank-nex update from the trailing input columns (cat(obs_history, latent))
+        float e[4], wl[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            e[t] = (t < g.nex && row_ok) ? __ldg(g.ex + (size_t)row * g.ldex + t) : 0.f;
+            wl[t] = (t < g.nex && lead_j) ? __ldg(g.wex + (size_t)cj * g.ldwex + t) : 0.f;
+        }
+        if (g.nex <= 2) {
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+                v[j] += fmaf(e[1], __shfl_sync(0xffffffffu, wl[1], j), e[0] * __shfl_sync(0xffffffffu, wl[0], j));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                float a = e[0] * __shfl_sync(0xffffffffu, wl[0], j);
+                a = fmaf(e[1], __shfl_sync(0xffffffffu, wl[1], j), a);
+                a = fmaf(e[2], __shfl_sync(0xffffffffu, wl[2], j), a);
+                v[j] += fmaf(e[3], __shfl_sync(0xffffffffu, wl[3], j), a);
+            }
+        }
+    }
+    if (g.bias) {
+        const float bl = cj < g.N ? __ldg(g.bias + cj) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] += __shfl_sync(0xffffffffu, bl, j);
+    }
+    if (!row_ok) return;
+    if (g.act == 1) {
+        const int nlead = g.lead <= 0 ? 32 : max(0, min(32, g.lead - col0));      // leading columns of this chunk that get the ELU
+#pragma unroll
+        for (int j = 0; j < 32; j++) if (j < nlead) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
+    } else if (g.act == 2) {   // multiply by ELU'(z) from the saved activation y: 1 if y > 0 else y + 1
+        const float* arow = g.aux + (size_t)row * g.ldaux + col0;
+        if (ncols == 32 && (g.ldaux & 3) == 0 && ((((uintptr_t)g.aux) & 15) == 0) && ((col0 & 3) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float4 y = __ldg(reinterpret_cast<const float4*>(arow) + j);
+                v[4 * j] *= (y.x > 0.f ? 1.0f : y.x + 1.0f); v[4 * j + 1] *= (y.y > 0.f ? 1.0f : y.y + 1.0f);
+                v[4 * j + 2] *= (y.z > 0.f ? 1.0f : y.z + 1.0f); v[4 * j + 3] *= (y.w > 0.f ? 1.0f : y.w + 1.0f);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) if (j < ncols) { const float y = __ldg(arow + j); v[j] *= (y > 0.f ? 1.0f : y + 1.0f); }
+        }
+    }
+    if (vec) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) reinterpret_cast<float4*>(crow)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; j++) if (j < ncols) crow[j] = v[j];
+    }
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1) gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -192,59 +276,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_kernel(const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 32; j++) r[j] = 0u;
             }
-            const int col0 = n0 + 32 * c;
-            if (row < g.M && col0 < g.N) {
-                float* crow = g.C + (size_t)row * g.ldc + col0;
-                const int ncols = min(32, g.N - col0);
-                if (split) {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) if (j < ncols) atomicAdd(crow + j, __uint_as_float(r[j]));
-                } else {
-                    const bool vec = (ncols == 32) && ((g.ldc & 3) == 0) && ((((uintptr_t)g.C) & 15) == 0) && ((col0 & 3) == 0);
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
-                    if (g.accumulate) {
-                        if (vec) {
-#pragma unroll
-                            for (int j = 0; j < 8; j++) { const float4 o = reinterpret_cast<const float4*>(crow)[j]; v[4 * j] += o.x; v[4 * j + 1] += o.y; v[4 * j + 2] += o.z; v[4 * j + 3] += o.w; }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; j++) if (j < ncols) v[j] += crow[j];
-                        }
-                    }
-                    if (g.nex > 0) {        // rank-nex update from the trailing input columns (cat(obs_history, latent))
-                        float e[4] = {0.f, 0.f, 0.f, 0.f};
-                        for (int t = 0; t < g.nex; t++) e[t] = __ldg(g.ex + (size_t)row * g.ldex + t);
-#pragma unroll
-                        for (int j = 0; j < 32; j++) if (j < ncols && (g.lead <= 0 || col0 + j < g.lead)) {
-                            const float* w = g.wex + (size_t)(col0 + j) * g.ldwex;
-                            float acc = 0.f;
-                            for (int t = 0; t < g.nex; t++) acc = fmaf(e[t], __ldg(w + t), acc);
-                            v[j] += acc;
-                        }
-                    }
-                    if (g.bias) {
-#pragma unroll
-                        for (int j = 0; j < 32; j++) if (j < ncols) v[j] += __ldg(g.bias + col0 + j);
-                    }
-                    if (g.act == 1) {
-#pragma unroll
-                        for (int j = 0; j < 32; j++) if (g.lead <= 0 || col0 + j < g.lead) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
-                    } else if (g.act == 2) {   // multiply by ELU'(z) from the saved activation y: 1 if y > 0 else y + 1
-                        const float* arow = g.aux + (size_t)row * g.ldaux + col0;
-#pragma unroll
-                        for (int j = 0; j < 32; j++) if (j < ncols) { const float y = __ldg(arow + j); v[j] *= (y > 0.f ? 1.0f : y + 1.0f); }
-                    }
-                    if (vec) {
-#pragma unroll
-                        for (int j = 0; j < 8; j++) reinterpret_cast<float4*>(crow)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; j++) if (j < ncols) crow[j] = v[j];
-                    }
-                }
-            }
+            epilogue_chunk(g, r, row, n0 + 32 * c, split, lane);
         }
     }
     // ===== teardown =====
@@ -365,59 +397,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_persistent(const __grid_cons
             for (int c = 0; c < BN / 32; c++) {
                 uint32_t r[32];
                 tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), r);
-                const int col0 = n0 + 32 * c;
-                if (row < g.M && col0 < g.N) {
-                    float* crow = g.C + (size_t)row * g.ldc + col0;
-                    const int ncols = min(32, g.N - col0);
-                    if (split) {
-#pragma unroll
-                        for (int jj = 0; jj < 32; jj++) if (jj < ncols) atomicAdd(crow + jj, __uint_as_float(r[jj]));
-                    } else {
-                        const bool vec = (ncols == 32) && ((g.ldc & 3) == 0) && ((((uintptr_t)g.C) & 15) == 0) && ((col0 & 3) == 0);
-                        float v[32];
-#pragma unroll
-                        for (int jj = 0; jj < 32; jj++) v[jj] = __uint_as_float(r[jj]);
-                        if (g.accumulate) {
-                            if (vec) {
-#pragma unroll
-                                for (int jj = 0; jj < 8; jj++) { const float4 o = reinterpret_cast<const float4*>(crow)[jj]; v[4 * jj] += o.x; v[4 * jj + 1] += o.y; v[4 * jj + 2] += o.z; v[4 * jj + 3] += o.w; }
-                            } else {
-#pragma unroll
-                                for (int jj = 0; jj < 32; jj++) if (jj < ncols) v[jj] += crow[jj];
-                            }
-                        }
-                        if (g.nex > 0) {
-                            float e[4] = {0.f, 0.f, 0.f, 0.f};
-                            for (int tt = 0; tt < g.nex; tt++) e[tt] = __ldg(g.ex + (size_t)row * g.ldex + tt);
-#pragma unroll
-                            for (int jj = 0; jj < 32; jj++) if (jj < ncols && (g.lead <= 0 || col0 + jj < g.lead)) {
-                                const float* w = g.wex + (size_t)(col0 + jj) * g.ldwex;
-                                float acc = 0.f;
-                                for (int tt = 0; tt < g.nex; tt++) acc = fmaf(e[tt], __ldg(w + tt), acc);
-                                v[jj] += acc;
-                            }
-                        }
-                        if (g.bias) {
-#pragma unroll
-                            for (int jj = 0; jj < 32; jj++) if (jj < ncols) v[jj] += __ldg(g.bias + col0 + jj);
-                        }
-                        if (g.act == 1) {
-#pragma unroll
-                            for (int jj = 0; jj < 32; jj++) if (g.lead <= 0 || col0 + jj < g.lead) v[jj] = v[jj] > 0.f ? v[jj] : expm1f(v[jj]);
-                        } else if (g.act == 2) {
-                            const float* arow = g.aux + (size_t)row * g.ldaux + col0;
-#pragma unroll
-                            for (int jj = 0; jj < 32; jj++) if (jj < ncols) { const float y = __ldg(arow + jj); v[jj] *= (y > 0.f ? 1.0f : y + 1.0f); }
-                        }
-                        if (vec) {
-#pragma unroll
-                            for (int jj = 0; jj < 8; jj++) reinterpret_cast<float4*>(crow)[jj] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
-                        } else {
-#pragma unroll
-                            for (int jj = 0; jj < 32; jj++) if (jj < ncols) crow[jj] = v[jj];
-                        }
-                    }
-                }
+                epilogue_chunk(g, r, row, n0 + 32 * c, split, lane);
             }
             // this thread's TMEM reads of the buffer are complete (tcgen05.wait::ld inside tmem_ld32): hand it back
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
