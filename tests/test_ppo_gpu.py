@@ -187,6 +187,7 @@ def test_full_ppo_cycle_matches_reference_golden(impl):
 # matmuls in TF32 by default on Ampere+).
 # ----------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 64, 64), (4096, 256, 2100), (300, 200, 70), (4, 512, 2100), (1000, 1280, 2100),
+                                   (8000, 1280, 1056), (24576, 256, 1024),      # 128 x 256 tiles (>= 60 wide tiles, K >= 1024)
                                    (24576, 128, 256), (256, 128, 24576), (2100, 1280, 4096)])
 def test_gemm_tcgen05_tf32(M, N, K):
     torch.manual_seed(M * 7 + N * 3 + K)

@@ -484,7 +484,7 @@ int launch_persistent(const CUtensorMap& ma, const CUtensorMap& mb, const GemmAr
 
 }  // namespace
 
-static int g_tf32_persistent = 1, g_tf32_wide = 0;   // wide (128x256, 1 CTA/SM) tiles: +25% on isolated big products, -8% on the whole update (no co-residency) -> opt-in
+static int g_tf32_persistent = 1, g_tf32_wide = 1;   // wide = 128 x 256 tiles where the heuristic in go1_gemm_tf32 says they pay
 extern "C" void go1_gemm_tf32_set_wide(int on) { g_tf32_wide = on; }
 extern "C" void go1_gemm_tf32_set_persistent(int on) { g_tf32_persistent = on; }
 
@@ -505,12 +505,16 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
     if (act == 2 && !g.aux) return go1_set_error("go1_gemm_ex: act 2 needs dact_y");
     const int num_kb = (K + BK - 1) / BK;
     // 128 x 256 tiles (one CTA per SM, 4-stage ring of 48 KB) raise the flop/byte ratio of the L2-bound big products by 1.33x
+    // 128 x 256 tiles (one CTA per SM, 4-stage ring of 48 KB) cut the L2->SM bytes per flop to 0.75x of the 128 x 128 tiling; the big
+    // products sit at the chip's TMA/L2 throughput cap (ncu: 11.4 TB/s), so that is what they are worth -- when the tile count
+    // still fills the 148 SMs evenly (a 160-tile product would run two half-empty rounds) and K is long enough to hide the epilogue
     static const int wide_min_k = getenv("GO1_TF32_WIDE_MINK") ? atoi(getenv("GO1_TF32_WIDE_MINK")) : 1024;
-    static const int wide_min_tiles = getenv("GO1_TF32_WIDE_MINTILES") ? atoi(getenv("GO1_TF32_WIDE_MINTILES")) : 120;
+    static const int wide_min_tiles = getenv("GO1_TF32_WIDE_MINTILES") ? atoi(getenv("GO1_TF32_WIDE_MINTILES")) : 60;
     static const int split_ctas = getenv("GO1_TF32_SPLIT_CTAS") ? atoi(getenv("GO1_TF32_SPLIT_CTAS")) : 2 * 148;
     static const int split_min_kb = getenv("GO1_TF32_SPLIT_MINKB") ? atoi(getenv("GO1_TF32_SPLIT_MINKB")) : 16;
-    const bool wide = g_tf32_persistent && g_tf32_wide && K >= wide_min_k && N >= 256 && (N % 256 == 0 || N >= 1024) &&
-                      ((M + BM - 1) / BM) * ((N + 255) / 256) >= wide_min_tiles;
+    const int wtiles = ((M + BM - 1) / BM) * ((N + 255) / 256);
+    const bool fills = wtiles < 148 ? wtiles >= wide_min_tiles : (double)wtiles / (148.0 * ((wtiles + 147) / 148)) >= 0.85;
+    const bool wide = g_tf32_persistent && g_tf32_wide && K >= wide_min_k && N >= 256 && (N % 256 == 0 || N >= 1024) && fills;
     const int BN = wide ? 256 : ((N > 64) ? 128 : (N > 32 ? 64 : 32));
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     int splits = 1;
