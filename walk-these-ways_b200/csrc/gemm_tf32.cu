@@ -120,10 +120,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, uint32_t (&r)[
     const int ncols = min(32, g.N - col0);
     const bool row_ok = row < g.M;
     float* crow = g.C + (size_t)(row_ok ? row : 0) * g.ldc + col0;
-    if (split) {
+    if (split) {            // split-K partial tile: reduce into C; 16-byte vector reductions cut the L2 atomic operations 4x
         if (row_ok) {
+            if ((ncols == 32) && ((g.ldc & 3) == 0) && ((((uintptr_t)g.C) & 15) == 0) && ((col0 & 3) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) if (j < ncols) atomicAdd(crow + j, __uint_as_float(r[j]));
+                for (int j = 0; j < 8; j++)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + 4 * j), "f"(__uint_as_float(r[4 * j])), "f"(__uint_as_float(r[4 * j + 1])),
+                                 "f"(__uint_as_float(r[4 * j + 2])), "f"(__uint_as_float(r[4 * j + 3])) : "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) if (j < ncols) atomicAdd(crow + j, __uint_as_float(r[j]));
+            }
         }
         return;
     }
