@@ -289,11 +289,14 @@ __global__ void __launch_bounds__(256) extra_fwd_kernel(float* __restrict__ y, i
     const int n = blockIdx.x * 256 + threadIdx.x;
     if (n >= o) return;
     float w[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int t = 0; t < E; t++) w[t] = __ldg(wex + (size_t)n * ldw + t);
+#pragma unroll
+    for (int t = 0; t < 4; t++) if (t < E) w[t] = __ldg(wex + (size_t)n * ldw + t);
     const int m0 = blockIdx.y * 8, m1 = min(M, m0 + 8);
+#pragma unroll 8
     for (int m = m0; m < m1; m++) {
         float acc = 0.f;
-        for (int t = 0; t < E; t++) acc = fmaf(__ldg(ex + (size_t)m * ldex + t), w[t], acc);
+#pragma unroll
+        for (int t = 0; t < 4; t++) if (t < E) acc = fmaf(__ldg(ex + (size_t)m * ldex + t), w[t], acc);
         float v = y[(size_t)m * ldy + n] + acc;
         if (act == 1) v = v > 0.f ? v : expm1f(v);
         y[(size_t)m * ldy + n] = v;
@@ -342,12 +345,59 @@ __global__ void __launch_bounds__(128) skinny_wgrad_kernel(const float* __restri
 #pragma unroll
     for (int j = 0; j < O; j++) if (j < o) atomicAdd(gW + (size_t)j * ldg + k, acc[j]);
 }
+// float4 variant: a warp owns rows (stride 8 inside a row slab), lanes own 4 consecutive input columns; the o gradients of
+// a row are fetched by the first o lanes and shuffle-broadcast.  Per-block partial sums meet in shared memory, then one
+// set of global atomics per block.
+template <int O>
+__global__ void __launch_bounds__(256) skinny_wgrad4_kernel(const float* __restrict__ dz, int lddz, const float* __restrict__ x, int ldx,
+                                                            float* __restrict__ gW, int ldg, int M, int o, int K, int rows_per_block) {
+    __shared__ float s_acc[O][128];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int k = blockIdx.x * 128 + lane * 4;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    for (int i = threadIdx.x; i < O * 128; i += 256) (&s_acc[0][0])[i] = 0.f;
+    __syncthreads();
+    float acc[O][4];
+#pragma unroll
+    for (int j = 0; j < O; j++) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+#pragma unroll 2
+    for (int m = r0 + w; m < r1; m += 8) {
+        const float4 xv = k < K ? *reinterpret_cast<const float4*>(x + (size_t)m * ldx + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float dl = lane < o ? __ldg(dz + (size_t)m * lddz + lane) : 0.f;
+#pragma unroll
+        for (int j = 0; j < O; j++) {
+            const float d = __shfl_sync(0xffffffffu, dl, j);
+            acc[j][0] = fmaf(d, xv.x, acc[j][0]); acc[j][1] = fmaf(d, xv.y, acc[j][1]);
+            acc[j][2] = fmaf(d, xv.z, acc[j][2]); acc[j][3] = fmaf(d, xv.w, acc[j][3]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < O; j++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) atomicAdd(&s_acc[j][lane * 4 + c], acc[j][c]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < o * 128; i += 256) {
+        const int j = i >> 7, kk = blockIdx.x * 128 + (i & 127);
+        if (kk < K) atomicAdd(gW + (size_t)j * ldg + kk, s_acc[j][i & 127]);
+    }
+}
 extern "C" int go1_skinny_wgrad(const float* dz, int lddz, const float* x, int ldx, float* gW, int ldg, int M, int o, int K, int accumulate, void* stream) {
     if (!dz || !x || !gW || M <= 0 || o < 1 || o > 16 || K <= 0 || ldg < K) return go1_set_error("go1_skinny_wgrad: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     if (!accumulate) {
         if (ldg == K) cudaMemsetAsync(gW, 0, sizeof(float) * (size_t)o * K, st);
         else cudaMemset2DAsync(gW, sizeof(float) * ldg, 0, sizeof(float) * K, o, st);
+    }
+    if ((K & 3) == 0 && (ldx & 3) == 0 && (((uintptr_t)x) & 15) == 0) {
+        const int kb = (K + 127) / 128;
+        int rpb4 = (M * kb + 147) / 148;                 // about one block per SM
+        rpb4 = (rpb4 + 7) / 8 * 8; if (rpb4 < 8) rpb4 = 8;
+        dim3 grid4(kb, (M + rpb4 - 1) / rpb4);
+        if (o <= 2) skinny_wgrad4_kernel<2><<<grid4, 256, 0, st>>>(dz, lddz, x, ldx, gW, ldg, M, o, K, rpb4);
+        else if (o <= 4) skinny_wgrad4_kernel<4><<<grid4, 256, 0, st>>>(dz, lddz, x, ldx, gW, ldg, M, o, K, rpb4);
+        else skinny_wgrad4_kernel<16><<<grid4, 256, 0, st>>>(dz, lddz, x, ldx, gW, ldg, M, o, K, rpb4);
+        go1_count_launch(1);
+        return cuda_rc("go1_skinny_wgrad");
     }
     const int rpb = 64;
     dim3 grid((K + 127) / 128, (M + rpb - 1) / rpb);
@@ -699,14 +749,17 @@ __global__ void __launch_bounds__(256) extra_dinput_kernel(const float* __restri
     if (warp >= M) return;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     const float* row = dz + (size_t)warp * lddz;
+#pragma unroll 4
     for (int j = lane; j < o; j += 32) {
         const float d = row[j];
-        for (int t = 0; t < E; t++) acc[t] = fmaf(d, __ldg(We + (size_t)j * ldw + t), acc[t]);
+#pragma unroll
+        for (int t = 0; t < 4; t++) if (t < E) acc[t] = fmaf(d, __ldg(We + (size_t)j * ldw + t), acc[t]);      // static indices: acc stays in registers
     }
-    for (int t = 0; t < E; t++) {
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
         float v = acc[t];
         for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-        if (lane == 0) dextra[(size_t)warp * ldde + t] = v;
+        if (lane == 0 && t < E) dextra[(size_t)warp * ldde + t] = v;
     }
 }
 __global__ void __launch_bounds__(256) extra_wgrad_kernel(const float* __restrict__ dz, int lddz, const float* __restrict__ extra, int ldex,
@@ -715,11 +768,14 @@ __global__ void __launch_bounds__(256) extra_wgrad_kernel(const float* __restric
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= o) return;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
     for (int m = r0; m < r1; m++) {
         const float d = dz[(size_t)m * lddz + j];
-        for (int t = 0; t < E; t++) acc[t] = fmaf(d, __ldg(extra + (size_t)m * ldex + t), acc[t]);
+#pragma unroll
+        for (int t = 0; t < 4; t++) if (t < E) acc[t] = fmaf(d, __ldg(extra + (size_t)m * ldex + t), acc[t]);
     }
-    for (int t = 0; t < E; t++) atomicAdd(gWe + (size_t)j * ldgw + t, acc[t]);
+#pragma unroll
+    for (int t = 0; t < 4; t++) if (t < E) atomicAdd(gWe + (size_t)j * ldgw + t, acc[t]);
 }
 __global__ void zero_small_kernel(float* p, int ld, int rows, int cols) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -734,7 +790,7 @@ extern "C" int go1_mlp_extra_backward(const float* dz, int lddz, const float* ex
         extra_dinput_kernel<<<(M * 32 + 255) / 256, 256, 0, st>>>(dz, lddz, w_extra, ldw, dextra, ldde, M, o, E); go1_count_launch(1);
     }
     if (!accumulate) { zero_small_kernel<<<(o * E + 255) / 256, 256, 0, st>>>(g_w_extra, ldgw, o, E); go1_count_launch(1); }
-    const int rpb = 32;
+    const int rpb = 64;
     dim3 grid((o + 255) / 256, (M + rpb - 1) / rpb);
     extra_wgrad_kernel<<<grid, 256, 0, st>>>(dz, lddz, extra, ldex, g_w_extra, ldgw, M, o, E, rpb); go1_count_launch(1);
     return cuda_rc("go1_mlp_extra_backward");
@@ -745,7 +801,8 @@ __global__ void skinny_dgrad_kernel(const float* __restrict__ dz, int lddz, cons
     if (idx >= (size_t)M * n) return;
     const int m = (int)(idx / n), c = (int)(idx - (size_t)m * n);
     float v = 0.f;
-    for (int t = 0; t < o; t++) v = fmaf(dz[(size_t)m * lddz + t], __ldg(W + (size_t)t * ldw + c), v);
+#pragma unroll
+    for (int t = 0; t < 16; t++) if (t < o) v = fmaf(__ldg(dz + (size_t)m * lddz + t), __ldg(W + (size_t)t * ldw + c), v);
     if (y) { const float yy = y[(size_t)m * ldy + c]; v *= (yy > 0.f ? 1.0f : yy + 1.0f); }
     dprev[(size_t)m * lddp + c] = v;
 }
