@@ -192,6 +192,14 @@ def run_b200(args):
     wall = time.perf_counter() - t0
     dev_ms = e0.elapsed_time(e1)
     launches = L.go1_kernel_launch_count() - l0
+    gemm_roof = None
+    if rank == 0 and args.gemm == 1:        # one more (untimed) iteration with CUDA events around every tcgen05 product
+        import ctypes as C
+        L.go1_gemm_timing(1, None, None, None)
+        iteration()
+        ms, fl, nl = C.c_double(), C.c_double(), C.c_longlong()
+        capi.check(L.go1_gemm_timing(0, C.byref(ms), C.byref(fl), C.byref(nl)), "go1_gemm_timing")
+        gemm_roof = (ms.value, fl.value, nl.value)
     t = torch.tensor([dev_ms, wall * 1e3], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -202,18 +210,28 @@ def run_b200(args):
     out = None
     if rank == 0:
         hbm, tf, src = peaks()
-        roof = sim_roofline(env, args.envs, hbm, src)
+        sim_roof = sim_roofline(env, args.envs, hbm, src)
+        roof = sim_roof
+        if gemm_roof is not None and gemm_roof[0] > 0:
+            g_ms, g_fl, g_n = gemm_roof
+            tf32_peak = tf / 2.0            # dense TF32 = half the dense bf16 rate measured by the driver
+            ach = g_fl / (g_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "gemm_tf32_persistent (tcgen05 kind::tf32)", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
+                    "frac": ach / tf32_peak, "traffic": None, "peak_source": src + " bf16 dense / 2",
+                    "scope": "every tcgen05 product of one PPO update + compute_returns (the rollout's products replay inside a CUDA graph)",
+                    "launches": int(g_n), "kernel_ms_per_iteration": g_ms, "tflop_per_iteration": g_fl / 1e12,
+                    "share_of_iteration": g_ms / (dev_ms / args.steps)}
         out = {
             "metric": METRIC, "value": env_steps / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.gemm == 0 else "tf32", "data": "synthetic (random-init policy, randomised flat terrain, device RNG)",
             "config": {"workload": "Go1 flat terrain, 4096 envs/GPU, 24-step rollout + ppo_cse update (scripts/train.py config)",
                        "envs_per_gpu": args.envs, "rollout_steps": T_ROLLOUT, "parallelism": f"dp{world}",
-                       "l2_policy": "roofline kernel timed alone with a 512 MiB L2 flush between launches; iteration timing uses the live working set (rollout slab 0.87 GB > L2)",
+                       "l2_policy": "iteration and GEMM timing use the live working set (rollout slab 0.87 GB and minibatch operands 0.2 GB > L2); the sim-step kernel is timed alone with a 512 MiB L2 flush between launches",
                        "gemm_impl": "fp32 CUDA cores" if args.gemm == 0 else "tcgen05 tf32"},
             "e2e": {"value": env_steps / (wall_ms / 1e3), "unit": UNIT,
                     "h2d_bytes_per_step": int(runner_h2d_bytes(env)), "d2h_bytes_per_step": int(runner_d2h_bytes(env)) + 28},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_sim_step": sim_roof,
             "losses": [float(x) for x in losses[:3]],
         }
         if args.breakdown:

@@ -261,6 +261,11 @@ typedef struct Go1GemmEpilogue {
 } Go1GemmEpilogue;
 int go1_gemm_ex(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                 float* C, int ldc, const Go1GemmEpilogue* ep, int impl, void* stream);
+/* Per-launch timing of the impl-1 (tcgen05) products for the roofline report: on = 1 starts collecting (CUDA events on the launch
+ * stream around every call that is not being graph-captured), on = 0 stops and returns the summed kernel time, flops and count. */
+int go1_gemm_timing(int on, double* total_ms, double* total_flop, long long* launches);
+/* number of kernels replayed through CUDA graphs, added to go1_kernel_launch_count() by the caller that replays them */
+void go1_kernel_launch_add(long long n);
 /* dst[c][r] = src[r][c] (rows x cols fp32, row strides lds/ldd): brings the dgrad (W^T) and wgrad (dz^T, x^T) operands into
  * the K-major form the tcgen05 kernel reads (impl=1 supports transA=0, transB=1 only). */
 int go1_transpose(const float* src, int lds, float* dst, int ldd, int rows, int cols, void* stream);

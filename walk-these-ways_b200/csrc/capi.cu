@@ -25,6 +25,7 @@ int go1_set_error(const char* m) { return fail(m); }
 static std::atomic<long long> g_launches{0};
 void go1_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 extern "C" long long go1_kernel_launch_count(void) { return g_launches.load(); }
+extern "C" void go1_kernel_launch_add(long long n) { g_launches += n; }
 
 struct Go1Sim {
     Go1SimConfig cfg;

@@ -493,6 +493,33 @@ int launch_persistent(const CUtensorMap& ma, const CUtensorMap& mb, const GemmAr
 
 static int g_tf32_persistent = 1, g_tf32_wide = 1;   // wide = 128 x 256 tiles where the heuristic in go1_gemm_tf32 says they pay
 extern "C" void go1_gemm_tf32_set_wide(int on) { g_tf32_wide = on; }
+
+// ---- optional per-launch timing of the tensor-core GEMM (bench.py's roofline): CUDA events on the launch stream around every
+// go1_gemm impl=1 call between go1_gemm_timing(1, ..) and go1_gemm_timing(0, ..)
+#include <vector>
+static bool g_time_on = false;
+static std::vector<cudaEvent_t> g_time_events;
+static size_t g_time_used = 0;
+static double g_time_flop = 0.0;
+static cudaEvent_t timing_event() {
+    if (g_time_used == g_time_events.size()) { cudaEvent_t e; cudaEventCreate(&e); g_time_events.push_back(e); }
+    return g_time_events[g_time_used++];
+}
+extern "C" int go1_gemm_timing(int on, double* total_ms, double* total_flop, long long* launches) {
+    if (on) { g_time_on = true; g_time_used = 0; g_time_flop = 0.0; return 0; }
+    g_time_on = false;
+    double ms = 0.0;
+    for (size_t i = 0; i + 1 < g_time_used; i += 2) {
+        if (cudaEventSynchronize(g_time_events[i + 1]) != cudaSuccess) return go1_set_error("go1_gemm_timing: event sync failed");
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, g_time_events[i], g_time_events[i + 1]) != cudaSuccess) return go1_set_error("go1_gemm_timing: elapsed time failed");
+        ms += t;
+    }
+    if (total_ms) *total_ms = ms;
+    if (total_flop) *total_flop = g_time_flop;
+    if (launches) *launches = (long long)(g_time_used / 2);
+    return 0;
+}
 extern "C" void go1_gemm_tf32_set_persistent(int on) { g_tf32_persistent = on; }
 
 extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
@@ -538,12 +565,16 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
         if (!accumulate) { const size_t tot = (size_t)M * N; zero_strided<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cm, ldc, M, N); go1_count_launch(1); }
         g.bias = nullptr; g.act = 0;
     }
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    const bool timed = g_time_on && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone;
+    if (timed) { cudaEventRecord(timing_event(), st); g_time_flop += 2.0 * (double)M * (double)N * (double)K; }
     int e;
     if (BN == 256) e = launch_persistent<256, 4>(ma, mb, g, splits, st);
     else if (g_tf32_persistent) e = (BN == 128) ? launch_persistent<128, 3>(ma, mb, g, splits, st) : (BN == 64 ? launch_persistent<64, 4>(ma, mb, g, splits, st) : launch_persistent<32, 4>(ma, mb, g, splits, st));
     else e = (BN == 128) ? launch<128, 3>(ma, mb, g, splits, st) : (BN == 64 ? launch<64, 4>(ma, mb, g, splits, st) : launch<32, 4>(ma, mb, g, splits, st));
     if (e) return e;
     if (splits > 1 && (bias || act)) { const size_t tot = (size_t)M * N; bias_act_strided<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cm, ldc, bias, M, N, act); go1_count_launch(1); }
+    if (timed) cudaEventRecord(timing_event(), st);
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return go1_set_error(cudaGetErrorString(ce));
     return 0;

@@ -119,7 +119,8 @@ def lib():
     vp, ip, i64 = C.c_void_p, C.c_int, C.c_int64
     sig = {
         "go1_version": ([], ip), "go1_device_count": ([], ip), "go1_sizeof_config": ([], ip), "go1_sizeof_buffers": ([], ip),
-        "go1_kernel_launch_count": ([], C.c_longlong),
+        "go1_kernel_launch_count": ([], C.c_longlong), "go1_kernel_launch_add": ([C.c_longlong], None),
+        "go1_gemm_timing": ([ip, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)], ip),
         "go1_sim_num_rows": ([ip], ip), "go1_sim_row": ([ip, C.c_char_p], ip),
         "go1_sim_create": ([C.POINTER(Go1SimConfig), vp, ip, C.POINTER(vp)], ip),
         "go1_sim_destroy": ([vp], ip), "go1_sim_bind": ([vp, C.POINTER(Go1SimBuffers)], ip),

@@ -125,16 +125,21 @@ class PPO:
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             ac.force_repack = True
+            L = capi.lib()
+            n0 = L.go1_kernel_launch_count()
             try:
                 with torch.cuda.graph(graph):
                     outs = self._act_eager(h_in, p_in)
             finally:
                 ac.force_repack = False
-            g = st[key] = (graph, h_in, p_in, outs, (ac._mean, ac._logp, ac._last_actions, ac._value, ac._latent), inplace)
-        graph, h_in, p_in, outs, attrs, inplace = g
+            n_kernels = L.go1_kernel_launch_count() - n0          # this library's kernels inside the graph
+            L.go1_kernel_launch_add(-n_kernels)                   # capture launched nothing
+            g = st[key] = (graph, h_in, p_in, outs, (ac._mean, ac._logp, ac._last_actions, ac._value, ac._latent), inplace, n_kernels)
+        graph, h_in, p_in, outs, attrs, inplace, n_kernels = g
         if not inplace:
             h_in.copy_(obs_history); p_in.copy_(privileged_obs)
         graph.replay()
+        capi.lib().go1_kernel_launch_add(n_kernels)
         ac._mean, ac._logp, ac._last_actions, ac._value, ac._latent = attrs     # the graph's static outputs
         return outs
 
