@@ -193,13 +193,14 @@ def run_b200(args):
     dev_ms = e0.elapsed_time(e1)
     launches = L.go1_kernel_launch_count() - l0
     gemm_roof = None
-    if rank == 0 and args.gemm == 1:        # one more (untimed) iteration with CUDA events around every tcgen05 product
+    if args.gemm == 1:        # one more (untimed) iteration with CUDA events around every tcgen05 product (every rank: collectives)
         import ctypes as C
         L.go1_gemm_timing(1, None, None, None)
         iteration()
         ms, fl, nl = C.c_double(), C.c_double(), C.c_longlong()
         capi.check(L.go1_gemm_timing(0, C.byref(ms), C.byref(fl), C.byref(nl)), "go1_gemm_timing")
         gemm_roof = (ms.value, fl.value, nl.value)
+        sync()
     t = torch.tensor([dev_ms, wall * 1e3], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
