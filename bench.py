@@ -193,7 +193,7 @@ def run_b200(args):
     dev_ms = e0.elapsed_time(e1)
     launches = L.go1_kernel_launch_count() - l0
     gemm_roof = None
-    if args.gemm == 1:        # one more (untimed) iteration with CUDA events around every tcgen05 product (every rank: collectives)
+    if args.gemm == 1 and not args.no_gemm_roofline:        # one more (untimed) iteration with CUDA events around every tcgen05 product (every rank: collectives)
         import ctypes as C
         L.go1_gemm_timing(1, None, None, None)
         iteration()
@@ -356,6 +356,7 @@ def main():
     ap.add_argument("--cpu-envs", type=int, default=256)
     ap.add_argument("--warmup-ref", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gemm-roofline", action="store_true", help="skip the extra event-timed iteration (profiler runs)")
     ap.add_argument("--profile", action="store_true", help="torch.profiler (CUPTI) kernel table + cProfile of the host loop -> gpurun_out/")
     ap.add_argument("--breakdown", action="store_true", help="per-phase CUDA-event timing (adds a sync per phase: not for headline numbers)")
     args = ap.parse_args()
