@@ -1,0 +1,71 @@
+"""The scripts/train.py flow end to end through the drop-in packages: Cfg + config_go1-style overrides ->
+VelocityTrackingEasyEnv -> HistoryWrapper -> Runner.learn() with logging, curriculum dumps and checkpoints, then the
+artefacts scripts/play.py consumes (ac_weights_last.pt, adaptation_module_latest.jit, body_latest.jit) reproduce the
+policy (play.py:24-45) and a resumed Runner starts from the saved weights and curriculum."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "walk-these-ways_b200"))
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "walk-these-ways_b200", "compat"))
+
+
+def _make(tmp_path, n=64):
+    for m in [k for k in sys.modules if k.startswith("go1_gym.envs.base.legged_robot_config")]:
+        del sys.modules[m]
+    from go1_gym.envs.base.legged_robot_config import Cfg
+    from go1_b200.train_config import apply_train_config
+    from go1_gym.envs.go1.velocity_tracking import VelocityTrackingEasyEnv
+    from go1_gym.envs.wrappers.history_wrapper import HistoryWrapper
+    from go1_gym_learn.ppo_cse import Runner, RunnerArgs
+    from ml_logger import logger
+    apply_train_config(Cfg)
+    Cfg.env.num_envs = n
+    logger.configure(prefix="run", root=str(tmp_path))
+    env = HistoryWrapper(VelocityTrackingEasyEnv(sim_device="cuda:0", headless=True, cfg=Cfg))
+    return env, Runner, RunnerArgs, logger
+
+
+def test_runner_learn_checkpoints_and_play_artifacts(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)                      # Runner.save writes ./tmp/legged_data like the reference
+    env, Runner, RunnerArgs, logger = _make(tmp_path)
+    RunnerArgs.num_steps_per_env, RunnerArgs.save_interval, RunnerArgs.log_freq, RunnerArgs.save_video_interval = 8, 2, 1, 100
+    RunnerArgs.resume = False
+    runner = Runner(env, device="cuda:0")
+    w0 = runner.alg.actor_critic.flat_params.clone()
+    runner.learn(num_learning_iterations=3, init_at_random_ep_len=True, eval_freq=100)
+    ac = runner.alg.actor_critic
+    assert torch.isfinite(ac.flat_params).all() and not torch.equal(ac.flat_params, w0)
+    run = os.path.join(str(tmp_path), "run")
+    ck = os.path.join(run, "checkpoints")
+    for f in ("ac_weights_last.pt", "ac_weights_000000.pt", "ac_weights_000002.pt", "adaptation_module_latest.jit", "body_latest.jit"):
+        assert os.path.exists(os.path.join(ck, f)), (f, os.listdir(ck))
+    assert os.path.exists(os.path.join(run, "curriculum", "distribution.pkl"))
+    # play.py:24-45: policy = body(cat(obs_history, adaptation_module(obs_history)))
+    sd = torch.load(os.path.join(ck, "ac_weights_last.pt"), map_location="cpu")
+    assert set(sd) == set(ac.state_dict()) and all(torch.equal(sd[k].cpu(), v.cpu()) for k, v in ac.state_dict().items())
+    body = torch.jit.load(os.path.join(ck, "body_latest.jit"))
+    adapt = torch.jit.load(os.path.join(ck, "adaptation_module_latest.jit"))
+    h = torch.randn(5, env.num_obs_history)
+    want = ac.act_student(h.cuda()).cpu()
+    lat = adapt(h)
+    got = body(torch.cat((h, lat), dim=-1))
+    assert torch.allclose(got, want, rtol=2e-2, atol=2e-2)          # TorchScript runs fp32 on the CPU, the kernels TF32
+    # resume (ppo_cse/__init__.py:76-91): weights and curriculum distribution come back
+    weights_before = [c.weights.copy() for c in env.curricula]
+    env.env._curriculum_to_host()
+    weights_before = [c.weights.copy() for c in env.curricula]
+    RunnerArgs.resume, RunnerArgs.resume_path = True, run
+    try:
+        env2, Runner2, _, _ = _make(tmp_path)
+        r2 = Runner2(env2, device="cuda:0")
+        assert torch.equal(r2.alg.actor_critic.flat_params, ac.flat_params)
+        for c, w in zip(env2.curricula, weights_before):
+            assert c.weights.shape == w.shape
+    finally:
+        RunnerArgs.resume = False

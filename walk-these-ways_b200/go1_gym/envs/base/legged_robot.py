@@ -90,6 +90,10 @@ class _LazyDict(dict):
     def __setitem__(self, k, v):
         self._fill(); dict.__setitem__(self, k, v)
 
+    def __reduce__(self):          # pickles (logger.save_pkl of the curriculum distribution) as the plain dict it stands for
+        self._fill()
+        return (dict, (dict(self),))
+
 
 class LeggedRobot(BaseTask):
     def __init__(self, cfg: Cfg, sim_params, physics_engine, sim_device, headless, eval_cfg=None, initial_dynamics_dict=None):
