@@ -89,6 +89,10 @@ typedef struct Go1SimConfig {
     float pen_k[4], pen_c[4], pen_mt, limit_k, limit_c;
     /* heightfield terrain (NULL/0 = flat): int16 samples [rows][cols] in device memory */
     const int16_t* hf; int32_t hf_rows, hf_cols; float hf_hscale, hf_vscale, hf_border;
+    /* measured terrain heights under the base (legged_robot.py:689-691, 1772-1806): a num_x x num_y grid of points in the
+     * yaw frame; only the body-height termination consumes them (legged_robot.py:146) */
+    int32_t measure_heights, num_height_points_x, num_height_points_y;
+    float height_points_x[32], height_points_y[32];
     uint64_t seed;                      /* Philox key for device-side randomisation */
 } Go1SimConfig;
 

@@ -10,6 +10,8 @@ Outputs (committed):
                      check_termination, compute_reward, compute_observations on a mock env (N=64)
   kats.npz           known-answer tests of SURVEY.md §8c: actuator net, gait clock, curriculum, policy MLPs
   ppo.npz            one full ppo_cse act->process_env_step->compute_returns->update cycle (BASELINE config 1)
+  terrain.npz        height fields + env origins built by the reference's Terrain class (curriculum / randomised / train.py
+                     modes) on top of this repository's terrain_utils restatement (tests/_stubs/isaacgym/terrain_utils.py)
   resample.npz       14 rounds of LeggedRobot._resample_commands (curriculum update + sampling + gait remap) on a mock
                      env with scripts/train.py's config (N=64), incl. the torch.rand category draws of every round
 """
@@ -418,6 +420,38 @@ def make_resample(Cfg):
     print("resample.npz:", len(out), "arrays; successes per round:", [int((out[f"r{r}/weights0"] > 0).sum()) for r in range(rounds)])
 
 
+TERRAIN_CASES = {
+    # name: (overrides of Cfg.terrain, numpy seed)
+    "curriculum": (dict(mesh_type="trimesh", curriculum=True, selected=False, num_rows=4, num_cols=6, border_size=5, terrain_length=8., terrain_width=8.,
+                        terrain_proportions=[0.1, 0.1, 0.35, 0.25, 0.2], terrain_noise_magnitude=0.1, difficulty_scale=1.0), 3),
+    "randomised": (dict(mesh_type="heightfield", curriculum=False, selected=False, num_rows=3, num_cols=5, border_size=4, terrain_length=8.,
+                        terrain_width=8., terrain_proportions=[0.1, 0.15, 0.15, 0.15, 0.15, 0.1, 0.0, 0.0, 0.1, 0.1], terrain_noise_magnitude=0.08,
+                        difficulty_scale=1.0), 11),
+    "train_py": (dict(num_rows=3, num_cols=3, border_size=2), 0),       # scripts/train.py's own terrain settings otherwise (flat tiles)
+}
+
+
+def make_terrain(Cfg):
+    """The reference's Terrain class (go1_gym/utils/terrain.py) driving OUR generators: pins tile layout, type/difficulty
+    selection, numpy RNG consumption and env origins of walk-these-ways_b200/go1_gym/utils/terrain.py."""
+    from go1_gym.utils.terrain import Terrain
+    out = {}
+    for name, (over, seed) in TERRAIN_CASES.items():
+        saved = {k: getattr(Cfg.terrain, k) for k in over}
+        for k, v in over.items():
+            setattr(Cfg.terrain, k, v)
+        np.random.seed(seed)
+        t = Terrain(Cfg.terrain, 16)
+        out[f"{name}/height_field_raw"] = t.height_field_raw.copy()
+        out[f"{name}/env_origins"] = Cfg.terrain.env_origins.copy()
+        if Cfg.terrain.mesh_type == "trimesh":
+            out[f"{name}/vertices_sample"] = t.vertices[::997].copy(); out[f"{name}/triangles_sample"] = t.triangles[::997].copy()
+        for k, v in saved.items():
+            setattr(Cfg.terrain, k, v)
+    np.savez_compressed(os.path.join(HERE, "terrain.npz"), **out)
+    print("terrain.npz:", {k: v.shape for k, v in out.items()}, "nonzero", {k: int(np.count_nonzero(v)) for k, v in out.items() if "height" in k})
+
+
 if __name__ == "__main__":
     Cfg, trees = reference_train_cfg()
     with open(os.path.join(HERE, "cfg_trees.json"), "w") as f:
@@ -426,3 +460,4 @@ if __name__ == "__main__":
     make_kats(Cfg)
     make_ppo()
     make_resample(Cfg)
+    make_terrain(Cfg)

@@ -151,11 +151,32 @@ def _load_phys_state(sim, st):
 @pytest.mark.parametrize("control", ["P", "actuator_net"])
 def test_physics_step_matches_fp64_oracle(control):
     """One policy step (4 substeps) from random near-ground states vs the fp64 oracle driven by the same torques."""
+    physics_vs_oracle(control, None)
+
+
+def physics_vs_oracle(control, hf):
+    """hf: None (flat) or (int16 samples [rows][cols], horizontal_scale, vertical_scale, border) for a height-field terrain."""
+    import ctypes
     from oracle import physics as ph
     from oracle import env_oracle as eo
+    from go1_b200.sim import SimCore
     n = 96
-    Cfg, c, info, sim = _sim(n, cfg_overrides={"control": {"control_type": control}})
+    Cfg, c, info = train_sim_config(n, cfg_overrides={"control": {"control_type": control}})
+    c.rand_interval = 0
     st, rng = _random_phys_state(n, 3)
+    hf_dev = None
+    if hf is not None:
+        samples, hs, vs, border = hf
+        hf_dev = torch.from_numpy(np.ascontiguousarray(samples)).cuda()
+        c.hf, c.hf_rows, c.hf_cols, c.hf_hscale, c.hf_vscale, c.hf_border = hf_dev.data_ptr(), samples.shape[0], samples.shape[1], hs, vs, border
+        # start every robot the same distance above ITS ground point (bilinear height, as both simulators sample it)
+        fx, fy = (st["pos"][:, 0] + border) / hs, (st["pos"][:, 1] + border) / hs
+        ix, iy = fx.astype(int), fy.astype(int)
+        ax, ay = fx - ix, fy - iy
+        h = (samples[ix, iy] * (1 - ax) * (1 - ay) + samples[ix + 1, iy] * ax * (1 - ay) + samples[ix, iy + 1] * (1 - ax) * ay
+             + samples[ix + 1, iy + 1] * ax * ay) * vs
+        st["pos"][:, 2] += h
+    sim = SimCore(c, inject_noise=True, inject_reset_rand=True)
     _load_phys_state(sim, st)
     actions = torch.from_numpy(rng.uniform(-1.5, 1.5, (n, 12)).astype(np.float32)).cuda()
     g = [0.0, 0.0, -9.8]
@@ -171,6 +192,10 @@ def test_physics_step_matches_fp64_oracle(control):
         s[k] = torch.zeros(n, 12)
     net = eo.ActuatorNet()
     pp = ph.default_params()
+    if hf is not None:
+        hf_host = np.ascontiguousarray(samples, dtype=np.int16)
+        pp.hf = hf_host.ctypes.data_as(ctypes.POINTER(ctypes.c_short))
+        pp.hf_rows, pp.hf_cols, pp.hf_hscale, pp.hf_vscale, pp.hf_border = samples.shape[0], samples.shape[1], hs, vs, border
     states = [ph.make_state(st["pos"][i], st["quat"][i], st["linvel"][i], st["angvel"][i], st["q"][i], st["qd"][i]) for i in range(n)]
     drs = [ph.make_dr(st["friction"][i], st["restitution"][i], st["payload"][i]) for i in range(n)]
     cf = None

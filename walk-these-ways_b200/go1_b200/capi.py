@@ -68,6 +68,8 @@ class Go1SimConfig(C.Structure):
         ("pgs_iters", _i), ("terrain_friction", _f), ("terrain_restitution", _f),
         ("pen_k", _f * 4), ("pen_c", _f * 4), ("pen_mt", _f), ("limit_k", _f), ("limit_c", _f),
         ("hf", C.c_void_p), ("hf_rows", _i), ("hf_cols", _i), ("hf_hscale", _f), ("hf_vscale", _f), ("hf_border", _f),
+        ("measure_heights", _i), ("num_height_points_x", _i), ("num_height_points_y", _i),
+        ("height_points_x", _f * 32), ("height_points_y", _f * 32),
         ("seed", C.c_uint64),
     ]
 

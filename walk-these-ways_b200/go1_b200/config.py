@@ -248,6 +248,15 @@ def build_sim_config(cfg, num_envs=None, num_train_envs=None, seed=0, physics=No
                 getattr(c, k)[:] = list(v)
             else:
                 setattr(c, k, v)
-    c.hf = None
+    c.hf = None                                  # set by LeggedRobot.create_sim once the Terrain exists
+    mh = bool(getattr(t, "measure_heights", False)) and t.mesh_type in ("heightfield", "trimesh")
+    px, py = list(getattr(t, "measured_points_x", [])), list(getattr(t, "measured_points_y", []))
+    if mh and (len(px) > 32 or len(py) > 32):
+        raise ValueError("at most 32 x 32 measured height points")
+    c.measure_heights = int(mh)
+    c.num_height_points_x, c.num_height_points_y = (len(px), len(py)) if mh else (0, 0)
+    if mh:
+        c.height_points_x[:len(px)] = px
+        c.height_points_y[:len(py)] = py
     c.seed = int(seed)
     return c, dict(active_reward_scales=active, dt=d["dt"], noise_scale_vec=nv)

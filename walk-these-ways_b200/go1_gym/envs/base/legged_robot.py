@@ -134,6 +134,7 @@ class LeggedRobot(BaseTask):
         mesh_type = cfg.terrain.mesh_type
         if mesh_type in ['heightfield', 'trimesh']:
             self.terrain = Terrain(cfg.terrain, self.num_train_envs)
+            self._bind_height_field()
         elif mesh_type not in (None, 'plane'):
             raise ValueError("Terrain mesh type not recognised. Allowed types are [None, plane, heightfield, trimesh]")
         self.core = SimCore(self.sim_cfg, device=self.device)
@@ -148,6 +149,50 @@ class LeggedRobot(BaseTask):
         self._randomize_rigid_body_props(torch.arange(self.num_envs, device=self.device), cfg)
         self.common_step_counter = 0
         self._randomize_gravity()
+
+    def _bind_height_field(self):
+        """_create_heightfield / _create_trimesh (legged_robot.py:1442-1479): the int16 samples go to the device once and the
+        step kernel samples them (bilinear) for every contact point; world (x, y) = (row, col) * horizontal_scale - border_size."""
+        t, tc = self.terrain, self.cfg.terrain
+        self.height_samples = torch.tensor(t.heightsamples).view(t.tot_rows, t.tot_cols).to(self.device)
+        c = self.sim_cfg
+        if t.is_flat:
+            c.hf = None                      # flat tiles (scripts/train.py): the analytic z = 0 plane
+            return
+        self._hf_dev = self.height_samples.contiguous()
+        c.hf, c.hf_rows, c.hf_cols = self._hf_dev.data_ptr(), int(t.tot_rows), int(t.tot_cols)
+        c.hf_hscale, c.hf_vscale, c.hf_border = float(tc.horizontal_scale), float(tc.vertical_scale), float(tc.border_size)
+
+    def _get_heights(self, env_ids, cfg=None):
+        """legged_robot.py:1772-1806 (reference-shaped helper; the step kernel evaluates the same expression itself for the
+        body-height termination)."""
+        cfg = cfg or self.cfg
+        t = cfg.terrain
+        px_, py_ = torch.tensor(t.measured_points_x, device=self.device), torch.tensor(t.measured_points_y, device=self.device)
+        n_pts = len(px_) * len(py_)
+        env_ids = torch.as_tensor(env_ids, device=self.device, dtype=torch.long)
+        if t.mesh_type == 'plane' or getattr(self, "height_samples", None) is None:
+            return torch.zeros(len(env_ids), n_pts, device=self.device)
+        gx, gy = torch.meshgrid(px_, py_, indexing="ij")
+        q = self.base_quat[env_ids]
+        yn = torch.rsqrt(q[:, 2] ** 2 + q[:, 3] ** 2)
+        yz, yw = q[:, 2] * yn, q[:, 3] * yn
+        cy, sy = (yw * yw - yz * yz)[:, None], (2 * yw * yz)[:, None]
+        lx, ly = gx.reshape(1, -1), gy.reshape(1, -1)
+        pos = self.base_pos[env_ids]
+        wx = cy * lx - sy * ly + pos[:, 0:1] + t.border_size
+        wy = sy * lx + cy * ly + pos[:, 1:2] + t.border_size
+        ix = torch.clip((wx / t.horizontal_scale).long(), 0, self.height_samples.shape[0] - 2)
+        iy = torch.clip((wy / t.horizontal_scale).long(), 0, self.height_samples.shape[1] - 2)
+        hs = self.height_samples
+        h = torch.min(torch.min(hs[ix, iy], hs[ix + 1, iy]), hs[ix, iy + 1])
+        return h.float() * t.vertical_scale
+
+    @property
+    def measured_heights(self):
+        if not self.cfg.terrain.measure_heights:
+            return 0
+        return self._get_heights(torch.arange(self.num_envs, device=self.device))
 
     def _get_env_origins(self):
         """legged_robot.py:1675-1714."""
@@ -273,7 +318,6 @@ class LeggedRobot(BaseTask):
         self._env_bins_flip = 0
         self._env_bins_dirty = True
         self.actions = torch.zeros(self.num_envs, self.num_actions, device=self.device)
-        self.measured_heights = 0
         self.lag_timesteps = self.cfg.domain_rand.lag_timesteps
 
     def _prepare_reward_function(self):
