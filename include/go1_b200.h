@@ -270,8 +270,8 @@ int go1_gemm_ex(int transA, int transB, int M, int N, int K, const float* A, int
 int go1_gemm_timing(int on, double* total_ms, double* total_flop, long long* launches);
 /* number of kernels replayed through CUDA graphs, added to go1_kernel_launch_count() by the caller that replays them */
 void go1_kernel_launch_add(long long n);
-/* dst[c][r] = src[r][c] (rows x cols fp32, row strides lds/ldd): brings the dgrad (W^T) and wgrad (dz^T, x^T) operands into
- * the K-major form the tcgen05 kernel reads (impl=1 supports transA=0, transB=1 only). */
+/* dst[c][r] = src[r][c] (rows x cols fp32, row strides lds/ldd).  Utility only: impl 1 reads operands in either major
+ * (transA / transB as given), so the learner no longer stages transposed copies. */
 int go1_transpose(const float* src, int lds, float* dst, int ldd, int rows, int cols, void* stream);
 /* dz = dy * ELU'(z) computed from the saved layer output y (autograd of nn.ELU). dz may alias dy. */
 int go1_elu_backward(const float* y, int ldy, const float* dy, int lddy, float* dz, int lddz, int M, int N, void* stream);

@@ -106,13 +106,6 @@ class _Net:
             ep.dact_y = None
         capi.check(capi.lib().go1_gemm_ex(ta, tb, M, N, K, self._p(A), lda, self._p(B), ldb, self._p(Cm), ldc, ep, impl, capi.stream_ptr()), "go1_gemm")
 
-    def _transpose(self, src, lds, rows, cols, out=None):
-        ldd = (rows + 3) // 4 * 4
-        if out is None or out.shape != (cols, ldd):
-            out = _empty(cols, ldd, device=self.flat.device)
-        capi.check(capi.lib().go1_transpose(self._p(src), lds, capi.ptr(out), ldd, rows, cols, capi.stream_ptr()), "go1_transpose")
-        return out
-
     @staticmethod
     def _tma_ok(x, ld):
         """TMA-readable K-major operand: 16-byte aligned base, row stride a multiple of 16 bytes."""
@@ -222,7 +215,7 @@ class ActorCritic(nn.Module):
         self.force_repack = False     # set while a CUDA graph of the forward pass is captured: weight packing must be IN the graph
         self.sample_seed = 0
         self.injected_eps = None      # parity tests inject the N(0,1) draws
-        self.weights_version = 0      # bumped by every optimizer step / load: invalidates packed + transposed weight copies
+        self.weights_version = 0      # bumped by every optimizer step / load: invalidates the packed first-layer weight copies
 
     # ------------------------------------------------------------------ flat storage
     def _ordered_params(self):
