@@ -52,10 +52,10 @@ def test_env_on_curriculum_tiles_stands_and_uses_tile_origins():
     origins = env.env_origins.clone()
     tile_z = torch.from_numpy(Cfg.terrain.env_origins).float().cuda()[env.terrain_levels, env.terrain_types][:, 2]
     assert torch.allclose(origins[:, 2], tile_z) and float(origins[:, 2].max()) > 0.05          # spawn above the tile's highest point
-    resets = 0
+    resets = torch.zeros(64, device="cuda")
     for i in range(60):
         obs, rew, done, info = env.step(torch.zeros(64, 12, device="cuda"))
-        resets += int(done.sum())
+        resets += done.float()
         assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
     # standing robots rest on THEIR terrain: base height above the ground sample right under the base stays near the
     # nominal 0.3 m (whatever the tile: slope, stairs, obstacles, at any curriculum level)
@@ -71,7 +71,8 @@ def test_env_on_curriculum_tiles_stands_and_uses_tile_origins():
     cl = clearance[on_top]
     assert float(cl.min()) > 0.15 and float(cl.max()) < 0.5, cl
     assert float(origins[:, 2].max() - origins[:, 2].min()) > 0.1            # the robots really are at different terrain heights
-    assert resets < 64
+    # robots dropped into the pits may crash and respawn; the ones standing on their platform never terminate
+    assert float(resets[on_top].sum()) <= 2, resets
 
 
 def test_measured_heights_termination_matches_torch_restatement():
