@@ -1,152 +1,160 @@
-"""Terrain (reference go1_gym/utils/terrain.py:12-180): the grid of num_rows x num_cols sub-terrain tiles (rows = difficulty
-levels, cols = terrain types), the int16 height field the simulator samples, and the env origin of every tile.
+"""Terrain: the grid of sub-terrain tiles (rows = difficulty levels, columns = terrain types), the int16 height field the
+simulator samples, and the spawn origin of every tile.  Same observable behaviour as the reference class
+(go1_gym/utils/terrain.py:12-180) -- attribute names, config side effects, tile order, numpy RNG consumption -- organised
+around a table of terrain-type bands instead of an if-chain.  tests/test_terrain.py runs the reference's own class on the
+same generators and seeds and compares height fields and origins bit for bit (tests/golden/terrain.npz)."""
+from types import SimpleNamespace
 
-Tile selection follows the reference exactly (curriculum / selected / randomised modes, the cumulative
-`terrain_proportions` thresholds and the per-tile parameters of make_terrain, terrain.py:105-156); the generators live in
-terrain_utils.py (a restatement of isaacgym.terrain_utils).  tests/test_terrain.py runs the reference's own Terrain class
-on the same generators and seeds and compares height fields and origins bit for bit."""
 import numpy as np
 
-from . import terrain_utils
+from . import terrain_utils as tu
+
+
+def _tile_parameters(cfg, difficulty):
+    """Difficulty -> generator parameters (terrain.py:110-114)."""
+    return SimpleNamespace(slope=0.4 * difficulty, step=0.05 + 0.18 * difficulty,
+                           obstacle=0.05 + difficulty * (cfg.max_platform_height - 0.05),
+                           stone=1.5 * (1.05 - difficulty), gap=0.05 if difficulty == 0 else 0.1)
+
+
+def _smooth_slope(T, tile, p, cfg, choice, bands):
+    tu.pyramid_sloped_terrain(tile, slope=-p.slope if choice < bands[0] / 2 else p.slope, platform_size=3.)
+
+
+def _rough_slope(T, tile, p, cfg, choice, bands):
+    tu.pyramid_sloped_terrain(tile, slope=p.slope, platform_size=3.)
+    tu.random_uniform_terrain(tile, min_height=-0.05, max_height=0.05, step=T.cfg.terrain_smoothness, downsampled_scale=0.2)
+
+
+def _stairs(T, tile, p, cfg, choice, bands):
+    tu.pyramid_stairs_terrain(tile, step_width=0.31, step_height=-p.step if choice < bands[2] else p.step, platform_size=3.)
+
+
+def _obstacles(T, tile, p, cfg, choice, bands):
+    tu.discrete_obstacles_terrain(tile, p.obstacle, 1., 2., 20, platform_size=3.)
+
+
+def _stones(T, tile, p, cfg, choice, bands):
+    tu.stepping_stones_terrain(tile, stone_size=p.stone, stone_distance=p.gap, max_height=0., platform_size=4.)
+
+
+def _flat(T, tile, p, cfg, choice, bands):
+    pass
+
+
+def _noise(T, tile, p, cfg, choice, bands):
+    m = cfg.terrain_noise_magnitude
+    tu.random_uniform_terrain(tile, min_height=-m, max_height=m, step=0.005, downsampled_scale=0.2)
+
+
+def _half_rough(T, tile, p, cfg, choice, bands):
+    tu.random_uniform_terrain(tile, min_height=-0.05, max_height=0.05, step=T.cfg.terrain_smoothness, downsampled_scale=0.2)
+    tile.height_field_raw[:tile.length // 2, :] = 0
+
+
+# upper band index (into the cumulative terrain_proportions) -> generator.  Bands 2 and 3 are both stairs (descending below
+# band 2's bound, ascending up to band 3's), which is why index 2 is absent: terrain.py:126-129 tests proportions[3] first.
+_BANDS = ((0, _smooth_slope), (1, _rough_slope), (3, _stairs), (4, _obstacles), (5, _stones), (6, _flat), (7, _flat),
+          (8, _noise), (9, _half_rough))
 
 
 class Terrain:
     def __init__(self, cfg, num_robots, eval_cfg=None, num_eval_robots=0):
         self.cfg, self.eval_cfg, self.num_robots, self.type = cfg, eval_cfg, num_robots, cfg.mesh_type
-        if self.type in ["none", "plane"]:
+        if self.type in ("none", "plane"):
             return
         self.train_rows, self.train_cols, self.eval_rows, self.eval_cols = self.load_cfgs()
         self.tot_rows = len(self.train_rows) + len(self.eval_rows)
         self.tot_cols = max(len(self.train_cols), len(self.eval_cols))
-        self.cfg.env_length, self.cfg.env_width = cfg.terrain_length, cfg.terrain_width
+        cfg.env_length, cfg.env_width = cfg.terrain_length, cfg.terrain_width
         self.height_field_raw = np.zeros((self.tot_rows, self.tot_cols), dtype=np.int16)
         self.initialize_terrains()
         self.heightsamples = self.height_field_raw
         self.is_flat = not self.height_field_raw.any()
         if self.type == "trimesh":
-            # kept for API parity (terrain.py:31-35); this simulator samples the height field itself (bilinear), so a step
-            # is a one-cell ramp rather than the vertical face slope_treshold would cut into the mesh
-            self.vertices, self.triangles = terrain_utils.convert_heightfield_to_trimesh(
-                self.height_field_raw, self.cfg.horizontal_scale, self.cfg.vertical_scale, self.cfg.slope_treshold)
+            # API parity only: this simulator samples the height field itself (bilinear), so a stair riser is a one-cell ramp
+            # rather than the vertical face slope_treshold cuts into the PhysX mesh
+            self.vertices, self.triangles = tu.convert_heightfield_to_trimesh(self.height_field_raw, cfg.horizontal_scale,
+                                                                              cfg.vertical_scale, cfg.slope_treshold)
 
-    # ------------------------------------------------------------------ configuration (terrain.py:37-66)
-    def load_cfgs(self):
-        self._load_cfg(self.cfg)
-        self.cfg.row_indices = np.arange(0, self.cfg.tot_rows)
-        self.cfg.col_indices = np.arange(0, self.cfg.tot_cols)
-        self.cfg.x_offset = 0
-        self.cfg.rows_offset = 0
-        if self.eval_cfg is None:
-            return self.cfg.row_indices, self.cfg.col_indices, [], []
-        self._load_cfg(self.eval_cfg)
-        self.eval_cfg.row_indices = np.arange(self.cfg.tot_rows, self.cfg.tot_rows + self.eval_cfg.tot_rows)
-        self.eval_cfg.col_indices = np.arange(0, self.eval_cfg.tot_cols)
-        self.eval_cfg.x_offset = self.cfg.tot_rows
-        self.eval_cfg.rows_offset = self.cfg.num_rows
-        return self.cfg.row_indices, self.cfg.col_indices, self.eval_cfg.row_indices, self.eval_cfg.col_indices
-
+    # ------------------------------------------------------------------ pixel geometry of one config's block of tiles
     @staticmethod
-    def _load_cfg(cfg):
-        cfg.proportions = [np.sum(cfg.terrain_proportions[:i + 1]) for i in range(len(cfg.terrain_proportions))]
-        cfg.num_sub_terrains = cfg.num_rows * cfg.num_cols
-        cfg.env_origins = np.zeros((cfg.num_rows, cfg.num_cols, 3))
-        cfg.width_per_env_pixels = int(cfg.terrain_length / cfg.horizontal_scale)
-        cfg.length_per_env_pixels = int(cfg.terrain_width / cfg.horizontal_scale)
-        cfg.border = int(cfg.border_size / cfg.horizontal_scale)
-        cfg.tot_cols = int(cfg.num_cols * cfg.width_per_env_pixels) + 2 * cfg.border
-        cfg.tot_rows = int(cfg.num_rows * cfg.length_per_env_pixels) + 2 * cfg.border
+    def _load_cfg(c):
+        px = lambda metres: int(metres / c.horizontal_scale)
+        c.proportions = [np.sum(c.terrain_proportions[:k + 1]) for k in range(len(c.terrain_proportions))]
+        c.num_sub_terrains = c.num_rows * c.num_cols
+        c.env_origins = np.zeros((c.num_rows, c.num_cols, 3))
+        c.width_per_env_pixels, c.length_per_env_pixels, c.border = px(c.terrain_length), px(c.terrain_width), px(c.border_size)
+        c.tot_cols = int(c.num_cols * c.width_per_env_pixels) + 2 * c.border
+        c.tot_rows = int(c.num_rows * c.length_per_env_pixels) + 2 * c.border
 
-    # ------------------------------------------------------------------ tile selection (terrain.py:68-103)
+    def load_cfgs(self):
+        """Train tiles first; eval tiles (if any) are appended below them along the row axis."""
+        blocks, first_row, first_level = [], 0, 0
+        for c in (self.cfg, self.eval_cfg):
+            if c is None:
+                blocks += [[], []]
+                continue
+            self._load_cfg(c)
+            c.row_indices, c.col_indices = np.arange(first_row, first_row + c.tot_rows), np.arange(0, c.tot_cols)
+            c.x_offset, c.rows_offset = first_row, first_level
+            blocks += [c.row_indices, c.col_indices]
+            first_row, first_level = first_row + c.tot_rows, first_level + c.num_rows
+        return tuple(blocks)
+
+    # ------------------------------------------------------------------ which tile goes where
     def initialize_terrains(self):
-        self._initialize_terrain(self.cfg)
-        if self.eval_cfg is not None:
-            self._initialize_terrain(self.eval_cfg)
+        for c in (self.cfg, self.eval_cfg):
+            if c is not None:
+                self._initialize_terrain(c)
 
-    def _initialize_terrain(self, cfg):
-        if cfg.curriculum:
-            self.curriculum(cfg)
-        elif cfg.selected:
-            self.selected_terrain(cfg)
-        else:
-            self.randomized_terrain(cfg)
+    def _initialize_terrain(self, c):
+        (self.curriculum if c.curriculum else self.selected_terrain if c.selected else self.randomized_terrain)(c)
 
-    def randomized_terrain(self, cfg):
-        for k in range(cfg.num_sub_terrains):
-            i, j = np.unravel_index(k, (cfg.num_rows, cfg.num_cols))
+    def curriculum(self, c):
+        """Column = terrain type (choice sweeps the proportion bands), row = difficulty level."""
+        for col in range(c.num_cols):
+            for row in range(c.num_rows):
+                tile = self.make_terrain(c, col / c.num_cols + 0.001, row / c.num_rows * c.difficulty_scale, c.proportions)
+                self.add_terrain_to_map(c, tile, row, col)
+
+    def randomized_terrain(self, c):
+        for k in range(c.num_sub_terrains):
+            row, col = np.unravel_index(k, (c.num_rows, c.num_cols))
             choice = np.random.uniform(0, 1)
             difficulty = np.random.choice([0.5, 0.75, 0.9])
-            self.add_terrain_to_map(cfg, self.make_terrain(cfg, choice, difficulty, cfg.proportions), i, j)
+            self.add_terrain_to_map(c, self.make_terrain(c, choice, difficulty, c.proportions), row, col)
 
-    def curriculum(self, cfg):
-        for j in range(cfg.num_cols):
-            for i in range(cfg.num_rows):
-                difficulty = i / cfg.num_rows * cfg.difficulty_scale
-                choice = j / cfg.num_cols + 0.001
-                self.add_terrain_to_map(cfg, self.make_terrain(cfg, choice, difficulty, cfg.proportions), i, j)
-
-    def selected_terrain(self, cfg):
-        terrain_type = cfg.terrain_kwargs.pop('type')
-        generator = getattr(terrain_utils, terrain_type.split(".")[-1])          # the reference eval()s "terrain_utils.<name>"
-        kwargs = cfg.terrain_kwargs.get("terrain_kwargs", cfg.terrain_kwargs) if isinstance(cfg.terrain_kwargs, dict) \
-            else cfg.terrain_kwargs.terrain_kwargs
-        for k in range(cfg.num_sub_terrains):
-            i, j = np.unravel_index(k, (cfg.num_rows, cfg.num_cols))
-            tile = self._new_tile(cfg)
+    def selected_terrain(self, c):
+        spec = c.terrain_kwargs
+        generator = getattr(tu, spec.pop('type').split(".")[-1])           # the reference eval()s "terrain_utils.<name>"
+        kwargs = spec.get("terrain_kwargs", spec) if isinstance(spec, dict) else spec.terrain_kwargs
+        for k in range(c.num_sub_terrains):
+            row, col = np.unravel_index(k, (c.num_rows, c.num_cols))
+            tile = self._blank_tile(c)
             generator(tile, **kwargs)
-            self.add_terrain_to_map(cfg, tile, i, j)
+            self.add_terrain_to_map(c, tile, row, col)
 
     @staticmethod
-    def _new_tile(cfg):
-        return terrain_utils.SubTerrain("terrain", width=cfg.width_per_env_pixels, length=cfg.width_per_env_pixels,
-                                        vertical_scale=cfg.vertical_scale, horizontal_scale=cfg.horizontal_scale)
+    def _blank_tile(c):
+        return tu.SubTerrain("terrain", width=c.width_per_env_pixels, length=c.width_per_env_pixels,
+                             vertical_scale=c.vertical_scale, horizontal_scale=c.horizontal_scale)
 
-    def make_terrain(self, cfg, choice, difficulty, proportions):
-        """terrain.py:105-156: the tile type is the first cumulative proportion above `choice`; difficulty scales slope,
-        step height, obstacle height and stepping-stone size."""
-        tile = self._new_tile(cfg)
-        slope = difficulty * 0.4
-        step_height = 0.05 + 0.18 * difficulty
-        discrete_obstacles_height = 0.05 + difficulty * (cfg.max_platform_height - 0.05)
-        stepping_stones_size = 1.5 * (1.05 - difficulty)
-        stone_distance = 0.05 if difficulty == 0 else 0.1
-        if choice < proportions[0]:                       # smooth pyramid slope (downhill for the first half of the band)
-            if choice < proportions[0] / 2:
-                slope *= -1
-            terrain_utils.pyramid_sloped_terrain(tile, slope=slope, platform_size=3.)
-        elif choice < proportions[1]:                     # rough pyramid slope
-            terrain_utils.pyramid_sloped_terrain(tile, slope=slope, platform_size=3.)
-            terrain_utils.random_uniform_terrain(tile, min_height=-0.05, max_height=0.05, step=self.cfg.terrain_smoothness,
-                                                 downsampled_scale=0.2)
-        elif choice < proportions[3]:                     # stairs: down for band 2, up for band 3
-            if choice < proportions[2]:
-                step_height *= -1
-            terrain_utils.pyramid_stairs_terrain(tile, step_width=0.31, step_height=step_height, platform_size=3.)
-        elif choice < proportions[4]:                     # discrete obstacles
-            terrain_utils.discrete_obstacles_terrain(tile, discrete_obstacles_height, 1., 2., 20, platform_size=3.)
-        elif choice < proportions[5]:
-            terrain_utils.stepping_stones_terrain(tile, stone_size=stepping_stones_size, stone_distance=stone_distance,
-                                                  max_height=0., platform_size=4.)
-        elif choice < proportions[6]:
-            pass
-        elif choice < proportions[7]:
-            pass
-        elif choice < proportions[8]:                     # uniform noise of Cfg.terrain.terrain_noise_magnitude (train.py: 0 -> flat)
-            terrain_utils.random_uniform_terrain(tile, min_height=-cfg.terrain_noise_magnitude, max_height=cfg.terrain_noise_magnitude,
-                                                 step=0.005, downsampled_scale=0.2)
-        elif choice < proportions[9]:                     # half flat, half rough
-            terrain_utils.random_uniform_terrain(tile, min_height=-0.05, max_height=0.05, step=self.cfg.terrain_smoothness,
-                                                 downsampled_scale=0.2)
-            tile.height_field_raw[0:tile.length // 2, :] = 0
+    def make_terrain(self, c, choice, difficulty, proportions):
+        """The tile type is the first band whose cumulative proportion exceeds `choice` (none: a flat tile)."""
+        tile = self._blank_tile(c)
+        params = _tile_parameters(c, difficulty)
+        for upper, generate in _BANDS:
+            if upper < len(proportions) and choice < proportions[upper]:
+                generate(self, tile, params, c, choice, proportions)
+                break
         return tile
 
-    def add_terrain_to_map(self, cfg, tile, row, col):
-        """terrain.py:158-180: paste the tile, record the env origin (tile centre, z = highest point of the tile)."""
-        start_x = cfg.border + row * cfg.length_per_env_pixels + cfg.x_offset
-        end_x = cfg.border + (row + 1) * cfg.length_per_env_pixels + cfg.x_offset
-        start_y = cfg.border + col * cfg.width_per_env_pixels
-        end_y = cfg.border + (col + 1) * cfg.width_per_env_pixels
-        self.height_field_raw[start_x:end_x, start_y:end_y] = tile.height_field_raw
-        env_origin_x = (row + 0.5) * cfg.terrain_length + cfg.x_offset * tile.horizontal_scale
-        env_origin_y = (col + 0.5) * cfg.terrain_width
-        env_origin_z = np.max(self.height_field_raw[start_x:end_x, start_y:end_y]) * tile.vertical_scale
-        cfg.env_origins[row, col] = [env_origin_x, env_origin_y, env_origin_z]
+    def add_terrain_to_map(self, c, tile, row, col):
+        """Paste the tile into the map; the env origin is the tile centre at the height of the tile's highest sample."""
+        r0 = c.border + c.x_offset + row * c.length_per_env_pixels
+        c0 = c.border + col * c.width_per_env_pixels
+        window = self.height_field_raw[r0:r0 + c.length_per_env_pixels, c0:c0 + c.width_per_env_pixels]
+        window[...] = tile.height_field_raw
+        c.env_origins[row, col] = ((row + 0.5) * c.terrain_length + c.x_offset * tile.horizontal_scale,
+                                   (col + 0.5) * c.terrain_width, np.max(window) * tile.vertical_scale)
