@@ -489,6 +489,184 @@ int launch_persistent(const CUtensorMap& ma, const CUtensorMap& mb, const GemmAr
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// EXPERIMENTAL (GO1_TF32_2CTA=1, off by default, not yet validated on hardware): cta_group::2 variant.  A cluster of two CTAs owns a
+// 256 x 256 output tile: CTA r holds rows [128r, 128r+128) of A and columns [128r, 128r+128) of B in ITS shared memory (32 KB per
+// k-block for a 128 x 256 accumulator per CTA = 0.5x the L2->SM bytes per flop of the 128 x 128 tiling), the leader CTA (rank 0)
+// issues tcgen05.mma.cta_group::2 (M = 256, N = 256) which reads both CTAs' operand slices and writes each CTA's half of the
+// accumulator into that CTA's TMEM.  Protocol: both producers load into their own smem and signal the LEADER's full barrier
+// (cp.async.bulk.tensor...cta_group::2, peer bit of the barrier address cleared); the leader's tcgen05.commit multicasts to the
+// empty / tmem_full barriers of both CTAs; both CTAs' epilogue threads release a TMEM buffer on the leader's tmem_empty barrier.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* leader_bar, void* dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(leader_bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {      // arrives on `bar` (same offset) in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, 0;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+                 ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(192, 1) gemm_tf32_2cta(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmArgs g,
+                                                          const int tiles_m2, const int tiles_n, const int total_tiles) {
+    constexpr int BN = 256, HB = 128;              // cluster tile 256 x 256; each CTA stages 128 rows of A and 128 columns of B
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    float* sA = (float*)base;
+    float* sB = (float*)(base + (size_t)STAGES * BM * BK * 4);
+    uint64_t* full = (uint64_t*)(base + (size_t)STAGES * (BM + HB) * BK * 4);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;        // [2]
+    uint64_t* tmem_empty = tmem_full + 2;        // [2] (the leader's are used)
+    uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int num_kb_total = (g.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 256); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {     // both CTAs of the pair allocate together (same warp id, same slot address)
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                          // the peer's barriers exist before anything signals them
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto tile_coords = [&](int t, int& m0, int& n0, int& kb0, int& nkb) {
+        const int tn = t % tiles_n; t /= tiles_n;
+        const int tm = t % tiles_m2; const int z = t / tiles_m2;
+        m0 = (2 * tm + (int)rank) * BM; n0 = tn * BN; kb0 = z * g.kb_per_split; nkb = min(g.kb_per_split, num_kb_total - kb0);
+    };
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int it = 0;
+            for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+                int m0, n0, kb0, nkb; tile_coords(t, m0, n0, kb0, nkb);
+                const int nb0 = n0 + (int)rank * HB;                     // this CTA's half of the B tile
+                for (int i = 0; i < nkb; i++, it++) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    if (rank == 0) mbar_expect_tx(&full[s], 2 * (BM + HB) * BK * 4);      // bytes of BOTH CTAs land on the leader's barrier
+                    float* a = sA + (size_t)s * BM * BK;
+                    float* b = sB + (size_t)s * HB * BK;
+                    if (g.amn) {
+#pragma unroll
+                        for (int x = 0; x < BM / 32; x++) tma_load_2d_2sm(&mapA, &full[s], a + x * 32 * BK, m0 + 32 * x, (kb0 + i) * BK);
+                    } else tma_load_2d_2sm(&mapA, &full[s], a, (kb0 + i) * BK, m0);
+                    if (g.bmn) {
+#pragma unroll
+                        for (int x = 0; x < HB / 32; x++) tma_load_2d_2sm(&mapB, &full[s], b + x * 32 * BK, nb0 + 32 * x, (kb0 + i) * BK);
+                    } else tma_load_2d_2sm(&mapB, &full[s], b, (kb0 + i) * BK, nb0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {         // the leader issues the pair's MMAs
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.amn ? 1 : 0) << 15) | ((uint32_t)(g.bmn ? 1 : 0) << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+            const uint32_t ka = g.amn ? (1024 >> 4) : 2, kb = g.bmn ? (1024 >> 4) : 2;
+            int it = 0, j = 0;
+            for (int t = cluster_id; t < total_tiles; t += num_clusters, j++) {
+                int m0, n0, kb0, nkb; tile_coords(t, m0, n0, kb0, nkb);
+                const int buf = j & 1;
+                mbar_wait(&tmem_empty[buf], ((j >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+                for (int i = 0; i < nkb; i++, it++) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
+                        const uint64_t da = g.amn ? make_desc_mn(sA + (size_t)s * BM * BK) : make_desc(sA + (size_t)s * BM * BK);
+                        const uint64_t db = g.bmn ? make_desc_mn(sB + (size_t)s * HB * BK) : make_desc(sB + (size_t)s * HB * BK);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; k++) umma_tf32_2sm(tmem_d, da + ka * k, db + kb * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                        umma_commit_2sm(&empty[s]);
+                        if (i == nkb - 1) umma_commit_2sm(&tmem_full[buf]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const bool split = g.kb_per_split < num_kb_total;
+        int j = 0;
+        for (int t = cluster_id; t < total_tiles; t += num_clusters, j++) {
+            int m0, n0, kb0, nkb; tile_coords(t, m0, n0, kb0, nkb);
+            const int buf = j & 1;
+            const int row = m0 + 32 * q + lane;
+            mbar_wait(&tmem_full[buf], (j >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; c++) {
+                uint32_t r[32];
+                tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), r);
+                epilogue_chunk(g, r, row, n0 + 32 * c, split, lane);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive_leader(&tmem_empty[buf]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                          // nobody leaves while the pair may still touch its shared memory / barriers / TMEM
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
+    }
+}
+
+template <int STAGES>
+int launch_2cta(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, int splits, cudaStream_t st) {
+    const size_t smem = (size_t)STAGES * (BM + 128) * BK * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_2cta<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return go1_set_error(cudaGetErrorString(e));
+        configured = true;
+    }
+    const int tiles_m2 = (g.M + 2 * BM - 1) / (2 * BM), tiles_n = (g.N + 255) / 256, total = tiles_m2 * tiles_n * splits;
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    const int clusters = total < sms / 2 ? total : sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32_2cta<STAGES>, ma, mb, g, tiles_m2, tiles_n, total);
+    if (e != cudaSuccess) return go1_set_error(cudaGetErrorString(e));
+    go1_count_launch(1);
+    return 0;
+}
+
 }  // namespace
 
 static int g_tf32_persistent = 1, g_tf32_wide = 1;   // wide = 128 x 256 tiles where the heuristic in go1_gemm_tf32 says they pay
@@ -549,6 +727,8 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
     const int wtiles = ((M + BM - 1) / BM) * ((N + 255) / 256);
     const bool fills = wtiles < 148 ? wtiles >= wide_min_tiles : (double)wtiles / (148.0 * ((wtiles + 147) / 148)) >= 0.85;
     const bool wide = g_tf32_persistent && g_tf32_wide && K >= wide_min_k && N >= 256 && (N % 256 == 0 || N >= 1024) && fills;
+    static const int use_2cta = getenv("GO1_TF32_2CTA") ? atoi(getenv("GO1_TF32_2CTA")) : 0;      // experimental cta_group::2 path
+    const bool two_cta = use_2cta && wide && M >= 256;
     const int BN = wide ? 256 : ((N > 64) ? 128 : (N > 32 ? 64 : 32));
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     int splits = 1;
@@ -560,7 +740,7 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
     CUtensorMap ma, mb;
     // K-major: rows = M (or N), cols = K, box BK x tile rows.  MN-major: rows = K, cols = M (or N), box 32 mn x BK k-rows.
     if (int e = amn ? make_map(&ma, A, K, M, lda, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) : make_map(&ma, A, M, K, lda, BM)) return e;
-    if (int e = bmn ? make_map(&mb, B, K, N, ldb, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) : make_map(&mb, B, N, K, ldb, BN)) return e;
+    if (int e = bmn ? make_map(&mb, B, K, N, ldb, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) : make_map(&mb, B, N, K, ldb, two_cta ? 128 : BN)) return e;
     if (splits > 1) {
         if (!accumulate) { const size_t tot = (size_t)M * N; zero_strided<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cm, ldc, M, N); go1_count_launch(1); }
         g.bias = nullptr; g.act = 0;
@@ -569,7 +749,8 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
     const bool timed = g_time_on && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone;
     if (timed) { cudaEventRecord(timing_event(), st); g_time_flop += 2.0 * (double)M * (double)N * (double)K; }
     int e;
-    if (BN == 256) e = launch_persistent<256, 4>(ma, mb, g, splits, st);
+    if (two_cta) e = launch_2cta<6>(ma, mb, g, splits, st);
+    else if (BN == 256) e = launch_persistent<256, 4>(ma, mb, g, splits, st);
     else if (g_tf32_persistent) e = (BN == 128) ? launch_persistent<128, 3>(ma, mb, g, splits, st) : (BN == 64 ? launch_persistent<64, 4>(ma, mb, g, splits, st) : launch_persistent<32, 4>(ma, mb, g, splits, st));
     else e = (BN == 128) ? launch<128, 3>(ma, mb, g, splits, st) : (BN == 64 ? launch<64, 4>(ma, mb, g, splits, st) : launch<32, 4>(ma, mb, g, splits, st));
     if (e) return e;
