@@ -187,7 +187,8 @@ def test_full_ppo_cycle_matches_reference_golden(impl):
 # matmuls in TF32 by default on Ampere+).
 # ----------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 64, 64), (4096, 256, 2100), (300, 200, 70), (4, 512, 2100), (1000, 1280, 2100),
-                                   (8000, 1280, 1056), (24576, 256, 1024),      # 128 x 256 tiles (>= 60 wide tiles, K >= 1024)
+                                   (8000, 1280, 1056), (24576, 256, 1024),
+                                   (3584, 1280, 1056), (24576, 1280, 1024), (3500, 1100, 2100),   # 128 x 256 tiles / cta_group::2 pairs (wide heuristic)
                                    (24576, 128, 256), (256, 128, 24576), (2100, 1280, 4096)])
 def test_gemm_tcgen05_tf32(M, N, K):
     torch.manual_seed(M * 7 + N * 3 + K)
