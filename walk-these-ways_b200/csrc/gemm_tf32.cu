@@ -490,8 +490,8 @@ int launch_persistent(const CUtensorMap& ma, const CUtensorMap& mb, const GemmAr
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// EXPERIMENTAL (GO1_TF32_2CTA=1, off by default, not yet validated on hardware): cta_group::2 variant.  A cluster of two CTAs owns a
-// 256 x 256 output tile: CTA r holds rows [128r, 128r+128) of A and columns [128r, 128r+128) of B in ITS shared memory (32 KB per
+// cta_group::2 variant (default for the shapes the wide heuristic selects; GO1_TF32_2CTA=0 falls back to the single-CTA 128 x 256
+// kernel).  A cluster of two CTAs owns a 256 x 256 output tile: CTA r holds rows [128r, 128r+128) of A and columns [128r, 128r+128) of B in ITS shared memory (32 KB per
 // k-block for a 128 x 256 accumulator per CTA = 0.5x the L2->SM bytes per flop of the 128 x 128 tiling), the leader CTA (rank 0)
 // issues tcgen05.mma.cta_group::2 (M = 256, N = 256) which reads both CTAs' operand slices and writes each CTA's half of the
 // accumulator into that CTA's TMEM.  Protocol: both producers load into their own smem and signal the LEADER's full barrier
@@ -727,7 +727,7 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
     const int wtiles = ((M + BM - 1) / BM) * ((N + 255) / 256);
     const bool fills = wtiles < 148 ? wtiles >= wide_min_tiles : (double)wtiles / (148.0 * ((wtiles + 147) / 148)) >= 0.85;
     const bool wide = g_tf32_persistent && g_tf32_wide && K >= wide_min_k && N >= 256 && (N % 256 == 0 || N >= 1024) && fills;
-    static const int use_2cta = getenv("GO1_TF32_2CTA") ? atoi(getenv("GO1_TF32_2CTA")) : 0;      // experimental cta_group::2 path
+    static const int use_2cta = getenv("GO1_TF32_2CTA") ? atoi(getenv("GO1_TF32_2CTA")) : 1;      // cta_group::2 pairs for the wide shapes
     const bool two_cta = use_2cta && wide && M >= 256;
     const int BN = wide ? 256 : ((N > 64) ? 128 : (N > 32 ? 64 : 32));
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
