@@ -16,6 +16,7 @@
 // tests/test_resample_host.py); tests/test_curriculum_gpu.py pins this kernel to the host twin.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "go1_layout.h"
 
 void go1_count_launch(int n);
@@ -29,7 +30,7 @@ struct CurArgs {
     Go1SimBuffers b;
     Go1CurriculumConfig c;
     Go1CurriculumBuffers cb;
-    int list, N;
+    int list, N, grouped;
 };
 
 // numpy's DOUBLE_pairwise_sum (contiguous): <8 plain loop, <=128 eight partial sums, else split at n/2 rounded down to
@@ -80,44 +81,47 @@ __device__ __forceinline__ uint32_t mt_mix(uint32_t u, uint32_t v) {
     const uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu);
     return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
 }
-// mt19937_gen over key[624] in shared memory, by the whole CTA.  The sequential recurrence
+// barrier among `nthr` threads: the whole CTA (id 0, __syncthreads) or one category group (named barrier id > 0)
+__device__ __forceinline__ void sync_threads(int bar_id, int nthr) {
+    if (bar_id == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthr) : "memory");
+}
+// mt19937_gen over key[624] in shared memory, by `nthr` >= 227 threads (tid = 0..nthr-1).  The sequential recurrence
 //   key[i] = key[(i + 397) % 624] ^ mix(key[i], key[i + 1])
 // only looks 397 ahead / 227 behind, so it splits into three parallel sweeps ([0,227) reads old words only,
 // [227,454) reads the new [0,227), [454,623) reads the new [227,396)) plus the last word.
-__device__ void mt_twist(uint32_t* key) {
-    const int t = threadIdx.x;
+__device__ void mt_twist(uint32_t* key, int tid, int nthr, int bar_id) {
     uint32_t v = 0;
-    if (t < 227) v = key[t + 397] ^ mt_mix(key[t], key[t + 1]);
-    __syncthreads();
-    if (t < 227) key[t] = v;
-    __syncthreads();
-    if (t >= 227 && t < 454) v = key[t - 227] ^ mt_mix(key[t], key[t + 1]);
-    __syncthreads();
-    if (t >= 227 && t < 454) key[t] = v;
-    __syncthreads();
-    if (t >= 454 && t < 623) v = key[t - 227] ^ mt_mix(key[t], key[t + 1]);
-    __syncthreads();
-    if (t >= 454 && t < 623) key[t] = v;
-    __syncthreads();
-    if (t == 0) key[623] = key[396] ^ mt_mix(key[623], key[0]);
-    __syncthreads();
+    if (tid < 227) v = key[tid + 397] ^ mt_mix(key[tid], key[tid + 1]);
+    sync_threads(bar_id, nthr);
+    if (tid < 227) key[tid] = v;
+    sync_threads(bar_id, nthr);
+    if (tid < 227) v = key[tid] ^ mt_mix(key[tid + 227], key[tid + 228]);          // word tid + 227 in [227, 454)
+    sync_threads(bar_id, nthr);
+    if (tid < 227) key[tid + 227] = v;
+    sync_threads(bar_id, nthr);
+    if (tid < 169) v = key[tid + 227] ^ mt_mix(key[tid + 454], key[tid + 455]);    // word tid + 454 in [454, 623)
+    sync_threads(bar_id, nthr);
+    if (tid < 169) key[tid + 454] = v;
+    sync_threads(bar_id, nthr);
+    if (tid == 0) key[623] = key[396] ^ mt_mix(key[623], key[0]);
+    sync_threads(bar_id, nthr);
 }
-// out[0..need) = the next `need` tempered words of the stream (uniform control flow across the CTA)
-__device__ void mt_draw(uint32_t* key, int* pos_sh, uint32_t* out, int need) {
-    const int t = threadIdx.x;
+// out[0..need) = the next `need` tempered words of the stream (uniform control flow across the participating threads)
+__device__ void mt_draw(uint32_t* key, int* pos_sh, uint32_t* out, int need, int tid, int nthr, int bar_id) {
     int done = 0;
     while (done < need) {
         int pos = *pos_sh;
-        __syncthreads();
+        sync_threads(bar_id, nthr);
         if (pos >= 624) {
-            mt_twist(key);
+            mt_twist(key, tid, nthr, bar_id);
             pos = 0;
         }
         const int take = min(624 - pos, need - done);
-        for (int i = t; i < take; i += CT) out[done + i] = mt_temper(key[pos + i]);
-        __syncthreads();
-        if (t == 0) *pos_sh = pos + take;
-        __syncthreads();
+        for (int i = tid; i < take; i += nthr) out[done + i] = mt_temper(key[pos + i]);
+        sync_threads(bar_id, nthr);
+        if (tid == 0) *pos_sh = pos + take;
+        sync_threads(bar_id, nthr);
         done += take;
     }
 }
@@ -142,11 +146,15 @@ __device__ __forceinline__ float half_plus_quarter(float x) { return __fadd_rn(_
 __device__ __forceinline__ float half_minus_quarter_mod1(float x) { return mod1(__fsub_rn(__fdiv_rn(x, 2.0f), 0.25f)); }
 
 __global__ void __launch_bounds__(CT, 1) go1_curriculum_kernel(const CurArgs A) {
-    __shared__ uint32_t s_key[624];
-    __shared__ int s_pos;
-    __shared__ int s_scan[CT];
-    __shared__ int s_n;
-    __shared__ double s_d[2];
+    __shared__ uint32_t s_key4[4][624];  // MT19937 words: [0] on the sequential path, one per category group on the grouped path
+    __shared__ int s_pos4[4];
+    __shared__ int s_scan[CT];           // block scan (sequential path) / four 256-entry index lists (grouped path)
+    __shared__ int s_n4[4];
+    __shared__ double s_d4[4][2];
+    uint32_t* const s_key = s_key4[0];
+    int& s_pos = s_pos4[0];
+    int& s_n = s_n4[0];
+    double* const s_d = s_d4[0];
     const int t = threadIdx.x;
     const int N = A.N;
     const Go1CurriculumConfig& c = A.c;
@@ -161,7 +169,8 @@ __global__ void __launch_bounds__(CT, 1) go1_curriculum_kernel(const CurArgs A) 
     // built by counting predecessors in parallel; the global-scratch path (n > SMALL) keeps the simple serial builders
     constexpr int SMALL = 512;
     __shared__ int s_arr[7][SMALL];
-    __shared__ double s_cdf[1024];       // cdf of the current category when it fits (searchsorted latency)
+    __shared__ double s_cdf4[4][512];    // cdf staging: flat [2048] on the sequential path, one row per category group otherwise
+    double* const s_cdf = &s_cdf4[0][0];
     const bool small = n <= SMALL;
     int* mark = cb.scratch_i32;          // [N], all zero between calls
     int* order = small ? s_arr[0] : mark + N;               // [n] event slot of the p-th smallest env id
@@ -173,6 +182,170 @@ __global__ void __launch_bounds__(CT, 1) go1_curriculum_kernel(const CurArgs A) 
     int* a_list = small ? s_arr[6] : mark + 7 * (size_t)N;  // [n] per-phase index list (successful bins / category members)
     double* dd = cb.scratch_f64;         // [(D + 1) N] doubles of the current category
     double* r2 = dd + (size_t)(D + 1) * N;   // [N] second category draw (exclusive / balanced gait modes)
+
+    // =============================================================================================================
+    // Grouped path (the usual call: a handful of envs).  The categories are independent -- own weights, own cdf, own
+    // RandomState -- so phases C and E run for all of them at once, one 256-thread group per category with a named
+    // barrier, instead of one category after the other; everything lives in shared memory.  Same arithmetic, same order
+    // inside every category, hence the same bits (tests/test_curriculum_gpu.py runs both paths).
+    // =============================================================================================================
+    constexpr int GS = 256, NSM = 256;
+    if (A.grouped && n <= NSM && ncat <= 4 && L <= 512 && N >= 1024) {
+        const int g = t / GS, gt = t % GS, bar = 1 + g;
+        int* ord = s_arr[0]; int* cat_old = s_arr[1]; int* bin_old = s_arr[2]; int* okf = s_arr[3];
+        int* cat_new = s_arr[4]; int* bin_new = s_arr[5]; int* ids = s_arr[6];
+        int* glist = s_scan + g * NSM;                      // this group's index list
+        // A: rank sort of the (unique) ids
+        if (t < n) ids[t] = (int)ev[(size_t)t * S];
+        __syncthreads();
+        if (t < n) {
+            const int me = ids[t];
+            int rank = 0;
+            for (int q = 0; q < n; q++) rank += ids[q] < me;
+            ord[rank] = t;
+        }
+        __syncthreads();
+        // B: success test, old bin / category
+        if (t < n) {
+            const float* e = ev + (size_t)ord[t] * S;
+            const int id = (int)e[0];
+            bool ok = c.num_task_keys > 0;
+            for (int q = 0; q < c.num_task_keys; q++) ok = ok && (__fdiv_rn(e[1 + c.task_col[q]], c.ep_len) > c.threshold[q]);
+            cb.out_ids[t] = id;
+            okf[t] = ok ? 1 : 0;
+            cat_old[t] = cb.env_categories[id];
+            bin_old[t] = cb.env_bins[id];
+        }
+        __syncthreads();
+        // C: curriculum update of category g by group g
+        if (g < ncat) {
+            if (gt == 0) s_n4[g] = 0;
+            sync_threads(bar, GS);
+            if (gt < n && okf[gt] && cat_old[gt] == g) {
+                int pos = 0;
+                for (int q = 0; q < gt; q++) pos += (okf[q] && cat_old[q] == g);
+                glist[pos] = bin_old[gt];
+                atomicAdd(&s_n4[g], 1);
+            }
+            sync_threads(bar, GS);
+            const int ns = s_n4[g];
+            if (ns > 0) {
+                double* w = cb.weights + (size_t)g * L;
+                double nv = 0.0;
+                if (gt < ns) nv = clip01(__dadd_rn(w[glist[gt]], 0.2));                 // from the OLD weights
+                sync_threads(bar, GS);
+                if (gt < ns) w[glist[gt]] = nv;
+                sync_threads(bar, GS);
+                for (int sidx = 0; sidx < ns; sidx++) {
+                    const int bsel = glist[sidx];
+                    for (int j = gt; j < L; j += GS) {
+                        bool adj = true;
+                        for (int d = 0; d < D; d++) {
+                            const double gg = cb.grid[(size_t)j * D + d], ce = cb.grid[(size_t)bsel * D + d], r = cb.local_range[d];
+                            adj = adj && (gg >= __dsub_rn(ce, r)) && (gg <= __dadd_rn(ce, r));
+                        }
+                        if (adj) w[j] = clip01(__dadd_rn(w[j], 0.2));
+                    }
+                    sync_threads(bar, GS);
+                }
+                if (gt == 0) cb.cdf_valid[g] = 0;
+            }
+        }
+        __syncthreads();
+        // D: new categories (one splitmix64 stream, env order)
+        if (t == 0) {
+            uint64_t st = cb.cat_rng[0];
+            const bool pow2 = (ncat & (ncat - 1)) == 0;
+            const double pc = 1.0 / (double)ncat;
+            for (int p = 0; p < n; p++) {
+                const double r = splitmix_next(st);
+                int cat = -1;
+                if (pow2) cat = (int)(r * (double)ncat);
+                else
+                    for (int i = 0; i < ncat; i++)
+                        if (pc * i <= r && r < pc * (i + 1)) cat = i;
+                cat_new[p] = cat;
+                bin_new[p] = bin_old[p];
+            }
+            cb.cat_rng[0] = st;
+        }
+        if (t < n)
+            for (int d = 0; d < GO1_NUM_COMMANDS; d++) cb.out_commands[(size_t)t * GO1_NUM_COMMANDS + d] = 0.0f;
+        __syncthreads();
+        // E: category g's members sampled by group g
+        if (g < ncat) {
+            if (gt == 0) s_n4[g] = 0;
+            sync_threads(bar, GS);
+            if (gt < n && cat_new[gt] == g) {
+                int pos = 0;
+                for (int q = 0; q < gt; q++) pos += cat_new[q] == g;
+                glist[pos] = gt;
+                atomicAdd(&s_n4[g], 1);
+            }
+            sync_threads(bar, GS);
+            const int ni = s_n4[g];
+            if (ni > 0) {
+                double* w = cb.weights + (size_t)g * L;
+                double* cdf = cb.cdf + (size_t)g * L;
+                if (!cb.cdf_valid[g]) {
+                    if (gt == 0) s_d4[g][0] = __dadd_rn(0.0, pairwise_sum(w, L));
+                    sync_threads(bar, GS);
+                    const double tot = s_d4[g][0];
+                    for (int j = gt; j < L; j += GS) cdf[j] = __ddiv_rn(w[j], tot);
+                    sync_threads(bar, GS);
+                    if (gt == 0) {
+                        double acc = cdf[0];
+                        for (int j = 1; j < L; j++) { acc = __dadd_rn(acc, cdf[j]); cdf[j] = acc; }
+                        s_d4[g][1] = acc;
+                    }
+                    sync_threads(bar, GS);
+                    const double last = s_d4[g][1];
+                    for (int j = gt; j < L; j += GS) cdf[j] = __ddiv_rn(cdf[j], last);
+                    sync_threads(bar, GS);
+                    if (gt == 0) cb.cdf_valid[g] = 1;
+                }
+                uint32_t* mt = cb.mt + (size_t)g * 625;
+                uint32_t* key = s_key4[g];
+                double* cdf_s = s_cdf4[g];
+                for (int j = gt; j < 624; j += GS) key[j] = mt[j];
+                if (gt == 0) s_pos4[g] = (int)mt[624];
+                for (int j = gt; j < L; j += GS) cdf_s[j] = cdf[j];
+                sync_threads(bar, GS);
+                const int nd = (D + 1) * ni;
+                uint32_t* words = cb.scratch_u32 + (size_t)g * 2 * (D + 1) * NSM;
+                double* ddg = dd + (size_t)g * (D + 1) * NSM;
+                mt_draw(key, &s_pos4[g], words, 2 * nd, gt, GS, bar);
+                for (int j = gt; j < 624; j += GS) mt[j] = key[j];
+                if (gt == 0) mt[624] = (uint32_t)s_pos4[g];
+                for (int q = gt; q < nd; q += GS) {
+                    const uint32_t a = words[2 * q] >> 5, bb = words[2 * q + 1] >> 6;
+                    ddg[q] = __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)bb), 9007199254740992.0);
+                }
+                sync_threads(bar, GS);
+                if (gt < ni) {
+                    const int p = glist[gt];
+                    const double u = ddg[gt];
+                    int lo = 0, hi = L;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (cdf_s[mid] <= u) lo = mid + 1; else hi = mid;
+                    }
+                    const int idx = min(lo, L - 1);
+                    bin_new[p] = idx;
+                    for (int d = 0; d < D; d++) {
+                        const double ce = cb.grid[(size_t)idx * D + d];
+                        const double lo_ = __dadd_rn(ce, cb.half_bins[d]), hi_ = __dsub_rn(ce, cb.half_bins[d]);
+                        const double val = __dadd_rn(lo_, __dmul_rn(__dsub_rn(hi_, lo_), ddg[ni + (size_t)gt * D + d]));
+                        if (d < nc && d < GO1_NUM_COMMANDS) cb.out_commands[(size_t)p * GO1_NUM_COMMANDS + d] = __double2float_rn(val);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // hand over to the common tail (second category draw, phase F) with the arrays it expects
+        order = ord; a_cat_old = cat_old; a_bin_old = bin_old; a_ok = okf; a_cat_new = cat_new; a_bin_new = bin_new;
+        goto tail;
+    }
 
     // ---- A: ascending env order --------------------------------------------------------------------------------
     if (small) {             // rank of every id among the n ids (ids are unique)
@@ -332,7 +505,7 @@ __global__ void __launch_bounds__(CT, 1) go1_curriculum_kernel(const CurArgs A) 
         if (t == 0) s_pos = (int)mt[624];
         __syncthreads();
         const int nd = (D + 1) * ni;
-        mt_draw(s_key, &s_pos, cb.scratch_u32, 2 * nd);
+        mt_draw(s_key, &s_pos, cb.scratch_u32, 2 * nd, t, CT, 0);
         for (int j = t; j < 624; j += CT) mt[j] = s_key[j];
         if (t == 0) mt[624] = (uint32_t)s_pos;
         for (int q = t; q < nd; q += CT) {
@@ -365,6 +538,7 @@ __global__ void __launch_bounds__(CT, 1) go1_curriculum_kernel(const CurArgs A) 
         __syncthreads();
     }
 
+tail:
     // second category draw of the two non-gaitwise gait modes (legged_robot.py:783, 795)
     const bool need_r2 = nc > 5 && !c.gaitwise_curricula && (c.exclusive_phase_offset || c.balance_gait_distribution);
     if (need_r2) {
@@ -434,6 +608,8 @@ extern "C" int go1_launch_curriculum(const Go1SimBuffers* b, const Go1Curriculum
                                      cudaStream_t st) {
     CurArgs a;
     a.b = *b; a.c = *cfg; a.cb = *cb; a.list = list; a.N = N;
+    static const int grouped = getenv("GO1_CUR_GROUPED") ? atoi(getenv("GO1_CUR_GROUPED")) : 0;
+    a.grouped = grouped;
     go1_curriculum_kernel<<<1, CT, 0, st>>>(a);
     go1_count_launch(1);
     return (int)cudaGetLastError();
