@@ -58,6 +58,7 @@ def _check_state(env, dc, tag, bins_snapshot):
 
 @pytest.mark.parametrize("mode", ["gaitwise", "nominal_binary", "exclusive", "balanced"])
 def test_device_curriculum_matches_host_twin(mode):
+    """Event counts 0..512: <= 256 events take the category-parallel grouped path of the kernel, more take the sequential one."""
     over = {"gaitwise": {}, "nominal_binary": dict(gaitwise_curricula=False, binary_phases=True),
             "exclusive": dict(gaitwise_curricula=False, exclusive_phase_offset=True),
             "balanced": dict(gaitwise_curricula=False, exclusive_phase_offset=False, balance_gait_distribution=True)}[mode]

@@ -608,7 +608,7 @@ extern "C" int go1_launch_curriculum(const Go1SimBuffers* b, const Go1Curriculum
                                      cudaStream_t st) {
     CurArgs a;
     a.b = *b; a.c = *cfg; a.cb = *cb; a.list = list; a.N = N;
-    static const int grouped = getenv("GO1_CUR_GROUPED") ? atoi(getenv("GO1_CUR_GROUPED")) : 0;
+    static const int grouped = getenv("GO1_CUR_GROUPED") ? atoi(getenv("GO1_CUR_GROUPED")) : 1;      // 0: force the sequential path
     a.grouped = grouped;
     go1_curriculum_kernel<<<1, CT, 0, st>>>(a);
     go1_count_launch(1);
