@@ -196,8 +196,8 @@ typedef struct Go1CurriculumBuffers {
     double* cdf;                 /* [num_categories][num_bins]   cached sampling cdf */
     int32_t* cdf_valid;          /* [num_categories]             0 after a weight change */
     int32_t* scratch_i32;        /* [8N + 64], zero on first use */
-    uint32_t* scratch_u32;       /* [2 (num_dims + 1) N] */
-    double* scratch_f64;         /* [(num_dims + 2) N] */
+    uint32_t* scratch_u32;       /* [2 (num_dims + 1) max(N, 1024)] */
+    double* scratch_f64;         /* [(num_dims + 2) max(N, 1024)] */
     int32_t* out_count;          /* [1]   number of envs processed (k for go1_sim_reset_idx_dev) */
     int32_t* out_ids;            /* [N]   their ids, ascending */
     float* out_commands;         /* [N][15] their new commands */
@@ -210,6 +210,10 @@ int go1_sizeof_curriculum(int which);
  * list 1: envs due for the periodic resample -> commands written and command_sums zeroed in place
  *         (go1_sim_set_commands semantics). */
 int go1_curriculum_resample(Go1Sim* sim, const Go1CurriculumConfig* cfg, const Go1CurriculumBuffers* bufs, int list, void* stream);
+
+/* 1: calls with <= 256 events process the (independent) categories concurrently, one 256-thread group each; 0 (default): one
+ * category after the other.  Same arithmetic either way. */
+void go1_curriculum_set_grouped(int on);
 
 /* go1_sim_reset_idx with the env count read from device memory (*k_dev <= num_envs) and an optional per-call
  * accumulator for extras["train/episode"] (NULL = the bound episode_acc). */

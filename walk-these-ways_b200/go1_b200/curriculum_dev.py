@@ -77,8 +77,8 @@ class DeviceCurriculum:
         self.cdf = torch.zeros(ncat, L, **f64)
         self.cdf_valid = torch.zeros(ncat, **i32)
         self.scratch_i32 = torch.zeros(8 * N + 64, **i32)
-        self.scratch_u32 = torch.zeros(2 * (D + 1) * N, **i32)
-        self.scratch_f64 = torch.zeros((D + 2) * N, **f64)
+        self.scratch_u32 = torch.zeros(2 * (D + 1) * max(N, 1024), **i32)
+        self.scratch_f64 = torch.zeros((D + 2) * max(N, 1024), **f64)
         self.out_count = torch.zeros(1, **i32)
         self.out_ids = torch.zeros(N, **i32)
         self.out_commands = torch.zeros(N, capi.NUM_COMMANDS, device=dev)
