@@ -431,6 +431,10 @@ TERRAIN_CASES = {
 }
 
 
+EVAL_TERRAIN_OVERRIDES = dict(curriculum=False, selected=False, num_rows=2, num_cols=3, border_size=3, terrain_noise_magnitude=0.05,
+                              terrain_proportions=[0.2, 0.2, 0.2, 0.2, 0.2])
+
+
 def make_terrain(Cfg):
     """The reference's Terrain class (go1_gym/utils/terrain.py) driving OUR generators: pins tile layout, type/difficulty
     selection, numpy RNG consumption and env origins of walk-these-ways_b200/go1_gym/utils/terrain.py."""
@@ -448,6 +452,23 @@ def make_terrain(Cfg):
             out[f"{name}/vertices_sample"] = t.vertices[::997].copy(); out[f"{name}/triangles_sample"] = t.triangles[::997].copy()
         for k, v in saved.items():
             setattr(Cfg.terrain, k, v)
+    # train + eval tile sets in one map (terrain.py:37-51: eval rows are appended below the train rows)
+    import copy
+    over, seed = TERRAIN_CASES["curriculum"]
+    saved = {k: getattr(Cfg.terrain, k) for k in over}
+    for k, v in over.items():
+        setattr(Cfg.terrain, k, v)
+    ev = type("eval_terrain", (), {k: copy.deepcopy(v) for k, v in vars(Cfg.terrain).items() if not k.startswith("__")})
+    for k, v in EVAL_TERRAIN_OVERRIDES.items():
+        setattr(ev, k, v)
+    np.random.seed(seed)
+    t = Terrain(Cfg.terrain, 16, ev, 8)
+    out["train_eval/height_field_raw"] = t.height_field_raw.copy()
+    out["train_eval/env_origins"] = Cfg.terrain.env_origins.copy()
+    out["train_eval/eval_env_origins"] = ev.env_origins.copy()
+    out["train_eval/eval_offsets"] = np.array([ev.x_offset, ev.rows_offset, t.tot_rows, t.tot_cols])
+    for k, v in saved.items():
+        setattr(Cfg.terrain, k, v)
     np.savez_compressed(os.path.join(HERE, "terrain.npz"), **out)
     print("terrain.npz:", {k: v.shape for k, v in out.items()}, "nonzero", {k: int(np.count_nonzero(v)) for k, v in out.items() if "height" in k})
 

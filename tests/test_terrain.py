@@ -39,6 +39,26 @@ def test_terrain_class_matches_reference_class():
         assert t.is_flat == (name == "train_py")
 
 
+def test_train_plus_eval_tile_sets_match_reference_class():
+    """terrain.py:37-51: the eval tiles are appended below the train tiles; offsets, both origin tables and the joint map."""
+    import copy
+    from go1_gym.utils.terrain import Terrain
+    from make_golden import TERRAIN_CASES, EVAL_TERRAIN_OVERRIDES
+    Cfg = _cfg()
+    over, seed = TERRAIN_CASES["curriculum"]
+    for k, v in over.items():
+        setattr(Cfg.terrain, k, v)
+    ev = type("eval_terrain", (), {k: copy.deepcopy(v) for k, v in vars(Cfg.terrain).items() if not k.startswith("__")})
+    for k, v in EVAL_TERRAIN_OVERRIDES.items():
+        setattr(ev, k, v)
+    np.random.seed(seed)
+    t = Terrain(Cfg.terrain, 16, ev, 8)
+    assert np.array_equal(t.height_field_raw, G["train_eval/height_field_raw"])
+    assert np.array_equal(Cfg.terrain.env_origins, G["train_eval/env_origins"])
+    assert np.array_equal(ev.env_origins, G["train_eval/eval_env_origins"])
+    assert np.array_equal(np.array([ev.x_offset, ev.rows_offset, t.tot_rows, t.tot_cols]), G["train_eval/eval_offsets"])
+
+
 def test_generators_defining_properties():
     from go1_gym.utils import terrain_utils as tu
     mk = lambda: tu.SubTerrain(width=80, length=80, vertical_scale=0.005, horizontal_scale=0.1)
