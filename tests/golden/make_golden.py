@@ -469,6 +469,30 @@ def make_terrain(Cfg):
     out["train_eval/eval_offsets"] = np.array([ev.x_offset, ev.rows_offset, t.tot_rows, t.tot_cols])
     for k, v in saved.items():
         setattr(Cfg.terrain, k, v)
+    # measured heights (legged_robot.py:1756-1806) on the curriculum map: the reference's own _init_height_points / _get_heights
+    from go1_gym.envs.base.legged_robot import LeggedRobot
+    over, seed = TERRAIN_CASES["curriculum"]
+    saved = {k: getattr(Cfg.terrain, k) for k in over}
+    for k, v in over.items():
+        setattr(Cfg.terrain, k, v)
+    hf = out["curriculum/height_field_raw"]
+    n = 48
+    g = torch.Generator().manual_seed(9)
+    env = types.SimpleNamespace(device="cpu", cfg=Cfg)
+    env.terrain = types.SimpleNamespace(cfg=Cfg.terrain)
+    env.height_samples = torch.tensor(hf)
+    rp = torch.rand(n, 3, generator=g) * torch.tensor([30.0, 46.0, 0.6]) + torch.tensor([1.0, 1.0, 0.1])
+    ang = (torch.rand(n, 3, generator=g) - 0.5) * torch.tensor([0.8, 0.8, 6.2])
+    cr, sr, cp, sp, cyw, syw = [f(ang[:, i] / 2) for i in range(3) for f in (torch.cos, torch.sin)]
+    q = torch.stack([sr * cp * cyw - cr * sp * syw, cr * sp * cyw + sr * cp * syw, cr * cp * syw - sr * sp * cyw, cr * cp * cyw + sr * sp * syw], 1)
+    env.root_states = torch.cat([rp, q, torch.zeros(n, 6)], 1)
+    env.base_quat = env.root_states[:, 3:7]
+    ids = torch.arange(n)
+    env.height_points = LeggedRobot._init_height_points(env, ids, Cfg)
+    out["heights/base_pos"] = rp.numpy(); out["heights/base_quat"] = q.numpy()
+    out["heights/measured"] = LeggedRobot._get_heights(env, ids, Cfg).numpy()
+    for k, v in saved.items():
+        setattr(Cfg.terrain, k, v)
     np.savez_compressed(os.path.join(HERE, "terrain.npz"), **out)
     print("terrain.npz:", {k: v.shape for k, v in out.items()}, "nonzero", {k: int(np.count_nonzero(v)) for k, v in out.items() if "height" in k})
 

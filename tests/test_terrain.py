@@ -59,6 +59,26 @@ def test_train_plus_eval_tile_sets_match_reference_class():
     assert np.array_equal(np.array([ev.x_offset, ev.rows_offset, t.tot_rows, t.tot_cols]), G["train_eval/eval_offsets"])
 
 
+def test_measured_heights_match_reference_get_heights():
+    """measured_heights_at (the torch restatement the GPU test checks the kernel against) vs the reference's own
+    _init_height_points + _get_heights (legged_robot.py:1756-1806) on the curriculum map, 48 tilted and yawed bases."""
+    import torch
+    from go1_gym.envs.base.legged_robot import measured_heights_at
+    from make_golden import TERRAIN_CASES
+    Cfg = _cfg()
+    for k, v in TERRAIN_CASES["curriculum"][0].items():
+        setattr(Cfg.terrain, k, v)
+    hs = torch.tensor(G["curriculum/height_field_raw"])
+    got = measured_heights_at(torch.tensor(G["heights/base_quat"]), torch.tensor(G["heights/base_pos"]), hs, Cfg.terrain).numpy()
+    want = G["heights/measured"]
+    assert got.shape == want.shape == (48, 17 * 11)
+    same = got == want
+    # the yaw rotation is evaluated as (cos, sin) here and as a quaternion product there: a point within float rounding of a cell
+    # edge may truncate to the neighbouring cell
+    assert same.mean() > 0.995, same.mean()
+    assert np.abs(got - want)[~same].max(initial=0.0) <= 0.2 and np.count_nonzero(want) > 1000
+
+
 def test_generators_defining_properties():
     from go1_gym.utils import terrain_utils as tu
     mk = lambda: tu.SubTerrain(width=80, length=80, vertical_scale=0.005, horizontal_scale=0.1)

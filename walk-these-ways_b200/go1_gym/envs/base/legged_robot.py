@@ -95,6 +95,26 @@ class _LazyDict(dict):
         return (dict, (dict(self),))
 
 
+def measured_heights_at(base_quat, base_pos, height_samples, terrain_cfg):
+    """_get_heights of the reference (legged_robot.py:1790-1806) as a pure function: the measured_points grid rotated by the
+    base YAW (quat_apply_yaw, go1_gym/utils/math_utils.py:12-16) and shifted to the base position; per point the minimum of
+    the three height samples at the truncated cell index (x, y), (x+1, y), (x, y+1).  Returns [n, len(px)*len(py)] metres."""
+    t = terrain_cfg
+    dev = base_quat.device
+    gx, gy = torch.meshgrid(torch.tensor(t.measured_points_x, device=dev), torch.tensor(t.measured_points_y, device=dev), indexing="ij")
+    lx, ly = gx.reshape(1, -1), gy.reshape(1, -1)
+    yn = torch.rsqrt(base_quat[:, 2] ** 2 + base_quat[:, 3] ** 2)
+    yz, yw = base_quat[:, 2] * yn, base_quat[:, 3] * yn
+    cy, sy = (yw * yw - yz * yz)[:, None], (2 * yw * yz)[:, None]
+    wx = cy * lx - sy * ly + base_pos[:, 0:1] + t.border_size
+    wy = sy * lx + cy * ly + base_pos[:, 1:2] + t.border_size
+    ix = torch.clip((wx / t.horizontal_scale).long(), 0, height_samples.shape[0] - 2)
+    iy = torch.clip((wy / t.horizontal_scale).long(), 0, height_samples.shape[1] - 2)
+    hs = height_samples
+    h = torch.min(torch.min(hs[ix, iy], hs[ix + 1, iy]), hs[ix, iy + 1])
+    return h.float() * t.vertical_scale
+
+
 class LeggedRobot(BaseTask):
     def __init__(self, cfg: Cfg, sim_params, physics_engine, sim_device, headless, eval_cfg=None, initial_dynamics_dict=None):
         if eval_cfg is not None:
@@ -168,25 +188,11 @@ class LeggedRobot(BaseTask):
         body-height termination)."""
         cfg = cfg or self.cfg
         t = cfg.terrain
-        px_, py_ = torch.tensor(t.measured_points_x, device=self.device), torch.tensor(t.measured_points_y, device=self.device)
-        n_pts = len(px_) * len(py_)
+        n_pts = len(t.measured_points_x) * len(t.measured_points_y)
         env_ids = torch.as_tensor(env_ids, device=self.device, dtype=torch.long)
         if t.mesh_type == 'plane' or getattr(self, "height_samples", None) is None:
             return torch.zeros(len(env_ids), n_pts, device=self.device)
-        gx, gy = torch.meshgrid(px_, py_, indexing="ij")
-        q = self.base_quat[env_ids]
-        yn = torch.rsqrt(q[:, 2] ** 2 + q[:, 3] ** 2)
-        yz, yw = q[:, 2] * yn, q[:, 3] * yn
-        cy, sy = (yw * yw - yz * yz)[:, None], (2 * yw * yz)[:, None]
-        lx, ly = gx.reshape(1, -1), gy.reshape(1, -1)
-        pos = self.base_pos[env_ids]
-        wx = cy * lx - sy * ly + pos[:, 0:1] + t.border_size
-        wy = sy * lx + cy * ly + pos[:, 1:2] + t.border_size
-        ix = torch.clip((wx / t.horizontal_scale).long(), 0, self.height_samples.shape[0] - 2)
-        iy = torch.clip((wy / t.horizontal_scale).long(), 0, self.height_samples.shape[1] - 2)
-        hs = self.height_samples
-        h = torch.min(torch.min(hs[ix, iy], hs[ix + 1, iy]), hs[ix, iy + 1])
-        return h.float() * t.vertical_scale
+        return measured_heights_at(self.base_quat[env_ids], self.base_pos[env_ids], self.height_samples, t)
 
     @property
     def measured_heights(self):
