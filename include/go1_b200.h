@@ -22,8 +22,9 @@ extern "C" {
 #define GO1_NUM_DOF 12
 #define GO1_NUM_COMMANDS 15
 #define GO1_MAX_OBS 128
-#define GO1_MAX_PRIV_OBS 32
+#define GO1_MAX_PRIV_OBS 48
 #define GO1_EVENT_STRIDE 6        /* floats per event record */
+#define GO1_RESET_RAND_STRIDE 48  /* injected uniform draws per env (Go1SimBuffers.reset_rand) */
 
 /* reward term ids: one per CoRLRewards._reward_<name> (go1_gym/envs/rewards/corl_rewards.py:15-201) */
 enum Go1RewardTerm {
@@ -35,6 +36,25 @@ enum Go1RewardTerm {
     GO1_REW_FEET_CLEARANCE_CMD_LINEAR, GO1_REW_FEET_IMPACT_VEL, GO1_REW_ORIENTATION_CONTROL,
     GO1_REW_RAIBERT_HEURISTIC, GO1_REW_TERMINATION, GO1_NUM_REWARD_TERMS
 };
+
+/* The part of Cfg that LeggedRobot._call_train_eval (legged_robot.py:531-544) switches between `cfg` (envs
+ * < num_train_envs) and `eval_cfg` (the rest): per-episode / periodic domain randomisation (:611-665), reset ranges
+ * (:965-1001), pushes (:1017-1026) and edge teleports (:1028-1051). */
+typedef struct Go1DomainRand {
+    int32_t randomize_motor_strength, randomize_motor_offset, randomize_Kp_factor, randomize_Kd_factor;
+    float motor_strength_range[2], motor_offset_range[2], Kp_factor_range[2], Kd_factor_range[2];
+    /* _randomize_rigid_body_props again at reset / every rand_interval steps (legged_robot.py:164-166, 706-708) */
+    int32_t randomize_rigids_after_start, randomize_base_mass, randomize_com_displacement, randomize_friction, randomize_restitution;
+    float added_mass_range[2], com_displacement_range[2], friction_range[2], restitution_range[2];
+    /* _push_robots: every push_interval steps the base xy velocity is redrawn in [-max_push_vel_xy, max_push_vel_xy] */
+    int32_t push_robots, push_interval;
+    float max_push_vel_xy;
+    /* _teleport_robots: x < x_lo -> x += dx; then x > x_hi -> x -= dx; same for y (thresholds as float32, like the tensor compare) */
+    int32_t teleport_robots;
+    float teleport_x_lo, teleport_x_hi, teleport_dx, teleport_y_lo, teleport_y_hi, teleport_dy;
+    /* _reset_root_states */
+    float x_init_range, y_init_range, yaw_init_range, x_init_offset, y_init_offset;
+} Go1DomainRand;
 
 /* Resolved configuration of the env hot path.  Field-by-field mirror of what LeggedRobot reads from
  * Cfg (go1_gym/envs/base/legged_robot_config.py) after _parse_cfg (legged_robot.py:1716-1732). */
@@ -74,13 +94,12 @@ typedef struct Go1SimConfig {
     /* termination (legged_robot.py:138-148) */
     int32_t use_terminal_body_height, max_episode_length;
     float terminal_body_height;
-    /* domain randomisation (legged_robot.py:645-665) and command resampling interval (:684-686) */
-    int32_t randomize_motor_strength, randomize_motor_offset, randomize_Kp_factor, randomize_Kd_factor,
-            rand_interval, resampling_interval;
-    float motor_strength_range[2], motor_offset_range[2], Kp_factor_range[2], Kd_factor_range[2];
+    /* domain randomisation: dr[0] for train envs, dr[1] for eval envs (= dr[0] without an eval_cfg); the interval of the
+     * periodic re-randomisation is the TRAIN cfg's for all envs (legged_robot.py:697-699); command resampling interval (:684-686) */
+    Go1DomainRand dr[2];
+    int32_t rand_interval, resampling_interval;
     /* reset (legged_robot.py:948-1001) */
     float base_init_state[13];
-    float x_init_range, y_init_range, yaw_init_range, x_init_offset, y_init_offset;
     int32_t custom_origins;
     /* rigid-body solver (our algorithm; PhysX parameters legged_robot_config.py:402-421) */
     float erp, cfm, max_depen_vel, contact_margin, bounce_threshold;
@@ -112,7 +131,10 @@ typedef struct Go1SimBuffers {
     float* events;       /* [2][N][GO1_EVENT_STRIDE]: env id + 4 curriculum command_sums + ep_len */
     float* episode_acc;  /* [GO1_NUM_REWARD_TERMS+2] sum of episode_sums over envs reset this step, + count */
     const float* noise;  /* optional [N][num_obs] uniform(0,1) draws injected for parity tests, or NULL */
-    const float* reset_rand; /* optional [N][40] uniform(0,1) draws injected for reset/DR parity tests, or NULL */
+    const float* reset_rand; /* optional [N][GO1_RESET_RAND_STRIDE] uniform(0,1) draws injected for reset/DR/push parity tests, or NULL.
+                              * slots: 0-11 dof pos, 12-14 x y yaw, 15-20 base twist, 21 motor strength, 22 Kp, 23 Kd, 24-35 motor offsets,
+                              * 36-37 push xy, 38 payload, 39-41 com displacement, 42 friction, 43 restitution */
+    float* episode_sums_eval;/* optional [GO1_NUM_REWARD_TERMS+1][N], -1 = unset: LeggedRobot.episode_sums_eval (legged_robot.py:188-195), or NULL */
 } Go1SimBuffers;
 
 typedef struct Go1Sim Go1Sim;
@@ -336,11 +358,16 @@ int go1_ppo_adaptive_lr(const float* scalars, float* lr_dev, float desired_kl, f
 
 /* Replaces RolloutStorage.add_transitions (rollout_storage.py:55-69) and the time-out bootstrap of
  * PPO.process_env_step (ppo.py:84-86: rewards += gamma * values * time_outs) in one launch.
- * in_f32[10]  = {obs[n][nobs], priv[n][npriv], obs_history[n][nhist], actions[n][nact], rewards[n], values[n], log_prob[n],
+ * in_f32[10]  = {obs[n][nobs] or NULL, priv[n][npriv] or NULL, obs_history[n][nhist], actions[n][nact], rewards[n], values[n], log_prob[n],
  *                action_mean[n][nact], std[nact], env_bins[n] or NULL};  dones/time_outs: uint8 [n] (time_outs may be NULL)
  * out_f32[10] = the slot `step` of the storage slabs in the same order (sigma[n][nact] for std);  s_dones: uint8 [n]. */
 int go1_store_transition(const float* const* in_f32, const uint8_t* dones, const uint8_t* time_outs, float* const* out_f32, uint8_t* s_dones,
                          int n, int nobs, int npriv, int nhist, int nact, float gamma, void* stream);
+
+/* The observation half of RolloutStorage.add_transitions (rollout_storage.py:58-59), done when PPO.act records the transition
+ * (ppo.py:73-76): s_obs[n][nobs] <- obs, s_priv[n][npriv] <- priv.  The env's observation buffers are overwritten in place by
+ * the next go1_sim_step, so the copy cannot wait for process_env_step; go1_store_transition then takes in_f32[0] = in_f32[1] = NULL. */
+int go1_store_observations(const float* obs, const float* priv, float* s_obs, float* s_priv, int n, int nobs, int npriv, void* stream);
 
 /* Replaces the fancy-index gathers of RolloutStorage.mini_batch_generator (rollout_storage.py:98-137):
  * dst[i][0:width] = src[idx[i]][0:width]; ldd = row stride of dst in floats (>= width). */

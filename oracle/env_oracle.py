@@ -258,10 +258,25 @@ def compute_observations(s, P, noise_u=None):
     if P["add_noise"]:
         obs = obs + (2 * noise_u - 1) * P["noise_scale_vec"]
     priv = []
-    if P["priv_friction"]:
-        sc, sh = P["friction_ss"]; priv.append((s["friction_coeffs"].unsqueeze(1) - sh) * sc)
-    if P["priv_restitution"]:
-        sc, sh = P["restitution_ss"]; priv.append((s["restitutions"].unsqueeze(1) - sh) * sc)
+    col = lambda v: v.unsqueeze(1) if v.dim() == 1 else v
+    for flag, ss, val in (("priv_friction", "friction_ss", lambda: col(s["friction_coeffs"])),
+                          ("priv_restitution", "restitution_ss", lambda: col(s["restitutions"])),
+                          ("priv_base_mass", "mass_ss", lambda: col(s["payloads"])),
+                          ("priv_com_displacement", "com_ss", lambda: s["com_displacements"]),
+                          ("priv_motor_strength", "motor_strength_ss", lambda: s["motor_strengths"]),
+                          ("priv_motor_offset", "motor_offset_ss", lambda: s["motor_offsets"]),
+                          ("priv_body_height", "body_height_ss", lambda: s["root_states"][:, 2:3]),
+                          ("priv_body_velocity", "body_velocity_ss", lambda: s["base_lin_vel"])):
+        if P.get(flag):
+            sc, sh = P[ss]
+            priv.append((val() - sh) * sc)
+    if P.get("priv_gravity"):                  # legged_robot.py:466-472 divides by the scale
+        sc, sh = P["gravity_ss"]
+        priv.append((s["gravities"] - sh) / sc)
+    if P.get("priv_clock_inputs"):
+        priv.append(s["clock_inputs"])
+    if P.get("priv_desired_contact_states"):
+        priv.append(s["desired_contact_states"])
     priv = torch.cat(priv, 1) if priv else torch.zeros(obs.shape[0], 0)
     c = P["clip_obs"]
     return torch.clip(obs, -c, c), torch.clip(priv, -c, c)
@@ -287,5 +302,159 @@ def params_from_sim_config(c, active_scales, dt):
         observe_yaw=bool(c.observe_yaw), observe_contact_states=bool(c.observe_contact_states), add_noise=bool(c.add_noise),
         commands_scale=f(c.commands_scale)[:c.num_commands], obs_scale_dof_pos=c.obs_scale_dof_pos, obs_scale_dof_vel=c.obs_scale_dof_vel,
         obs_scale_lin_vel=c.obs_scale_lin_vel, obs_scale_ang_vel=c.obs_scale_ang_vel, noise_scale_vec=f(c.noise_scale_vec)[:c.num_obs],
-        priv_friction=bool(c.priv_friction), priv_restitution=bool(c.priv_restitution), friction_ss=tuple(c.friction_ss),
-        restitution_ss=tuple(c.restitution_ss), clip_obs=c.clip_obs, clip_actions=c.clip_actions)
+        clip_obs=c.clip_obs, clip_actions=c.clip_actions, num_train_envs=int(c.num_train_envs), rand_interval=int(c.rand_interval),
+        custom_origins=bool(c.custom_origins), base_init_state=f(c.base_init_state),
+        dr=[{k: (list(getattr(d, k)) if hasattr(getattr(d, k), "__len__") else getattr(d, k)) for k, _ in d._fields_} for d in c.dr],
+        **{k: bool(getattr(c, k)) for k in ("priv_friction", "priv_restitution", "priv_base_mass", "priv_com_displacement", "priv_motor_strength",
+                                            "priv_motor_offset", "priv_body_height", "priv_body_velocity", "priv_gravity", "priv_clock_inputs",
+                                            "priv_desired_contact_states")},
+        **{k: tuple(getattr(c, k)) for k in ("friction_ss", "restitution_ss", "mass_ss", "com_ss", "motor_strength_ss", "motor_offset_ss",
+                                             "body_height_ss", "body_velocity_ss", "gravity_ss")})
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# domain randomisation, pushes, teleports and resets (legged_robot.py:150-239, 611-665, 948-1051).  Every torch.rand of the
+# reference is replaced by the injected table U [N][48] (slot map: include/go1_b200.h, Go1SimBuffers.reset_rand); ranges are
+# {low, float32(high - low)} as the resolved config stores them, evaluated as `u * span + low` in float32 like torch does.
+# ---------------------------------------------------------------------------------------------------------------------
+def _split(P, ids):
+    """_call_train_eval (legged_robot.py:531-544): (ids, domain-rand table) for the train envs, then for the eval envs."""
+    nt = P["num_train_envs"]
+    return [(ids[ids < nt], P["dr"][0]), (ids[ids >= nt], P["dr"][1])]
+
+
+def _draw(U, ids, slots, rng):
+    return U[ids][:, slots] * rng[1] + rng[0]
+
+
+def teleport_robots(s, P):
+    n = s["root_states"].shape[0]
+    for ids, D in _split(P, torch.arange(n)):
+        if not D["teleport_robots"] or len(ids) == 0:
+            continue
+        rs = s["root_states"]
+        lo = ids[rs[ids, 0] < D["teleport_x_lo"]]; rs[lo, 0] += D["teleport_dx"]
+        hi = ids[rs[ids, 0] > D["teleport_x_hi"]]; rs[hi, 0] -= D["teleport_dx"]
+        lo = ids[rs[ids, 1] < D["teleport_y_lo"]]; rs[lo, 1] += D["teleport_dy"]
+        hi = ids[rs[ids, 1] > D["teleport_y_hi"]]; rs[hi, 1] -= D["teleport_dy"]
+
+
+def push_robots(s, P, U):
+    n = s["root_states"].shape[0]
+    for ids, D in _split(P, torch.arange(n)):
+        if not D["push_robots"] or len(ids) == 0:
+            continue
+        ids = ids[s["episode_length_buf"][ids] % int(D["push_interval"]) == 0]
+        m = D["max_push_vel_xy"]
+        s["root_states"][ids, 7:9] = (m - (-m)) * U[ids][:, [36, 37]] + (-m)
+
+
+def randomize_dof_props(s, P, ids, U):
+    for i, D in _split(P, ids):
+        if len(i) == 0:
+            continue
+        if D["randomize_motor_strength"]:
+            s["motor_strengths"][i, :] = _draw(U, i, [21], D["motor_strength_range"])
+        if D["randomize_motor_offset"]:
+            s["motor_offsets"][i, :] = _draw(U, i, list(range(24, 36)), D["motor_offset_range"])
+        if D["randomize_Kp_factor"]:
+            s["Kp_factors"][i, :] = _draw(U, i, [22], D["Kp_factor_range"])
+        if D["randomize_Kd_factor"]:
+            s["Kd_factors"][i, :] = _draw(U, i, [23], D["Kd_factor_range"])
+
+
+def randomize_rigid_body_props(s, P, ids, U):
+    for i, D in _split(P, ids):
+        if len(i) == 0:
+            continue
+        if D["randomize_base_mass"]:
+            s["payloads"][i] = _draw(U, i, [38], D["added_mass_range"])[:, 0]
+        if D["randomize_com_displacement"]:
+            s["com_displacements"][i, :] = _draw(U, i, [39, 40, 41], D["com_displacement_range"])
+        if D["randomize_friction"]:
+            s["friction_coeffs"][i] = _draw(U, i, [42], D["friction_range"])[:, 0]
+        if D["randomize_restitution"]:
+            s["restitutions"][i] = _draw(U, i, [43], D["restitution_range"])[:, 0]
+
+
+def reset_idx(s, P, ids, new_commands, U):
+    """legged_robot.py:150-239 for `ids` (tensor, ascending); the curriculum's part is `new_commands` [N][15].
+    Returns (train/episode reward means dict or None, whether an eval env finished)."""
+    if len(ids) == 0:
+        return None, False
+    s["commands"][ids] = new_commands[ids]                                 # _resample_commands: new commands, sums cleared
+    for k in s["command_sums"]:
+        s["command_sums"][k][ids] = 0.
+    randomize_dof_props(s, P, ids, U)
+    for i, D in _split(P, ids):
+        if D["randomize_rigids_after_start"]:
+            randomize_rigid_body_props(s, P, i, U)
+    for i, D in _split(P, ids):                                            # _reset_dofs, _reset_root_states
+        if len(i) == 0:
+            continue
+        s["dof_pos"][i] = P["default_dof_pos"] * ((1.5 - 0.5) * U[i][:, :12] + 0.5)
+        s["dof_vel"][i] = 0.
+    for i, D in _split(P, ids):
+        if len(i) == 0:
+            continue
+        rs = s["root_states"]
+        rs[i] = P["base_init_state"]
+        rs[i, :3] += s["env_origins"][i]
+        if P["custom_origins"]:
+            rs[i, 0:1] += (D["x_init_range"] - (-D["x_init_range"])) * U[i][:, 12:13] + (-D["x_init_range"])
+            rs[i, 1:2] += (D["y_init_range"] - (-D["y_init_range"])) * U[i][:, 13:14] + (-D["y_init_range"])
+            rs[i, 0] += D["x_init_offset"]
+            rs[i, 1] += D["y_init_offset"]
+        yaw = (D["yaw_init_range"] - (-D["yaw_init_range"])) * U[i][:, 14:15] + (-D["yaw_init_range"])
+        rs[i, 3:7] = quat_from_angle_axis(yaw[:, 0], torch.tensor([0., 0., 1.]))
+        rs[i, 7:13] = (0.5 - (-0.5)) * U[i][:, 15:21] + (-0.5)
+    for k in ("last_actions", "last_last_actions", "last_dof_vel"):
+        s[k][ids] = 0.
+    s["episode_length_buf"][ids] = 0
+    nt = P["num_train_envs"]
+    tr, ev = ids[ids < nt], ids[ids >= nt]
+    means = None
+    if len(tr) > 0:
+        means = {}
+        for k in s["episode_sums"]:
+            means["rew_" + k] = torch.mean(s["episode_sums"][k][tr])
+            s["episode_sums"][k][tr] = 0.
+    if len(ev) > 0:
+        for k in s["episode_sums"]:
+            unset = ev[s["episode_sums_eval"][k][ev] == -1]
+            s["episode_sums_eval"][k][unset] = s["episode_sums"][k][unset]
+            s["episode_sums"][k][ev] = 0.
+    s["gait_indices"][ids] = 0
+    for b in s["lag_buffer"]:
+        b[ids, :] = 0
+    return means, len(ev) > 0
+
+
+def post_physics_step(s, P, U_step, U_reset, noise_u, new_commands):
+    """legged_robot.py:90-136 on physics outputs already in `s` (root_states, dof state, contact forces, foot kinematics):
+    counters, base-frame quantities, callback (teleport, gait clock, push, periodic re-randomisation), termination, reward,
+    reset_idx, observations, last_* rolls.  Returns dict(obs, priv, rew, reset, time_out, reset_ids, episode_means)."""
+    s["episode_length_buf"] = s["episode_length_buf"] + 1
+    quat = s["root_states"][:, 3:7]
+    s["base_lin_vel"] = quat_rotate_inverse(quat, s["root_states"][:, 7:10])
+    s["base_ang_vel"] = quat_rotate_inverse(quat, s["root_states"][:, 10:13])
+    s["projected_gravity"] = quat_rotate_inverse(quat, s["gravity_vec"])
+    teleport_robots(s, P)
+    step_contact_targets(s, P)
+    push_robots(s, P, U_step)
+    if P["rand_interval"] > 0:
+        due = torch.nonzero(s["episode_length_buf"] % P["rand_interval"] == 0).flatten()
+        randomize_dof_props(s, P, due, U_step)
+        for i, D in _split(P, due):
+            if D["randomize_rigids_after_start"]:
+                randomize_rigid_body_props(s, P, i, U_step)
+    reset, time_out = check_termination(s, P)
+    rew, pos, neg = compute_reward(s, P)
+    ids = torch.nonzero(reset).flatten()
+    means, _ = reset_idx(s, P, ids, new_commands, U_reset)
+    obs, priv = compute_observations(s, P, noise_u)
+    s["last_last_actions"] = s["last_actions"].clone(); s["last_actions"] = s["actions"].clone()
+    s["last_last_joint_pos_target"] = s["last_joint_pos_target"].clone(); s["last_joint_pos_target"] = s["joint_pos_target"].clone()
+    s["last_dof_vel"] = s["dof_vel"].clone()
+    out_reset = reset.clone(); out_reset[ids] = True
+    return dict(obs=obs, priv=priv, rew=rew, rew_pos=pos, rew_neg=neg, reset=out_reset, time_out=time_out, reset_ids=ids, episode_means=means)

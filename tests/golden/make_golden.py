@@ -72,12 +72,9 @@ def reference_train_cfg():
     return Cfg, trees
 
 
-def make_env_logic(Cfg):
+def mock_env(Cfg, N, g):
+    """A namespace carrying every attribute the reference's step-path methods read, filled with seeded state."""
     from go1_gym.envs.base.legged_robot import LeggedRobot
-    from isaacgym.torch_utils import quat_rotate_inverse
-
-    N = 64
-    g = torch.Generator().manual_seed(1234)
     R = lambda *s, lo=-1.0, hi=1.0: torch.rand(*s, generator=g) * (hi - lo) + lo
     dt = 4 * float(np.float32(0.005))
     env = types.SimpleNamespace()
@@ -176,7 +173,16 @@ def make_env_logic(Cfg):
         xs = torch.cat((jp.unsqueeze(-1), jpl.unsqueeze(-1), jpll.unsqueeze(-1), jv.unsqueeze(-1), jvl.unsqueeze(-1), jvll.unsqueeze(-1)), dim=-1)
         return net(xs.view(N * 12, 6)).view(N, 12)
     env.actuator_network = eval_actuator_network
+    return env
 
+
+def make_env_logic(Cfg):
+    from go1_gym.envs.base.legged_robot import LeggedRobot
+    from isaacgym.torch_utils import quat_rotate_inverse
+
+    N = 64
+    g = torch.Generator().manual_seed(1234)
+    env = mock_env(Cfg, N, g)
     out = {}
 
     def snap(prefix, names):
@@ -242,6 +248,266 @@ def make_env_logic(Cfg):
         out["obs/privileged_obs_buf"] = torch.clip(env.privileged_obs_buf, -100, 100).numpy().copy()
     np.savez_compressed(os.path.join(HERE, "env_logic.npz"), **out)
     print("env_logic.npz:", len(out), "arrays")
+
+
+def clone_cfg(C, name="CfgClone"):
+    """A deep copy of a Cfg class tree (sections are plain classes under the params_proto stub)."""
+    import copy
+    sections = {}
+    for k, v in clean(vars(C)).items():
+        if isinstance(v, types.MappingProxyType):       # Cfg.command_ranges = vars(Cfg.commands), re-derived by _parse_cfg
+            continue
+        if isinstance(v, type):
+            inner = {}
+            for kk, vv in clean(vars(v)).items():
+                inner[kk] = type(kk, (), {a: copy.deepcopy(b) for a, b in clean(vars(vv)).items()}) if isinstance(vv, type) else copy.deepcopy(vv)
+            sections[k] = type(k, (), inner)
+        else:
+            sections[k] = copy.deepcopy(v)
+    return type(name, (), sections)
+
+
+# slot of every uniform draw in the [N][48] table the CUDA kernels read (include/go1_b200.h: Go1SimBuffers.reset_rand)
+def _draw_slots(name, cfg, custom_origins):
+    dr = cfg.domain_rand
+    if name == "_push_robots":
+        return [[36, 37]] if dr.push_robots else []
+    if name == "_randomize_dof_props":
+        return ([[21]] if dr.randomize_motor_strength else []) + ([list(range(24, 36))] if dr.randomize_motor_offset else []) + \
+               ([[22]] if dr.randomize_Kp_factor else []) + ([[23]] if dr.randomize_Kd_factor else [])
+    if name == "_randomize_rigid_body_props":
+        return ([[38]] if dr.randomize_base_mass else []) + ([[39, 40, 41]] if dr.randomize_com_displacement else []) + \
+               ([[42]] if dr.randomize_friction else []) + ([[43]] if dr.randomize_restitution else [])
+    if name == "_reset_dofs":
+        return [list(range(12))]
+    if name == "_reset_root_states":
+        return ([[12], [13]] if custom_origins else []) + [[14], list(range(15, 21))]
+    return []
+
+
+DR_OVERRIDES = dict(
+    domain_rand=dict(randomize_rigids_after_start=True, randomize_com_displacement=True, com_displacement_range=[-0.15, 0.15],
+                     randomize_restitution=True, restitution_range=[0.0, 0.4], randomize_Kp_factor=True, Kp_factor_range=[0.8, 1.3],
+                     randomize_Kd_factor=True, Kd_factor_range=[0.5, 1.5], push_robots=True, push_interval_s=3, max_push_vel_xy=0.5),
+    terrain=dict(teleport_robots=True, teleport_thresh=0.3, num_rows=4, num_cols=5, terrain_length=5.0, terrain_width=5.0,
+                 x_init_range=0.2, y_init_range=0.2, yaw_init_range=3.14, x_init_offset=0.1, y_init_offset=-0.05),
+    env=dict(priv_observe_friction=True, priv_observe_restitution=True, priv_observe_base_mass=True, priv_observe_com_displacement=True,
+             priv_observe_motor_strength=True, priv_observe_motor_offset=True, priv_observe_body_height=True, priv_observe_body_velocity=True,
+             priv_observe_gravity=True, priv_observe_clock_inputs=True, priv_observe_desired_contact_states=True, num_privileged_obs=45))
+EVAL_OVERRIDES = dict(
+    domain_rand=dict(motor_strength_range=[0.7, 0.8], motor_offset_range=[-0.05, 0.01], Kp_factor_range=[1.0, 1.1], Kd_factor_range=[0.9, 1.0],
+                     added_mass_range=[2.0, 4.0], com_displacement_range=[0.0, 0.05], friction_range=[0.05, 0.2], restitution_range=[0.3, 0.5],
+                     push_interval_s=2, max_push_vel_xy=1.5, randomize_Kd_factor=False),
+    terrain=dict(teleport_thresh=0.5, num_rows=3, num_cols=4, x_init_range=0.5, y_init_range=0.1, yaw_init_range=1.0, x_init_offset=-0.3,
+                 y_init_offset=0.2))
+
+
+def apply_overrides(C, over):
+    for sec, kv in over.items():
+        for k, v in kv.items():
+            setattr(getattr(C, sec), k, v)
+    return C
+
+
+def make_dr_step(Cfg0):
+    """the reference's whole post_physics_step -- teleport, push, periodic re-randomisation, termination,
+    rewards, reset_idx (_randomize_dof_props, _randomize_rigid_body_props, _reset_dofs, _reset_root_states, buffer clears,
+    extras), compute_observations, last_* rolls -- on a mock env with full domain randomisation and a train/eval split
+    (40 + 24 envs, different ranges), every torch.rand draw recorded in the slot the CUDA kernels read it from."""
+    import math
+    from go1_gym.envs.base.legged_robot import LeggedRobot
+    import isaacgym.gymtorch as gymtorch
+    gymtorch.unwrap_tensor = lambda t: t
+    NT, NE = 40, 24
+    N = NT + NE
+    Cfg = apply_overrides(clone_cfg(Cfg0, "CfgDR"), DR_OVERRIDES)
+    ECfg = apply_overrides(clone_cfg(Cfg, "CfgDREval"), EVAL_OVERRIDES)
+    Cfg.terrain.x_offset, Cfg.terrain.rows_offset = 0, 0                     # set by Terrain.__init__ (go1_gym/utils/terrain.py:42-51)
+    ECfg.terrain.x_offset, ECfg.terrain.rows_offset = 250, Cfg.terrain.num_rows
+    g = torch.Generator().manual_seed(4321)
+    env = mock_env(Cfg, N, g)
+
+    class Env:                                    # unbound reference methods become bound methods of the mock
+        def __getattr__(self, name):
+            f = getattr(LeggedRobot, name, None)
+            if callable(f):
+                return types.MethodType(f, self)
+            raise AttributeError(name)
+    e = Env()
+    e.__dict__.update(vars(env))
+    env = e
+    env.eval_cfg = ECfg
+    env.num_train_envs, env.num_eval_envs = NT, NE
+    LeggedRobot._parse_cfg(env, ECfg)
+    LeggedRobot._parse_cfg(env, Cfg)
+    env.reward_scales = clean(vars(Cfg.reward_scales))
+    env.curriculum_thresholds = clean(vars(Cfg.curriculum_thresholds))
+    R = lambda *s, lo=-1.0, hi=1.0: torch.rand(*s, generator=g) * (hi - lo) + lo
+
+    class AnyCall:
+        def __getattr__(self, name):
+            return lambda *a, **k: None
+    env.gym, env.sim, env.viewer, env.record_now, env.debug_viz, env.enable_viewer_sync = AnyCall(), None, None, False, False, False
+    env._render_headless = lambda: None
+    env._randomize_gravity = lambda *a, **k: None
+    env.refresh_actor_rigid_shape_props = lambda ids, cfg: None      # pushes friction / restitution into PhysX: no arithmetic
+    env.common_step_counter = 5
+    env.custom_origins = True
+    env.base_init_state = torch.tensor(list(Cfg.init_state.pos) + list(Cfg.init_state.rot) + list(Cfg.init_state.lin_vel) + list(Cfg.init_state.ang_vel))
+    env.env_origins = torch.cat((R(N, 2, lo=0.0, hi=18.0), torch.zeros(N, 1)), 1)
+    env.terrain_levels = torch.zeros(N, dtype=torch.long)
+    # robots spread over the tile grids, some beyond the teleport thresholds (train grid 20 x 25 m; eval grid offset by x_offset * hscale)
+    xo = torch.cat((torch.zeros(NT), torch.full((NE,), float(int(ECfg.terrain.x_offset * ECfg.terrain.horizontal_scale)))))
+    env.root_states[:, 0] = R(N, lo=-0.5, hi=20.5) * torch.cat((torch.ones(NT), torch.full((NE,), 0.75))) + xo
+    env.root_states[:, 1] = R(N, lo=-0.5, hi=25.5) * torch.cat((torch.ones(NT), torch.full((NE,), 0.8)))
+    env.foot_positions[:, :, :2] = env.root_states[:, None, :2] + R(N, 4, 2, lo=-0.35, hi=0.35)
+    env.com_displacements = R(N, 3, lo=-0.1, hi=0.1)
+    env.Kp_factors = R(N, 1, lo=0.8, hi=1.3).repeat(1, 12)
+    env.Kd_factors = R(N, 1, lo=0.5, hi=1.5).repeat(1, 12)
+    env.gravities = torch.tensor([0.05, -0.03, 0.0]).repeat(N, 1)
+    # episode lengths: pushes every 151 (train) / 101 (eval) steps, re-randomisation every 201, time-outs above 1001
+    ep = torch.randint(1, 990, (N,), generator=g)
+    ep[[1, 7, 13, 22]] = torch.tensor([150, 301, 452, 905])           # train pushes at 151, 302, 453, 906
+    ep[[41, 44, 50]] = torch.tensor([100, 201, 504])                 # eval pushes at 101, 202, 505
+    ep[[3, 9, 30, 45, 52]] = torch.tensor([200, 401, 803, 602, 200])  # re-randomisation at multiples of 201
+    ep[[5, 47]] = torch.tensor([1001, 1003])                         # time-outs
+    ep[11] = 603 - 1                                                  # 603 = 3*201: re-randomised, and (below) terminated in the same step
+    env.episode_length_buf = ep
+    env.contact_forces[11, 0] = torch.tensor([0.0, 3.0, 4.0])
+    env.feet_air_time = R(N, 4, lo=0.0, hi=0.4)
+    env.last_root_vel = torch.zeros(N, 6)
+    env.base_lin_vel, env.base_ang_vel, env.projected_gravity = torch.zeros(N, 3), torch.zeros(N, 3), torch.zeros(N, 3)
+    env.reset_buf = torch.ones(N, dtype=torch.long)
+    env.time_out_buf = torch.zeros(N, dtype=torch.bool)
+    env.extras = {}
+    rbs = torch.zeros(N, 17, 13)
+    rbs[:, [4, 8, 12, 16], 0:3] = env.foot_positions
+    rbs[:, [4, 8, 12, 16], 7:10] = env.foot_velocities
+    env.rigid_body_state = rbs.view(N * 17, 13)
+    env.dof_state = torch.zeros(N * 12, 2)
+    env.torques = R(N, 12, lo=-20, hi=20)
+    env.joint_pos_target = env.default_dof_pos + R(N, 12, lo=-0.5, hi=0.5)
+    env.noise_scale_vec = LeggedRobot._get_noise_scale_vec(env, Cfg)
+    env.env_command_bins = np.arange(N)
+    env.curricula, env.category_names = [], []
+    # new commands the (stubbed) curriculum hands to resetting envs; command sums cleared like legged_robot.py:822-824
+    cmd_lo = torch.tensor([-1, -0.6, -1, -0.25, 2.0, 0, 0, 0, 0.5, 0.03, -0.4, 0.0, 0.10, 0.35, 0.0])
+    cmd_hi = torch.tensor([1, 0.6, 1, 0.15, 4.0, 1, 1, 1, 0.5, 0.35, 0.4, 0.0, 0.45, 0.45, 0.01])
+    new_cmd = torch.rand(N, 15, generator=g) * (cmd_hi - cmd_lo) + cmd_lo
+    resample_calls = []
+
+    def resample(ids):
+        resample_calls.append(ids.clone())
+        if len(resample_calls) == 2:          # call 1 = the periodic resample of the callback (left alone), call 2 = reset_idx
+            env.commands[ids] = new_cmd[ids]
+            for k in env.command_sums:
+                env.command_sums[k][ids] = 0.
+    env._resample_commands = resample
+    LeggedRobot._prepare_reward_function(env)
+    for k in env.episode_sums:
+        env.episode_sums[k] = R(N, lo=0.0, hi=2.0)
+    for k in env.command_sums:
+        env.command_sums[k] = R(N, lo=0.0, hi=2.0)
+    for k in env.episode_sums_eval:
+        env.episode_sums_eval[k][NT + 3] = 0.25                        # one eval env already holds a finished episode
+
+    out = {}
+    state_in = ["root_states", "dof_pos", "dof_vel", "actions", "last_actions", "last_last_actions", "last_dof_vel",
+                "last_joint_pos_target", "last_last_joint_pos_target", "lag_buffer", "motor_offsets", "motor_strengths", "Kp_factors", "Kd_factors",
+                "friction_coeffs", "restitutions", "payloads", "com_displacements", "gravities", "gravity_vec", "commands", "gait_indices",
+                "contact_forces", "foot_positions", "foot_velocities", "prev_foot_velocities", "last_contacts", "episode_length_buf",
+                "torques", "joint_pos_target", "env_origins"]
+
+    def snap(prefix, names):
+        for n in names:
+            v = getattr(env, n)
+            v = torch.stack(v) if isinstance(v, list) else v
+            out[f"{prefix}/{n}"] = v.detach().clone().numpy()
+    snap("in", state_in)
+    for k, v in env.episode_sums.items():
+        out[f"in/episode_sums/{k}"] = v.numpy().copy()
+    for k, v in env.command_sums.items():
+        out[f"in/command_sums/{k}"] = v.numpy().copy()
+    out["in/new_commands"] = new_cmd.numpy().copy()
+
+    # ---- recorder: every torch.rand of the randomisation / reset methods lands in its kernel slot
+    U = {"step": torch.full((N, 48), 0.5), "reset": torch.full((N, 48), 0.5)}
+    active = []
+    orig_rand, orig_rand_like = torch.rand, torch.rand_like
+
+    def rec_rand(*shape, **kw):
+        kw.pop("device", None); kw.pop("requires_grad", None)
+        v = orig_rand(*shape, generator=g, **kw)
+        if active:
+            plane, ids, slots = active[0]
+            sl = slots.pop(0)
+            assert v.shape[0] == len(ids) and v.numel() == len(ids) * len(sl), (v.shape, len(ids), sl)
+            U[plane][ids.unsqueeze(1), torch.tensor(sl).unsqueeze(0)] = v.reshape(len(ids), len(sl))
+        return v
+
+    phase = ["step"]
+
+    def hook(name):
+        def f(ids, cfg):
+            use = ids
+            if name == "_push_robots" and cfg.domain_rand.push_robots:
+                use = ids[env.episode_length_buf[ids] % int(cfg.domain_rand.push_interval) == 0]
+            active.insert(0, (phase[0], use, _draw_slots(name, cfg, env.custom_origins)))
+            try:
+                return getattr(LeggedRobot, name)(env, ids, cfg)
+            finally:
+                assert not active[0][2] or len(use) == 0, (name, active[0][2])
+                active.pop(0)
+        return f
+    for name in ("_push_robots", "_randomize_dof_props", "_randomize_rigid_body_props", "_reset_dofs", "_reset_root_states"):
+        setattr(env, name, hook(name))
+    reset_orig = LeggedRobot.reset_idx
+
+    def reset_idx(ids):
+        phase[0] = "reset"
+        out["reset/ids"] = ids.numpy().copy()
+        out["mid/episode_sums_total"] = env.episode_sums["total"].numpy().copy()
+        reset_orig(env, ids)
+        phase[0] = "step"
+    env.reset_idx = reset_idx
+    noise_u = orig_rand(N, 70, generator=g)
+    out["obs/noise_u"] = noise_u.numpy().copy()
+    torch.rand = rec_rand
+    torch.rand_like = lambda t, **k: noise_u
+    try:
+        with torch.no_grad():
+            LeggedRobot.post_physics_step(env)
+    finally:
+        torch.rand, torch.rand_like = orig_rand, orig_rand_like
+    out["rand/step"] = U["step"].numpy().copy(); out["rand/reset"] = U["reset"].numpy().copy()
+    out["meta/num_train_envs"] = np.int64(NT); out["meta/push_interval"] = np.array([Cfg.domain_rand.push_interval, ECfg.domain_rand.push_interval])
+    out["meta/rand_interval"] = np.int64(Cfg.domain_rand.rand_interval)
+    out["meta/interval_resample_ids"] = resample_calls[0].numpy().copy()
+    snap("out", ["root_states", "dof_pos", "dof_vel", "last_actions", "last_last_actions", "last_dof_vel", "last_joint_pos_target",
+                 "last_last_joint_pos_target", "lag_buffer", "motor_offsets", "motor_strengths", "Kp_factors", "Kd_factors", "friction_coeffs",
+                 "restitutions", "payloads", "com_displacements", "commands", "gait_indices", "episode_length_buf", "base_lin_vel",
+                 "base_ang_vel", "projected_gravity", "clock_inputs", "desired_contact_states", "foot_indices", "rew_buf", "rew_buf_pos",
+                 "rew_buf_neg", "last_contacts", "last_root_vel", "feet_air_time"])
+    out["out/reset_buf"] = env.reset_buf.numpy().astype(bool); out["out/time_out_buf"] = env.time_out_buf.numpy().copy()
+    out["out/obs_buf"] = torch.clip(env.obs_buf, -100, 100).numpy().copy()
+    out["out/privileged_obs_buf"] = torch.clip(env.privileged_obs_buf, -100, 100).numpy().copy()
+    for k, v in env.episode_sums.items():
+        out[f"out/episode_sums/{k}"] = v.numpy().copy()
+        out[f"out/episode_sums_eval/{k}"] = env.episode_sums_eval[k].numpy().copy()
+    for k, v in env.command_sums.items():
+        out[f"out/command_sums/{k}"] = v.numpy().copy()
+    for k, v in env.extras["train/episode"].items():
+        out[f"out/extras_train_episode/{k}"] = np.asarray(v, dtype=np.float64)
+    out["out/extras_time_outs"] = env.extras["time_outs"].numpy().copy()
+    out["out/extras_has_eval_episode"] = np.bool_("eval/episode" in env.extras)
+    # the resolved config trees of this case (the GPU test rebuilds the same Cfg pair from them)
+    with open(os.path.join(HERE, "env_dr_cfg.json"), "w") as f:
+        json.dump({"overrides": DR_OVERRIDES, "eval_overrides": EVAL_OVERRIDES,
+                   "x_offset": [Cfg.terrain.x_offset, ECfg.terrain.x_offset]}, f, indent=1)
+    np.savez_compressed(os.path.join(HERE, "env_dr.npz"), **out)
+    n_tel = int((out["out/root_states"][:, :2] != out["in/root_states"][:, :2]).any(1).sum())
+    print("env_dr.npz:", len(out), "arrays; resets", out["reset/ids"].tolist(), "moved xy", n_tel,
+          "pushed", int((out["rand/step"][:, 36] != 0.5).sum()), "re-randomised", int((out["rand/step"][:, 21] != 0.5).sum()))
 
 
 def make_kats(Cfg):
@@ -502,6 +768,7 @@ if __name__ == "__main__":
     with open(os.path.join(HERE, "cfg_trees.json"), "w") as f:
         json.dump(trees, f, indent=0, sort_keys=False)
     make_env_logic(Cfg)
+    make_dr_step(Cfg)
     make_kats(Cfg)
     make_ppo()
     make_resample(Cfg)

@@ -104,3 +104,45 @@ def test_gait_clock_known_answer():
     assert np.allclose(s["clock_inputs"].numpy(), k["gait/clock_inputs"], atol=1e-5)
     assert np.allclose(s["desired_contact_states"].numpy(), k["gait/desired_contact_states"], atol=1e-5)
     assert np.allclose(k["gait/clock_inputs"].ravel(), [-.9048, .9048, .9048, -.9048], atol=1e-4)
+
+
+def test_full_dr_post_physics_step_matches_reference():
+    """The reference's whole post_physics_step with teleports, pushes, periodic re-randomisation, reset_idx (dof props, rigid
+    props, dof / root reset, buffer clears, episode means, eval sums) and a train/eval split: tests/golden/env_dr.npz.
+    Injected-draw arithmetic is bit-exact; transcendental paths (gait clock, rewards, yaw quaternion) to 1e-6."""
+    from env_golden_util import dr_case, dr_oracle_state
+    g, Cfg, ECfg, c, info = dr_case()
+    P = eo.params_from_sim_config(c, info["active_reward_scales"], info["dt"])
+    s = dr_oracle_state(g, P)
+    T = lambda k: torch.from_numpy(np.array(g[k]))
+    r = eo.post_physics_step(s, P, T("rand/step"), T("rand/reset"), T("obs/noise_u"), T("in/new_commands"))
+    assert np.array_equal(r["reset_ids"].numpy(), g["reset/ids"])
+    assert np.array_equal(r["reset"].numpy(), g["out/reset_buf"]) and np.array_equal(r["time_out"].numpy(), g["out/time_out_buf"])
+    assert np.array_equal(s["episode_length_buf"].numpy(), g["out/episode_length_buf"])
+    exact = ["dof_pos", "dof_vel", "last_actions", "last_last_actions", "last_dof_vel", "last_joint_pos_target", "last_last_joint_pos_target",
+             "motor_offsets", "motor_strengths", "Kp_factors", "Kd_factors", "payloads", "com_displacements", "commands"]
+    for k in exact:
+        assert np.array_equal(s[k].numpy(), g[f"out/{k}"]), k
+    assert np.array_equal(s["friction_coeffs"].numpy(), g["out/friction_coeffs"][:, 0]) and np.array_equal(s["restitutions"].numpy(), g["out/restitutions"][:, 0])
+    assert np.array_equal(torch.stack(s["lag_buffer"]).numpy(), g["out/lag_buffer"])
+    rs, want = s["root_states"].numpy(), g["out/root_states"]
+    assert np.array_equal(rs[:, [0, 1, 2, 7, 8, 9, 10, 11, 12]], want[:, [0, 1, 2, 7, 8, 9, 10, 11, 12]])        # positions / twists: exact
+    assert np.allclose(rs[:, 3:7], want[:, 3:7], rtol=0, atol=1e-6)                                              # yaw quaternion: sin / cos
+    for k in ("base_lin_vel", "base_ang_vel", "projected_gravity", "gait_indices", "clock_inputs", "desired_contact_states", "foot_indices"):
+        assert np.allclose(s[k].numpy(), g[f"out/{k}"], rtol=1e-5, atol=2e-6), k
+    assert np.allclose(r["rew"].numpy(), g["out/rew_buf"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(r["rew_pos"].numpy(), g["out/rew_buf_pos"], rtol=1e-5, atol=1e-6) and np.allclose(r["rew_neg"].numpy(), g["out/rew_buf_neg"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(r["obs"].numpy(), g["out/obs_buf"], rtol=1e-5, atol=2e-6)
+    assert np.allclose(r["priv"].numpy(), g["out/privileged_obs_buf"], rtol=1e-5, atol=2e-6)
+    for k in s["episode_sums"]:
+        assert np.allclose(s["episode_sums"][k].numpy(), g[f"out/episode_sums/{k}"], rtol=1e-5, atol=1e-6), k
+        assert np.allclose(s["episode_sums_eval"][k].numpy(), g[f"out/episode_sums_eval/{k}"], rtol=1e-5, atol=1e-6), k
+    for k in s["command_sums"]:
+        assert np.allclose(s["command_sums"][k].numpy(), g[f"out/command_sums/{k}"], rtol=1e-5, atol=1e-6), k
+    for k, v in r["episode_means"].items():
+        assert np.allclose(float(v), g[f"out/extras_train_episode/{k}"], rtol=1e-5, atol=1e-6), k
+    # the case exercises every branch
+    moved = (g["out/root_states"][:, :2] != g["in/root_states"][:, :2]).any(1)
+    moved[g["reset/ids"]] = False
+    assert moved.sum() >= 4 and (g["rand/step"][:, 36] != 0.5).sum() >= 5 and (g["rand/step"][:, 21] != 0.5).sum() >= 5
+    assert (g["reset/ids"] >= int(g["meta/num_train_envs"])).sum() >= 3

@@ -134,7 +134,7 @@ def test_clip_adam_matches_torch_optim():
 def test_full_ppo_cycle_matches_reference_golden(impl):
     """BASELINE config 1: act x24 -> process_env_step -> compute_returns -> update (5 epochs x 4 minibatches + adaptation
     steps) on the reference's own vectors.  impl 0: fp32 CUDA-core GEMMs (tolerances ~1e-4); impl 1: tcgen05 TF32 GEMMs
-    (10-bit mantissa products: tolerances x20, stated as `k`)."""
+    (10-bit mantissa products: tolerances x250 on the rollout quantities, x25 on the losses, stated as `k` / `kl`)."""
     from ppo_golden_util import seeded_weights, sample_tensor
     from go1_gym_learn.ppo_cse import ActorCritic
     from go1_gym_learn.ppo_cse.ppo import PPO
@@ -163,7 +163,7 @@ def test_full_ppo_cycle_matches_reference_golden(impl):
     alg.fixed_minibatch_indices = C(g["in/perm"])
     losses = alg.update()
     ref = g["update/losses"]
-    AC_Args.gemm_impl = 0
+    AC_Args.gemm_impl = 1      # back to the product default
     kl = 1.0 if impl == 0 else 25.0
     assert abs(losses[0] - ref[0]) < 2e-3 * kl * abs(ref[0]) and abs(losses[1] - ref[1]) < 2e-3 * kl and abs(losses[2] - ref[2]) < 2e-3 * kl * abs(ref[2])
     assert abs(losses[5] - ref[5]) < 2e-3 * kl * abs(ref[5])

@@ -37,6 +37,7 @@ def _load_golden_state(sim, g, substeps_done=0):
     sim.env("friction_coeffs")[0].copy_(T(g["in/friction_coeffs"])[:, 0])
     sim.env("restitutions")[0].copy_(T(g["in/restitutions"])[:, 0])
     sim.env("payloads")[0].copy_(T(g["in/payloads"]))
+    sim.sync_rigid_props()
     sim.env("commands").copy_(T(g["in/commands"]).t())
     sim.env("gait_indices")[0].copy_(T(g["in/gait_indices"]))
     cf = T(g["in/contact_forces"])
@@ -146,6 +147,7 @@ def _load_phys_state(sim, st):
     sim.set_joint_aos("dof_pos", T(st["q"])); sim.set_joint_aos("dof_vel", T(st["qd"]))
     sim.env("friction_coeffs")[0].copy_(T(st["friction"])); sim.env("restitutions")[0].copy_(T(st["restitution"]))
     sim.env("payloads")[0].copy_(T(st["payload"]))
+    sim.sync_rigid_props()
 
 
 @pytest.mark.parametrize("control", ["P", "actuator_net"])

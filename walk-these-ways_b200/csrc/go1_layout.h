@@ -11,7 +11,7 @@
     X(root_pos, 3) X(root_quat, 4) X(root_lin_vel, 3) X(root_ang_vel, 3) \
     X(commands, GO1_NUM_COMMANDS) X(gait_indices, 1) \
     X(friction_coeffs, 1) X(restitutions, 1) X(payloads, 1) X(com_displacements, 3) \
-    X(motor_strengths, 1) X(Kp_factors, 1) X(Kd_factors, 1) X(env_origins, 3) \
+    X(motor_strengths, 1) X(Kp_factors, 1) X(Kd_factors, 1) X(env_origins, 3) X(rigid_payload, 1) X(rigid_com, 3) \
     X(base_lin_vel, 3) X(base_ang_vel, 3) X(projected_gravity, 3) X(rew_buf_pos, 1) X(rew_buf_neg, 1) \
     X(episode_sums, GO1_NUM_EPISODE_SUMS) X(command_sums, GO1_NUM_COMMAND_SUMS)
 

@@ -836,8 +836,8 @@ __global__ void __launch_bounds__(256) store_transition_kernel(const StoreArgs a
     } else {
         for (int c = t; c < a.nhist; c += blockDim.x) a.s_hist[(size_t)e * a.nhist + c] = a.hist[(size_t)e * a.nhist + c];
     }
-    for (int c = t; c < a.nobs; c += blockDim.x) a.s_obs[(size_t)e * a.nobs + c] = a.obs[(size_t)e * a.nobs + c];
-    if (t < a.npriv) a.s_priv[(size_t)e * a.npriv + t] = a.priv[(size_t)e * a.npriv + t];
+    if (a.obs) for (int c = t; c < a.nobs; c += blockDim.x) a.s_obs[(size_t)e * a.nobs + c] = a.obs[(size_t)e * a.nobs + c];
+    if (a.priv && t < a.npriv) a.s_priv[(size_t)e * a.npriv + t] = a.priv[(size_t)e * a.npriv + t];
     if (t < a.nact) {
         a.s_actions[(size_t)e * a.nact + t] = a.actions[(size_t)e * a.nact + t];
         a.s_mu[(size_t)e * a.nact + t] = a.mean[(size_t)e * a.nact + t];
@@ -846,11 +846,26 @@ __global__ void __launch_bounds__(256) store_transition_kernel(const StoreArgs a
     if (t == 0) {
         const float v = a.values[e];
         float r = a.rewards[e];
-        if (a.time_outs) r += a.gamma * v * (a.time_outs[e] ? 1.0f : 0.0f);
+        // rewards += gamma * (values * time_outs): a rounded product, then a rounded add (ppo.py:84-86), never an FMA
+        if (a.time_outs) r = __fadd_rn(r, __fmul_rn(a.gamma, a.time_outs[e] ? v : 0.0f));
         a.s_rewards[e] = r; a.s_values[e] = v; a.s_logp[e] = a.logp[e]; a.s_dones[e] = a.dones[e] ? 1 : 0;
         a.s_env_bins[e] = a.env_bins ? a.env_bins[e] : 0.f;
     }
 }
+// obs / privileged obs of the step the policy is ABOUT to act on: copied at act() time, before env.step overwrites the env's buffers
+__global__ void store_observations_kernel(const float* __restrict__ obs, const float* __restrict__ priv, float* __restrict__ s_obs,
+                                          float* __restrict__ s_priv, size_t n_obs, size_t n_priv) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_obs) s_obs[i] = obs[i];
+    if (i < n_priv) s_priv[i] = priv[i];
+}
+extern "C" int go1_store_observations(const float* obs, const float* priv, float* s_obs, float* s_priv, int n, int nobs, int npriv, void* stream) {
+    if (!obs || !s_obs || n <= 0 || nobs <= 0 || npriv < 0 || (npriv > 0 && (!priv || !s_priv))) return go1_set_error("go1_store_observations: bad arguments");
+    const size_t n_obs = (size_t)n * nobs, n_priv = (size_t)n * npriv;
+    store_observations_kernel<<<(unsigned)((n_obs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(obs, priv, s_obs, s_priv, n_obs, n_priv); go1_count_launch(1);
+    return cuda_rc("go1_store_observations");
+}
+
 extern "C" int go1_store_transition(const float* const* in_f32, const uint8_t* dones, const uint8_t* time_outs, float* const* out_f32, uint8_t* s_dones,
                                     int n, int nobs, int npriv, int nhist, int nact, float gamma, void* stream) {
     if (!in_f32 || !out_f32 || !dones || !s_dones || n <= 0 || nact > 256 || npriv > 256) return go1_set_error("go1_store_transition: bad arguments");
@@ -861,7 +876,8 @@ extern "C" int go1_store_transition(const float* const* in_f32, const uint8_t* d
     a.s_obs = out_f32[0]; a.s_priv = out_f32[1]; a.s_hist = out_f32[2]; a.s_actions = out_f32[3]; a.s_rewards = out_f32[4]; a.s_values = out_f32[5];
     a.s_logp = out_f32[6]; a.s_mu = out_f32[7]; a.s_sigma = out_f32[8]; a.s_env_bins = out_f32[9]; a.s_dones = s_dones;
     a.n = n; a.nobs = nobs; a.npriv = npriv; a.nhist = nhist; a.nact = nact; a.gamma = gamma;
-    for (int i = 0; i < 9; i++) if (!in_f32[i] || !out_f32[i]) return go1_set_error("go1_store_transition: null tensor");
+    for (int i = 2; i < 9; i++) if (!in_f32[i] || !out_f32[i]) return go1_set_error("go1_store_transition: null tensor");
+    if ((in_f32[0] && !out_f32[0]) || (in_f32[1] && !out_f32[1])) return go1_set_error("go1_store_transition: null tensor");
     if (!out_f32[9]) return go1_set_error("go1_store_transition: null tensor");
     store_transition_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(a); go1_count_launch(1);
     return cuda_rc("go1_store_transition");

@@ -232,7 +232,7 @@ DI uint4 philox4x32(uint4 c, uint32_t k0, uint32_t k1) {
 }
 DI float u01(uint32_t x) { return (x >> 8) * (1.0f / 16777216.0f); }   // [0,1)
 // uniform draw for (seed, env, step counter, slot)
-DI float philox_uniform(uint64_t seed, uint32_t env, uint64_t step, uint32_t slot) {
+static __device__ __noinline__ float philox_uniform(uint64_t seed, uint32_t env, uint64_t step, uint32_t slot) {
     uint4 c = make_uint4(slot >> 2, env, (uint32_t)step, (uint32_t)(step >> 32));
     uint4 r = philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
     uint32_t s = slot & 3;

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libgo1b200.so")
 NUM_DOF = 12
 NUM_COMMANDS = 15
 MAX_OBS = 128
-MAX_PRIV_OBS = 32
+MAX_PRIV_OBS = 48
 EVENT_STRIDE = 6
 
 REWARD_TERMS = [
@@ -28,7 +28,22 @@ NUM_EPISODE_SUMS = NUM_REWARD_TERMS + 1
 NUM_COMMAND_SUMS = NUM_REWARD_TERMS + 5
 COMMAND_SUM_EXTRAS = ["lin_vel_raw", "ang_vel_raw", "lin_vel_residual", "ang_vel_residual", "ep_timesteps"]
 
+RESET_RAND_STRIDE = 48
 _i, _f = C.c_int32, C.c_float
+
+
+class Go1DomainRand(C.Structure):
+    _fields_ = [
+        ("randomize_motor_strength", _i), ("randomize_motor_offset", _i), ("randomize_Kp_factor", _i), ("randomize_Kd_factor", _i),
+        ("motor_strength_range", _f * 2), ("motor_offset_range", _f * 2), ("Kp_factor_range", _f * 2), ("Kd_factor_range", _f * 2),
+        ("randomize_rigids_after_start", _i), ("randomize_base_mass", _i), ("randomize_com_displacement", _i),
+        ("randomize_friction", _i), ("randomize_restitution", _i),
+        ("added_mass_range", _f * 2), ("com_displacement_range", _f * 2), ("friction_range", _f * 2), ("restitution_range", _f * 2),
+        ("push_robots", _i), ("push_interval", _i), ("max_push_vel_xy", _f),
+        ("teleport_robots", _i),
+        ("teleport_x_lo", _f), ("teleport_x_hi", _f), ("teleport_dx", _f), ("teleport_y_lo", _f), ("teleport_y_hi", _f), ("teleport_dy", _f),
+        ("x_init_range", _f), ("y_init_range", _f), ("yaw_init_range", _f), ("x_init_offset", _f), ("y_init_offset", _f),
+    ]
 
 
 class Go1SimConfig(C.Structure):
@@ -57,12 +72,8 @@ class Go1SimConfig(C.Structure):
         ("sigma_rew_neg", _f), ("tracking_sigma", _f), ("tracking_sigma_yaw", _f), ("gait_force_sigma", _f),
         ("gait_vel_sigma", _f), ("base_height_target", _f), ("max_contact_force", _f),
         ("use_terminal_body_height", _i), ("max_episode_length", _i), ("terminal_body_height", _f),
-        ("randomize_motor_strength", _i), ("randomize_motor_offset", _i), ("randomize_Kp_factor", _i),
-        ("randomize_Kd_factor", _i), ("rand_interval", _i), ("resampling_interval", _i),
-        ("motor_strength_range", _f * 2), ("motor_offset_range", _f * 2), ("Kp_factor_range", _f * 2),
-        ("Kd_factor_range", _f * 2),
+        ("dr", Go1DomainRand * 2), ("rand_interval", _i), ("resampling_interval", _i),
         ("base_init_state", _f * 13),
-        ("x_init_range", _f), ("y_init_range", _f), ("yaw_init_range", _f), ("x_init_offset", _f), ("y_init_offset", _f),
         ("custom_origins", _i),
         ("erp", _f), ("cfm", _f), ("max_depen_vel", _f), ("contact_margin", _f), ("bounce_threshold", _f),
         ("pgs_iters", _i), ("terrain_friction", _f), ("terrain_restitution", _f),
@@ -77,7 +88,7 @@ class Go1SimConfig(C.Structure):
 class Go1SimBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "env_f32", "leg_f32", "env_i32", "obs", "priv_obs", "rew", "reset", "time_out", "event_count", "events",
-        "episode_acc", "noise", "reset_rand")]
+        "episode_acc", "noise", "reset_rand", "episode_sums_eval")]
 
 
 CUR_MAX_CATEGORIES = 8
@@ -154,6 +165,7 @@ def lib():
         "go1_ppo_adam_step": ([vp, vp, vp, vp, i64, vp, _f, _f, vp, _f, _f, _f, ip, vp], ip),
         "go1_ppo_adaptive_lr": ([vp, vp, _f, _f, _f, vp], ip),
         "go1_store_transition": ([vp, vp, vp, vp, vp, ip, ip, ip, ip, ip, _f, vp], ip),
+        "go1_store_observations": ([vp, vp, vp, vp, ip, ip, ip, vp], ip),
         "go1_gather_rows": ([vp, vp, vp, i64, ip, ip, vp], ip),
     }
     for name, (args, res) in sig.items():

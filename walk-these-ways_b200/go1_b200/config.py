@@ -137,9 +137,59 @@ def reward_tables(cfg, dt):
     return active, order, table, unknown
 
 
-def build_sim_config(cfg, num_envs=None, num_train_envs=None, seed=0, physics=None):
-    """Resolve `cfg` (a Cfg-like class tree) into a Go1SimConfig.  `physics` overrides solver parameters."""
+def _lo_span(rng):
+    """{low, float32(high - low)}: the reference evaluates torch.rand(...) * (high - low) + low with the difference taken in
+    Python double precision (legged_robot.py:611-665)."""
+    lo, hi = float(rng[0]), float(rng[1])
+    return [lo, float(np.float32(hi - lo))]
+
+
+def fill_domain_rand(D, cfg, dt):
+    """One Go1DomainRand from a Cfg tree (the train cfg or the eval cfg): everything _call_train_eval switches."""
+    dr, t = cfg.domain_rand, cfg.terrain
+    g = lambda name, default: getattr(dr, name, default)
+    D.randomize_motor_strength = int(bool(dr.randomize_motor_strength))
+    D.randomize_motor_offset = int(bool(g("randomize_motor_offset", False)))
+    D.randomize_Kp_factor = int(bool(dr.randomize_Kp_factor))
+    D.randomize_Kd_factor = int(bool(dr.randomize_Kd_factor))
+    D.motor_strength_range[:] = _lo_span(dr.motor_strength_range)
+    D.motor_offset_range[:] = _lo_span(g("motor_offset_range", [0., 0.]))
+    D.Kp_factor_range[:] = _lo_span(dr.Kp_factor_range)
+    D.Kd_factor_range[:] = _lo_span(dr.Kd_factor_range)
+    D.randomize_rigids_after_start = int(bool(g("randomize_rigids_after_start", False)))
+    D.randomize_base_mass = int(bool(dr.randomize_base_mass))
+    D.randomize_com_displacement = int(bool(g("randomize_com_displacement", False)))
+    D.randomize_friction = int(bool(dr.randomize_friction))
+    D.randomize_restitution = int(bool(g("randomize_restitution", False)))
+    D.added_mass_range[:] = _lo_span(dr.added_mass_range)
+    D.com_displacement_range[:] = _lo_span(g("com_displacement_range", [0., 0.]))
+    D.friction_range[:] = _lo_span(dr.friction_range)
+    D.restitution_range[:] = _lo_span(g("restitution_range", [0., 0.]))
+    D.push_robots = int(bool(dr.push_robots))
+    D.push_interval = int(np.ceil(dr.push_interval_s / dt))            # _parse_cfg (legged_robot.py:1727)
+    D.max_push_vel_xy = float(dr.max_push_vel_xy)
+    # _teleport_robots (legged_robot.py:1028-1051); thresholds rounded to float32 like the scalar side of the tensor compare
+    tiles = t.mesh_type in ["heightfield", "trimesh"]
+    D.teleport_robots = int(bool(t.teleport_robots) and tiles)
+    if D.teleport_robots:
+        thresh = t.teleport_thresh
+        x_offset = int(getattr(t, "x_offset", 0) * t.horizontal_scale)
+        D.teleport_x_lo = float(np.float32(thresh + x_offset))
+        D.teleport_x_hi = float(np.float32(t.terrain_length * t.num_rows - thresh + x_offset))
+        D.teleport_dx = float(np.float32(t.terrain_length * (t.num_rows - 1)))
+        D.teleport_y_lo = float(np.float32(thresh))
+        D.teleport_y_hi = float(np.float32(t.terrain_width * t.num_cols - thresh))
+        D.teleport_dy = float(np.float32(t.terrain_width * (t.num_cols - 1)))
+    D.x_init_range, D.y_init_range, D.yaw_init_range = t.x_init_range, t.y_init_range, t.yaw_init_range
+    D.x_init_offset, D.y_init_offset = t.x_init_offset, t.y_init_offset
+
+
+def build_sim_config(cfg, num_envs=None, num_train_envs=None, seed=0, physics=None, eval_cfg=None):
+    """Resolve `cfg` (a Cfg-like class tree) into a Go1SimConfig.  `physics` overrides solver parameters; `eval_cfg` is the
+    second Cfg tree of the train/eval split (its randomisation / reset ranges apply to envs >= num_train_envs)."""
     d = derive(cfg)
+    if eval_cfg is not None:
+        derive(eval_cfg)
     model = load_model()
     c = capi.Go1SimConfig()
     n = int(num_envs if num_envs is not None else cfg.env.num_envs)
@@ -216,22 +266,13 @@ def build_sim_config(cfg, num_envs=None, num_train_envs=None, seed=0, physics=No
     c.use_terminal_body_height = int(bool(r.use_terminal_body_height))
     c.max_episode_length = int(cfg.env.max_episode_length)
     c.terminal_body_height = r.terminal_body_height
-    dr = cfg.domain_rand
-    c.randomize_motor_strength = int(bool(dr.randomize_motor_strength))
-    c.randomize_motor_offset = int(bool(getattr(dr, "randomize_motor_offset", False)))
-    c.randomize_Kp_factor = int(bool(dr.randomize_Kp_factor))
-    c.randomize_Kd_factor = int(bool(dr.randomize_Kd_factor))
-    c.rand_interval = int(dr.rand_interval)
+    fill_domain_rand(c.dr[0], cfg, d["dt"])
+    fill_domain_rand(c.dr[1], eval_cfg if eval_cfg is not None else cfg, d["dt"])
+    c.rand_interval = int(cfg.domain_rand.rand_interval)
     c.resampling_interval = int(cfg.commands.resampling_time / d["dt"])
-    c.motor_strength_range[:] = list(dr.motor_strength_range)
-    c.motor_offset_range[:] = list(getattr(dr, "motor_offset_range", [0., 0.]))
-    c.Kp_factor_range[:] = list(dr.Kp_factor_range)
-    c.Kd_factor_range[:] = list(dr.Kd_factor_range)
     ist = cfg.init_state
     c.base_init_state[:] = list(ist.pos) + list(ist.rot) + list(ist.lin_vel) + list(ist.ang_vel)
     t = cfg.terrain
-    c.x_init_range, c.y_init_range, c.yaw_init_range = t.x_init_range, t.y_init_range, t.yaw_init_range
-    c.x_init_offset, c.y_init_offset = t.x_init_offset, t.y_init_offset
     c.custom_origins = int(t.mesh_type in ["heightfield", "trimesh"])
     px = cfg.sim.physx
     c.erp, c.cfm, c.pgs_iters = 0.2, 1e-4, 8

@@ -40,7 +40,8 @@ class SimCore:
         self.events = torch.zeros(2, N, capi.EVENT_STRIDE, device=dev)
         self.episode_acc = torch.zeros(capi.NUM_EPISODE_SUMS + 1, device=dev)
         self.noise = torch.zeros(N, self.num_obs, device=dev) if inject_noise else None
-        self.reset_rand = torch.zeros(N, 40, device=dev) if inject_reset_rand else None
+        self.reset_rand = torch.zeros(N, capi.RESET_RAND_STRIDE, device=dev) if inject_reset_rand else None
+        self.episode_sums_eval = None
         # pinned staging for the per-step host round trip (event list down, new commands up)
         self.h_count = torch.zeros(2, dtype=torch.int32).pin_memory()
         self.h_events = torch.zeros(2, N, capi.EVENT_STRIDE).pin_memory()
@@ -81,9 +82,22 @@ class SimCore:
         b.event_count, b.events, b.episode_acc = self.event_count.data_ptr(), self.events.data_ptr(), self.episode_acc.data_ptr()
         b.noise = self.noise.data_ptr() if self.noise is not None else None
         b.reset_rand = self.reset_rand.data_ptr() if self.reset_rand is not None else None
+        b.episode_sums_eval = self.episode_sums_eval.data_ptr() if self.episode_sums_eval is not None else None
         if self.num_priv and self._priv_store.shape[1] != self.num_priv:
             raise AssertionError
         capi.check(self.L.go1_sim_bind(self._handle, C.byref(b)), "go1_sim_bind")
+
+    def sync_rigid_props(self):
+        """The rigid bodies take their mass / centre of mass from `payloads` / `com_displacements` as they are NOW (Isaac Gym
+        applies them once at actor creation, legged_robot.py:667-673); later re-draws only change the observed buffers."""
+        self.env("rigid_payload").copy_(self.env("payloads"))
+        self.env("rigid_com").copy_(self.env("com_displacements"))
+
+    def enable_eval_sums(self):
+        """LeggedRobot.episode_sums_eval (legged_robot.py:1420-1424): [NUM_EPISODE_SUMS][N], -1 = not yet recorded."""
+        self.episode_sums_eval = torch.full((capi.NUM_EPISODE_SUMS, self.N), -1.0, device=self.device)
+        self.episode_sums_eval[capi.NUM_REWARD_TERMS].zero_()     # "total" starts at 0 in the reference (:1423): never recorded
+        self._bind()
 
     def close(self):
         if self._handle:
@@ -217,7 +231,7 @@ class SimCore:
 
 _FIELD_NAMES = {
     0: ["root_pos", "root_quat", "root_lin_vel", "root_ang_vel", "commands", "gait_indices", "friction_coeffs", "restitutions",
-        "payloads", "com_displacements", "motor_strengths", "Kp_factors", "Kd_factors", "env_origins", "base_lin_vel",
+        "payloads", "com_displacements", "motor_strengths", "Kp_factors", "Kd_factors", "env_origins", "rigid_payload", "rigid_com", "base_lin_vel",
         "base_ang_vel", "projected_gravity", "rew_buf_pos", "rew_buf_neg", "episode_sums", "command_sums"],
     1: ["dof_pos", "dof_vel", "last_dof_vel", "actions", "last_actions", "last_last_actions", "joint_pos_target",
         "last_joint_pos_target", "last_last_joint_pos_target", "lag_buffer", "joint_pos_err_last", "joint_pos_err_last_last",

@@ -14,9 +14,14 @@ class BaseTask:
         self.num_obs = cfg.env.num_observations
         self.num_privileged_obs = cfg.env.num_privileged_obs
         self.num_actions = cfg.env.num_actions
-        self.num_eval_envs = 0
-        self.num_train_envs = cfg.env.num_envs
-        self.num_envs = cfg.env.num_envs
+        if eval_cfg is not None:           # base_task.py:43-50: eval envs are appended after the train envs
+            self.num_eval_envs = eval_cfg.env.num_envs
+            self.num_train_envs = cfg.env.num_envs
+            self.num_envs = self.num_eval_envs + self.num_train_envs
+        else:
+            self.num_eval_envs = 0
+            self.num_train_envs = cfg.env.num_envs
+            self.num_envs = cfg.env.num_envs
         self.extras = {}
         self.create_sim()
         self.enable_viewer_sync = True

@@ -117,10 +117,13 @@ def measured_heights_at(base_quat, base_pos, height_samples, terrain_cfg):
 
 class LeggedRobot(BaseTask):
     def __init__(self, cfg: Cfg, sim_params, physics_engine, sim_device, headless, eval_cfg=None, initial_dynamics_dict=None):
-        if eval_cfg is not None:
-            raise NotImplementedError("eval_cfg / num_eval_envs split (SURVEY.md §8f row 3) is not built yet")
         self.cfg = cfg
         self.eval_cfg = eval_cfg
+        # one process per GPU: every rank draws its device randomness (observation noise, reset / DR / push draws) and its
+        # command curriculum from its own streams, otherwise env i of every rank would see identical noise and commands
+        self.rank_seed_offset = 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.rank_seed_offset = int(torch.distributed.get_rank())
         self.sim_params = sim_params
         self.height_samples = None
         self.debug_viz = False
@@ -141,22 +144,29 @@ class LeggedRobot(BaseTask):
     def create_sim(self):
         """Replaces create_sim/_create_envs (legged_robot.py:493-515, 1481-1609): build the resolved kernel
         configuration, allocate the SoA state, place the env origins, draw the creation-time randomisation."""
-        cfg = self.cfg
+        cfg, ecfg = self.cfg, self.eval_cfg
         seed = int(getattr(cfg, "seed", 0)) if hasattr(cfg, "seed") else 0
-        self.sim_cfg, info = build_sim_config(cfg, num_envs=self.num_envs, num_train_envs=self.num_train_envs, seed=seed)
+        seed += 1000 * self.rank_seed_offset
+        mesh_type = cfg.terrain.mesh_type
+        if mesh_type in ['heightfield', 'trimesh']:     # before the kernel config: Terrain sets the x_offset the teleport reads
+            if ecfg is not None:
+                self.terrain = Terrain(cfg.terrain, self.num_train_envs, ecfg.terrain, self.num_eval_envs)
+            else:
+                self.terrain = Terrain(cfg.terrain, self.num_train_envs)
+        elif mesh_type not in (None, 'plane'):
+            raise ValueError("Terrain mesh type not recognised. Allowed types are [None, plane, heightfield, trimesh]")
+        self.sim_cfg, info = build_sim_config(cfg, num_envs=self.num_envs, num_train_envs=self.num_train_envs, seed=seed, eval_cfg=ecfg)
         self.dt = info["dt"]
         self.reward_scales = dict(info["active_reward_scales"])
         self.obs_scales = cfg.obs_scales
         self.curriculum_thresholds = cfg_dict(cfg.curriculum_thresholds)
         cfg.command_ranges = cfg_dict(cfg.commands)
+        if ecfg is not None:
+            ecfg.command_ranges = cfg_dict(ecfg.commands)
         self.max_episode_length = cfg.env.max_episode_length
         self.up_axis_idx = 2
-        mesh_type = cfg.terrain.mesh_type
         if mesh_type in ['heightfield', 'trimesh']:
-            self.terrain = Terrain(cfg.terrain, self.num_train_envs)
             self._bind_height_field()
-        elif mesh_type not in (None, 'plane'):
-            raise ValueError("Terrain mesh type not recognised. Allowed types are [None, plane, heightfield, trimesh]")
         self.core = SimCore(self.sim_cfg, device=self.device)
         self.num_dof = self.num_dofs = self.num_actuated_dof = 12
         self.num_bodies = 17
@@ -164,9 +174,16 @@ class LeggedRobot(BaseTask):
         self.feet_indices = torch.tensor([4, 8, 12, 16], device=self.device)
         self.penalised_contact_indices = torch.tensor([2, 6, 10, 14, 3, 7, 11, 15], device=self.device)
         self.termination_contact_indices = torch.tensor([0], device=self.device)
-        self._get_env_origins()
+        self.env_origins = torch.zeros(self.num_envs, 3, device=self.device)
+        self.terrain_levels = torch.zeros(self.num_envs, device=self.device, dtype=torch.long)
+        self.terrain_types = torch.zeros(self.num_envs, device=self.device, dtype=torch.long)
+        self._call_train_eval(self._get_env_origins, torch.arange(self.num_envs, device=self.device))
+        self.core.env("env_origins").copy_(self.env_origins.t())
         self._init_custom_buffers__()
-        self._randomize_rigid_body_props(torch.arange(self.num_envs, device=self.device), cfg)
+        self._call_train_eval(self._randomize_rigid_body_props, torch.arange(self.num_envs, device=self.device))
+        self.core.sync_rigid_props()          # the bodies are created with these payloads / com displacements (legged_robot.py:667-673)
+        if self.num_eval_envs > 0:
+            self.core.enable_eval_sums()
         self.common_step_counter = 0
         self._randomize_gravity()
 
@@ -200,12 +217,21 @@ class LeggedRobot(BaseTask):
             return 0
         return self._get_heights(torch.arange(self.num_envs, device=self.device))
 
-    def _get_env_origins(self):
+    def _call_train_eval(self, func, env_ids):
+        """legged_robot.py:531-544: `func(ids, cfg)` for the train envs, `func(ids, eval_cfg)` for the eval envs."""
+        train, ev = env_ids[env_ids < self.num_train_envs], env_ids[env_ids >= self.num_train_envs]
+        ret = ret_eval = None
+        if len(train) > 0:
+            ret = func(train, self.cfg)
+        if len(ev) > 0:
+            ret_eval = func(ev, self.eval_cfg)
+            if ret is not None and ret_eval is not None:
+                ret = torch.cat((ret, ret_eval), axis=-1)
+        return ret
+
+    def _get_env_origins(self, env_ids, cfg):
         """legged_robot.py:1675-1714."""
-        cfg, N, dev = self.cfg, self.num_envs, self.device
-        self.env_origins = torch.zeros(N, 3, device=dev)
-        self.terrain_levels = torch.zeros(N, device=dev, dtype=torch.long)
-        self.terrain_types = torch.zeros(N, device=dev, dtype=torch.long)
+        n, dev = len(env_ids), self.device
         if cfg.terrain.mesh_type in ["heightfield", "trimesh"]:
             self.custom_origins = True
             t = cfg.terrain
@@ -215,23 +241,23 @@ class LeggedRobot(BaseTask):
             if t.center_robots:
                 lo_l, hi_l = t.num_rows // 2 - t.center_span, t.num_rows // 2 + t.center_span - 1
                 lo_t, hi_t = t.num_cols // 2 - t.center_span, t.num_cols // 2 + t.center_span - 1
-                self.terrain_levels = torch.randint(lo_l, hi_l + 1, (N,), device=dev)
-                self.terrain_types = torch.randint(lo_t, hi_t + 1, (N,), device=dev)
+                self.terrain_levels[env_ids] = torch.randint(lo_l, hi_l + 1, (n,), device=dev)
+                self.terrain_types[env_ids] = torch.randint(lo_t, hi_t + 1, (n,), device=dev)
             else:
-                self.terrain_levels = torch.randint(min_init, max_init + 1, (N,), device=dev)
-                self.terrain_types = torch.div(torch.arange(N, device=dev), (N / t.num_cols), rounding_mode='floor').to(torch.long)
+                self.terrain_levels[env_ids] = torch.randint(min_init, max_init + 1, (n,), device=dev)
+                self.terrain_types[env_ids] = torch.div(torch.arange(n, device=dev), (n / t.num_cols), rounding_mode='floor').to(torch.long)
             t.max_terrain_level = t.num_rows
             t.terrain_origins = torch.from_numpy(t.env_origins).to(dev).to(torch.float)
-            self.env_origins = t.terrain_origins[self.terrain_levels, self.terrain_types]
+            self.env_origins[env_ids] = t.terrain_origins[self.terrain_levels[env_ids], self.terrain_types[env_ids]]
         else:
             self.custom_origins = False
-            num_cols = np.floor(np.sqrt(N))
-            num_rows = np.ceil(N / num_cols)
+            num_cols = np.floor(np.sqrt(n))
+            num_rows = np.ceil(self.num_envs / num_cols)
             xx, yy = torch.meshgrid(torch.arange(num_rows), torch.arange(num_cols), indexing="ij")
             sp = cfg.env.env_spacing
-            self.env_origins[:, 0] = sp * xx.flatten()[:N].to(dev)
-            self.env_origins[:, 1] = sp * yy.flatten()[:N].to(dev)
-        self.core.env("env_origins").copy_(self.env_origins.t())
+            self.env_origins[env_ids, 0] = sp * xx.flatten()[:n].to(dev)
+            self.env_origins[env_ids, 1] = sp * yy.flatten()[:n].to(dev)
+            self.env_origins[env_ids, 2] = 0.
 
     def _init_custom_buffers__(self):
         """legged_robot.py:1260-1297: DR defaults (the SimCore constructor already set 1.0 where needed)."""
@@ -293,11 +319,12 @@ class LeggedRobot(BaseTask):
                 ("body_pitch", "body_pitch"), ("body_roll", "body_roll"), ("stance_width", "stance_width"),
                 ("stance_length", "stance_length"), ("aux_reward_coef", "aux_reward_coef")]
         kw = {name: (getattr(c, f"limit_{key}")[0], getattr(c, f"limit_{key}")[1], getattr(c, f"num_bins_{key}")) for name, key in dims}
-        self.curricula = [RewardThresholdCurriculum(seed=c.curriculum_seed, **kw) for _ in self.category_names]
+        cur_seed = c.curriculum_seed + 1000 * getattr(self, "rank_seed_offset", 0)
+        self.curricula = [RewardThresholdCurriculum(seed=cur_seed, **kw) for _ in self.category_names]
         self.env_command_bins = np.zeros(len(env_ids), dtype=int)
         self.env_command_categories = np.zeros(len(env_ids), dtype=int)
         from go1_b200.curriculum_dev import SplitMix64
-        self._cat_rng = SplitMix64(c.curriculum_seed + 1)      # category draws (torch.rand on the device in the reference)
+        self._cat_rng = SplitMix64(cur_seed + 1)      # category draws (torch.rand on the device in the reference)
         rng_keys = ["lin_vel_x", "lin_vel_y", "ang_vel_yaw", "body_height_cmd", "gait_frequency_cmd_range", "gait_phase_cmd_range",
                     "gait_offset_cmd_range", "gait_bound_cmd_range", "gait_duration_cmd_range", "footswing_height_range",
                     "body_pitch_range", "body_roll_range", "stance_width_range", "stance_length_range", "aux_reward_coef_range"]

@@ -26,7 +26,7 @@ class AC_Args(PrefixProto, cli=False):
     activation = 'elu'  # only elu runs on the fused kernels
     adaptation_module_branch_hidden_dims = [256, 128]
     use_decoder = False
-    gemm_impl = 0       # 0 = fp32 CUDA cores (exact), 1 = tcgen05 TF32 tensor cores
+    gemm_impl = 1       # 1 = tcgen05 TF32 tensor cores (default; torch 1.10, the reference's pin, also ran these matmuls in TF32), 0 = fp32 CUDA cores (exact)
 
 
 def _mlp(in_dim, hidden, out_dim):

@@ -102,13 +102,15 @@ class PPO:
         tensors fall back to one graph with static input copies."""
         ac = self.actor_critic
         st = self.__dict__.setdefault("_graph_state", {})
-        key = (obs_history.shape[0], ac._impl(), obs_history.data_ptr(), privileged_obs.data_ptr())
+        key = (obs_history.shape[0], ac._impl(), obs_history.data_ptr(), privileged_obs.data_ptr(), ac.flat_params.data_ptr())
+        for stale in [k2 for k2 in st if k2[4] != key[4]]:      # graphs captured against a flat weight buffer that was rebuilt (.to())
+            del st[stale]
         g = st.get(key)
         if g is None:
             inplace = obs_history.is_contiguous() and privileged_obs.is_contiguous() and \
                 sum(1 for k2 in st if k2[2] is not None) < self._MAX_INPLACE_GRAPHS
             if not inplace:
-                key = (obs_history.shape[0], ac._impl(), None, None)
+                key = (obs_history.shape[0], ac._impl(), None, None, ac.flat_params.data_ptr())
                 g = st.get(key)
         if g is None:
             if inplace:
@@ -158,9 +160,9 @@ class PPO:
         tr.actions_log_prob = self.actor_critic.get_actions_log_prob(tr.actions).detach()
         tr.action_mean = self.actor_critic.action_mean.detach()
         tr.action_sigma = self.actor_critic.action_std.detach()
-        tr.observations = obs
-        tr.critic_observations = obs
-        tr.privileged_observations = privileged_obs
+        # obs / privileged_obs are views of buffers the next env.step overwrites in place: snapshot them into the storage slot now
+        tr.observations, tr.privileged_observations = self.storage.snapshot_observations(obs, privileged_obs)
+        tr.critic_observations = tr.observations
         tr.observation_histories = obs_history
         return tr.actions
 
@@ -168,7 +170,8 @@ class PPO:
         tr = self.transition
         tr.dones = dones
         tr.env_bins = infos["env_bins"]
-        fused = rewards.is_cuda and rewards.is_contiguous() and tr.observation_histories.is_contiguous() and tr.env_bins.is_cuda
+        f32 = lambda x: x.is_cuda and x.is_contiguous() and x.dtype == torch.float32
+        fused = f32(rewards) and f32(tr.observation_histories) and f32(tr.env_bins) and f32(tr.values) and tr.env_bins.numel() == rewards.numel()
         if fused:   # rewards += gamma * values * time_outs (ppo.py:84-86) happens inside the store kernel
             tr.rewards = rewards
             tr.action_sigma_vec = self.actor_critic.std.data

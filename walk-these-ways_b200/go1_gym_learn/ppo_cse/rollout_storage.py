@@ -65,6 +65,22 @@ class RolloutStorage:
         self.env_bins[t].copy_(transition.env_bins.view(-1, 1))
         self.step += 1
 
+    def snapshot_observations(self, obs, privileged_obs):
+        """Copy the observations the policy acts on into slot `step` NOW.  The env writes its next observations into the same
+        buffers during env.step, so a reference kept until process_env_step would store s_{t+1} next to a_t (the reference is
+        safe only because its compute_observations allocates fresh tensors).  Returns the two storage views."""
+        if self.step >= self.num_transitions_per_env:
+            raise AssertionError("Rollout buffer overflow")
+        t = self.step
+        so, sp = self.observations[t], self.privileged_observations[t]
+        if obs.is_cuda and obs.dtype == torch.float32 and obs.is_contiguous() and privileged_obs.dtype == torch.float32 and privileged_obs.is_contiguous():
+            capi.check(capi.lib().go1_store_observations(capi.ptr(obs), capi.ptr(privileged_obs) if sp.shape[-1] else None, capi.ptr(so),
+                                                         capi.ptr(sp) if sp.shape[-1] else None, self.num_envs, so.shape[-1], sp.shape[-1],
+                                                         capi.stream_ptr()), "go1_store_observations")
+        else:
+            so.copy_(obs); sp.copy_(privileged_obs)
+        return so, sp
+
     def add_transitions_fused(self, tr, time_outs, gamma):
         """add_transitions + the time-out bootstrap in ONE kernel (go1_store_transition)."""
         import ctypes as C
@@ -73,12 +89,14 @@ class RolloutStorage:
         t = self.step
         u8 = lambda x: x if x.dtype == torch.uint8 else (x.view(torch.uint8) if x.dtype == torch.bool else x.to(torch.uint8))
         dones, touts = u8(tr.dones), (u8(time_outs) if time_outs is not None else None)
-        ins = [tr.observations, tr.privileged_observations, tr.observation_histories, tr.actions, tr.rewards, tr.values, tr.actions_log_prob,
-               tr.action_mean, tr.action_sigma_vec, tr.env_bins]
+        stored = lambda x, slot: None if (x is None or x.data_ptr() == slot.data_ptr()) else x       # already snapshotted by act()
+        ins = [stored(tr.observations, self.observations[t]), stored(tr.privileged_observations, self.privileged_observations[t]),
+               tr.observation_histories, tr.actions, tr.rewards, tr.values, tr.actions_log_prob, tr.action_mean, tr.action_sigma_vec, tr.env_bins]
         outs = [self.observations[t], self.privileged_observations[t], self.observation_histories[t], self.actions[t], self.rewards[t], self.values[t],
                 self.actions_log_prob[t], self.mu[t], self.sigma[t], self.env_bins[t]]
-        for x in ins[:9]:
-            assert x.is_contiguous(), "transition tensors must be contiguous"
+        for x in ins:
+            assert x is None or (x.is_contiguous() and x.dtype == torch.float32 and x.is_cuda), "transition tensors must be contiguous float32 CUDA tensors"
+        assert tr.env_bins.numel() == self.num_envs and dones.numel() == self.num_envs
         arr_in = (C.c_void_p * 10)(*[x.data_ptr() if x is not None else None for x in ins])
         arr_out = (C.c_void_p * 10)(*[x.data_ptr() for x in outs])
         capi.check(capi.lib().go1_store_transition(arr_in, capi.ptr(dones), capi.ptr(touts), arr_out, capi.ptr(self.dones[t]), self.num_envs,
@@ -113,6 +131,7 @@ class RolloutStorage:
     def gather(self, src, idx, out=None, ldd=None, key=None):
         """out[i] = src.flatten(0,1)[idx[i]] through go1_gather_rows (destination buffers are reused across updates)."""
         flat = src.flatten(0, 1)
+        assert idx.dtype == torch.int64 and idx.is_contiguous() and flat.dtype == torch.float32
         w = flat.shape[1]
         ldd = ldd or w
         if out is None and key is not None:
