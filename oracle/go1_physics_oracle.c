@@ -460,9 +460,12 @@ void go1_oracle_aba(const Go1PhysParams* P, const Go1PhysDR* dr, const Go1PhysSt
 }
 
 typedef struct { const Go1PhysParams* P; const Go1PhysDR* dr; Go1PhysState* s; const double* tau; Go1PhysOut* out; double* fp; double* fv; int e0, e1; } BatchJob;
+static int g_max_threads = 0;        /* 0 = all online processors */
+void go1_oracle_set_threads(int t) { g_max_threads = t > 0 ? t : 0; }
 static int n_threads(int n) {
     long c = sysconf(_SC_NPROCESSORS_ONLN);
     int T = (int)(c > 0 ? c : 1);
+    if (g_max_threads > 0 && T > g_max_threads) T = g_max_threads;
     if (T > 256) T = 256;
     if (T > n / 4) T = n / 4;
     return T < 1 ? 1 : T;

@@ -19,6 +19,8 @@ typedef struct { double contact_force[17][3]; } Go1PhysOut;  /* Isaac Gym body o
 void go1_oracle_default_params(Go1PhysParams* P);
 void go1_oracle_substep(const Go1PhysParams* P, const Go1PhysDR* dr, Go1PhysState* s, const double tau[12], Go1PhysOut* out);
 void go1_oracle_substep_batch(const Go1PhysParams* P, int n, const Go1PhysDR* dr, Go1PhysState* s, const double* tau, Go1PhysOut* out);
+/* cap on the worker threads of the *_batch calls (0 = all online processors) */
+void go1_oracle_set_threads(int t);
 void go1_oracle_feet_batch(int n, const Go1PhysState* s, double* foot_pos, double* foot_vel);
 void go1_oracle_feet(const Go1PhysState* s, double foot_pos[4][3], double foot_vel[4][3]);
 void go1_oracle_aba(const Go1PhysParams* P, const Go1PhysDR* dr, const Go1PhysState* s, const double tau[12], double a0_out[6], double qdd_out[12]);

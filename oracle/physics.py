@@ -62,6 +62,11 @@ def lib():
     return _lib
 
 
+def set_threads(t):
+    """Worker threads of the batched calls (bench.py pins them to the torch thread count: no oversubscription)."""
+    lib().go1_oracle_set_threads(int(t))
+
+
 def substep_batch(p, drs, states, tau):
     """All envs in one C call (OpenMP over envs). drs/states: ctypes arrays; tau: float64 [n,12]. Returns contact forces [n,17,3]."""
     n = len(states)

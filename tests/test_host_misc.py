@@ -47,13 +47,16 @@ def test_lazy_containers_build_once_and_pickle_as_plain_dicts():
 
 
 def test_bench_reference_arm_prints_the_contract_line():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup-ref", "0", "--cpu-envs", "8"],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-envs", "8"],
                          capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "0"})
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "env_steps_per_s" and line["unit"] == "env-steps/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the same workload definition as the B200 arm prints (the bounded sample is named separately), fixed thread count <= 32
+    assert line["config"]["name"] == "flat" and line["config"]["envs_per_gpu"] == 4096 and line["scaling"] == "weak" and line["warmup"] == 1
+    assert "8 envs x 24-step rollout" in line["sample"] and line["cpu_baseline"]["cores"] <= 32
     # other ranks of a torchrun launch do no work and print nothing
     out1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1"], capture_output=True, text=True,
                           timeout=120, env={**os.environ, "RANK": "1"})

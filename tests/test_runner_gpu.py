@@ -69,3 +69,59 @@ def test_runner_learn_checkpoints_and_play_artifacts(tmp_path, monkeypatch):
             assert c.weights.shape == w.shape
     finally:
         RunnerArgs.resume = False
+
+
+def test_train_eval_split_rollout_and_update(tmp_path, monkeypatch):
+    """SURVEY.md §8f row 3 (legged_robot.py:531-544, ppo_cse/__init__.py:142-146): eval envs are appended after the train envs,
+    take their randomisation / reset ranges from eval_cfg, are driven by the student policy, never enter the rollout storage,
+    and their first finished episode lands in episode_sums_eval."""
+    monkeypatch.chdir(tmp_path)
+    for m in [k for k in sys.modules if k.startswith("go1_gym.envs.base.legged_robot_config")]:
+        del sys.modules[m]
+    sys.path.insert(0, HERE)
+    from env_golden_util import clone_cfg
+    from go1_gym.envs.base.legged_robot_config import Cfg
+    from go1_b200.train_config import apply_train_config
+    from go1_gym.envs.go1.velocity_tracking import VelocityTrackingEasyEnv
+    from go1_gym.envs.wrappers.history_wrapper import HistoryWrapper
+    from go1_gym_learn.ppo_cse import Runner, RunnerArgs
+    from ml_logger import logger
+    apply_train_config(Cfg)
+    Cfg.env.num_envs = 96
+    ECfg = clone_cfg(Cfg, "EvalCfg")
+    ECfg.env.num_envs = 32
+    ECfg.domain_rand.friction_range = [2.9, 3.0]
+    ECfg.domain_rand.added_mass_range = [2.5, 3.0]
+    ECfg.domain_rand.motor_strength_range = [0.5, 0.6]
+    ECfg.terrain.yaw_init_range = 0.0
+    logger.configure(prefix="run_eval", root=str(tmp_path))
+    env = HistoryWrapper(VelocityTrackingEasyEnv(sim_device="cuda:0", headless=True, cfg=Cfg, eval_cfg=ECfg))
+    assert (env.num_envs, env.num_train_envs, env.num_eval_envs) == (128, 96, 32)
+    RunnerArgs.num_steps_per_env, RunnerArgs.resume = 12, False
+    runner = Runner(env, device="cuda:0")
+    st = runner.alg.storage
+    assert st.observations.shape[:2] == (12, 96) and st.observation_histories.shape == (12, 96, env.num_obs_history)
+    core = env.env.core
+    fr, pay = core.env("friction_coeffs")[0], core.env("payloads")[0]
+    assert (fr[96:] >= 2.9).all() and (fr[:96] < 3.0001).all() and (fr[:96] < 2.9).any()          # creation-time draws per cfg
+    assert (pay[96:] >= 2.5).all() and (pay[:96].min() < 2.0)
+    assert torch.equal(core.env("rigid_payload")[0], pay)
+    ms = core.env("motor_strengths")[0]
+    assert ((ms[96:] >= 0.5) & (ms[96:] <= 0.6)).all() and (ms[:96] >= 0.9).all()                # env.reset() re-drew the dof props per cfg
+    q = core.env("root_quat")
+    assert (q[2, 96:].abs() < 1e-6).all() and (q[2, :96].abs() > 1e-3).any()                     # eval yaw_init_range = 0
+    od = env.get_observations()
+    obs, priv, hist = od["obs"], od["privileged_obs"], od["obs_history"]
+    # make the eval robots fall so that eval episodes finish inside the rollout
+    core.env("root_quat")[0, 96:112] = 1.0; core.env("root_quat")[3, 96:112] = 0.0; core.env("root_quat")[2, 96:112] = 0.0
+    obs, priv, hist, infos = runner.rollout(obs, priv, hist)
+    assert "eval/episode" in infos and infos["env_bins"].shape[0] == 96 and infos["time_outs"].shape[0] == 96
+    with torch.inference_mode():
+        runner.alg.compute_returns(hist[:96], priv[:96])
+    losses = runner.alg.update()
+    assert all(np.isfinite(losses))
+    ev = env.env.episode_sums_eval
+    assert set(ev) >= {"tracking_lin_vel", "total"}
+    rec = ev["tracking_lin_vel"]
+    assert (rec[:96] == -1).all() and (rec[96:112] != -1).all()                                   # train envs never write it
+    assert (ev["total"] == 0).all()                                                               # "total" starts at 0: never recorded (:1423)

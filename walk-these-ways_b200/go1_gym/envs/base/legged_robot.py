@@ -414,6 +414,16 @@ class LeggedRobot(BaseTask):
         return d
 
     @property
+    def episode_sums_eval(self):
+        """legged_robot.py:1420-1424: the first finished episode of every eval env (-1 = none yet; "total" starts at 0)."""
+        ev = self.core.episode_sums_eval
+        if ev is None:
+            return {}
+        d = {n: ev[capi.REWARD_TERMS.index(n)] for n in self.reward_scales if n in capi.REWARD_TERMS}
+        d["total"] = ev[capi.NUM_REWARD_TERMS]
+        return d
+
+    @property
     def command_sums(self):
         cs = self.core.env("command_sums")
         d = {n: cs[capi.REWARD_TERMS.index(n)] for n in self.reward_scales if n in capi.REWARD_TERMS}
@@ -514,6 +524,8 @@ class LeggedRobot(BaseTask):
             ex["curriculum/distribution"] = _LazyDict(self._distribution_builder())
         if self.cfg.env.send_timeouts:
             ex["time_outs"] = dc.time_outs
+        if self.num_eval_envs > 0:
+            ex["eval/episode"] = {}            # legged_robot.py:188-195: the entry carries no values (the sums go to episode_sums_eval)
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
 
     def _apply_pending_interval_resample(self):
@@ -713,6 +725,8 @@ class LeggedRobot(BaseTask):
         core, ex = self.core, self.extras
         if (ids < self.num_train_envs).any():
             ex["train/episode"] = _LazyDict(self._episode_builder(core.episode_acc.clone()))
+        if (ids >= self.num_train_envs).any():
+            ex["eval/episode"] = {}
         if self.cfg.commands.command_curriculum:
             if self._env_bins_dirty:
                 f = self._env_bins_flip = self._env_bins_flip ^ 1
