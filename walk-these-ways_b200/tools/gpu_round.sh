@@ -1,0 +1,34 @@
+#!/bin/bash
+# One gpurun call's worth of evidence: GPU test suite, bench lines of the BASELINE configs, the reference arm, ncu launch list and
+# `ncu --set full` captures of the step kernel and the dominant GEMM.  Everything lands in gpurun_out/ (tag = $1).
+#   gpurun --timeout 1500 -- 'bash walk-these-ways_b200/tools/gpu_round.sh r2a'
+TAG=${1:-r2}
+WHAT=${2:-all}
+O=gpurun_out
+mkdir -p $O
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/${TAG}_gpu.txt 2>&1
+if [[ $WHAT == all || $WHAT == *tests* ]]; then
+  timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -60 > $O/${TAG}_tests.txt
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.txt 2>&1
+fi
+if [[ $WHAT == all || $WHAT == *bench* ]]; then
+  timeout 600 python bench.py --steps 10 --warmup 3 > $O/${TAG}_bench_flat.json 2> $O/${TAG}_bench_flat.err
+  timeout 600 python bench.py --steps 5 --warmup 3 --breakdown --no-cpu-baseline > $O/${TAG}_bench_flat_breakdown.json 2>> $O/${TAG}_bench_flat.err
+  timeout 600 python bench.py --config rough_dr --steps 5 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_rough_dr.json 2> $O/${TAG}_bench_rough_dr.err
+  timeout 600 python bench.py --config mob16k --steps 3 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_mob16k.json 2> $O/${TAG}_bench_mob16k.err
+fi
+if [[ $WHAT == all || $WHAT == *sweep* ]]; then
+  timeout 900 python bench.py --config sweep --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_sweep.json 2> $O/${TAG}_bench_sweep.err
+fi
+if [[ $WHAT == all || $WHAT == *ref* ]]; then
+  ( time timeout 900 python bench.py --impl reference --steps 20 --warmup 5 ) > $O/${TAG}_bench_reference.json 2> $O/${TAG}_bench_reference.err
+fi
+if [[ $WHAT == all || $WHAT == *ncu* ]]; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 2300 -c 2300 --csv --log-file $O/${TAG}_launches.csv \
+      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-gemm-roofline > $O/${TAG}_ncu_launches.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:go1_step_kernel -s 30 -c 2 -f -o $O/${TAG}_step_kernel \
+      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-gemm-roofline > $O/${TAG}_ncu_step.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32 -s 400 -c 12 -f -o $O/${TAG}_gemm \
+      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-gemm-roofline > $O/${TAG}_ncu_gemm.log 2>&1
+fi
+ls -la $O | tail -30
