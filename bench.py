@@ -201,7 +201,7 @@ def run_b200(args):
         out = runner.alg.update()          # returns host floats: one D2H sync per iteration
         if ev:
             ev[3].record(); torch.cuda.synchronize()
-            if phase_ms[3] >= args.warmup:
+            if args.warmup <= phase_ms[3] < args.warmup + args.steps:      # the timed iterations only
                 for i in range(3):
                     phase_ms[i] += ev[i].elapsed_time(ev[i + 1])
             phase_ms[3] += 1

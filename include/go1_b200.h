@@ -134,6 +134,11 @@ typedef struct Go1SimBuffers {
     const float* reset_rand; /* optional [N][GO1_RESET_RAND_STRIDE] uniform(0,1) draws injected for reset/DR/push parity tests, or NULL.
                               * slots: 0-11 dof pos, 12-14 x y yaw, 15-20 base twist, 21 motor strength, 22 Kp, 23 Kd, 24-35 motor offsets,
                               * 36-37 push xy, 38 payload, 39-41 com displacement, 42 friction, 43 restitution */
+    const float* gravity_dev;/* optional [6] in device memory: gravity[3], gravity_vec[3].  When set, go1_sim_step / go1_sim_reset_idx* read
+                              * gravity from here instead of their host arguments, so a captured CUDA graph of the env step sees later
+                              * _randomize_gravity calls (legged_robot.py:546-561) */
+    const int64_t* step_dev; /* optional [1] in device memory: added to the `common_step` argument (device-side common_step_counter of a
+                              * graph-replayed rollout, advanced by go1_rollout_advance) */
     float* episode_sums_eval;/* optional [GO1_NUM_REWARD_TERMS+1][N], -1 = unset: LeggedRobot.episode_sums_eval (legged_robot.py:188-195), or NULL */
 } Go1SimBuffers;
 
@@ -368,6 +373,18 @@ int go1_store_transition(const float* const* in_f32, const uint8_t* dones, const
  * (ppo.py:73-76): s_obs[n][nobs] <- obs, s_priv[n][npriv] <- priv.  The env's observation buffers are overwritten in place by
  * the next go1_sim_step, so the copy cannot wait for process_env_step; go1_store_transition then takes in_f32[0] = in_f32[1] = NULL. */
 int go1_store_observations(const float* obs, const float* priv, float* s_obs, float* s_priv, int n, int nobs, int npriv, void* stream);
+
+/* The two stores above with the slot index `*slot_dev` read on the device and slab BASE pointers ([T][n][.]) as outputs, so that ONE
+ * captured CUDA graph of a whole env step (policy, sim step, curriculum, reset, history roll, stores) is replayed for every step of the
+ * rollout (ppo_cse/__init__.py:138-147); go1_rollout_advance closes a step: it files the step's extras["train/episode"] accumulator
+ * `acc[W]` (last element = number of train envs reset; 0 -> the previous slot's entry is carried forward, like the reference's extras
+ * entry that stays in place) into acc_hist[T][W], then *slot_dev = (*slot_dev + 1) % T and *step_dev += 1 (Go1SimBuffers.step_dev). */
+int go1_rollout_store_observations(const float* obs, const float* priv, float* s_obs_base, float* s_priv_base, const int32_t* slot_dev,
+                                   int n, int nobs, int npriv, void* stream);
+int go1_rollout_store_transition(const float* const* in_f32, const uint8_t* dones, const uint8_t* time_outs, float* const* out_base_f32,
+                                 uint8_t* s_dones_base, const int32_t* slot_dev, int n, int nobs, int npriv, int nhist, int nact, float gamma,
+                                 void* stream);
+int go1_rollout_advance(const float* acc, float* acc_hist, int W, int T, int32_t* slot_dev, int64_t* step_dev, void* stream);
 
 /* Replaces the fancy-index gathers of RolloutStorage.mini_batch_generator (rollout_storage.py:98-137):
  * dst[i][0:width] = src[idx[i]][0:width]; ldd = row stride of dst in floats (>= width). */

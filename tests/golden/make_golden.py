@@ -763,6 +763,32 @@ def make_terrain(Cfg):
     print("terrain.npz:", {k: v.shape for k, v in out.items()}, "nonzero", {k: int(np.count_nonzero(v)) for k, v in out.items() if "height" in k})
 
 
+def make_metrics_envelope():
+    """the reward-term trajectories of the shipped training log (runs/.../metrics.pkl, one record per 10
+    iterations, 4000 envs on Isaac Gym): the first 60 records of the terms the learning-level comparison looks at."""
+    class U(pickle.Unpickler):
+        def find_class(self, mod, name):
+            if mod == "torch.storage" and name == "_load_from_bytes":
+                return lambda b: torch.load(io.BytesIO(b), map_location="cpu", weights_only=False)
+            return super().find_class(mod, name)
+    rows = []
+    with open(f"{REF}/runs/gait-conditioned-agility/pretrain-v0/train/025417.456545/metrics.pkl", "rb") as f:
+        u = U(f)
+        while len(rows) < 60:
+            try:
+                rows.append(u.load())
+            except EOFError:
+                break
+    keys = ["train/episode/rew_total/mean", "train/episode/rew_tracking_lin_vel/mean", "train/episode/rew_tracking_ang_vel/mean",
+            "train/episode/rew_tracking_contacts_shaped_force/mean", "train/episode/rew_tracking_contacts_shaped_vel/mean",
+            "train/episode/rew_collision/mean", "train/episode/rew_action_rate/mean", "train/episode/rew_torques/mean",
+            "train/episode/command_area_trot/mean", "adaptation_loss/mean", "mean_value_loss/mean", "mean_surrogate_loss/mean", "iterations", "timesteps"]
+    out = {k: [float(r[k]) if k in r else None for r in rows] for k in keys}
+    with open(os.path.join(HERE, "metrics_envelope.json"), "w") as f:
+        json.dump(out, f)
+    print("metrics_envelope.json:", len(rows), "records; rew_total", [round(x, 3) for x in out["train/episode/rew_total/mean"][:6]])
+
+
 if __name__ == "__main__":
     Cfg, trees = reference_train_cfg()
     with open(os.path.join(HERE, "cfg_trees.json"), "w") as f:
@@ -773,3 +799,4 @@ if __name__ == "__main__":
     make_ppo()
     make_resample(Cfg)
     make_terrain(Cfg)
+    make_metrics_envelope()

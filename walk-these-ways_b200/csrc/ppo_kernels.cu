@@ -823,12 +823,18 @@ struct StoreArgs {
     const uint8_t *dones, *time_outs;
     float *s_obs, *s_priv, *s_hist, *s_actions, *s_rewards, *s_values, *s_logp, *s_mu, *s_sigma, *s_env_bins;
     uint8_t* s_dones;
+    const int* slot_dev;          // optional: the output pointers are slab BASES and the slot index is read from device memory
     int n, nobs, npriv, nhist, nact; float gamma;
 };
-__global__ void __launch_bounds__(256) store_transition_kernel(const StoreArgs a) {
+__global__ void __launch_bounds__(256) store_transition_kernel(StoreArgs a) {
     const int e = blockIdx.x;
     if (e >= a.n) return;
     const int t = threadIdx.x;
+    if (a.slot_dev) {
+        const size_t off = (size_t)(*a.slot_dev) * a.n;
+        a.s_obs += off * a.nobs; a.s_priv += off * a.npriv; a.s_hist += off * a.nhist; a.s_actions += off * a.nact; a.s_rewards += off;
+        a.s_values += off; a.s_logp += off; a.s_mu += off * a.nact; a.s_sigma += off * a.nact; a.s_env_bins += off; a.s_dones += off;
+    }
     if ((a.nhist & 3) == 0) {
         const float4* src = reinterpret_cast<const float4*>(a.hist + (size_t)e * a.nhist);
         float4* dst = reinterpret_cast<float4*>(a.s_hist + (size_t)e * a.nhist);
@@ -854,16 +860,48 @@ __global__ void __launch_bounds__(256) store_transition_kernel(const StoreArgs a
 }
 // obs / privileged obs of the step the policy is ABOUT to act on: copied at act() time, before env.step overwrites the env's buffers
 __global__ void store_observations_kernel(const float* __restrict__ obs, const float* __restrict__ priv, float* __restrict__ s_obs,
-                                          float* __restrict__ s_priv, size_t n_obs, size_t n_priv) {
+                                          float* __restrict__ s_priv, size_t n_obs, size_t n_priv, const int* __restrict__ slot_dev) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_obs) s_obs[i] = obs[i];
-    if (i < n_priv) s_priv[i] = priv[i];
+    const size_t slot = slot_dev ? (size_t)*slot_dev : 0;
+    if (i < n_obs) s_obs[slot * n_obs + i] = obs[i];
+    if (i < n_priv) s_priv[slot * n_priv + i] = priv[i];
 }
 extern "C" int go1_store_observations(const float* obs, const float* priv, float* s_obs, float* s_priv, int n, int nobs, int npriv, void* stream) {
     if (!obs || !s_obs || n <= 0 || nobs <= 0 || npriv < 0 || (npriv > 0 && (!priv || !s_priv))) return go1_set_error("go1_store_observations: bad arguments");
     const size_t n_obs = (size_t)n * nobs, n_priv = (size_t)n * npriv;
-    store_observations_kernel<<<(unsigned)((n_obs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(obs, priv, s_obs, s_priv, n_obs, n_priv); go1_count_launch(1);
+    store_observations_kernel<<<(unsigned)((n_obs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(obs, priv, s_obs, s_priv, n_obs, n_priv, nullptr); go1_count_launch(1);
     return cuda_rc("go1_store_observations");
+}
+
+// ---- the same two stores with the slot index in device memory: one captured CUDA graph serves every step of the rollout ----
+extern "C" int go1_rollout_store_observations(const float* obs, const float* priv, float* s_obs_base, float* s_priv_base, const int32_t* slot_dev,
+                                              int n, int nobs, int npriv, void* stream) {
+    if (!obs || !s_obs_base || !slot_dev || n <= 0 || nobs <= 0 || npriv < 0 || (npriv > 0 && (!priv || !s_priv_base)))
+        return go1_set_error("go1_rollout_store_observations: bad arguments");
+    const size_t n_obs = (size_t)n * nobs, n_priv = (size_t)n * npriv;
+    store_observations_kernel<<<(unsigned)((n_obs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(obs, priv, s_obs_base, s_priv_base, n_obs, n_priv, slot_dev);
+    go1_count_launch(1);
+    return cuda_rc("go1_rollout_store_observations");
+}
+
+// Ends one env step of a graph-replayed rollout: files the step's extras["train/episode"] accumulator (episode sums of the envs reset in
+// this step + their count; a step without a reset carries the previous entry forward, like the reference's extras entry that just
+// stays in place) under the step's slot, then advances the slot index and the device-side common_step_counter.
+__global__ void rollout_advance_kernel(const float* __restrict__ acc, float* __restrict__ acc_hist, int W, int T, int* slot_dev, long long* step_dev) {
+    const int t = *slot_dev;
+    const int i = threadIdx.x;
+    if (acc && acc_hist && i < W) {
+        float v = acc[i];
+        if (acc[W - 1] == 0.0f) v = acc_hist[(size_t)((t + T - 1) % T) * W + i];
+        acc_hist[(size_t)t * W + i] = v;
+    }
+    __syncthreads();
+    if (i == 0) { *slot_dev = (t + 1) % T; if (step_dev) *step_dev += 1; }
+}
+extern "C" int go1_rollout_advance(const float* acc, float* acc_hist, int W, int T, int32_t* slot_dev, int64_t* step_dev, void* stream) {
+    if (!slot_dev || T <= 0 || W < 0 || W > 256) return go1_set_error("go1_rollout_advance: bad arguments");
+    rollout_advance_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(acc, acc_hist, W, T, slot_dev, (long long*)step_dev); go1_count_launch(1);
+    return cuda_rc("go1_rollout_advance");
 }
 
 extern "C" int go1_store_transition(const float* const* in_f32, const uint8_t* dones, const uint8_t* time_outs, float* const* out_f32, uint8_t* s_dones,
@@ -875,10 +913,28 @@ extern "C" int go1_store_transition(const float* const* in_f32, const uint8_t* d
     a.dones = dones; a.time_outs = time_outs;
     a.s_obs = out_f32[0]; a.s_priv = out_f32[1]; a.s_hist = out_f32[2]; a.s_actions = out_f32[3]; a.s_rewards = out_f32[4]; a.s_values = out_f32[5];
     a.s_logp = out_f32[6]; a.s_mu = out_f32[7]; a.s_sigma = out_f32[8]; a.s_env_bins = out_f32[9]; a.s_dones = s_dones;
-    a.n = n; a.nobs = nobs; a.npriv = npriv; a.nhist = nhist; a.nact = nact; a.gamma = gamma;
+    a.n = n; a.nobs = nobs; a.npriv = npriv; a.nhist = nhist; a.nact = nact; a.gamma = gamma; a.slot_dev = nullptr;
     for (int i = 2; i < 9; i++) if (!in_f32[i] || !out_f32[i]) return go1_set_error("go1_store_transition: null tensor");
     if ((in_f32[0] && !out_f32[0]) || (in_f32[1] && !out_f32[1])) return go1_set_error("go1_store_transition: null tensor");
     if (!out_f32[9]) return go1_set_error("go1_store_transition: null tensor");
     store_transition_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(a); go1_count_launch(1);
     return cuda_rc("go1_store_transition");
+}
+extern "C" int go1_rollout_store_transition(const float* const* in_f32, const uint8_t* dones, const uint8_t* time_outs, float* const* out_base_f32,
+                                            uint8_t* s_dones_base, const int32_t* slot_dev, int n, int nobs, int npriv, int nhist, int nact, float gamma,
+                                            void* stream) {
+    if (!in_f32 || !out_base_f32 || !dones || !s_dones_base || !slot_dev || n <= 0 || nact > 256 || npriv > 256)
+        return go1_set_error("go1_rollout_store_transition: bad arguments");
+    StoreArgs a;
+    a.obs = in_f32[0]; a.priv = in_f32[1]; a.hist = in_f32[2]; a.actions = in_f32[3]; a.rewards = in_f32[4]; a.values = in_f32[5];
+    a.logp = in_f32[6]; a.mean = in_f32[7]; a.std = in_f32[8]; a.env_bins = in_f32[9];
+    a.dones = dones; a.time_outs = time_outs;
+    a.s_obs = out_base_f32[0]; a.s_priv = out_base_f32[1]; a.s_hist = out_base_f32[2]; a.s_actions = out_base_f32[3]; a.s_rewards = out_base_f32[4];
+    a.s_values = out_base_f32[5]; a.s_logp = out_base_f32[6]; a.s_mu = out_base_f32[7]; a.s_sigma = out_base_f32[8]; a.s_env_bins = out_base_f32[9];
+    a.s_dones = s_dones_base; a.slot_dev = slot_dev;
+    a.n = n; a.nobs = nobs; a.npriv = npriv; a.nhist = nhist; a.nact = nact; a.gamma = gamma;
+    for (int i = 2; i < 9; i++) if (!in_f32[i] || !out_base_f32[i]) return go1_set_error("go1_rollout_store_transition: null tensor");
+    if (!out_base_f32[9] || (in_f32[0] && !out_base_f32[0]) || (in_f32[1] && !out_base_f32[1])) return go1_set_error("go1_rollout_store_transition: null tensor");
+    store_transition_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(a); go1_count_launch(1);
+    return cuda_rc("go1_rollout_store_transition");
 }

@@ -88,7 +88,7 @@ class Go1SimConfig(C.Structure):
 class Go1SimBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "env_f32", "leg_f32", "env_i32", "obs", "priv_obs", "rew", "reset", "time_out", "event_count", "events",
-        "episode_acc", "noise", "reset_rand", "episode_sums_eval")]
+        "episode_acc", "noise", "reset_rand", "gravity_dev", "step_dev", "episode_sums_eval")]
 
 
 CUR_MAX_CATEGORIES = 8
@@ -166,6 +166,9 @@ def lib():
         "go1_ppo_adaptive_lr": ([vp, vp, _f, _f, _f, vp], ip),
         "go1_store_transition": ([vp, vp, vp, vp, vp, ip, ip, ip, ip, ip, _f, vp], ip),
         "go1_store_observations": ([vp, vp, vp, vp, ip, ip, ip, vp], ip),
+        "go1_rollout_store_observations": ([vp, vp, vp, vp, vp, ip, ip, ip, vp], ip),
+        "go1_rollout_store_transition": ([vp, vp, vp, vp, vp, vp, ip, ip, ip, ip, ip, _f, vp], ip),
+        "go1_rollout_advance": ([vp, vp, ip, ip, vp, vp, vp], ip),
         "go1_gather_rows": ([vp, vp, vp, i64, ip, ip, vp], ip),
     }
     for name, (args, res) in sig.items():

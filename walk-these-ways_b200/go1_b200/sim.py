@@ -60,6 +60,10 @@ class SimCore:
         self.iters_counted = 1
         self.gravity = (C.c_float * 3)(0.0, 0.0, -9.8)
         self.gravity_vec = (C.c_float * 3)(0.0, 0.0, -1.0)
+        # gravity and the step counter also live in device memory (the kernels read them from there), so that a captured CUDA
+        # graph of the env step follows _randomize_gravity and the Philox streams keep advancing across replays
+        self.gravity_dev = torch.tensor([0.0, 0.0, -9.8, 0.0, 0.0, -1.0], device=dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
 
         w = load_actuator_weights()
         self._handle = C.c_void_p()
@@ -83,6 +87,7 @@ class SimCore:
         b.noise = self.noise.data_ptr() if self.noise is not None else None
         b.reset_rand = self.reset_rand.data_ptr() if self.reset_rand is not None else None
         b.episode_sums_eval = self.episode_sums_eval.data_ptr() if self.episode_sums_eval is not None else None
+        b.gravity_dev, b.step_dev = self.gravity_dev.data_ptr(), self.step_dev.data_ptr()
         if self.num_priv and self._priv_store.shape[1] != self.num_priv:
             raise AssertionError
         capi.check(self.L.go1_sim_bind(self._handle, C.byref(b)), "go1_sim_bind")
@@ -162,6 +167,7 @@ class SimCore:
     def set_gravity(self, g, gvec):
         self.gravity[:] = [float(x) for x in g]
         self.gravity_vec[:] = [float(x) for x in gvec]
+        self.gravity_dev.copy_(torch.tensor(list(self.gravity) + list(self.gravity_vec), dtype=torch.float32))    # stream-ordered; ~1 call / 400 steps
 
     def step(self, actions, common_step=0, mode=0):
         assert actions.is_cuda and actions.dtype == torch.float32 and actions.is_contiguous() and actions.shape == (self.N, 12)

@@ -494,17 +494,8 @@ class LeggedRobot(BaseTask):
         """step() with the curriculum on the device: five stream-ordered launches, no synchronisation.
         [resample list 1 (envs marked last step)] -> [step kernel] -> [resample list 0] -> [reset kernel]."""
         core = self.core
-        if self._ep_len_dirty:          # episode lengths were overwritten from outside: rebuild the pending interval list
-            interval = int(self.sim_cfg.resampling_interval)
-            ep = core.episode_length_buf
-            ids = torch.nonzero((ep + 1) % interval == 0).squeeze(1) if interval > 0 else ep.new_zeros(0, dtype=torch.long)
-            k = int(ids.numel())
-            if k:
-                rows = [capi.REWARD_TERMS.index(key) for key in _TASK_KEYS]
-                core.events[1, :k, 0] = ids.float()
-                core.events[1, :k, 1:5] = core.env("command_sums")[rows][:, ids].t()
-            core.event_count[1] = k
-            self._ep_len_dirty = False
+        if self._ep_len_dirty:
+            self._sync_interval_events_after_ep_len_write()
         dc.to_device()
         dc.resample(1)
         core.step(actions, common_step=self.common_step_counter, mode=0)
@@ -527,6 +518,21 @@ class LeggedRobot(BaseTask):
         if self.num_eval_envs > 0:
             ex["eval/episode"] = {}            # legged_robot.py:188-195: the entry carries no values (the sums go to episode_sums_eval)
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    def _sync_interval_events_after_ep_len_write(self):
+        """Episode lengths were overwritten from outside (Runner: init_at_random_ep_len): rebuild the device-side list of envs
+        due for the periodic command resample at the next step."""
+        core = self.core
+        interval = int(self.sim_cfg.resampling_interval)
+        ep = core.episode_length_buf
+        ids = torch.nonzero((ep + 1) % interval == 0).squeeze(1) if interval > 0 else ep.new_zeros(0, dtype=torch.long)
+        k = int(ids.numel())
+        if k:
+            rows = [capi.REWARD_TERMS.index(key) for key in _TASK_KEYS]
+            core.events[1, :k, 0] = ids.float()
+            core.events[1, :k, 1:5] = core.env("command_sums")[rows][:, ids].t()
+        core.event_count[1] = k
+        self._ep_len_dirty = False
 
     def _apply_pending_interval_resample(self):
         """legged_robot.py:683-686: envs whose episode length hits a multiple of resampling_time/dt."""

@@ -111,8 +111,140 @@ class Runner:
 
         self.env.reset()
 
+    # ------------------------------------------------------------------ graph-replayed rollout
+    step_graph = True       # class switch; GO1_STEP_GRAPH=0 in the environment forces the eager per-launch path
+
+    def _step_graph_state(self):
+        """Static state of the graph-replayed rollout, or None when the configuration does not allow it (eval envs, host
+        curriculum, injected noise, a wrapper other than HistoryWrapper): then rollout() launches kernel by kernel."""
+        st = self.__dict__.get("_sg", False)
+        if st is not False:
+            return st
+        st = None
+        env = self.env
+        base = getattr(env, "env", None)
+        ok = self.step_graph and os.environ.get("GO1_STEP_GRAPH", "1") != "0" and base is not None and hasattr(env, "_bufs") \
+            and hasattr(base, "_device_curriculum") and self.env.num_eval_envs == 0 and self.alg.use_cuda_graph is True \
+            and self.alg.actor_critic.injected_eps is None and str(self.device).startswith("cuda")
+        if ok and base._device_curriculum() is not None and base.cfg.commands.command_curriculum:
+            from go1_b200 import capi
+            dev, T = base.core.device, self.num_steps_per_env
+            W = capi.NUM_EPISODE_SUMS + 1
+            with torch.inference_mode(False):
+                st = dict(slot=torch.zeros(1, dtype=torch.int32, device=dev), acc=torch.zeros(W, device=dev),
+                          acc_hist=torch.zeros(T, W, device=dev), graphs={}, warm={0: 0, 1: 0}, W=W, T=T)
+        self._sg = st
+        return st
+
+    def _graph_step_body(self, sg):
+        """One env step of the rollout as a fixed launch sequence on static buffers (what PPO.act, LeggedRobot._step_device,
+        HistoryWrapper.step and PPO.process_env_step launch, minus the per-step host logic); the storage slot, the Philox step
+        counter and gravity are read from device memory, so the captured sequence serves every step."""
+        import ctypes as C
+        from go1_b200 import capi
+        env, alg = self.env, self.alg
+        base, ac, stg = env.env, alg.actor_critic, alg.storage
+        core, dc, L, sp = base.core, base._dev_cur, capi.lib(), capi.stream_ptr
+        hist, obs, priv = env.obs_history, core.obs, core.priv_obs
+        N = core.N
+        actions, values = alg._act_eager(hist, priv)
+        capi.check(L.go1_rollout_store_observations(capi.ptr(obs), capi.ptr(priv) if core.num_priv else None, capi.ptr(stg.observations),
+                                                    capi.ptr(stg.privileged_observations) if core.num_priv else None, capi.ptr(sg["slot"]), N,
+                                                    core.num_obs, core.num_priv, sp()), "go1_rollout_store_observations")
+        dc.resample(1)
+        core.step(actions, common_step=0, mode=0)
+        sg["acc"].zero_()
+        dc.resample(0)
+        dc.reset_envs(actions, True, 0, sg["acc"])
+        env._roll(core.obs)
+        send_to = bool(base.cfg.env.send_timeouts)
+        ins = [None, None, hist, actions, core.rew, values, ac._logp, ac._mean, ac.std.data, dc.env_bins_f32]
+        outs = [stg.observations, stg.privileged_observations, stg.observation_histories, stg.actions, stg.rewards, stg.values, stg.actions_log_prob,
+                stg.mu, stg.sigma, stg.env_bins]
+        for x in ins[2:]:
+            assert x.is_contiguous() and x.dtype == torch.float32
+        from .ppo import PPO_Args
+        capi.check(L.go1_rollout_store_transition((C.c_void_p * 10)(*[x.data_ptr() if x is not None else None for x in ins]), capi.ptr(core.reset_u8),
+                                                  capi.ptr(dc.time_outs_u8) if send_to else None, (C.c_void_p * 10)(*[x.data_ptr() for x in outs]),
+                                                  capi.ptr(stg.dones), capi.ptr(sg["slot"]), N, core.num_obs, core.num_priv, hist.shape[1],
+                                                  actions.shape[1], float(PPO_Args.gamma), sp()), "go1_rollout_store_transition")
+        capi.check(L.go1_rollout_advance(capi.ptr(sg["acc"]), capi.ptr(sg["acc_hist"]), sg["W"], sg["T"], capi.ptr(sg["slot"]), capi.ptr(core.step_dev), sp()),
+                   "go1_rollout_advance")
+        return actions
+
+    def _rollout_graphed(self, sg):
+        """The 24-step collection phase as CUDA-graph replays: one graph per parity of the history ping-pong buffers; the first
+        two steps of either parity run eagerly (they are ordinary steps of the rollout), the third is captured."""
+        from go1_b200 import capi
+        from go1_gym.envs.base.legged_robot import _LazyDict
+        env, alg = self.env, self.alg
+        base, ac = env.env, alg.actor_critic
+        core, dc, L = base.core, base._dev_cur, capi.lib()
+        if base._ep_len_dirty:
+            base._sync_interval_events_after_ep_len_write()
+        dc.to_device()
+        sg["slot"].zero_()
+        core.step_dev.fill_(base.common_step_counter + 1)
+        with torch.inference_mode():
+            for i in range(self.num_steps_per_env):
+                p = env._cur
+                key = (p, ac.flat_params.data_ptr())
+                g = sg["graphs"].get(key)
+                if g is None and sg["warm"][p] < 2:
+                    sg["warm"][p] += 1
+                    actions = self._graph_step_body(sg)
+                elif g is None:
+                    for stale in [k for k in sg["graphs"] if k[1] != key[1]]:
+                        del sg["graphs"][stale]
+                    graph = torch.cuda.CUDAGraph()
+                    ac.force_repack = True
+                    n0 = L.go1_kernel_launch_count()
+                    try:
+                        with torch.cuda.graph(graph):
+                            actions = self._graph_step_body(sg)
+                    finally:
+                        ac.force_repack = False
+                    n_kernels = L.go1_kernel_launch_count() - n0
+                    L.go1_kernel_launch_add(-n_kernels)
+                    env._cur = p; env.obs_history = env._bufs[p]       # capture ran the host half of _roll without executing anything
+                    g = sg["graphs"][key] = (graph, actions, n_kernels)
+                if g is not None:
+                    graph, actions, n_kernels = g
+                    graph.replay()
+                    L.go1_kernel_launch_add(n_kernels)
+                    env._cur = p ^ 1; env.obs_history = env._bufs[p ^ 1]
+                base._raw_actions = actions
+                base.common_step_counter += 1
+                base._post_physics_step_callback_host()
+        core.step_dev.zero_()
+        alg.storage.step = self.num_steps_per_env
+        alg.transition.clear()
+        # extras / metrics of the whole rollout from ONE snapshot of the per-step accumulators
+        acc_hist = sg["acc_hist"].clone()
+        base._episode_acc_prev = acc_hist[-1]
+        ex = base.extras
+        ex["train/episode"] = _LazyDict(base._episode_builder(acc_hist[-1], may_be_empty=True))
+        ex["env_bins"] = dc.env_bins_f32
+        ex["curriculum/distribution"] = _LazyDict(base._distribution_builder())
+        if base.cfg.env.send_timeouts:
+            ex["time_outs"] = dc.time_outs
+        ex["privileged_obs"] = core.priv_obs
+        if hasattr(logger, "store_metrics_lazy"):
+            for t in range(self.num_steps_per_env):
+                logger.store_metrics_lazy('train/episode', _LazyDict(base._episode_builder(acc_hist[t], may_be_empty=True)))
+        return core.obs, core.priv_obs, env.obs_history, ex
+
     def rollout(self, obs, privileged_obs, obs_history, eval_expert=False):
         """The 24-step collection phase of learn() (ppo_cse/__init__.py:138-187)."""
+        sg = self._step_graph_state()
+        if sg is not None and obs_history is self.env.obs_history and self.env.env._dev_cur is not None:
+            try:
+                return self._rollout_graphed(sg)
+            except Exception as e:          # capture not possible in this context: same kernels, launched one by one
+                if sg["graphs"] or any(sg["warm"].values()):
+                    raise
+                print(f"[go1_b200] graph-replayed rollout disabled: {type(e).__name__}: {e}")
+                self._sg = None
         num_train_envs = self.env.num_train_envs
         infos = {}
         with torch.inference_mode():

@@ -194,6 +194,7 @@ class _Net:
 
 class ActorCritic(nn.Module):
     is_recurrent = False
+    HEAD = 16          # floats reserved in front of the flat parameter / gradient buffers (see flatten())
 
     def __init__(self, num_obs, num_privileged_obs, num_obs_history, num_actions, **kwargs):
         if kwargs:
@@ -239,7 +240,11 @@ class ActorCritic(nn.Module):
         dev = ps[0].device
         # every tensor starts on a 16-byte boundary (zero padding in between: zero gradient, never moves) so that weights
         # are TMA-readable in place wherever their row length allows it
-        offsets, off = {}, 0
+        # The first HEAD floats of both buffers belong to no parameter: in the gradient buffer they carry the loss scalars of the
+        # minibatch (KL, surrogate / value loss, ... and the adaptation MSE pair), so that ONE all-reduce per optimizer step moves
+        # gradients and scalars together; [HEAD : n_adapt_params] is the adaptation module (a prefix, so its own optimizer step
+        # all-reduces the prefix [0 : n_adapt_params]: scalars + adaptation gradients).
+        offsets, off = {}, self.HEAD
         for p in ps:
             off = (off + 3) // 4 * 4
             offsets[id(p)] = off
@@ -252,7 +257,7 @@ class ActorCritic(nn.Module):
             p.data = flat[o:o + n].view(p.shape)
         self._flat = flat
         self._grad = torch.zeros_like(flat)
-        self.n_params = total                 # length of the flat buffers (3,054,619 parameters + alignment padding)
+        self.n_params = total                 # length of the flat buffers (HEAD + 3,054,619 parameters + alignment padding)
         self._nets = {}
         for name, seq in (("adapt", self.adaptation_module), ("actor", self.actor_body), ("critic", self.critic_body)):
             self._nets[name] = _Net(seq, self._flat, self._grad, offsets, self)

@@ -62,21 +62,23 @@ class PPO:
         self.actor_critic.flatten()
         self.storage = None  # initialized later
         ac = self.actor_critic
-        self.optimizer = _FlatAdam(ac, 0, ac.n_params, PPO_Args.learning_rate)
+        self.optimizer = _FlatAdam(ac, ac.HEAD, ac.n_params, PPO_Args.learning_rate)
         # the reference builds a second Adam over ALL parameters (ppo.py:45-46); only the adaptation module ever
         # receives a non-zero gradient from it, so its state is kept for that slice only (identical updates).
-        self.adaptation_module_optimizer = _FlatAdam(ac, 0, ac.n_adapt_params, PPO_Args.adaptation_module_learning_rate)
+        self.adaptation_module_optimizer = _FlatAdam(ac, ac.HEAD, ac.n_adapt_params, PPO_Args.adaptation_module_learning_rate)
         self.transition = RolloutStorage.Transition()
         self.learning_rate = PPO_Args.learning_rate
         dev = ac.flat_params.device
         self._lr_dev = torch.full((1,), PPO_Args.learning_rate, device=dev)
-        self._scalars = torch.zeros(8, device=dev)
-        self._mse_scalars = torch.zeros(2, device=dev)
         self._grad_sq = torch.zeros(1, dtype=torch.float64, device=dev)
         self._dstd = torch.zeros(ac.num_actions, device=dev)
         self._acc = torch.zeros(6, device=dev)
         self.process_group = None          # set by the multi-GPU runner
         self.fixed_minibatch_indices = None  # parity tests inject the permutation
+
+    # the loss scalars live in the head of the flat gradient buffer and ride in the gradient all-reduce
+    _scalars = property(lambda self: self.actor_critic.flat_grads[0:8])
+    _mse_scalars = property(lambda self: self.actor_critic.flat_grads[8:10])
 
     def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, privileged_obs_shape, obs_history_shape, action_shape):
         self.storage = RolloutStorage(num_envs, num_transitions_per_env, actor_obs_shape, privileged_obs_shape, obs_history_shape, action_shape, self.device)
@@ -217,12 +219,12 @@ class PPO:
                                       capi.ptr(dmean), ac.num_actions, capi.ptr(dvalue), capi.ptr(self._dstd), capi.ptr(self._scalars), M, ac.num_actions,
                                       PPO_Args.clip_param, PPO_Args.value_loss_coef, PPO_Args.entropy_coef, int(PPO_Args.use_clipped_value_loss),
                                       1.0 / (M * world), st()), "ppo_loss")
-            self._allreduce(self._scalars)
-            if PPO_Args.desired_kl is not None and PPO_Args.schedule == 'adaptive':   # ppo.py:118-132, on the device
-                capi.check(L.go1_ppo_adaptive_lr(capi.ptr(self._scalars), capi.ptr(self._lr_dev), PPO_Args.desired_kl, 1e-5, 1e-2, st()), "adaptive_lr")
             ac.backward_ppo(hist_b, priv_b, dmean, dvalue, self._dstd)
+            # ONE collective per optimizer step: gradients (already scaled by 1/global batch) + the 8 loss scalars in the buffer head
             self._allreduce(ac.flat_grads)
-            capi.check(L.go1_ppo_grad_sqnorm(capi.ptr(ac.flat_grads), ac.n_params, capi.ptr(self._grad_sq), st()), "sqnorm")
+            if PPO_Args.desired_kl is not None and PPO_Args.schedule == 'adaptive':   # ppo.py:118-132, on the device, from the global KL
+                capi.check(L.go1_ppo_adaptive_lr(capi.ptr(self._scalars), capi.ptr(self._lr_dev), PPO_Args.desired_kl, 1e-5, 1e-2, st()), "adaptive_lr")
+            capi.check(L.go1_ppo_grad_sqnorm(capi.ptr(ac.flat_grads[ac.HEAD:]), ac.n_params - ac.HEAD, capi.ptr(self._grad_sq), st()), "sqnorm")
             self.optimizer.step(self._grad_sq, PPO_Args.max_grad_norm, self._lr_dev)
             self._acc[0:2] += self._scalars[0:2]
 
@@ -234,10 +236,9 @@ class PPO:
                 capi.check(L.go1_ppo_mse(capi.ptr(pred), pred.stride(0), capi.ptr(priv_b), priv_b.stride(0), capi.ptr(dpred), dpred.stride(0),
                                          capi.ptr(self._mse_scalars), M, num_train, pred.shape[1], st()), "mse")
                 ac.backward_adaptation(hist_b, outs, dpred)
-                if self.process_group is not None:
-                    self._allreduce(ac.flat_grads[:ac.n_adapt_params])
-                    ac.flat_grads[:ac.n_adapt_params].div_(world)
-                    self._allreduce(self._mse_scalars); self._mse_scalars.div_(world)
+                if self.process_group is not None:      # adaptation gradients + the MSE pair (buffer head) in one averaging all-reduce
+                    import torch.distributed as dist
+                    dist.all_reduce(ac.flat_grads[:ac.n_adapt_params], op=dist.ReduceOp.AVG, group=self.process_group)
                 self.adaptation_module_optimizer.step()
                 self._acc[2:4] += self._mse_scalars
             n_updates += 1

@@ -11,9 +11,20 @@ if [[ $WHAT == all || $WHAT == *tests* ]]; then
   timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -60 > $O/${TAG}_tests.txt
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.txt 2>&1
 fi
+if [[ $WHAT == *hunt* ]]; then
+  timeout 600 python walk-these-ways_b200/tools/nan_hunt.py --config rough_dr --envs 4096 --steps 200 --bisect > $O/${TAG}_nan_hunt.txt 2>&1
+fi
+if [[ $WHAT == *refscripts* ]]; then
+  timeout 900 python walk-these-ways_b200/tools/run_reference_scripts.py --iterations 2 --num-envs 4096 --out $O/${TAG}_reference_scripts.json > $O/${TAG}_reference_scripts.log 2>&1
+fi
+if [[ $WHAT == *compare* ]]; then
+  timeout 900 python walk-these-ways_b200/tools/train_compare.py --iterations 200 --out $O/${TAG}_train_compare.json > $O/${TAG}_train_compare.log 2>&1
+fi
 if [[ $WHAT == all || $WHAT == *bench* ]]; then
   timeout 600 python bench.py --steps 10 --warmup 3 > $O/${TAG}_bench_flat.json 2> $O/${TAG}_bench_flat.err
   timeout 600 python bench.py --steps 5 --warmup 3 --breakdown --no-cpu-baseline > $O/${TAG}_bench_flat_breakdown.json 2>> $O/${TAG}_bench_flat.err
+fi
+if [[ $WHAT == all || $WHAT == *benchall* ]]; then
   timeout 600 python bench.py --config rough_dr --steps 5 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_rough_dr.json 2> $O/${TAG}_bench_rough_dr.err
   timeout 600 python bench.py --config mob16k --steps 3 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_mob16k.json 2> $O/${TAG}_bench_mob16k.err
 fi
