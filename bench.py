@@ -156,7 +156,7 @@ def build_training(num_envs, device, gemm_impl, config="flat"):
     Cfg.env.num_envs = num_envs
     AC_Args.gemm_impl = gemm_impl
     RunnerArgs.num_steps_per_env = T_ROLLOUT
-    logger.configure(prefix="bench", root=os.path.join(ROOT, "gpurun_out", "bench_runs"))
+    logger.configure(prefix="bench", root=os.path.join("/tmp", "go1_b200_runs", "bench"))
     env = HistoryWrapper(VelocityTrackingEasyEnv(sim_device=device, headless=True, cfg=Cfg))
     runner = Runner(env, device=device)
     env.episode_length_buf = torch.randint_like(env.episode_length_buf, high=int(env.max_episode_length))   # learn(init_at_random_ep_len=True)

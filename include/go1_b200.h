@@ -178,6 +178,9 @@ int go1_sim_update_config(Go1Sim* sim, const Go1SimConfig* cfg, void* stream);
 int go1_sim_step(Go1Sim* sim, const float* actions /*[N][12]*/, const float gravity[3],
                  const float gravity_vec[3], int64_t common_step, int mode, void* stream);
 
+/* Threads per CTA of the step kernel: 32, 64 or 128; 0 (default) = 32 up to 16384 envs, 128 above (tuning knob). */
+void go1_sim_set_step_block(int threads);
+
 /* Replaces LeggedRobot.reset_idx (+ _resample_commands' device part, _randomize_dof_props,
  * _reset_dofs, _reset_root_states; legged_robot.py:150-239, 645-665, 948-1001) for `k` envs, followed —
  * when post_step != 0 — by compute_observations and the last_* rolls for those envs
@@ -293,6 +296,8 @@ typedef struct Go1GemmEpilogue {
     const float* dact_y; int32_t ld_dact_y;
     int32_t lead_cols;   /* > 0: the extra columns and the activation apply to output columns < lead_cols only (the rest gets
                           * bias only): lets several first layers that share their input run as ONE product (impl 1) */
+    float* colsum;       /* optional [N] (impl 1): colsum[n] += sum_m C[m][n] of the FINAL values this call writes -- the bias gradient
+                          * of the layer whose dz this dgrad product produces, reduced in the epilogue (atomic adds: zero it first) */
 } Go1GemmEpilogue;
 int go1_gemm_ex(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                 float* C, int ldc, const Go1GemmEpilogue* ep, int impl, void* stream);

@@ -110,6 +110,7 @@ struct GemmArgs {
     int ldex, ldwex, nex, ldaux;
     int lead;                // > 0: extra columns + activation only for output columns < lead
     int amn, bmn;            // operand is MN-major in HBM (A given as [K][M], B given as [K][N]); persistent kernel only
+    float* colsum;           // optional [N]: += column sums of the values written (bias gradient fused into the dgrad epilogue)
 };
 
 // Epilogue of one 32-column chunk held in registers (thread = output row, r[j] = column col0 + j).  Called by all 32 lanes
@@ -175,7 +176,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, uint32_t (&r)[
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] += __shfl_sync(0xffffffffu, bl, j);
     }
-    if (!row_ok) return;
+    if (row_ok) {
     if (g.act == 1) {
         const int nlead = g.lead <= 0 ? 32 : max(0, min(32, g.lead - col0));      // leading columns of this chunk that get the ELU
 #pragma unroll
@@ -194,6 +195,24 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, uint32_t (&r)[
             for (int j = 0; j < 32; j++) if (j < ncols) { const float y = __ldg(arow + j); v[j] *= (y > 0.f ? 1.0f : y + 1.0f); }
         }
     }
+    }
+    if (g.colsum) {         // warp-uniform.  Column sums over the warp's 32 rows by a transpose-reduce: 31 shuffles for 32 columns
+        float sred[32];     // (each halving step trades half of the columns for the partner's partial sums), then one atomic per lane
+#pragma unroll
+        for (int j = 0; j < 32; j++) sred[j] = (row_ok && j < ncols) ? v[j] : 0.f;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int j = 0; j < off; j++) {
+                const float send = upper ? sred[j] : sred[j + off];
+                const float keep = upper ? sred[j + off] : sred[j];
+                sred[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+        }
+        if (lane < ncols) atomicAdd(g.colsum + col0 + lane, sred[0]);      // lane l ends up with column col0 + l
+    }
+    if (!row_ok) return;
     if (vec) {
 #pragma unroll
         for (int j = 0; j < 8; j++) reinterpret_cast<float4*>(crow)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -712,7 +731,7 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
     g.C = Cm; g.bias = bias; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.act = act; g.accumulate = accumulate;
     g.ex = ep->extra; g.ldex = ep->ld_extra; g.wex = ep->w_extra; g.ldwex = ep->ld_w_extra; g.nex = ep->extra ? ep->num_extra : 0;
     g.aux = ep->dact_y; g.ldaux = ep->ld_dact_y;
-    g.amn = amn; g.bmn = bmn; g.lead = ep->lead_cols;
+    g.amn = amn; g.bmn = bmn; g.lead = ep->lead_cols; g.colsum = ep->colsum;
     if (g.nex < 0 || g.nex > 4) return go1_set_error("go1_gemm_ex: num_extra must be 0..4");
     if (act == 2 && !g.aux) return go1_set_error("go1_gemm_ex: act 2 needs dact_y");
     const int num_kb = (K + BK - 1) / BK;
@@ -732,7 +751,7 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
     const int BN = wide ? 256 : ((N > 64) ? 128 : (N > 32 ? 64 : 32));
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     int splits = 1;
-    if (tiles < 148 && num_kb >= split_min_kb && g.nex == 0 && act != 2 && g.lead <= 0) {      // one wave of 2 CTAs/SM, >= 16 k-blocks each
+    if (tiles < 148 && num_kb >= split_min_kb && g.nex == 0 && act != 2 && g.lead <= 0 && !g.colsum) {      // one wave of 2 CTAs/SM, >= 16 k-blocks each
         splits = split_ctas / tiles; if (splits > num_kb / split_min_kb) splits = num_kb / split_min_kb; if (splits < 1) splits = 1;
     }
     g.kb_per_split = (num_kb + splits - 1) / splits;

@@ -66,6 +66,28 @@ template <int AXIS> DI V3 rot_p2c(float c, float s, V3 v) {   // R^T v
     return v3(c * v.x - s * v.z, v.y, s * v.x + c * v.z);
 }
 
+// M * R_axis(c, s): only two columns mix
+template <int AXIS> DI M3 mul_axis(const M3& M, float c, float s) {
+    M3 O = M;
+    if (AXIS == 0) {
+        O.m01 = c * M.m01 + s * M.m02; O.m11 = c * M.m11 + s * M.m12; O.m21 = c * M.m21 + s * M.m22;
+        O.m02 = c * M.m02 - s * M.m01; O.m12 = c * M.m12 - s * M.m11; O.m22 = c * M.m22 - s * M.m21;
+    } else {
+        O.m00 = c * M.m00 - s * M.m02; O.m10 = c * M.m10 - s * M.m12; O.m20 = c * M.m20 - s * M.m22;
+        O.m02 = s * M.m00 + c * M.m02; O.m12 = s * M.m10 + c * M.m12; O.m22 = s * M.m20 + c * M.m22;
+    }
+    return O;
+}
+// R_axis(c, s) * M * R_axis(c, s)^T: rotate the columns, then the rows (6 two-term rotations instead of two 3x3 products)
+template <int AXIS> DI M3 rot_mat_axis(float c, float s, const M3& M) {
+    const V3 c0 = rot_c2p<AXIS>(c, s, v3(M.m00, M.m10, M.m20)), c1 = rot_c2p<AXIS>(c, s, v3(M.m01, M.m11, M.m21)),
+             c2 = rot_c2p<AXIS>(c, s, v3(M.m02, M.m12, M.m22));                     // X = R M (column k of X = R * column k of M)
+    const V3 r0 = rot_c2p<AXIS>(c, s, v3(c0.x, c1.x, c2.x)), r1 = rot_c2p<AXIS>(c, s, v3(c0.y, c1.y, c2.y)),
+             r2 = rot_c2p<AXIS>(c, s, v3(c0.z, c1.z, c2.z));                        // row i of X R^T = R * (row i of X)
+    M3 O; O.m00 = r0.x; O.m01 = r0.y; O.m02 = r0.z; O.m10 = r1.x; O.m11 = r1.y; O.m12 = r1.z; O.m20 = r2.x; O.m21 = r2.y; O.m22 = r2.z;
+    return O;
+}
+
 DI M3 quat_to_R(float x, float y, float z, float w) {   // xyzw, body -> world
     M3 R;
     R.m00 = 1 - 2 * (y * y + z * z); R.m01 = 2 * (x * y - z * w);     R.m02 = 2 * (x * z + y * w);
@@ -125,11 +147,10 @@ DI M3 skew_mul(V3 r, const M3& M) {   // [r]x M : cross r with every column
     M3 O; O.m00 = c0.x; O.m10 = c0.y; O.m20 = c0.z; O.m01 = c1.x; O.m11 = c1.y; O.m21 = c1.z; O.m02 = c2.x; O.m12 = c2.y; O.m22 = c2.z;
     return O;
 }
-// X^T Ia X: express the child's articulated inertia in the parent frame (R: child->parent, r: child origin in parent)
-DI SI transform_to_parent(const SI& Ia, const M3& R, V3 r) {
-    M3 Rt = transpose(R);
-    Sym3 Ar = rot_sym(R, Ia.A), Cr = rot_sym(R, Ia.C);
-    M3 Br = matmul(matmul(R, Ia.B), Rt);
+// X^T Ia X: express the child's articulated inertia in the parent frame (child frame rotated by (c, s) about AXIS, origin r in parent)
+template <int AXIS> DI SI transform_to_parent(const SI& Ia, float c, float s, V3 r) {
+    Sym3 Ar = symof(rot_mat_axis<AXIS>(c, s, tofull(Ia.A))), Cr = symof(rot_mat_axis<AXIS>(c, s, tofull(Ia.C)));
+    M3 Br = rot_mat_axis<AXIS>(c, s, Ia.B);
     SI P;
     P.C = Cr;
     M3 KC = skew_mul(r, tofull(Cr));

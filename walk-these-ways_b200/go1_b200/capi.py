@@ -109,7 +109,7 @@ class Go1CurriculumBuffers(C.Structure):
 
 class Go1GemmEpilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("act", _i), ("accumulate", _i), ("extra", C.c_void_p), ("ld_extra", _i), ("w_extra", C.c_void_p),
-                ("ld_w_extra", _i), ("num_extra", _i), ("dact_y", C.c_void_p), ("ld_dact_y", _i), ("lead_cols", _i)]
+                ("ld_w_extra", _i), ("num_extra", _i), ("dact_y", C.c_void_p), ("ld_dact_y", _i), ("lead_cols", _i), ("colsum", C.c_void_p)]
 
 
 class Go1Error(RuntimeError):
@@ -141,6 +141,7 @@ def lib():
         "go1_sim_step": ([vp, vp, C.POINTER(_f * 3), C.POINTER(_f * 3), i64, ip, vp], ip),
         "go1_sim_reset_idx": ([vp, vp, ip, vp, vp, ip, i64, vp], ip),
         "go1_sim_set_commands": ([vp, vp, ip, vp, vp], ip),
+        "go1_sim_set_step_block": ([ip], None),
         "go1_sizeof_curriculum": ([ip], ip), "go1_curriculum_set_grouped": ([ip], None),
         "go1_curriculum_resample": ([vp, C.POINTER(Go1CurriculumConfig), C.POINTER(Go1CurriculumBuffers), ip, vp], ip),
         "go1_sim_reset_idx_dev": ([vp, vp, vp, vp, vp, ip, i64, vp, vp], ip),

@@ -91,9 +91,11 @@ class _Net:
     def _p(x):
         return x.data_ptr() if torch.is_tensor(x) else x
 
-    def _gemm(self, ta, tb, M, N, K, A, lda, B, ldb, Cm, ldc, bias=None, act=0, acc=0, impl=0, extra=None, w_extra=0, ld_w_extra=0, dact_y=None, lead_cols=0):
+    def _gemm(self, ta, tb, M, N, K, A, lda, B, ldb, Cm, ldc, bias=None, act=0, acc=0, impl=0, extra=None, w_extra=0, ld_w_extra=0, dact_y=None, lead_cols=0,
+              colsum=None):
         ep = self._ep
         ep.lead_cols = lead_cols
+        ep.colsum = self._p(colsum) if colsum is not None else None
         ep.bias = self._p(bias) if bias is not None else None
         ep.act, ep.accumulate = act, acc
         if extra is not None:
@@ -153,12 +155,15 @@ class _Net:
         n = len(self.specs)
         dz = dout
         dextra = None
+        bias_done = False      # this layer's bias gradient was already reduced in the epilogue of the dgrad product that made its dz
         for li in range(n - 1, -1, -1):
             wo, bo, o, i = self.specs[li]
             W = self.flat[wo:wo + o * i]
             gW, gb = self.grad[wo:wo + o * i], self.grad[bo:bo + o]
             ldz = dz.stride(0)
-            capi.check(L.go1_colsum(capi.ptr(dz), ldz, capi.ptr(gb), M, o, accumulate, st), "colsum")
+            if not bias_done:
+                capi.check(L.go1_colsum(capi.ptr(dz), ldz, capi.ptr(gb), M, o, accumulate, st), "colsum")
+            bias_done = False
             if li == 0:
                 inp, ld_in, K = x, ldx, (K0 if extra is not None else i)
             else:
@@ -183,7 +188,14 @@ class _Net:
                 ldp = dprev.stride(0)
                 yprev = outs[li - 1]
                 if impl == 1 and self._tma_ok(dz, ldz) and self._tma_ok(W, i) and M >= 64:
-                    self._gemm(0, 0, M, i, o, dz, ldz, W, i, dprev, ldp, None, 2, 0, 1, dact_y=yprev)      # W read MN-major in place
+                    # W read MN-major in place; the bias gradient of layer li-1 (column sums of dprev) rides in the epilogue
+                    pwo, pbo, po, pi = self.specs[li - 1]
+                    gb_prev = self.grad[pbo:pbo + po]
+                    fuse = self.owner.fuse_bias_grad
+                    if fuse and not accumulate and not self.owner.grads_prezeroed:
+                        gb_prev.zero_()
+                    self._gemm(0, 0, M, i, o, dz, ldz, W, i, dprev, ldp, None, 2, 0, 1, dact_y=yprev, colsum=gb_prev if fuse else None)
+                    bias_done = bool(fuse)
                 elif o <= 16:
                     capi.check(L.go1_skinny_dgrad(capi.ptr(dz), ldz, capi.ptr(W), i, capi.ptr(yprev), yprev.stride(0), capi.ptr(dprev), ldp, M, o, i, st), "skinny_dgrad")
                 else:
@@ -217,6 +229,9 @@ class ActorCritic(nn.Module):
         self.sample_seed = 0
         self.injected_eps = None      # parity tests inject the N(0,1) draws
         self.weights_version = 0      # bumped by every optimizer step / load: invalidates the packed first-layer weight copies
+        import os
+        self.fuse_bias_grad = os.environ.get("GO1_FUSE_BIAS_GRAD", "1") != "0"     # bias gradients reduced in the dgrad GEMM epilogues
+        self.grads_prezeroed = False  # PPO.update zeroes the flat gradient buffer once per optimizer step (one fill instead of one per layer)
 
     # ------------------------------------------------------------------ flat storage
     def _ordered_params(self):

@@ -211,6 +211,8 @@ class PPO:
             bi = it_mb % len(batches)
             (obs_b, critic_obs_b, priv_b, hist_b, actions_b, target_values_b, adv_b, returns_b, old_logp_b, old_mu_b, old_sigma_b, masks_b, env_bins_b) = batches[bi]
             M = hist_b.shape[0]
+            ac.flat_grads.zero_()           # the fused bias-gradient epilogues accumulate with atomics; the loss scalars land in the head afterwards
+            ac.grads_prezeroed = True
             mean_b, value_b = ac.forward_all(hist_b, priv_b, tag="train")
             dmean = ac._nets["actor"]._buf(("train", "dmean"), M, ac.num_actions)
             dvalue = ac._nets["critic"]._buf(("train", "dvalue"), M, 1)
@@ -235,6 +237,7 @@ class PPO:
                 dpred = ac._nets["adapt"]._buf(("adapt", "dpred"), M, pred.shape[1])
                 capi.check(L.go1_ppo_mse(capi.ptr(pred), pred.stride(0), capi.ptr(priv_b), priv_b.stride(0), capi.ptr(dpred), dpred.stride(0),
                                          capi.ptr(self._mse_scalars), M, num_train, pred.shape[1], st()), "mse")
+                ac.flat_grads[ac.HEAD:ac.n_adapt_params].zero_()
                 ac.backward_adaptation(hist_b, outs, dpred)
                 if self.process_group is not None:      # adaptation gradients + the MSE pair (buffer head) in one averaging all-reduce
                     import torch.distributed as dist
@@ -242,6 +245,7 @@ class PPO:
                 self.adaptation_module_optimizer.step()
                 self._acc[2:4] += self._mse_scalars
             n_updates += 1
+        ac.grads_prezeroed = False
 
         acc = self._acc.tolist()                      # the only host sync of the update
         self.learning_rate = float(self._lr_dev.item())

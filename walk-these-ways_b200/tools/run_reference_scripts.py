@@ -51,7 +51,8 @@ def run_train(stage, iterations, num_envs, out):
     from ml_logger import logger
     import go1_gym_learn.ppo_cse as ppo_cse
     from go1_gym.envs.go1 import go1_config
-    logger.configure(prefix="reference_train_py", root=os.path.join(ROOT, "gpurun_out", "reference_scripts"))
+    run_root = os.path.join("/tmp", "go1_b200_runs", "reference_scripts")       # checkpoints are large: keep them out of gpurun_out/
+    logger.configure(prefix="reference_train_py", root=run_root)
     mod = load(os.path.join(stage, "scripts", "train.py"), "reference_train")
     learn = ppo_cse.Runner.learn
     seen = {}
@@ -82,7 +83,7 @@ def run_train(stage, iterations, num_envs, out):
     out["train"] = {"iterations_asked_by_script": seen["asked"], "iterations_run": iterations, "num_envs": seen["num_envs"],
                     "seconds": round(seen["seconds"], 2), "gemm_impl": int(AC_Args.gemm_impl), "weights_finite": bool(torch.isfinite(ac.flat_params).all()),
                     "env_steps_per_s": round(iterations * r.num_steps_per_env * seen["num_envs"] / seen["seconds"]),
-                    "checkpoint_files": sorted(os.listdir(os.path.join(ROOT, "gpurun_out", "reference_scripts", "reference_train_py", "checkpoints")))}
+                    "checkpoint_files": sorted(os.listdir(os.path.join(run_root, "reference_train_py", "checkpoints")))}
     assert out["train"]["weights_finite"]
 
 

@@ -17,7 +17,11 @@ def main():
     hbm, _, src = bench.peaks()
     flush = torch.empty(512 * 1024 * 1024 // 4, device="cuda")
     rows = []
-    for n in (1024, 4096, 16384, 65536, 131072, 262144):
+    from go1_b200 import capi
+    blocks = [int(x) for x in os.environ.get("GO1_SWEEP_BLOCKS", "0").split(",")]
+    counts = [int(x) for x in os.environ.get("GO1_SWEEP_ENVS", "1024,4096,16384,65536,131072,262144").split(",")]
+    for n, blk in [(n, b) for n in counts for b in blocks]:
+        capi.lib().go1_sim_set_step_block(blk)
         _, c, _ = train_sim_config(n)
         core = SimCore(c, device="cuda:0")
         core.env("root_pos")[2].fill_(0.34)
@@ -32,7 +36,7 @@ def main():
                 ts.append(e0.elapsed_time(e1))
         ms = sum(ts) / len(ts)
         gbs = bench.SIM_BYTES_PER_ENV_STEP * n / (ms * 1e-3) / 1e9
-        rows.append({"envs": n, "kernel_ms": round(ms, 4), "env_steps_per_s": round(n / (ms * 1e-3)), "algorithmic_GBps": round(gbs, 1),
+        rows.append({"envs": n, "block": blk, "kernel_ms": round(ms, 4), "env_steps_per_s": round(n / (ms * 1e-3)), "algorithmic_GBps": round(gbs, 1),
                      "frac_of_hbm_peak": round(gbs / hbm, 4)})
         print(rows[-1], flush=True)
         del core

@@ -28,7 +28,7 @@ def run(impl, iterations, envs, tag):
     env, runner = bench.build_training(envs, "cuda:0", impl, "flat")
     from go1_gym_learn.ppo_cse import RunnerArgs
     RunnerArgs.log_freq, RunnerArgs.save_interval, RunnerArgs.save_video_interval = 10, 10 ** 9, 0
-    logger.configure(prefix=f"train_compare_{tag}", root=os.path.join(ROOT, "gpurun_out", "train_compare_runs"))
+    logger.configure(prefix=f"train_compare_{tag}", root=os.path.join("/tmp", "go1_b200_runs", "train_compare"))
     logger.summaries = []
     t0 = time.time()
     runner.learn(num_learning_iterations=iterations, init_at_random_ep_len=True, eval_freq=100)
