@@ -210,6 +210,11 @@ typedef struct Go1CurriculumConfig {
     float ep_len;                                    /* min(max_episode_length, resampling_time / dt) */
     int32_t gaitwise_curricula, exclusive_phase_offset, balance_gait_distribution, binary_phases;
     int32_t num_train_envs, snapshot_time_outs;
+    /* cross-rank replay: with xr_world > 1 the call consumes the event records of ALL ranks (gathered into
+     * Go1CurriculumBuffers.xr_events) in ascending GLOBAL env id = xr_rank * num_envs + local id, exactly as one process owning
+     * xr_world * num_envs envs would: every rank applies the same weight updates and draws the same RandomState words, so the
+     * curricula stay identical everywhere; only the envs of this rank receive their commands / bins. */
+    int32_t xr_world, xr_rank, xr_cap;
 } Go1CurriculumConfig;
 
 typedef struct Go1CurriculumBuffers {
@@ -231,7 +236,13 @@ typedef struct Go1CurriculumBuffers {
     int32_t* out_count;          /* [1]   number of envs processed (k for go1_sim_reset_idx_dev) */
     int32_t* out_ids;            /* [N]   their ids, ascending */
     float* out_commands;         /* [N][15] their new commands */
+    /* cross-rank replay only (xr_world > 1; NULL otherwise).  Scratch sizes above then scale with xr_world * N instead of N. */
+    float* xr_send;              /* [2][1 + xr_cap * GO1_XR_STRIDE]  this rank's records of both lists, written by go1_curriculum_pack */
+    const float* xr_events;      /* [xr_world][2][1 + xr_cap * GO1_XR_STRIDE]  all ranks' xr_send blocks (an all-gather of xr_send) */
+    int32_t* xr_ids;             /* [xr_world * N]      working list of global ids */
+    float* xr_commands;          /* [xr_world * N][15]  working list of sampled commands */
 } Go1CurriculumBuffers;
+#define GO1_XR_STRIDE 8           /* floats per gathered record: global env id, 4 task command sums, ep_len, old bin, old category */
 
 /* sizeof(Go1CurriculumConfig) (which = 0) / sizeof(Go1CurriculumBuffers) (which = 1) as compiled */
 int go1_sizeof_curriculum(int which);
@@ -240,6 +251,11 @@ int go1_sizeof_curriculum(int which);
  * list 1: envs due for the periodic resample -> commands written and command_sums zeroed in place
  *         (go1_sim_set_commands semantics). */
 int go1_curriculum_resample(Go1Sim* sim, const Go1CurriculumConfig* cfg, const Go1CurriculumBuffers* bufs, int list, void* stream);
+
+/* Cross-rank replay, step 1: pack this rank's two event lists (after go1_sim_step) into bufs->xr_send with global ids and the
+ * envs' current bins / categories; the caller all-gathers xr_send into xr_events (one collective per env step, NCCL) before
+ * the go1_curriculum_resample calls of the step (list 0) and of the next step (list 1). */
+int go1_curriculum_pack(Go1Sim* sim, const Go1CurriculumConfig* cfg, const Go1CurriculumBuffers* bufs, void* stream);
 
 /* 1: calls with <= 256 events process the (independent) categories concurrently, one 256-thread group each; 0 (default): one
  * category after the other.  Same arithmetic either way. */

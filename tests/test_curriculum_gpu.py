@@ -150,3 +150,68 @@ def test_env_rollout_device_curriculum_equals_host_curriculum():
     assert ep[0].keys() == ep[1].keys()
     for k in ep[0]:
         assert abs(float(ep[0][k]) - float(ep[1][k])) <= 1e-6 * max(1.0, abs(float(ep[0][k]))), k
+
+
+@pytest.mark.parametrize("mode", ["gaitwise", "nominal_binary"])
+def test_cross_rank_replay_equals_one_process_over_all_envs(mode):
+    """two "ranks" of N envs whose event records are gathered (here: concatenated by hand; in production one NCCL
+    all-gather per env step) and replayed by go1_curriculum_resample in cross-rank mode must evolve exactly like ONE process that
+    owns 2N envs: identical curriculum weights, RandomState words and category stream on both ranks and on the reference, and every
+    env gets the command / bin / category the single process gives to env rank * N + i."""
+    from go1_b200.curriculum_dev import DeviceCurriculum
+    from go1_gym.envs.base.legged_robot import _LOCAL_RANGE, _TASK_KEYS
+    from go1_b200 import capi
+    over = {"gaitwise": {}, "nominal_binary": dict(gaitwise_curricula=False, binary_phases=True)}[mode]
+    N, W = 192, 2
+    ref = _env(W * N, True, **over)
+    ranks = [_env(N, True, **over) for _ in range(W)]
+    for r, e in enumerate(ranks):
+        e._dev_cur = DeviceCurriculum(e, _LOCAL_RANGE, _TASK_KEYS, emulate_world_rank=(W, r))
+    dcs = [e._dev_cur for e in ranks]
+    ref._dev_cur.to_device()
+    for dc in dcs:
+        dc.to_device()
+    rs = np.random.RandomState(5)
+    ep_len, cols, thr = ref._resample_constants()
+    counts = [2 * N, 0, 3, 11, 40, 1, 300, 7, 64, 350, 5]          # > 256 and > 512 records exercise the global-scratch path
+    for rnd, k in enumerate(counts):
+        which = rnd % 2 if rnd > 0 else 0
+        gids = rs.choice(W * N, k, replace=False).astype(np.int64)
+        sums = np.zeros((k, 4), dtype=np.float32)
+        for j in range(4):
+            t = float(thr[cols.index(j)]) * float(ep_len) if j in cols else 1.0
+            sums[:, j] = (t * (1.0 + rs.uniform(-0.2, 0.25 + 0.08 * rnd, size=k))).astype(np.float32)
+
+        def load(core, ids, sm):
+            ev = np.zeros((len(ids), 6), dtype=np.float32)
+            ev[:, 0], ev[:, 1:5] = ids, sm
+            core.events[which, :len(ids)] = torch.from_numpy(ev).cuda()
+            core.event_count.zero_(); core.event_count[which] = len(ids)
+        load(ref.core, gids, sums)
+        ref._dev_cur.resample(which)
+        for r, (e, dc) in enumerate(zip(ranks, dcs)):
+            m = (gids >= r * N) & (gids < (r + 1) * N)
+            load(e.core, gids[m] - r * N, sums[m])
+            capi.check(e.core.L.go1_curriculum_pack(e.core._handle, dc._cfg_ref, dc._bufs_ref, capi.stream_ptr()), "pack")
+        gathered = torch.stack([dc.xr_send for dc in dcs])                 # what all_gather_into_tensor delivers to every rank
+        for dc in dcs:
+            dc.xr_recv.copy_(gathered)
+            dc.resample(which)
+        torch.cuda.synchronize()
+        R = _device_state(ref._dev_cur)
+        for r, (e, dc) in enumerate(zip(ranks, dcs)):
+            d = _device_state(dc)
+            tag = (mode, rnd, k, r)
+            assert np.array_equal(d["weights"], R["weights"]) and np.array_equal(d["mt"], R["mt"]) and d["cat"] == R["cat"], tag
+            assert np.array_equal(d["bins"], R["bins"][r * N:(r + 1) * N]) and np.array_equal(d["cats"], R["cats"][r * N:(r + 1) * N]), tag
+            sl = slice(r * N, (r + 1) * N)
+            if which == 1:
+                assert torch.equal(e.core.env("commands"), ref.core.env("commands")[:, sl]), tag
+            else:
+                kr = int(ref._dev_cur.out_count.item())
+                rid = ref._dev_cur.out_ids[:kr].cpu().numpy(); rcmd = ref._dev_cur.out_commands[:kr].cpu().numpy()
+                m = (rid >= r * N) & (rid < (r + 1) * N)
+                kl = int(dc.out_count.item())
+                assert kl == int(m.sum()), tag
+                assert np.array_equal(dc.out_ids[:kl].cpu().numpy(), rid[m] - r * N) and np.array_equal(dc.out_commands[:kl].cpu().numpy(), rcmd[m]), tag
+    assert float(R["weights"].sum()) > sum(float(c.weights.sum()) for c in ref.curricula) - 1e-9      # weights grew on the device

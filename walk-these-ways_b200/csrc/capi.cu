@@ -12,6 +12,7 @@ extern "C" int go1_launch_reset(const Go1SimBuffers*, const Go1DevTable*, const 
 extern "C" int go1_launch_set_commands(const Go1SimBuffers*, const int*, int, const float*, int, cudaStream_t);
 extern "C" int go1_launch_reset_dev(const Go1SimBuffers*, const Go1DevTable*, const int*, const int*, const float*, const float*, int, long long, const float*, float*, int, cudaStream_t);
 extern "C" int go1_launch_curriculum(const Go1SimBuffers*, const Go1CurriculumConfig*, const Go1CurriculumBuffers*, int, int, cudaStream_t);
+extern "C" int go1_launch_curriculum_pack(const Go1SimBuffers*, const Go1CurriculumConfig*, const Go1CurriculumBuffers*, int, cudaStream_t);
 extern "C" int go1_launch_history_roll(const float*, const float*, float*, int, int, int, cudaStream_t);
 
 static thread_local std::string g_err;
@@ -237,8 +238,21 @@ extern "C" int go1_curriculum_resample(Go1Sim* s, const Go1CurriculumConfig* cfg
         !cb->env_bins_f32 || !cb->cdf || !cb->cdf_valid || !cb->scratch_i32 || !cb->scratch_u32 || !cb->scratch_f64 || !cb->out_count ||
         !cb->out_ids || !cb->out_commands || (cfg->snapshot_time_outs && !cb->time_outs_snapshot))
         return fail("go1_curriculum_resample: null buffer");
+    if (cfg->xr_world > 1) {
+        if (cfg->xr_world > GO1_CUR_MAX_CATEGORIES || cfg->xr_rank < 0 || cfg->xr_rank >= cfg->xr_world || cfg->xr_cap < s->cfg.num_envs)
+            return fail("go1_curriculum_resample: bad cross-rank configuration (xr_world <= 8, 0 <= xr_rank < xr_world, xr_cap >= num_envs)");
+        if (!cb->xr_events || !cb->xr_ids || !cb->xr_commands) return fail("go1_curriculum_resample: cross-rank replay needs xr_events / xr_ids / xr_commands");
+    }
     int e = go1_launch_curriculum(&s->bufs, cfg, cb, list, s->cfg.num_envs, (cudaStream_t)stream);
     return e ? cuda_fail("go1_curriculum_resample launch", e) : 0;
+}
+
+extern "C" int go1_curriculum_pack(Go1Sim* s, const Go1CurriculumConfig* cfg, const Go1CurriculumBuffers* cb, void* stream) {
+    if (!s || !s->bound) return fail("go1_curriculum_pack: sim not bound");
+    if (!cfg || !cb || cfg->xr_world < 2 || !cb->xr_send || !cb->env_bins || !cb->env_categories || cfg->xr_cap < s->cfg.num_envs)
+        return fail("go1_curriculum_pack: bad arguments");
+    int e = go1_launch_curriculum_pack(&s->bufs, cfg, cb, s->cfg.num_envs, (cudaStream_t)stream);
+    return e ? cuda_fail("go1_curriculum_pack launch", e) : 0;
 }
 
 extern "C" int go1_sim_reset_idx_dev(Go1Sim* s, const int32_t* env_ids, const int32_t* k_dev, const float* new_commands, const float* actions,

@@ -160,10 +160,32 @@ __global__ void __launch_bounds__(CT, 1) go1_curriculum_kernel(const CurArgs A) 
     const Go1CurriculumConfig& c = A.c;
     const Go1CurriculumBuffers& cb = A.cb;
     const int L = c.num_bins, D = c.num_dims, ncat = c.num_categories, nc = c.num_commands;
-    const int n = A.b.event_count[A.list];
-    if (t == 0 && A.list == 0) cb.out_count[0] = n;
+    // cross-rank replay: the records of every rank (gathered), walked in ascending GLOBAL id; NT = envs of all ranks
+    const bool xr = c.xr_world > 1;
+    const int NT = xr ? N * c.xr_world : N;
+    __shared__ int s_xcnt[GO1_CUR_MAX_CATEGORIES + 2];          // exclusive prefix of the per-rank record counts (xr_world <= 8)
+    const size_t xr_block = 1 + (size_t)c.xr_cap * GO1_XR_STRIDE;
+    if (xr) {
+        if (t == 0) {
+            int acc = 0;
+            for (int r = 0; r < c.xr_world; r++) { s_xcnt[r] = acc; acc += (int)cb.xr_events[((size_t)r * 2 + A.list) * xr_block]; }
+            s_xcnt[c.xr_world] = acc;
+        }
+        __syncthreads();
+    }
+    const int n = xr ? s_xcnt[c.xr_world] : A.b.event_count[A.list];
+    if (t == 0 && A.list == 0) cb.out_count[0] = xr ? 0 : n;
     if (n <= 0) return;
     const float* ev = A.b.events + (size_t)A.list * N * S;
+    // record i of the (unsorted) list: [env id, 4 task command sums, ep_len (, old bin, old category when gathered)]
+    auto rec = [&](int i) -> const float* {
+        if (!xr) return ev + (size_t)i * S;
+        int r = 0;
+        while (i >= s_xcnt[r + 1]) r++;
+        return cb.xr_events + ((size_t)r * 2 + A.list) * xr_block + 1 + (size_t)(i - s_xcnt[r]) * GO1_XR_STRIDE;
+    };
+    int* const w_ids = xr ? cb.xr_ids : cb.out_ids;              // working lists: global ids / commands of all n records
+    float* const w_cmd = xr ? cb.xr_commands : cb.out_commands;
 
     // the usual call handles a handful of envs: then every per-env array lives in shared memory and the index lists are
     // built by counting predecessors in parallel; the global-scratch path (n > SMALL) keeps the simple serial builders
@@ -172,16 +194,16 @@ __global__ void __launch_bounds__(CT, 1) go1_curriculum_kernel(const CurArgs A) 
     __shared__ double s_cdf4[4][512];    // cdf staging: flat [2048] on the sequential path, one row per category group otherwise
     double* const s_cdf = &s_cdf4[0][0];
     const bool small = n <= SMALL;
-    int* mark = cb.scratch_i32;          // [N], all zero between calls
-    int* order = small ? s_arr[0] : mark + N;               // [n] event slot of the p-th smallest env id
-    int* a_cat_old = small ? s_arr[1] : mark + 2 * (size_t)N;
-    int* a_bin_old = small ? s_arr[2] : mark + 3 * (size_t)N;
-    int* a_ok = small ? s_arr[3] : mark + 4 * (size_t)N;
-    int* a_cat_new = small ? s_arr[4] : mark + 5 * (size_t)N;
-    int* a_bin_new = small ? s_arr[5] : mark + 6 * (size_t)N;
-    int* a_list = small ? s_arr[6] : mark + 7 * (size_t)N;  // [n] per-phase index list (successful bins / category members)
-    double* dd = cb.scratch_f64;         // [(D + 1) N] doubles of the current category
-    double* r2 = dd + (size_t)(D + 1) * N;   // [N] second category draw (exclusive / balanced gait modes)
+    int* mark = cb.scratch_i32;          // [NT], all zero between calls
+    int* order = small ? s_arr[0] : mark + NT;               // [n] event slot of the p-th smallest env id
+    int* a_cat_old = small ? s_arr[1] : mark + 2 * (size_t)NT;
+    int* a_bin_old = small ? s_arr[2] : mark + 3 * (size_t)NT;
+    int* a_ok = small ? s_arr[3] : mark + 4 * (size_t)NT;
+    int* a_cat_new = small ? s_arr[4] : mark + 5 * (size_t)NT;
+    int* a_bin_new = small ? s_arr[5] : mark + 6 * (size_t)NT;
+    int* a_list = small ? s_arr[6] : mark + 7 * (size_t)NT;  // [n] per-phase index list (successful bins / category members)
+    double* dd = cb.scratch_f64;         // [(D + 1) NT] doubles of the current category
+    double* r2 = dd + (size_t)(D + 1) * NT;   // [NT] second category draw (exclusive / balanced gait modes)
 
     // =============================================================================================================
     // Grouped path (the usual call: a handful of envs).  The categories are independent -- own weights, own cdf, own
@@ -190,7 +212,7 @@ __global__ void __launch_bounds__(CT, 1) go1_curriculum_kernel(const CurArgs A) 
     // inside every category, hence the same bits (tests/test_curriculum_gpu.py runs both paths).
     // =============================================================================================================
     constexpr int GS = 256, NSM = 256;
-    if (A.grouped && n <= NSM && ncat <= 4 && L <= 512) {      // scratch: >= 4 x 2(D+1) x 256 words and 4 x (D+1) x 256 doubles (curriculum_dev.py)
+    if (A.grouped && !xr && n <= NSM && ncat <= 4 && L <= 512) {      // scratch: >= 4 x 2(D+1) x 256 words and 4 x (D+1) x 256 doubles (curriculum_dev.py)
         const int g = t / GS, gt = t % GS, bar = 1 + g;
         int* ord = s_arr[0]; int* cat_old = s_arr[1]; int* bin_old = s_arr[2]; int* okf = s_arr[3];
         int* cat_new = s_arr[4]; int* bin_new = s_arr[5]; int* ids = s_arr[6];
@@ -350,7 +372,7 @@ __global__ void __launch_bounds__(CT, 1) go1_curriculum_kernel(const CurArgs A) 
     // ---- A: ascending env order --------------------------------------------------------------------------------
     if (small) {             // rank of every id among the n ids (ids are unique)
         int* ids = a_list;
-        for (int i = t; i < n; i += CT) ids[i] = (int)ev[(size_t)i * S];
+        for (int i = t; i < n; i += CT) ids[i] = (int)rec(i)[0];
         __syncthreads();
         for (int i = t; i < n; i += CT) {
             const int me = ids[i];
@@ -359,11 +381,11 @@ __global__ void __launch_bounds__(CT, 1) go1_curriculum_kernel(const CurArgs A) 
             order[rank] = i;
         }
     } else {
-    for (int i = t; i < n; i += CT) mark[(int)ev[(size_t)i * S]] = i + 1;
+    for (int i = t; i < n; i += CT) mark[(int)rec(i)[0]] = i + 1;
     __syncthreads();
     {
-        const int chunk = (N + CT - 1) / CT;
-        const int lo = min(t * chunk, N), hi = min(lo + chunk, N);
+        const int chunk = (NT + CT - 1) / CT;
+        const int lo = min(t * chunk, NT), hi = min(lo + chunk, NT);
         int cnt = 0;
         for (int e = lo; e < hi; e++) cnt += mark[e] != 0;
         s_scan[t] = cnt;
@@ -383,14 +405,14 @@ __global__ void __launch_bounds__(CT, 1) go1_curriculum_kernel(const CurArgs A) 
 
     // ---- B: success test (legged_robot.py:727-732; curriculum.py:136-139), old bin / category ---------------------
     for (int p = t; p < n; p += CT) {
-        const float* e = ev + (size_t)order[p] * S;
+        const float* e = rec(order[p]);
         const int id = (int)e[0];
         bool ok = c.num_task_keys > 0;
         for (int q = 0; q < c.num_task_keys; q++) ok = ok && (__fdiv_rn(e[1 + c.task_col[q]], c.ep_len) > c.threshold[q]);
-        cb.out_ids[p] = id;
+        w_ids[p] = id;
         a_ok[p] = ok ? 1 : 0;
-        a_cat_old[p] = cb.env_categories[id];
-        a_bin_old[p] = cb.env_bins[id];
+        a_cat_old[p] = xr ? (int)e[7] : cb.env_categories[id];      // gathered records carry the owner's bin / category
+        a_bin_old[p] = xr ? (int)e[6] : cb.env_bins[id];
     }
     __syncthreads();
 
@@ -456,7 +478,7 @@ __global__ void __launch_bounds__(CT, 1) go1_curriculum_kernel(const CurArgs A) 
     }
     __syncthreads();
     for (int p = t; p < n; p += CT)
-        for (int d = 0; d < GO1_NUM_COMMANDS; d++) cb.out_commands[(size_t)p * GO1_NUM_COMMANDS + d] = 0.0f;
+        for (int d = 0; d < GO1_NUM_COMMANDS; d++) w_cmd[(size_t)p * GO1_NUM_COMMANDS + d] = 0.0f;
     __syncthreads();
 
     // ---- E: sample each category's members from its curriculum (curriculum.py:67-89) ---------------------------------
@@ -532,7 +554,7 @@ __global__ void __launch_bounds__(CT, 1) go1_curriculum_kernel(const CurArgs A) 
                 const double ce = cb.grid[(size_t)idx * D + d];
                 const double lo_ = __dadd_rn(ce, cb.half_bins[d]), hi_ = __dsub_rn(ce, cb.half_bins[d]);
                 const double val = __dadd_rn(lo_, __dmul_rn(__dsub_rn(hi_, lo_), dd[ni + (size_t)m * D + d]));
-                if (d < nc && d < GO1_NUM_COMMANDS) cb.out_commands[(size_t)p * GO1_NUM_COMMANDS + d] = __double2float_rn(val);
+                if (d < nc && d < GO1_NUM_COMMANDS) w_cmd[(size_t)p * GO1_NUM_COMMANDS + d] = __double2float_rn(val);
             }
         }
         __syncthreads();
@@ -552,8 +574,9 @@ tail:
 
     // ---- F: gait remap (legged_robot.py:762-817), small-command zeroing (:820), bookkeeping, output ---------------------
     for (int p = t; p < n; p += CT) {
-        float* cm = cb.out_commands + (size_t)p * GO1_NUM_COMMANDS;
-        const int id = cb.out_ids[p];
+        float* cm = w_cmd + (size_t)p * GO1_NUM_COMMANDS;
+        const int id = xr ? w_ids[p] - c.xr_rank * N : w_ids[p];       // local env id; other ranks' envs fall outside [0, N)
+        const bool mine = id >= 0 && id < N;
         const int cat = a_cat_new[p];
         if (nc > 5) {
             if (c.gaitwise_curricula) {
@@ -585,11 +608,29 @@ tail:
         const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(cm[0], cm[0]), __fmul_rn(cm[1], cm[1])));
         const float keep = nrm > 0.2f ? 1.0f : 0.0f;
         cm[0] = __fmul_rn(cm[0], keep); cm[1] = __fmul_rn(cm[1], keep);
-        if (cat >= 0) { cb.env_bins[id] = a_bin_new[p]; cb.env_categories[id] = cat; }
-        if (A.list == 1) {              // periodic resample: commands take effect here (go1_sim_set_commands)
+        if (mine && cat >= 0) { cb.env_bins[id] = a_bin_new[p]; cb.env_categories[id] = cat; }
+        if (mine && A.list == 1) {      // periodic resample: commands take effect here (go1_sim_set_commands)
             for (int d = 0; d < GO1_NUM_COMMANDS; d++) A.b.env_f32[(size_t)(EROW(commands) + d) * N + id] = cm[d];
             for (int d = 0; d < GO1_NUM_COMMAND_SUMS; d++) A.b.env_f32[(size_t)(EROW(command_sums) + d) * N + id] = 0.f;
         }
+    }
+    // cross-rank replay: hand this rank's envs (a contiguous run of the sorted list) to the reset kernel as local ids + commands
+    if (xr && A.list == 0) {
+        __shared__ int s_before, s_mine;
+        if (t == 0) { s_before = 0; s_mine = 0; }
+        __syncthreads();
+        const int g0 = c.xr_rank * N;
+        int before = 0, mine_cnt = 0;
+        for (int p = t; p < n; p += CT) { before += w_ids[p] < g0; mine_cnt += (w_ids[p] >= g0 && w_ids[p] < g0 + N); }
+        if (before) atomicAdd(&s_before, before);
+        if (mine_cnt) atomicAdd(&s_mine, mine_cnt);
+        __syncthreads();
+        const int p0 = s_before, k = s_mine;
+        for (int q = t; q < k; q += CT) {
+            cb.out_ids[q] = w_ids[p0 + q] - g0;
+            for (int d = 0; d < GO1_NUM_COMMANDS; d++) cb.out_commands[(size_t)q * GO1_NUM_COMMANDS + d] = w_cmd[(size_t)(p0 + q) * GO1_NUM_COMMANDS + d];
+        }
+        if (t == 0) cb.out_count[0] = k;
     }
     // extras["env_bins"] / extras["time_outs"] are snapshots taken inside reset_idx (legged_robot.py:231-234): refreshed
     // only by a step in which some env reset, and then for ALL train envs
@@ -602,7 +643,31 @@ tail:
     }
 }
 
+// cross-rank replay: this rank's two event lists with global ids and the envs' current bins / categories
+__global__ void go1_curriculum_pack_kernel(const Go1SimBuffers b, const Go1CurriculumConfig c, const Go1CurriculumBuffers cb, int N) {
+    const int list = blockIdx.y;
+    const int n = b.event_count[list];
+    float* out = cb.xr_send + (size_t)list * (1 + (size_t)c.xr_cap * GO1_XR_STRIDE);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) out[0] = (float)n;
+    if (i >= n || i >= c.xr_cap) return;
+    const float* e = b.events + ((size_t)list * N + i) * S;
+    const int id = (int)e[0];
+    float* o = out + 1 + (size_t)i * GO1_XR_STRIDE;
+    o[0] = (float)(c.xr_rank * N + id);
+    for (int k = 1; k < S; k++) o[k] = e[k];
+    o[6] = (float)cb.env_bins[id];
+    o[7] = (float)cb.env_categories[id];
+}
+
 }  // namespace
+
+extern "C" int go1_launch_curriculum_pack(const Go1SimBuffers* b, const Go1CurriculumConfig* cfg, const Go1CurriculumBuffers* cb, int N, cudaStream_t st) {
+    dim3 grid((N + 255) / 256, 2);
+    go1_curriculum_pack_kernel<<<grid, 256, 0, st>>>(*b, *cfg, *cb, N);
+    go1_count_launch(1);
+    return (int)cudaGetLastError();
+}
 
 // The category-parallel grouped path is OFF by default: it ran the training bench 1 % faster (rollout 15.5 -> 14.9 ms) but the
 // parity tests of this round only reached it for N >= 1024 envs, which no test used; GO1_CUR_GROUPED=1 or

@@ -15,6 +15,7 @@ NUM_COMMANDS = 15
 MAX_OBS = 128
 MAX_PRIV_OBS = 48
 EVENT_STRIDE = 6
+XR_STRIDE = 8
 
 REWARD_TERMS = [
     "tracking_lin_vel", "tracking_ang_vel", "lin_vel_z", "ang_vel_xy", "orientation", "torques", "dof_acc",
@@ -98,13 +99,14 @@ class Go1CurriculumConfig(C.Structure):
     _fields_ = [("num_categories", _i), ("category_kind", _i * CUR_MAX_CATEGORIES), ("num_bins", _i), ("num_dims", _i), ("num_commands", _i),
                 ("num_task_keys", _i), ("task_col", _i * 4), ("threshold", _f * 4), ("ep_len", _f),
                 ("gaitwise_curricula", _i), ("exclusive_phase_offset", _i), ("balance_gait_distribution", _i), ("binary_phases", _i),
-                ("num_train_envs", _i), ("snapshot_time_outs", _i)]
+                ("num_train_envs", _i), ("snapshot_time_outs", _i), ("xr_world", _i), ("xr_rank", _i), ("xr_cap", _i)]
 
 
 class Go1CurriculumBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "weights", "grid", "half_bins", "local_range", "mt", "cat_rng", "env_bins", "env_categories", "env_bins_f32", "time_outs_snapshot",
-        "cdf", "cdf_valid", "scratch_i32", "scratch_u32", "scratch_f64", "out_count", "out_ids", "out_commands")]
+        "cdf", "cdf_valid", "scratch_i32", "scratch_u32", "scratch_f64", "out_count", "out_ids", "out_commands",
+        "xr_send", "xr_events", "xr_ids", "xr_commands")]
 
 
 class Go1GemmEpilogue(C.Structure):
@@ -144,6 +146,7 @@ def lib():
         "go1_sim_set_step_block": ([ip], None),
         "go1_sizeof_curriculum": ([ip], ip), "go1_curriculum_set_grouped": ([ip], None),
         "go1_curriculum_resample": ([vp, C.POINTER(Go1CurriculumConfig), C.POINTER(Go1CurriculumBuffers), ip, vp], ip),
+        "go1_curriculum_pack": ([vp, C.POINTER(Go1CurriculumConfig), C.POINTER(Go1CurriculumBuffers), vp], ip),
         "go1_sim_reset_idx_dev": ([vp, vp, vp, vp, vp, ip, i64, vp, vp], ip),
         "go1_history_roll": ([vp, vp, vp, ip, ip, ip, vp], ip),
         "go1_ppo_gae": ([vp, vp, vp, vp, vp, vp, vp, ip, ip, _f, _f, vp], ip),

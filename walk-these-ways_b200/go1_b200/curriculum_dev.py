@@ -35,8 +35,18 @@ class SplitMix64:
 
 
 class DeviceCurriculum:
-    def __init__(self, env, local_range, task_keys):
+    def __init__(self, env, local_range, task_keys, process_group=None, emulate_world_rank=None):
         core, cfg = env.core, env.cfg
+        # cross-rank replay: one curriculum shared by the envs of all ranks, kept identical on every rank by
+        # running the (deterministic) kernel on the all-gathered event records
+        self.group = process_group
+        self.world = self.rank = 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world, self.rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+        if emulate_world_rank is not None:           # tests: the kernel side of the cross-rank replay without a process group
+            self.world, self.rank = emulate_world_rank
+        self.shared = self.world > 1
         self.env, self.core = env, core
         dev, N = core.device, core.N
         curs = env.curricula
@@ -60,6 +70,11 @@ class DeviceCurriculum:
         c.gaitwise_curricula, c.exclusive_phase_offset = int(bool(cc.gaitwise_curricula)), int(bool(cc.exclusive_phase_offset))
         c.balance_gait_distribution, c.binary_phases = int(bool(cc.balance_gait_distribution)), int(bool(cc.binary_phases))
         c.num_train_envs, c.snapshot_time_outs = int(env.num_train_envs), int(bool(cfg.env.send_timeouts))
+        NT = N * self.world if self.shared else N
+        if self.shared:
+            if self.world > capi.CUR_MAX_CATEGORIES:
+                raise capi.Go1Error("cross-rank curriculum replay supports up to 8 ranks")
+            c.xr_world, c.xr_rank, c.xr_cap = self.world, self.rank, N
 
         f64 = dict(dtype=torch.float64, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
@@ -76,13 +91,23 @@ class DeviceCurriculum:
         self.time_outs = self.time_outs_u8.view(torch.bool)
         self.cdf = torch.zeros(ncat, L, **f64)
         self.cdf_valid = torch.zeros(ncat, **i32)
-        self.scratch_i32 = torch.zeros(8 * N + 64, **i32)
-        self.scratch_u32 = torch.zeros(2 * (D + 1) * max(N, 1024), **i32)
-        self.scratch_f64 = torch.zeros((D + 2) * max(N, 1024), **f64)
+        self.scratch_i32 = torch.zeros(8 * NT + 64, **i32)
+        self.scratch_u32 = torch.zeros(2 * (D + 1) * max(NT, 1024), **i32)
+        self.scratch_f64 = torch.zeros((D + 2) * max(NT, 1024), **f64)
         self.out_count = torch.zeros(1, **i32)
         self.out_ids = torch.zeros(N, **i32)
         self.out_commands = torch.zeros(N, capi.NUM_COMMANDS, device=dev)
+        self.xr_send = self.xr_recv = self.xr_ids = self.xr_commands = None
+        if self.shared:
+            blk = 1 + N * capi.XR_STRIDE
+            self.xr_send = torch.zeros(2, blk, device=dev)
+            self.xr_recv = torch.zeros(self.world, 2, blk, device=dev)
+            self.xr_ids = torch.zeros(NT, **i32)
+            self.xr_commands = torch.zeros(NT, capi.NUM_COMMANDS, device=dev)
         b = self.bufs = capi.Go1CurriculumBuffers()
+        if self.shared:
+            b.xr_send, b.xr_events = self.xr_send.data_ptr(), self.xr_recv.data_ptr()
+            b.xr_ids, b.xr_commands = self.xr_ids.data_ptr(), self.xr_commands.data_ptr()
         for name, t in (("weights", self.weights), ("grid", self.grid), ("half_bins", self.half_bins), ("local_range", self.local_range),
                         ("mt", self.mt), ("cat_rng", self.cat_rng), ("env_bins", self.env_bins), ("env_categories", self.env_categories),
                         ("env_bins_f32", self.env_bins_f32), ("time_outs_snapshot", self.time_outs_u8), ("cdf", self.cdf),
@@ -134,6 +159,15 @@ class DeviceCurriculum:
         """which = 0: terminated envs -> out_ids/out_commands/out_count; 1: periodic resample, applied in place."""
         capi.check(self.core.L.go1_curriculum_resample(self.core._handle, self._cfg_ref, self._bufs_ref, int(which), capi.stream_ptr()),
                    "go1_curriculum_resample")
+
+    def gather(self):
+        """Cross-rank replay: pack this rank's two event lists (global ids, current bins / categories) and all-gather them.  Called
+        once per env step right after go1_sim_step; the step's resample(0) and the next step's resample(1) consume the result."""
+        if not self.shared:
+            return
+        import torch.distributed as dist
+        capi.check(self.core.L.go1_curriculum_pack(self.core._handle, self._cfg_ref, self._bufs_ref, capi.stream_ptr()), "go1_curriculum_pack")
+        dist.all_gather_into_tensor(self.xr_recv.view(-1, self.xr_recv.shape[-1]), self.xr_send, group=self.group)     # [world * 2][block]
 
     def reset_envs(self, actions, post_step, common_step, episode_acc):
         capi.check(self.core.L.go1_sim_reset_idx_dev(self.core._handle, self.out_ids.data_ptr(), self.out_count.data_ptr(),

@@ -122,8 +122,14 @@ class LeggedRobot(BaseTask):
         # one process per GPU: every rank draws its device randomness (observation noise, reset / DR / push draws) and its
         # command curriculum from its own streams, otherwise env i of every rank would see identical noise and commands
         self.rank_seed_offset = 0
+        self.shared_curriculum = False
         if torch.distributed.is_available() and torch.distributed.is_initialized():
+            import os
             self.rank_seed_offset = int(torch.distributed.get_rank())
+            # ONE command curriculum for the envs of all ranks (replayed identically on every rank from the
+            # all-gathered event records) instead of one per rank; needs the device curriculum
+            self.shared_curriculum = torch.distributed.get_world_size() > 1 and self.device_curriculum and not os.environ.get("GO1_HOST_CURRICULUM") \
+                and os.environ.get("GO1_SHARED_CURRICULUM", "1") != "0"
         self.sim_params = sim_params
         self.height_samples = None
         self.debug_viz = False
@@ -319,7 +325,8 @@ class LeggedRobot(BaseTask):
                 ("body_pitch", "body_pitch"), ("body_roll", "body_roll"), ("stance_width", "stance_width"),
                 ("stance_length", "stance_length"), ("aux_reward_coef", "aux_reward_coef")]
         kw = {name: (getattr(c, f"limit_{key}")[0], getattr(c, f"limit_{key}")[1], getattr(c, f"num_bins_{key}")) for name, key in dims}
-        cur_seed = c.curriculum_seed + 1000 * getattr(self, "rank_seed_offset", 0)
+        # per-rank curricula get per-rank streams; the shared curriculum must start identical everywhere
+        cur_seed = c.curriculum_seed + (0 if getattr(self, "shared_curriculum", False) else 1000 * getattr(self, "rank_seed_offset", 0))
         self.curricula = [RewardThresholdCurriculum(seed=cur_seed, **kw) for _ in self.category_names]
         self.env_command_bins = np.zeros(len(env_ids), dtype=int)
         self.env_command_categories = np.zeros(len(env_ids), dtype=int)
@@ -481,7 +488,7 @@ class LeggedRobot(BaseTask):
             dc = None
             if self.device_curriculum and not os.environ.get("GO1_HOST_CURRICULUM") and self.core.noise is None and self.core.reset_rand is None:
                 from go1_b200.curriculum_dev import DeviceCurriculum
-                dc = DeviceCurriculum(self, _LOCAL_RANGE, _TASK_KEYS)
+                dc = DeviceCurriculum(self, _LOCAL_RANGE, _TASK_KEYS, torch.distributed.group.WORLD if self.shared_curriculum else None)
             self._dev_cur = dc
         return dc
 
@@ -499,6 +506,7 @@ class LeggedRobot(BaseTask):
         dc.to_device()
         dc.resample(1)
         core.step(actions, common_step=self.common_step_counter, mode=0)
+        dc.gather()
         self._post_physics_step_callback_host()
         acc = torch.zeros(capi.NUM_EPISODE_SUMS + 1, device=self.device)
         dc.resample(0)
@@ -533,6 +541,9 @@ class LeggedRobot(BaseTask):
             core.events[1, :k, 1:5] = core.env("command_sums")[rows][:, ids].t()
         core.event_count[1] = k
         self._ep_len_dirty = False
+        dc = self.__dict__.get("_dev_cur")
+        if dc:
+            dc.gather()           # cross-rank replay: every rank needs every rank's rebuilt list
 
     def _apply_pending_interval_resample(self):
         """legged_robot.py:683-686: envs whose episode length hits a multiple of resampling_time/dt."""
@@ -658,6 +669,8 @@ class LeggedRobot(BaseTask):
         ids = np.sort(np.asarray(env_ids.cpu() if hasattr(env_ids, "cpu") else env_ids, dtype=np.int64))
         if len(ids) == 0:
             return
+        if self.shared_curriculum:
+            raise NotImplementedError("shared (cross-rank) curriculum: _resample_commands on the host would desynchronise the ranks")
         self._curriculum_to_host()
         idx = torch.as_tensor(ids, device=self.device)
         cs = self.core.env("command_sums")[[capi.REWARD_TERMS.index(k) for k in _TASK_KEYS]][:, idx].t().cpu().numpy()
@@ -675,10 +688,40 @@ class LeggedRobot(BaseTask):
             _sums = self.core.env("command_sums")[[capi.REWARD_TERMS.index(k) for k in _TASK_KEYS]][:, idx].t().cpu().numpy()
         self._reset_sorted(ids, _sums, _post_step, _actions)
 
+    def _resample_commands_host_all_ranks(self, sums):
+        """The host twin for ALL envs of ALL ranks at once (env.reset() under the shared curriculum): every rank replays the
+        single-process call reset_idx(arange(world * N)) -- same successes, same category draws, same RandomState words -- and
+        keeps its own slice, so the curricula stay identical everywhere.  Collective: every rank must call it."""
+        import torch.distributed as dist
+        W, r, N = dist.get_world_size(), dist.get_rank(), self.num_envs
+        dev = self.device
+
+        def gather(a, dtype):
+            loc = torch.as_tensor(np.ascontiguousarray(a), device=dev).to(dtype)
+            out = torch.empty((W * loc.shape[0],) + tuple(loc.shape[1:]), device=dev, dtype=dtype)      # concatenated along dim 0
+            dist.all_gather_into_tensor(out, loc)
+            return out.cpu().numpy()
+        sums_g = gather(sums, torch.float32)
+        bins_l, cats_l = self.env_command_bins, self.env_command_categories
+        self.env_command_bins, self.env_command_categories = gather(bins_l, torch.int64), gather(cats_l, torch.int64)
+        try:
+            cmds = self._resample_commands_host(np.arange(W * N), sums_g)
+            bins_l[:] = self.env_command_bins[r * N:(r + 1) * N]
+            cats_l[:] = self.env_command_categories[r * N:(r + 1) * N]
+        finally:
+            self.env_command_bins, self.env_command_categories = bins_l, cats_l
+        return cmds[r * N:(r + 1) * N]
+
     def _reset_sorted(self, ids, sums, post_step, actions):
         """reset_idx for ascending numpy ids whose task command sums are already on the host (the step() path)."""
         core = self.core
-        cmds = self._resample_commands_host(ids, sums)
+        if self.shared_curriculum:
+            if len(ids) != self.num_envs:
+                raise NotImplementedError("shared (cross-rank) curriculum: host-side reset_idx is collective and resets ALL envs of every rank; "
+                                          "partial resets happen on the device inside step()")
+            cmds = self._resample_commands_host_all_ranks(sums)
+        else:
+            cmds = self._resample_commands_host(ids, sums)
         core.episode_acc.zero_()
         core.reset_idx(ids, cmds, actions=actions, post_step=post_step, common_step=self.common_step_counter)
         self._env_bins_dirty = True

@@ -153,6 +153,7 @@ class Runner:
                                                     core.num_obs, core.num_priv, sp()), "go1_rollout_store_observations")
         dc.resample(1)
         core.step(actions, common_step=0, mode=0)
+        dc.gather()
         sg["acc"].zero_()
         dc.resample(0)
         dc.reset_envs(actions, True, 0, sg["acc"])

@@ -11,6 +11,9 @@ if [[ $WHAT == all || $WHAT == *tests* ]]; then
   timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -60 > $O/${TAG}_tests.txt
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.txt 2>&1
 fi
+if [[ $WHAT == *blocks* ]]; then
+  GO1_SWEEP_BLOCKS=32,64,128 GO1_SWEEP_ENVS=4096,16384 timeout 300 python walk-these-ways_b200/tools/sim_sweep.py > $O/${TAG}_sim_blocks.txt 2>&1
+fi
 if [[ $WHAT == *hunt* ]]; then
   timeout 600 python walk-these-ways_b200/tools/nan_hunt.py --config rough_dr --envs 4096 --steps 200 --bisect > $O/${TAG}_nan_hunt.txt 2>&1
 fi
@@ -42,4 +45,4 @@ if [[ $WHAT == all || $WHAT == *ncu* ]]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32 -s 400 -c 12 -f -o $O/${TAG}_gemm \
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-gemm-roofline > $O/${TAG}_ncu_gemm.log 2>&1
 fi
-ls -la $O | tail -30
+du -sh $O; ls -la $O | tail -30
