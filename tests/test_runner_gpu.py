@@ -140,6 +140,8 @@ def test_graph_replayed_rollout_equals_eager_rollout(tmp_path, monkeypatch):
         RunnerArgs.num_steps_per_env, RunnerArgs.resume = 24, False
         runner = Runner(env, device="cuda:0")
         runner.step_graph = graphed
+        if not graphed:       # launch by launch, and without the policy-only graph (its capture warm-up draws from the action-noise stream)
+            runner.alg.use_cuda_graph = False
         g = torch.Generator().manual_seed(1)
         env.episode_length_buf = torch.randint(0, 1001, (256,), generator=g)
         od = env.get_observations()

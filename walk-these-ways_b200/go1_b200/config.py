@@ -274,11 +274,12 @@ def build_sim_config(cfg, num_envs=None, num_train_envs=None, seed=0, physics=No
     c.base_init_state[:] = list(ist.pos) + list(ist.rot) + list(ist.lin_vel) + list(ist.ang_vel)
     t = cfg.terrain
     c.custom_origins = int(t.mesh_type in ["heightfield", "trimesh"])
-    px = cfg.sim.physx
+    px = cfg.sim.physx            # a config class, or the plain dict scripts/play.py restores from parameters.pkl
+    pxg = (lambda k: px[k]) if isinstance(px, dict) else (lambda k: getattr(px, k))
     c.erp, c.cfm, c.pgs_iters = 0.2, 1e-4, 8
-    c.max_depen_vel = px.max_depenetration_velocity
-    c.contact_margin = px.contact_offset
-    c.bounce_threshold = px.bounce_threshold_velocity
+    c.max_depen_vel = pxg("max_depenetration_velocity")
+    c.contact_margin = pxg("contact_offset")
+    c.bounce_threshold = pxg("bounce_threshold_velocity")
     c.terrain_friction, c.terrain_restitution = t.static_friction, t.restitution
     c.pen_k[:] = [20000., 20000., 5000., 5000.]
     c.pen_c[:] = [150., 150., 30., 30.]

@@ -11,11 +11,19 @@ if [[ $WHAT == all || $WHAT == *tests* ]]; then
   timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -60 > $O/${TAG}_tests.txt
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.txt 2>&1
 fi
+if [[ $WHAT == *dist2* ]]; then
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 5 --warmup 3 \
+      > $O/${TAG}_bench_flat_n2.json 2> $O/${TAG}_bench_flat_n2.err
+  GO1_SHARED_CURRICULUM=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 2 --steps 5 --warmup 3 \
+      > $O/${TAG}_bench_flat_n2_percurr.json 2>> $O/${TAG}_bench_flat_n2.err
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus 2 --config rough_dr --steps 5 --warmup 3 \
+      > $O/${TAG}_bench_rough_dr_n2.json 2>> $O/${TAG}_bench_flat_n2.err
+fi
 if [[ $WHAT == *blocks* ]]; then
   GO1_SWEEP_BLOCKS=32,64,128 GO1_SWEEP_ENVS=4096,16384 timeout 300 python walk-these-ways_b200/tools/sim_sweep.py > $O/${TAG}_sim_blocks.txt 2>&1
 fi
 if [[ $WHAT == *hunt* ]]; then
-  timeout 600 python walk-these-ways_b200/tools/nan_hunt.py --config rough_dr --envs 4096 --steps 200 --bisect > $O/${TAG}_nan_hunt.txt 2>&1
+  timeout 600 python walk-these-ways_b200/tools/nan_hunt.py --config rough_dr --envs 4096 --train 8 > $O/${TAG}_nan_hunt.txt 2>&1
 fi
 if [[ $WHAT == *refscripts* ]]; then
   timeout 900 python walk-these-ways_b200/tools/run_reference_scripts.py --iterations 2 --num-envs 4096 --out $O/${TAG}_reference_scripts.json > $O/${TAG}_reference_scripts.log 2>&1

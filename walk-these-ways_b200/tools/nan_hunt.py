@@ -78,6 +78,44 @@ def hunt(config, envs, steps, off, scale):
     return True
 
 
+def hunt_train(config, envs, iterations):
+    """Whole training iterations of a bench configuration with a finiteness check after every phase."""
+    env, runner = bench.build_training(envs, "cuda:0", 1, config)
+    od = env.get_observations()
+    state = [od["obs"], od["privileged_obs"], od["obs_history"]]
+    st = runner.alg.storage
+    ac = runner.alg.actor_critic
+
+    def check(tag, tensors):
+        for name, t in tensors.items():
+            if not torch.isfinite(t.float()).all():
+                bad = torch.nonzero(~torch.isfinite(t.float()))[0].tolist()
+                print(f"[{config}] iteration {it}: non-finite {name} after {tag} at {bad}: {t[tuple(bad)].item() if len(bad) == t.dim() else '?'}")
+                return False
+        return True
+    for it in range(iterations):
+        obs, priv, hist, infos = runner.rollout(*state)
+        state[:] = [obs, priv, hist]
+        core = env.env.core
+        if not check("rollout", dict(obs=st.observations, priv=st.privileged_observations, hist=st.observation_histories, actions=st.actions,
+                                     rewards=st.rewards, values=st.values, logp=st.actions_log_prob, mu=st.mu, env_bins=st.env_bins,
+                                     env_f32=core.env_f32, leg_f32=core.leg_f32)):
+            return False
+        with torch.inference_mode():
+            runner.alg.compute_returns(hist[:env.num_train_envs], priv[:env.num_train_envs])
+        if not check("compute_returns", dict(returns=st.returns, advantages=st.advantages)):
+            print("   rewards min/max", float(st.rewards.min()), float(st.rewards.max()), "values min/max", float(st.values.min()), float(st.values.max()))
+            return False
+        losses = runner.alg.update()
+        if not check("update", dict(params=ac.flat_params, losses=torch.tensor(losses[:6]))):
+            print("   losses", losses, "grad head", ac.flat_grads[:10].tolist(), "lr", runner.alg.learning_rate)
+            print("   rewards min/max", float(st.rewards.min()), float(st.rewards.max()), "adv min/max", float(st.advantages.min()), float(st.advantages.max()),
+                  "returns min/max", float(st.returns.min()), float(st.returns.max()), "logp min", float(st.actions_log_prob.min()))
+            return False
+    print(f"[{config}] {iterations} training iterations finite; last losses {[round(x, 4) for x in losses[:3]]}")
+    return True
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="rough_dr")
@@ -85,7 +123,10 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--bisect", action="store_true", help="if the full configuration fails, retry with each feature switched off")
+    ap.add_argument("--train", type=int, default=0, help="instead: run this many whole training iterations with finiteness checks")
     a = ap.parse_args()
+    if a.train:
+        raise SystemExit(0 if hunt_train(a.config, a.envs, a.train) else 1)
     ok = hunt(a.config, a.envs, a.steps, [], a.scale)
     if not ok and a.bisect:
         for f in ("terrain", "com", "rigids", "push", "teleport", "init_range", "gravity"):
