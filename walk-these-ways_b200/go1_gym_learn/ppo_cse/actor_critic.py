@@ -175,7 +175,9 @@ class _Net:
                 capi.check(L.go1_skinny_wgrad(capi.ptr(dz), ldz, capi.ptr(inp), ld_in, gW.data_ptr(), i, M, o, K, accumulate, st), "skinny_wgrad")
             else:       # impl 1: both operands MN-major, read in place by the tcgen05 kernel
                 tc = impl == 1 and M >= 64 and K >= 8 and self._tma_ok(dz, ldz) and self._tma_ok(inp, ld_in)
-                self._gemm(1, 0, o, K, M, dz, ldz, inp, ld_in, gW, i, None, 0, accumulate, 1 if tc else 0)
+                # into a gradient buffer the caller has already zeroed the split-K partial tiles can accumulate directly (no zeroing pass)
+                acc_w = 1 if (accumulate or (tc and self.owner.grads_prezeroed)) else 0
+                self._gemm(1, 0, o, K, M, dz, ldz, inp, ld_in, gW, i, None, 0, acc_w, 1 if tc else 0)
             if li == 0 and extra is not None:
                 E = i - K0
                 if want_dextra:
@@ -421,7 +423,8 @@ class ActorCritic(nn.Module):
         return actions
 
     def get_actions_log_prob(self, actions):
-        if actions is getattr(self, "_last_actions", None):
+        last = getattr(self, "_last_actions", None)
+        if last is not None and actions.data_ptr() == last.data_ptr() and actions.shape == last.shape:      # the sample kernel already produced it
             return self._logp
         d = actions - self._mean
         sd = self.std.detach()

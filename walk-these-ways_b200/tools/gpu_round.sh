@@ -19,6 +19,17 @@ if [[ $WHAT == *dist2* ]]; then
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus 2 --config rough_dr --steps 5 --warmup 3 \
       > $O/${TAG}_bench_rough_dr_n2.json 2>> $O/${TAG}_bench_flat_n2.err
 fi
+if [[ $WHAT == *gemmtune* ]]; then
+  for V in "GO1_TF32_SPLIT_CTAS=148" "GO1_TF32_SPLIT_CTAS=592" "GO1_TF32_SPLIT_MINKB=32" "GO1_TF32_SPLIT_MINKB=64 GO1_TF32_SPLIT_CTAS=148" "GO1_FUSE_BIAS_GRAD=0" "GO1_STEP_GRAPH=0"; do
+    echo "== $V" >> $O/${TAG}_gemmtune.txt
+    env $V timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d = json.loads(l); print(d['ms_per_step'], d['roofline']['kernel_ms_per_iteration'], d['roofline']['frac'])
+" >> $O/${TAG}_gemmtune.txt
+  done
+fi
 if [[ $WHAT == *blocks* ]]; then
   GO1_SWEEP_BLOCKS=32,64,128 GO1_SWEEP_ENVS=4096,16384 timeout 300 python walk-these-ways_b200/tools/sim_sweep.py > $O/${TAG}_sim_blocks.txt 2>&1
 fi
