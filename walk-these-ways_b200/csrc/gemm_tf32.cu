@@ -698,20 +698,30 @@ static bool g_time_on = false;
 static std::vector<cudaEvent_t> g_time_events;
 static size_t g_time_used = 0;
 static double g_time_flop = 0.0;
+struct TimeRec { int M, N, K, amn, bmn, act, nex, splits, kern, colsum; };      // what each timed launch was (GO1_GEMM_TIMING_CSV dump)
+static std::vector<TimeRec> g_time_recs;
 static cudaEvent_t timing_event() {
     if (g_time_used == g_time_events.size()) { cudaEvent_t e; cudaEventCreate(&e); g_time_events.push_back(e); }
     return g_time_events[g_time_used++];
 }
 extern "C" int go1_gemm_timing(int on, double* total_ms, double* total_flop, long long* launches) {
-    if (on) { g_time_on = true; g_time_used = 0; g_time_flop = 0.0; return 0; }
+    if (on) { g_time_on = true; g_time_used = 0; g_time_flop = 0.0; g_time_recs.clear(); return 0; }
     g_time_on = false;
     double ms = 0.0;
+    FILE* csv = getenv("GO1_GEMM_TIMING_CSV") ? fopen(getenv("GO1_GEMM_TIMING_CSV"), "w") : nullptr;
+    if (csv) fprintf(csv, "M,N,K,a_mn_major,b_mn_major,act,num_extra,splits,kernel,colsum,us\n");
     for (size_t i = 0; i + 1 < g_time_used; i += 2) {
         if (cudaEventSynchronize(g_time_events[i + 1]) != cudaSuccess) return go1_set_error("go1_gemm_timing: event sync failed");
         float t = 0.f;
         if (cudaEventElapsedTime(&t, g_time_events[i], g_time_events[i + 1]) != cudaSuccess) return go1_set_error("go1_gemm_timing: elapsed time failed");
         ms += t;
+        if (csv && i / 2 < g_time_recs.size()) {
+            const TimeRec& r = g_time_recs[i / 2];
+            fprintf(csv, "%d,%d,%d,%d,%d,%d,%d,%d,%s,%d,%.2f\n", r.M, r.N, r.K, r.amn, r.bmn, r.act, r.nex, r.splits,
+                    r.kern == 2 ? "2cta" : (r.kern == 256 ? "p256" : (r.kern == 128 ? "p128" : (r.kern == 64 ? "p64" : "p32"))), r.colsum, 1e3 * t);
+        }
     }
+    if (csv) fclose(csv);
     if (total_ms) *total_ms = ms;
     if (total_flop) *total_flop = g_time_flop;
     if (launches) *launches = (long long)(g_time_used / 2);
@@ -766,7 +776,10 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
     }
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     const bool timed = g_time_on && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone;
-    if (timed) { cudaEventRecord(timing_event(), st); g_time_flop += 2.0 * (double)M * (double)N * (double)K; }
+    if (timed) {
+        cudaEventRecord(timing_event(), st); g_time_flop += 2.0 * (double)M * (double)N * (double)K;
+        g_time_recs.push_back({M, N, K, amn, bmn, act, g.nex, splits, two_cta ? 2 : BN, g.colsum ? 1 : 0});
+    }
     int e;
     if (two_cta) e = launch_2cta<6>(ma, mb, g, splits, st);
     else if (BN == 256) e = launch_persistent<256, 4>(ma, mb, g, splits, st);

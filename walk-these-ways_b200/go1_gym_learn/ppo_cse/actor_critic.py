@@ -233,6 +233,8 @@ class ActorCritic(nn.Module):
         self.weights_version = 0      # bumped by every optimizer step / load: invalidates the packed first-layer weight copies
         import os
         self.fuse_bias_grad = os.environ.get("GO1_FUSE_BIAS_GRAD", "1") != "0"     # bias gradients reduced in the dgrad GEMM epilogues
+        self.update_streams = os.environ.get("GO1_UPDATE_STREAMS", "0") == "1"     # critic chain on a second stream during the update (experimental)
+        self._side = None
         self.grads_prezeroed = False  # PPO.update zeroes the flat gradient buffer once per optimizer step (one fill instead of one per layer)
 
     # ------------------------------------------------------------------ flat storage
@@ -380,15 +382,42 @@ class ActorCritic(nn.Module):
         na._gemm(0, 1, M, oa + oc + op, K0, h, h.stride(0), Wcat, K0, y, y.stride(0), bcat, 1, 0, 1,
                  extra=priv, w_extra=xcat.data_ptr(), ld_w_extra=E, lead_cols=oa + oc)
         ya, yc, yp = y[:, :oa], y[:, oa:oa + oc], y[:, oa + oc:]
+        side = self._side_stream(M)
+        if side is not None:        # the critic's tail does not depend on the adaptation module: it runs beside adapt -> actor
+            self._fork(side)
+            with torch.cuda.stream(side):
+                self._c_out = ncr.forward(h, h.stride(0), K0, priv, M, impl, tag, first_out=yc)
         self._a_out = na.forward(h, h.stride(0), K0, None, M, impl, tag, first_out=ya)
         latent = self._latent = self._a_out[-1]
         capi.check(capi.lib().go1_mlp_extra_forward(capi.ptr(yp), yp.stride(0), capi.ptr(latent), latent.stride(0), Wp.data_ptr() + 4 * K0, K0 + E,
                                                     M, op, E, 1, capi.stream_ptr()), "go1_mlp_extra_forward")
         self._p_out = npol.forward(h, h.stride(0), K0, latent, M, impl, tag, first_out=yp)
         self._mean = self._p_out[-1]
-        self._c_out = ncr.forward(h, h.stride(0), K0, priv, M, impl, tag, first_out=yc)
+        if side is not None:
+            self._join(side)
+        else:
+            self._c_out = ncr.forward(h, h.stride(0), K0, priv, M, impl, tag, first_out=yc)
         self._value = self._c_out[-1]
         return self._mean, self._value
+
+    # ------------------------------------------------------------------ two-stream update (independent sub-chains side by side)
+    def _side_stream(self, M):
+        """A second stream for the critic's chain during the update (M = minibatch rows), or None: the mid-size products leave SMs
+        idle at their ramp-up and tail (one 128 x 128 tile per CTA), which an independent chain on another stream fills."""
+        if not self.update_streams or M < 4096 or torch.cuda.is_current_stream_capturing():
+            return None
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+            self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+        return self._side
+
+    def _fork(self, side):
+        self._ev_fork.record()
+        side.wait_event(self._ev_fork)
+
+    def _join(self, side):
+        self._ev_join.record(side)
+        torch.cuda.current_stream().wait_event(self._ev_join)
 
     def act_and_evaluate(self, observation_history, privileged_observations):
         """PPO.act's two calls (actor_critic.act + evaluate, ppo.py:67-68) on one fused forward pass."""
@@ -477,9 +506,17 @@ class ActorCritic(nn.Module):
             # column slice of `dz1` by that net's layer-2 dgrad)
             oa, op, oc = nets["adapt"].specs[0][2], nets["actor"].specs[0][2], nets["critic"].specs[0][2]
             dz1 = nets["adapt"]._buf(("train", "dz1cat"), M, oa + op + oc)
+            side = self._side_stream(M)
+            if side is not None:    # critic chain beside actor -> adaptation chain
+                self._fork(side)
+                with torch.cuda.stream(side):
+                    nets["critic"].backward(h, h.stride(0), K0, priv, self._c_out, dvalue, M, impl, 0, tag="train", dz1_out=dz1[:, oa + op:])
             dlat = nets["actor"].backward(h, h.stride(0), K0, self._latent, self._p_out, dmean, M, impl, 0, want_dextra=True, tag="train", dz1_out=dz1[:, oa:oa + op])
-            nets["critic"].backward(h, h.stride(0), K0, priv, self._c_out, dvalue, M, impl, 0, tag="train", dz1_out=dz1[:, oa + op:])
+            if side is None:
+                nets["critic"].backward(h, h.stride(0), K0, priv, self._c_out, dvalue, M, impl, 0, tag="train", dz1_out=dz1[:, oa + op:])
             nets["adapt"].backward(h, h.stride(0), K0, None, self._a_out, dlat, M, impl, 0, tag="train", dz1_out=dz1[:, :oa])
+            if side is not None:
+                self._join(side)
             n0 = nets["adapt"]
             gcat = n0._buf(("train", "gWcat"), oa + op + oc, K0)
             n0._gemm(1, 0, oa + op + oc, K0, M, dz1, dz1.stride(0), h, h.stride(0), gcat, K0, None, 0, 0, 1)

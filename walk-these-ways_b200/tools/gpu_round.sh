@@ -20,7 +20,7 @@ if [[ $WHAT == *dist2* ]]; then
       > $O/${TAG}_bench_rough_dr_n2.json 2>> $O/${TAG}_bench_flat_n2.err
 fi
 if [[ $WHAT == *gemmtune* ]]; then
-  for V in "GO1_TF32_SPLIT_CTAS=148" "GO1_TF32_SPLIT_CTAS=592" "GO1_TF32_SPLIT_MINKB=32" "GO1_TF32_SPLIT_MINKB=64 GO1_TF32_SPLIT_CTAS=148" "GO1_FUSE_BIAS_GRAD=0" "GO1_STEP_GRAPH=0"; do
+  for V in ${GEMMTUNE_VARIANTS:-"GO1_X=0" "GO1_UPDATE_STREAMS=1" "GO1_TF32_WIDE_MINK=256" "GO1_TF32_WIDE_MINK=512" "GO1_CUR_GROUPED=1"}; do
     echo "== $V" >> $O/${TAG}_gemmtune.txt
     env $V timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | python -c "
 import sys, json
@@ -29,6 +29,10 @@ for l in sys.stdin:
         d = json.loads(l); print(d['ms_per_step'], d['roofline']['kernel_ms_per_iteration'], d['roofline']['frac'])
 " >> $O/${TAG}_gemmtune.txt
   done
+fi
+if [[ $WHAT == *gemmcsv* ]]; then
+  GO1_GEMM_TIMING_CSV=$O/${TAG}_gemm_launches.csv timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_gemmcsv.json 2>&1
+  GO1_TEST_GROUPED=1 timeout 300 python -m pytest tests/test_curriculum_gpu.py -q -k grouped 2>&1 | tail -5 > $O/${TAG}_grouped_test.txt
 fi
 if [[ $WHAT == *blocks* ]]; then
   GO1_SWEEP_BLOCKS=32,64,128 GO1_SWEEP_ENVS=4096,16384 timeout 300 python walk-these-ways_b200/tools/sim_sweep.py > $O/${TAG}_sim_blocks.txt 2>&1
