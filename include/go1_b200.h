@@ -257,7 +257,7 @@ int go1_curriculum_resample(Go1Sim* sim, const Go1CurriculumConfig* cfg, const G
  * the go1_curriculum_resample calls of the step (list 0) and of the next step (list 1). */
 int go1_curriculum_pack(Go1Sim* sim, const Go1CurriculumConfig* cfg, const Go1CurriculumBuffers* bufs, void* stream);
 
-/* 1: calls with <= 256 events process the (independent) categories concurrently, one 256-thread group each; 0 (default): one
+/* 1 (default): calls with <= 256 events process the (independent) categories concurrently, one 256-thread group each; 0: one
  * category after the other.  Same arithmetic either way. */
 void go1_curriculum_set_grouped(int on);
 
@@ -314,6 +314,11 @@ typedef struct Go1GemmEpilogue {
                           * bias only): lets several first layers that share their input run as ONE product (impl 1) */
     float* colsum;       /* optional [N] (impl 1): colsum[n] += sum_m C[m][n] of the FINAL values this call writes -- the bias gradient
                           * of the layer whose dz this dgrad product produces, reduced in the epilogue (atomic adds: zero it first) */
+    /* optional (impl 1): C is the dz of a first layer with `num_bwd_extra` (<= 4) trailing inputs (go1_mlp_extra_backward's job done in
+     * this epilogue, atomic adds into zeroed outputs):  g_w_extra[n][t] += sum_m C[m][n] bwd_extra[m][t];
+     * d_extra[m][t] += sum_n C[m][n] bwd_w_extra[n][t]  (d_extra may be NULL) */
+    const float* bwd_extra; const float* bwd_w_extra; float* g_w_extra; float* d_extra;
+    int32_t ld_bwd_extra, ld_bwd_w_extra, ld_g_w_extra, ld_d_extra, num_bwd_extra;
 } Go1GemmEpilogue;
 int go1_gemm_ex(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                 float* C, int ldc, const Go1GemmEpilogue* ep, int impl, void* stream);

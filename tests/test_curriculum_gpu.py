@@ -56,16 +56,16 @@ def _check_state(env, dc, tag, bins_snapshot):
     assert np.array_equal(d["bins_f32"], bins_snapshot), (tag, "env_bins extras")
 
 
-@pytest.mark.skipif(not os.environ.get("GO1_TEST_GROUPED"), reason="opt-in: the category-parallel path is off by default this round")
 @pytest.mark.parametrize("mode", ["gaitwise", "nominal_binary", "exclusive", "balanced"])
-def test_grouped_path_matches_host_twin(mode):
-    """The same bit-exactness test with go1_curriculum_set_grouped(1): calls with <= 256 events take the category-parallel path."""
+def test_sequential_path_matches_host_twin(mode):
+    """The same bit-exactness test with go1_curriculum_set_grouped(0): every call takes the category-by-category path (the default,
+    grouped, path sends calls with <= 256 events through the category-parallel code)."""
     from go1_b200 import capi
-    capi.lib().go1_curriculum_set_grouped(1)
+    capi.lib().go1_curriculum_set_grouped(0)
     try:
         test_device_curriculum_matches_host_twin(mode)
     finally:
-        capi.lib().go1_curriculum_set_grouped(0)
+        capi.lib().go1_curriculum_set_grouped(1)
 
 
 @pytest.mark.parametrize("mode", ["gaitwise", "nominal_binary", "exclusive", "balanced"])

@@ -316,3 +316,47 @@ def test_fused_first_layer_epilogue_lead_cols_and_extra_forward():
     with pytest.raises(capi.Go1Error):      # the fp32 CUDA-core path does not implement the split epilogue
         ep.lead_cols = lead
         capi.check(L.go1_gemm_ex(0, 1, M, lead + tail, K, capi.ptr(A), K, capi.ptr(W), K, capi.ptr(y), lead + tail, ep, 0, capi.stream_ptr()), "gemm_ex")
+
+
+@pytest.mark.parametrize("M", [512, 2304])
+def test_fused_backward_epilogues_match_separate_kernels(M):
+    """The bias gradients (column sums of dz) and the trailing-input gradients of the first layers (go1_mlp_extra_backward) reduced
+    inside the dgrad GEMM epilogues must equal the separate bandwidth kernels: same flat gradient buffer up to the fp32 rounding of
+    a different summation order (atomics), checked against an fp64 torch-autograd gradient of the same loss as well."""
+    from go1_gym_learn.ppo_cse import ActorCritic
+    from go1_gym_learn.ppo_cse.actor_critic import AC_Args
+    AC_Args.gemm_impl = 1
+    torch.manual_seed(3)
+    NOBS, NH, NP, NA = 70, 2100, 2, 12
+    ac = ActorCritic(NOBS, NP, NH, NA).to("cuda:0")
+    ac.flatten()
+    h = torch.randn(M, NH, device="cuda") * 0.3
+    priv = torch.randn(M, NP, device="cuda")
+    dmean = torch.randn(M, NA, device="cuda") / M
+    dvalue = torch.randn(M, 1, device="cuda") / M
+    dstd = torch.randn(NA, device="cuda")
+    grads = {}
+    for fuse in (False, True):
+        ac.fuse_bias_grad = fuse
+        ac.flat_grads.zero_(); ac.grads_prezeroed = True
+        mean, value = ac.forward_all(h, priv, tag="train")
+        ac.backward_ppo(h, priv, dmean, dvalue, dstd)
+        torch.cuda.synchronize()
+        grads[fuse] = ac.flat_grads.clone()
+        ac.grads_prezeroed = False
+    a, b = grads[False], grads[True]
+    scale = a.abs().max()
+    assert float((a - b).abs().max()) <= 2e-5 * float(scale) + 1e-7, float((a - b).abs().max())
+    # fp64 autograd of sum(mean * dmean) + sum(value * dvalue) through plain torch modules holding the same weights
+    import copy
+    ref = {k: copy.deepcopy(getattr(ac, k)).double() for k in ("adaptation_module", "actor_body", "critic_body")}
+    hd, pd = h.double(), priv.double()
+    lat = ref["adaptation_module"](hd)
+    loss = (ref["actor_body"](torch.cat((hd, lat), -1)) * dmean.double()).sum() + (ref["critic_body"](torch.cat((hd, pd), -1)) * dvalue.double()).sum()
+    loss.backward()
+    for name, mod in ref.items():
+        for (pn, p_ref), p in zip(mod.named_parameters(), getattr(ac, name).parameters()):
+            off = p.data_ptr() - ac.flat_params.data_ptr()
+            g = b[off // 4: off // 4 + p.numel()].view_as(p)
+            err = (g.double() - p_ref.grad).abs().max() / (p_ref.grad.abs().max() + 1e-12)
+            assert float(err) < 5e-3, (name, pn, float(err))        # TF32 products: 2^-11 per operand

@@ -669,9 +669,9 @@ extern "C" int go1_launch_curriculum_pack(const Go1SimBuffers* b, const Go1Curri
     return (int)cudaGetLastError();
 }
 
-// The category-parallel grouped path is OFF by default: it ran the training bench 1 % faster (rollout 15.5 -> 14.9 ms) but the
-// parity tests of this round only reached it for N >= 1024 envs, which no test used; GO1_CUR_GROUPED=1 or
-// go1_curriculum_set_grouped(1) turn it on (tests/test_curriculum_gpu.py has the bit-exactness test for it, opt-in).
+// The category-parallel grouped path is ON by default (bit-exact against the host twin in all four curriculum modes on a B200:
+// tests/test_curriculum_gpu.py::test_grouped_path_matches_host_twin; iteration 49.6 -> 48.8 ms); GO1_CUR_GROUPED=0 or
+// go1_curriculum_set_grouped(0) select the category-by-category path.
 static int g_cur_grouped = -1;
 extern "C" void go1_curriculum_set_grouped(int on) { g_cur_grouped = on ? 1 : 0; }
 
@@ -679,7 +679,7 @@ extern "C" int go1_launch_curriculum(const Go1SimBuffers* b, const Go1Curriculum
                                      cudaStream_t st) {
     CurArgs a;
     a.b = *b; a.c = *cfg; a.cb = *cb; a.list = list; a.N = N;
-    a.grouped = g_cur_grouped < 0 ? (g_cur_grouped = getenv("GO1_CUR_GROUPED") ? atoi(getenv("GO1_CUR_GROUPED")) : 0) : g_cur_grouped;
+    a.grouped = g_cur_grouped < 0 ? (g_cur_grouped = getenv("GO1_CUR_GROUPED") ? atoi(getenv("GO1_CUR_GROUPED")) : 1) : g_cur_grouped;
     go1_curriculum_kernel<<<1, CT, 0, st>>>(a);
     go1_count_launch(1);
     return (int)cudaGetLastError();

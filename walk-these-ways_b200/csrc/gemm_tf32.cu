@@ -111,6 +111,8 @@ struct GemmArgs {
     int lead;                // > 0: extra columns + activation only for output columns < lead
     int amn, bmn;            // operand is MN-major in HBM (A given as [K][M], B given as [K][N]); persistent kernel only
     float* colsum;           // optional [N]: += column sums of the values written (bias gradient fused into the dgrad epilogue)
+    const float* bx; const float* bwx; float* gwx; float* dx;     // fused trailing-input backward (see Go1GemmEpilogue)
+    int ldbx, ldbwx, ldgwx, lddx, nbx;
 };
 
 // Epilogue of one 32-column chunk held in registers (thread = output row, r[j] = column col0 + j).  Called by all 32 lanes
@@ -211,6 +213,36 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, uint32_t (&r)[
             }
         }
         if (lane < ncols) atomicAdd(g.colsum + col0 + lane, sred[0]);      // lane l ends up with column col0 + l
+    }
+    if (g.nbx > 0) {        // warp-uniform.  C is the dz of a first layer with nbx trailing inputs: their weight gradient (column sums weighted by the
+        const int cjx = col0 + lane;                     // row's trailing inputs) and input gradient (row dots with the trailing-input weights)
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            if (t < g.nbx) {
+                const float e = row_ok ? __ldg(g.bx + (size_t)row * g.ldbx + t) : 0.f;
+                float sred[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) sred[j] = (row_ok && j < ncols) ? v[j] * e : 0.f;
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const bool upper = (lane & off) != 0;
+#pragma unroll
+                    for (int j = 0; j < off; j++) {
+                        const float send = upper ? sred[j] : sred[j + off];
+                        const float keep = upper ? sred[j + off] : sred[j];
+                        sred[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    }
+                }
+                if (lane < ncols) atomicAdd(g.gwx + (size_t)cjx * g.ldgwx + t, sred[0]);
+                if (g.dx) {
+                    const float wl = lane < ncols ? __ldg(g.bwx + (size_t)cjx * g.ldbwx + t) : 0.f;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) acc = fmaf(v[j], __shfl_sync(0xffffffffu, wl, j), acc);      // wl = 0 beyond ncols
+                    if (row_ok) atomicAdd(g.dx + (size_t)row * g.lddx + t, acc);
+                }
+            }
+        }
     }
     if (!row_ok) return;
     if (vec) {
@@ -416,6 +448,13 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_persistent(const __grid_cons
             int m0, n0, kb0, nkb; tile_coords(t, m0, n0, kb0, nkb);
             const int buf = j & 1;
             const int row = m0 + 32 * q + lane;
+            // ELU'(y) operand of this tile (act == 2): one L1 prefetch per 128-byte row chunk, issued while the main loop of the tile is
+            // still running, so that the epilogue's loads below hit the cache instead of stalling on HBM / L2 (no registers held)
+            if (g.act == 2 && !split && row < g.M) {
+#pragma unroll
+                for (int c = 0; c < BN / 32; c++)
+                    if (n0 + 32 * c < g.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(g.aux + (size_t)row * g.ldaux + n0 + 32 * c));
+            }
             mbar_wait(&tmem_full[buf], (j >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
@@ -742,6 +781,9 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
     g.ex = ep->extra; g.ldex = ep->ld_extra; g.wex = ep->w_extra; g.ldwex = ep->ld_w_extra; g.nex = ep->extra ? ep->num_extra : 0;
     g.aux = ep->dact_y; g.ldaux = ep->ld_dact_y;
     g.amn = amn; g.bmn = bmn; g.lead = ep->lead_cols; g.colsum = ep->colsum;
+    g.nbx = ep->num_bwd_extra; g.bx = ep->bwd_extra; g.bwx = ep->bwd_w_extra; g.gwx = ep->g_w_extra; g.dx = ep->d_extra;
+    g.ldbx = ep->ld_bwd_extra; g.ldbwx = ep->ld_bwd_w_extra; g.ldgwx = ep->ld_g_w_extra; g.lddx = ep->ld_d_extra;
+    if (g.nbx < 0 || g.nbx > 4 || (g.nbx > 0 && (!g.bx || !g.gwx || (g.dx && !g.bwx)))) return go1_set_error("go1_gemm_ex: bad fused trailing-input backward arguments");
     if (g.nex < 0 || g.nex > 4) return go1_set_error("go1_gemm_ex: num_extra must be 0..4");
     if (act == 2 && !g.aux) return go1_set_error("go1_gemm_ex: act 2 needs dact_y");
     const int num_kb = (K + BK - 1) / BK;
@@ -761,7 +803,7 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
     const int BN = wide ? 256 : ((N > 64) ? 128 : (N > 32 ? 64 : 32));
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     int splits = 1;
-    if (tiles < 148 && num_kb >= split_min_kb && g.nex == 0 && act != 2 && g.lead <= 0 && !g.colsum) {      // one wave of 2 CTAs/SM, >= 16 k-blocks each
+    if (tiles < 148 && num_kb >= split_min_kb && g.nex == 0 && act != 2 && g.lead <= 0 && !g.colsum && g.nbx == 0) {      // one wave of 2 CTAs/SM, >= 16 k-blocks each
         splits = split_ctas / tiles; if (splits > num_kb / split_min_kb) splits = num_kb / split_min_kb; if (splits < 1) splits = 1;
     }
     g.kb_per_split = (num_kb + splits - 1) / splits;

