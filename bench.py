@@ -252,8 +252,11 @@ def run_b200(args):
     gemm_roof = None
     if args.gemm == 1 and not args.no_gemm_roofline:        # one more (untimed) iteration with CUDA events around every tcgen05 product (every rank: collectives)
         import ctypes as C
+        ac_ = runner.alg.actor_critic
+        streams_, ac_.update_streams = ac_.update_streams, False       # one stream: per-launch durations must not overlap to be summed
         L.go1_gemm_timing(1, None, None, None)
         iteration()
+        ac_.update_streams = streams_
         ms, fl, nl = C.c_double(), C.c_double(), C.c_longlong()
         capi.check(L.go1_gemm_timing(0, C.byref(ms), C.byref(fl), C.byref(nl)), "go1_gemm_timing")
         gemm_roof = (ms.value, fl.value, nl.value)

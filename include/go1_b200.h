@@ -322,6 +322,15 @@ typedef struct Go1GemmEpilogue {
 } Go1GemmEpilogue;
 int go1_gemm_ex(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                 float* C, int ldc, const Go1GemmEpilogue* ep, int impl, void* stream);
+/* The layers BEHIND a first layer of one of ActorCritic's MLPs in one launch (impl 1, tcgen05; actor_critic.py:38-77, 113-144):
+ *   y2 = ELU(x W2^T + b2) [M][N2];   y3 = ELU(y2 W3^T + b3) [M][N3]  (N3 = 0: skipped);   out = y_last Wh^T + bh [M][nh], nh <= 16.
+ * x is the first layer's activated output (K1 columns, row stride ldx); W* are torch nn.Linear weights [out][in], contiguous; y2 / y3 are
+ * kept for the backward pass.  Supported tails: K1-N2-N3 = 512-256-128 (actor / critic bodies of scripts/train.py) and 256-128-0
+ * (adaptation module); the activations between the layers never leave the SM (TMEM -> registers -> shared memory -> tensor core). */
+int go1_mlp_tail_forward(const float* x, int ldx, int M, int K1, const float* W2, const float* b2, int N2, float* y2, int ldy2,
+                         const float* W3, const float* b3, int N3, float* y3, int ldy3, const float* Wh, const float* bh, int nh,
+                         float* out, int ldout, void* stream);
+
 /* Per-launch timing of the impl-1 (tcgen05) products for the roofline report: on = 1 starts collecting (CUDA events on the launch
  * stream around every call that is not being graph-captured), on = 0 stops and returns the summed kernel time, flops and count. */
 int go1_gemm_timing(int on, double* total_ms, double* total_flop, long long* launches);

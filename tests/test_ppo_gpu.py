@@ -360,3 +360,44 @@ def test_fused_backward_epilogues_match_separate_kernels(M):
             g = b[off // 4: off // 4 + p.numel()].view_as(p)
             err = (g.double() - p_ref.grad).abs().max() / (p_ref.grad.abs().max() + 1e-12)
             assert float(err) < 5e-3, (name, pn, float(err))        # TF32 products: 2^-11 per operand
+
+
+@pytest.mark.parametrize("M", [4, 100, 4096, 24576 + 37])
+def test_fused_mlp_tail_forward_matches_layer_by_layer(M):
+    """go1_mlp_tail_forward (layers behind the first one in ONE tcgen05 launch, activations kept on the SM) against the
+    layer-by-layer tcgen05 path and an fp64 torch evaluation of the same modules: all three MLPs, every saved activation."""
+    from go1_gym_learn.ppo_cse import ActorCritic
+    from go1_gym_learn.ppo_cse.actor_critic import AC_Args
+    AC_Args.gemm_impl = 1
+    torch.manual_seed(11)
+    NOBS, NH, NP, NA = 70, 2100, 2, 12
+    ac = ActorCritic(NOBS, NP, NH, NA).to("cuda:0")
+    ac.flatten()
+    with torch.no_grad():
+        for p in ac.parameters():
+            p.mul_(1.7)          # push some pre-activations well away from zero: both ELU branches in play
+    h = torch.randn(M, NH, device="cuda") * 0.5
+    priv = torch.randn(M, NP, device="cuda")
+    res = {}
+    for fuse in (False, True):
+        ac.fuse_tail = fuse
+        ac.forward_all(h, priv, tag="tailtest%d" % fuse)
+        torch.cuda.synchronize()
+        res[fuse] = [[t.clone() for t in outs] for outs in (ac._a_out, ac._p_out, ac._c_out)]
+    import copy
+    hd = h.double()
+    mods = [copy.deepcopy(m).double() for m in (ac.adaptation_module, ac.actor_body, ac.critic_body)]
+    lat = mods[0](hd)
+    ins = [hd, torch.cat((hd, lat), -1), torch.cat((hd, priv.double()), -1)]
+    for net in range(3):
+        x, ref = ins[net], []
+        for layer in mods[net]:
+            x = layer(x)
+            if isinstance(layer, torch.nn.ELU) or layer is mods[net][-1]:
+                ref.append(x)
+        assert len(ref) == len(res[True][net]) == len(res[False][net])
+        for li, (a, b, r) in enumerate(zip(res[False][net], res[True][net], ref)):
+            scale = float(r.abs().max()) + 1e-6
+            assert torch.isfinite(b).all()
+            assert float((b.double() - r).abs().max()) < 6e-3 * scale, (net, li, "fused vs fp64", float((b.double() - r).abs().max()), scale)
+            assert float((a - b).abs().max()) < 4e-3 * scale, (net, li, "fused vs layered", float((a - b).abs().max()), scale)

@@ -725,6 +725,256 @@ int launch_2cta(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g,
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused MLP tail, forward: the layers behind a first layer of ActorCritic's MLPs (actor_critic.py:38-77) in ONE launch,
+//     y2 = ELU(x W2^T + b2)   [M][N2]        x = the first layer's activated output, K1 wide (a column slice of the fused first-layer product)
+//     y3 = ELU(y2 W3^T + b3)  [M][N3]        (N3 = 0: two-layer tail, the head reads y2)
+//     out = y_last Wh^T + bh  [M][nh]        nh <= 16 (12 action means / 1 value / 2 latents): CUDA cores, from registers
+// One CTA owns a 128-row block.  Product 1 streams x and W2 through a TMA ring into tcgen05 (accumulator in TMEM columns 0..N2);
+// its epilogue writes y2 to global memory (the backward pass needs it) AND, 128B-swizzled, into the (now idle) ring as the K-major A
+// operand of product 2, whose B operand (W3) arrives through a second small ring; accumulator 2 lives in TMEM columns 256..256+N3.
+// The separate launches this replaces ran at 50-120 TFLOP/s (one short tile per CTA, activations re-read from HBM / L2 in between).
+// ---------------------------------------------------------------------------------------------------------------
+struct TailArgs {
+    const float* b2; const float* b3; const float* Wh; const float* bh;
+    float* y2; float* y3; float* out;
+    int ldy2, ldy3, ldwh, ldout, nh, M;
+};
+
+__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
+
+template <int K1, int N2, int N3>
+__global__ void __launch_bounds__(192, 1) mlp_tail_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW2,
+                                                              const __grid_constant__ CUtensorMap mapW3, const TailArgs g, const int tiles) {
+    constexpr int S1 = 3, S2 = (N3 > 0) ? 4 : 1;
+    constexpr int KB1 = K1 / BK, KB2 = N2 / BK;
+    constexpr int STAGE1 = (BM + N2) * BK * 4;
+    constexpr int Y2TILE = KB2 * BM * BK * 4;
+    constexpr int R1 = (N3 > 0 && Y2TILE > S1 * STAGE1) ? Y2TILE : S1 * STAGE1;      // ring 1; later overlaid by the y2 tile
+    constexpr int STAGE2 = (N3 > 0 ? N3 : 8) * BK * 4;
+    constexpr int R2 = (N3 > 0) ? S2 * STAGE2 : 0;
+    constexpr int NL = (N3 > 0) ? N3 : N2;
+    constexpr uint32_t TMEM_COLS = (N3 > 0) ? 512u : (uint32_t)N2;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* r1 = base;
+    uint8_t* r2 = base + R1;
+    float* s_b2 = (float*)(base + R1 + R2);
+    float* s_b3 = s_b2 + N2;
+    float* s_wh = s_b3 + (N3 > 0 ? N3 : 0);          // [16][NL]
+    float* s_bh = s_wh + 16 * NL;
+    uint64_t* full1 = (uint64_t*)(s_bh + 16);
+    uint64_t* empty1 = full1 + S1;
+    uint64_t* full2 = empty1 + S1;
+    uint64_t* empty2 = full2 + S2;
+    uint64_t* acc1_full = empty2 + S2;
+    uint64_t* acc2_full = acc1_full + 1;
+    uint64_t* y2_ready = acc2_full + 1;
+    uint64_t* acc_free = y2_ready + 1;
+    uint64_t* r1_free = acc_free + 1;
+    uint32_t* tmem_slot = (uint32_t*)(r1_free + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW2) : "memory");
+        if (N3 > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW3) : "memory");
+        for (int s = 0; s < S1; s++) { mbar_init(&full1[s], 1); mbar_init(&empty1[s], 1); }
+        for (int s = 0; s < S2; s++) { mbar_init(&full2[s], 1); mbar_init(&empty2[s], 1); }
+        mbar_init(acc1_full, 1); mbar_init(acc2_full, 1); mbar_init(y2_ready, 128); mbar_init(acc_free, 128); mbar_init(r1_free, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // biases and head weights: read by every epilogue thread for every row -> shared memory (zero rows beyond nh)
+    for (int i = threadIdx.x; i < N2; i += blockDim.x) s_b2[i] = g.b2 ? __ldg(g.b2 + i) : 0.f;
+    if (N3 > 0) for (int i = threadIdx.x; i < N3; i += blockDim.x) s_b3[i] = g.b3 ? __ldg(g.b3 + i) : 0.f;
+    for (int i = threadIdx.x; i < 16 * NL; i += blockDim.x) { const int n = i / NL, k = i - n * NL; s_wh[i] = n < g.nh ? __ldg(g.Wh + (size_t)n * g.ldwh + k) : 0.f; }
+    if (threadIdx.x < 16) s_bh[threadIdx.x] = (threadIdx.x < g.nh && g.bh) ? __ldg(g.bh + threadIdx.x) : 0.f;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            int it1 = 0, it2 = 0, tl = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x, tl++) {
+                const int m0 = t * BM;
+                if (N3 > 0 && tl > 0) mbar_wait(r1_free, (tl - 1) & 1);       // product 2 of the previous tile is done with the y2 tile in ring 1
+                for (int i = 0; i < KB1; i++, it1++) {
+                    const int s = it1 % S1, ph = (it1 / S1) & 1;
+                    mbar_wait(&empty1[s], ph ^ 1);
+                    mbar_expect_tx(&full1[s], STAGE1);
+                    tma_load_2d(&mapX, &full1[s], r1 + (size_t)s * STAGE1, i * BK, m0);
+                    tma_load_2d(&mapW2, &full1[s], r1 + (size_t)s * STAGE1 + BM * BK * 4, i * BK, 0);
+                }
+                if (N3 > 0) {
+                    for (int i = 0; i < KB2; i++, it2++) {
+                        const int s = it2 % S2, ph = (it2 / S2) & 1;
+                        mbar_wait(&empty2[s], ph ^ 1);
+                        mbar_expect_tx(&full2[s], STAGE2);
+                        tma_load_2d(&mapW3, &full2[s], r2 + (size_t)s * STAGE2, i * BK, 0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N2 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((N3 > 0 ? N3 : 8) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        int it1 = 0, it2 = 0, tl = 0;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x, tl++) {
+            if (tl > 0) { mbar_wait(acc_free, (tl - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+            for (int i = 0; i < KB1; i++, it1++) {
+                const int s = it1 % S1, ph = (it1 / S1) & 1;
+                mbar_wait(&full1[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint64_t da = make_desc(r1 + (size_t)s * STAGE1), db = make_desc(r1 + (size_t)s * STAGE1 + BM * BK * 4);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; k++) umma_tf32(tmem_base, da + 2 * k, db + 2 * k, idesc1, (i > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&empty1[s]);
+                    if (i == KB1 - 1) umma_commit(acc1_full);
+                }
+                __syncwarp();
+            }
+            if (N3 > 0) {
+                mbar_wait(y2_ready, tl & 1);                                   // the epilogue has laid the y2 tile out in ring 1
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int i = 0; i < KB2; i++, it2++) {
+                    const int s = it2 % S2, ph = (it2 / S2) & 1;
+                    mbar_wait(&full2[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
+                        const uint64_t da = make_desc(r1 + (size_t)i * BM * BK * 4), db = make_desc(r2 + (size_t)s * STAGE2);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; k++) umma_tf32(tmem_base + 256u, da + 2 * k, db + 2 * k, idesc2, (i > 0 || k > 0) ? 1u : 0u);
+                        umma_commit(&empty2[s]);
+                        if (i == KB2 - 1) { umma_commit(acc2_full); umma_commit(r1_free); }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: thread = one row of the block =====
+        const int q = warp & 3, rl = 32 * q + lane;
+        int tl = 0;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x, tl++) {
+            const int row = t * BM + rl;
+            const bool row_ok = row < g.M;
+            float h[16];
+#pragma unroll
+            for (int n = 0; n < 16; n++) h[n] = s_bh[n];
+            mbar_wait(acc1_full, tl & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c = 0; c < N2 / 32; c++) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), r);
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = elu1(__uint_as_float(r[j]) + s_b2[32 * c + j]);
+                if (row_ok) {
+                    float4* dst = reinterpret_cast<float4*>(g.y2 + (size_t)row * g.ldy2 + 32 * c);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                if (N3 > 0) {
+                    // k-block c of product 2's A operand: [128 rows][32 floats], 128-byte rows, 16-byte chunks XOR-swizzled by row % 8
+                    // (the layout TMA writes with CU_TENSOR_MAP_SWIZZLE_128B, which the K-major UMMA descriptor expects)
+                    uint8_t* trow = r1 + (size_t)c * (BM * BK * 4) + (size_t)rl * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        *reinterpret_cast<float4*>(trow + ((j ^ (rl & 7)) << 4)) = row_ok ? make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3])
+                                                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+#pragma unroll
+                    for (int n = 0; n < 16; n++) {
+                        if (n < g.nh) {
+                            const float4* w = reinterpret_cast<const float4*>(s_wh + n * NL + 32 * c);
+                            float a = h[n];
+#pragma unroll
+                            for (int j = 0; j < 8; j++) { const float4 ww = w[j]; a = fmaf(v[4 * j], ww.x, a); a = fmaf(v[4 * j + 1], ww.y, a); a = fmaf(v[4 * j + 2], ww.z, a); a = fmaf(v[4 * j + 3], ww.w, a); }
+                            h[n] = a;
+                        }
+                    }
+                }
+            }
+            if (N3 > 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores above -> visible to the tensor core's async proxy
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(y2_ready);
+                mbar_wait(acc2_full, tl & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                for (int c = 0; c < (N3 > 0 ? N3 : 32) / 32; c++) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + 256u + (uint32_t)(32 * c), r);
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = elu1(__uint_as_float(r[j]) + s_b3[32 * c + j]);
+                    if (row_ok) {
+                        float4* dst = reinterpret_cast<float4*>(g.y3 + (size_t)row * g.ldy3 + 32 * c);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+#pragma unroll
+                    for (int n = 0; n < 16; n++) {
+                        if (n < g.nh) {
+                            const float4* w = reinterpret_cast<const float4*>(s_wh + n * NL + 32 * c);
+                            float a = h[n];
+#pragma unroll
+                            for (int j = 0; j < 8; j++) { const float4 ww = w[j]; a = fmaf(v[4 * j], ww.x, a); a = fmaf(v[4 * j + 1], ww.y, a); a = fmaf(v[4 * j + 2], ww.z, a); a = fmaf(v[4 * j + 3], ww.w, a); }
+                            h[n] = a;
+                        }
+                    }
+                }
+            }
+            if (row_ok) {
+#pragma unroll
+                for (int n = 0; n < 16; n++) if (n < g.nh) g.out[(size_t)row * g.ldout + n] = h[n];
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(acc_free);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+template <int K1, int N2, int N3>
+int launch_tail(const CUtensorMap& mx, const CUtensorMap& mw2, const CUtensorMap& mw3, const TailArgs& g, cudaStream_t st) {
+    constexpr int S1 = 3, S2 = (N3 > 0) ? 4 : 1;
+    constexpr int STAGE1 = (BM + N2) * BK * 4, Y2TILE = (N2 / BK) * BM * BK * 4;
+    constexpr int R1 = (N3 > 0 && Y2TILE > S1 * STAGE1) ? Y2TILE : S1 * STAGE1;
+    constexpr int R2 = (N3 > 0) ? S2 * N3 * BK * 4 : 0;
+    constexpr int NL = (N3 > 0) ? N3 : N2;
+    const size_t smem = (size_t)R1 + R2 + (size_t)(N2 + N3 + 16 * NL + 16) * 4 + (2 * S1 + 2 * S2 + 5) * 8 + 16 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_tail_fwd_kernel<K1, N2, N3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return go1_set_error(cudaGetErrorString(e));
+        configured = true;
+    }
+    const int tiles = (g.M + BM - 1) / BM;
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    const int per_sm = (smem > 113 * 1024) ? 1 : 2;
+    const int grid = tiles < per_sm * sms ? tiles : per_sm * sms;
+    mlp_tail_fwd_kernel<K1, N2, N3><<<grid, 192, smem, st>>>(mx, mw2, mw3, g, tiles);
+    go1_count_launch(1);
+    return 0;
+}
+
 }  // namespace
 
 static int g_tf32_persistent = 1, g_tf32_wide = 1;   // wide = 128 x 256 tiles where the heuristic in go1_gemm_tf32 says they pay
@@ -757,7 +1007,7 @@ extern "C" int go1_gemm_timing(int on, double* total_ms, double* total_flop, lon
         if (csv && i / 2 < g_time_recs.size()) {
             const TimeRec& r = g_time_recs[i / 2];
             fprintf(csv, "%d,%d,%d,%d,%d,%d,%d,%d,%s,%d,%.2f\n", r.M, r.N, r.K, r.amn, r.bmn, r.act, r.nex, r.splits,
-                    r.kern == 2 ? "2cta" : (r.kern == 256 ? "p256" : (r.kern == 128 ? "p128" : (r.kern == 64 ? "p64" : "p32"))), r.colsum, 1e3 * t);
+                    r.kern >= 1000 ? (r.kern == 1003 ? "tail3" : "tail2") : r.kern == 2 ? "2cta" : (r.kern == 256 ? "p256" : (r.kern == 128 ? "p128" : (r.kern == 64 ? "p64" : "p32"))), r.colsum, 1e3 * t);
         }
     }
     if (csv) fclose(csv);
@@ -854,6 +1104,41 @@ extern "C" int go1_transpose(const float* src, int lds, float* dst, int ldd, int
     dim3 grid((cols + 31) / 32, (rows + 31) / 32);
     transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, rows, cols);
     go1_count_launch(1);
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return go1_set_error(cudaGetErrorString(ce));
+    return 0;
+}
+
+
+// ---- fused MLP tail (forward), see mlp_tail_fwd_kernel
+extern "C" int go1_mlp_tail_forward(const float* x, int ldx, int M, int K1, const float* W2, const float* b2, int N2, float* y2, int ldy2,
+                                    const float* W3, const float* b3, int N3, float* y3, int ldy3, const float* Wh, const float* bh, int nh,
+                                    float* out, int ldout, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!x || !W2 || !y2 || !Wh || !out || M <= 0 || nh < 1 || nh > 16 || ldout < nh) return go1_set_error("go1_mlp_tail_forward: bad arguments");
+    if (N3 > 0 && (!W3 || !y3)) return go1_set_error("go1_mlp_tail_forward: the three-layer tail needs W3 / y3");
+    const bool shape_a = (K1 == 512 && N2 == 256 && N3 == 128), shape_b = (K1 == 256 && N2 == 128 && N3 == 0);
+    if (!shape_a && !shape_b) return go1_set_error("go1_mlp_tail_forward: supported tails are 512-256-128-head and 256-128-head");
+    if ((ldx & 3) || (ldy2 & 3) || (N3 > 0 && (ldy3 & 3)) || ((((uintptr_t)x | (uintptr_t)W2 | (uintptr_t)y2 | (uintptr_t)(N3 > 0 ? (const void*)W3 : (const void*)W2) |
+                                                                 (uintptr_t)(N3 > 0 ? (const void*)y3 : (const void*)y2)) & 15) != 0))
+        return go1_set_error("go1_mlp_tail_forward: operands must be 16-byte aligned with row strides that are multiples of 4 floats");
+    CUtensorMap mx, mw2, mw3;
+    if (int e = make_map(&mx, x, M, K1, ldx, BM)) return e;
+    if (int e = make_map(&mw2, W2, N2, K1, K1, N2)) return e;
+    if (N3 > 0) { if (int e = make_map(&mw3, W3, N3, N2, N2, N3)) return e; } else mw3 = mw2;
+    TailArgs g;
+    g.b2 = b2; g.b3 = b3; g.Wh = Wh; g.bh = bh; g.y2 = y2; g.y3 = y3; g.out = out;
+    g.ldy2 = ldy2; g.ldy3 = ldy3; g.ldwh = (N3 > 0 ? N3 : N2); g.ldout = ldout; g.nh = nh; g.M = M;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    const bool timed = g_time_on && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone;
+    if (timed) {
+        cudaEventRecord(timing_event(), st);
+        g_time_flop += 2.0 * (double)M * ((double)K1 * N2 + (double)N2 * N3 + (double)(N3 > 0 ? N3 : N2) * nh);
+        g_time_recs.push_back({M, N2, K1, 0, 0, 1, 0, 1, shape_a ? 1003 : 1002, 0});
+    }
+    int e = shape_a ? launch_tail<512, 256, 128>(mx, mw2, mw3, g, st) : launch_tail<256, 128, 0>(mx, mw2, mw3, g, st);
+    if (e) return e;
+    if (timed) cudaEventRecord(timing_event(), st);
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return go1_set_error(cudaGetErrorString(ce));
     return 0;

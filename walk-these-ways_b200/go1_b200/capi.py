@@ -156,6 +156,7 @@ def lib():
         "go1_gemm": ([ip, ip, ip, ip, ip, vp, ip, vp, ip, vp, ip, vp, ip, ip, ip, vp], ip),
         "go1_gemm_ex": ([ip, ip, ip, ip, ip, vp, ip, vp, ip, vp, ip, C.POINTER(Go1GemmEpilogue), ip, vp], ip),
         "go1_gemm_tf32_set_persistent": ([ip], None),
+        "go1_mlp_tail_forward": ([vp, ip, ip, ip, vp, vp, ip, vp, ip, vp, vp, ip, vp, ip, vp, vp, ip, vp, ip, vp], ip),
         "go1_gemm_tf32_set_wide": ([ip], None),
         "go1_transpose": ([vp, ip, vp, ip, ip, ip, vp], ip),
         "go1_elu_backward": ([vp, ip, vp, ip, vp, ip, ip, ip, vp], ip),

@@ -131,6 +131,8 @@ class _Net:
                 outs.append(first_out)
                 inp, ld_in = first_out, first_out.stride(0)
                 continue
+            if li == 1 and impl == 1 and self._tail_ok(inp, ld_in, M):
+                return outs + self._forward_tail(inp, ld_in, M, tag)
             y = self._buf((tag, li), M, o)
             W = self.flat[wo:wo + o * i]
             b = self.flat[bo:bo + o]
@@ -152,6 +154,41 @@ class _Net:
             outs.append(y)
             inp, ld_in = y, y.stride(0)
         return outs
+
+    _TAILS = {(512, 256, 128): 3, (256, 128): 2}       # hidden widths behind the first layer that go1_mlp_tail_forward fuses
+
+    def _tail_ok(self, x1, ldx1, M):
+        """The layers behind the first one form a tail the fused kernel supports (and its TMA operands are aligned)."""
+        if not self.owner.fuse_tail:
+            return False
+        widths = tuple(sp[2] for sp in self.specs[:-1])
+        if self._TAILS.get(widths) != len(self.specs) - 1 or self.specs[-1][2] > 16:
+            return False
+        ok = self._tma_ok(x1, ldx1)
+        for wo, bo, o, i in self.specs[1:-1]:
+            ok = ok and ((self.flat.data_ptr() + 4 * wo) & 15) == 0 and i % 4 == 0
+        return ok
+
+    def _forward_tail(self, x1, ldx1, M, tag):
+        """Layers 1.. (and the head) in ONE launch; returns their outputs in layer order."""
+        L = capi.lib()
+        sp = self.specs
+        flat = self.flat
+        ptr = lambda off: flat.data_ptr() + 4 * off
+        (w2, b2, n2, k1) = sp[1]
+        y2 = self._buf((tag, 1), M, n2)
+        if len(sp) == 4:
+            (w3, b3, n3, _), (wh, bh, nh, _) = sp[2], sp[3]
+            y3 = self._buf((tag, 2), M, n3)
+            out = self._buf((tag, 3), M, nh)
+            capi.check(L.go1_mlp_tail_forward(capi.ptr(x1), ldx1, M, k1, ptr(w2), ptr(b2), n2, capi.ptr(y2), y2.stride(0), ptr(w3), ptr(b3), n3, capi.ptr(y3),
+                                              y3.stride(0), ptr(wh), ptr(bh), nh, capi.ptr(out), out.stride(0), capi.stream_ptr()), "go1_mlp_tail_forward")
+            return [y2, y3, out]
+        (wh, bh, nh, _) = sp[2]
+        out = self._buf((tag, 2), M, nh)
+        capi.check(L.go1_mlp_tail_forward(capi.ptr(x1), ldx1, M, k1, ptr(w2), ptr(b2), n2, capi.ptr(y2), y2.stride(0), None, None, 0, None, 0,
+                                          ptr(wh), ptr(bh), nh, capi.ptr(out), out.stride(0), capi.stream_ptr()), "go1_mlp_tail_forward")
+        return [y2, out]
 
     def backward(self, x, ldx, K0, extra, outs, dout, M, impl, accumulate, want_dextra=False, tag="a", dz1_out=None):
         """dout: gradient w.r.t. the network output [M][out] (the last layer has no activation).  Writes weight/bias grads
@@ -254,6 +291,7 @@ class ActorCritic(nn.Module):
         self.fuse_bias_grad = os.environ.get("GO1_FUSE_BIAS_GRAD", "1") != "0"     # bias gradients reduced in the dgrad GEMM epilogues
         self.update_streams = os.environ.get("GO1_UPDATE_STREAMS", "1") != "0"     # critic chain on a second stream during the update (measured -1.3 ms / iteration)
         self._side = None
+        self.fuse_tail = os.environ.get("GO1_FUSE_TAIL", "1") != "0"     # layers behind a first layer in one tcgen05 launch (go1_mlp_tail_forward)
         self.grads_prezeroed = False  # PPO.update zeroes the flat gradient buffer once per optimizer step (one fill instead of one per layer)
 
     # ------------------------------------------------------------------ flat storage
