@@ -34,8 +34,12 @@ if [[ $WHAT == *gemmcsv* ]]; then
   GO1_GEMM_TIMING_CSV=$O/${TAG}_gemm_launches.csv timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_gemmcsv.json 2>&1
   GO1_TEST_GROUPED=1 timeout 300 python -m pytest tests/test_curriculum_gpu.py -q -k grouped 2>&1 | tail -5 > $O/${TAG}_grouped_test.txt
 fi
+if [[ $WHAT == *tailbench* ]]; then
+  timeout 200 python walk-these-ways_b200/tools/tail_bench.py > $O/${TAG}_tail_bench.txt 2>&1
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:mlp_tail -s 4 -c 2 -f -o $O/${TAG}_tail python walk-these-ways_b200/tools/tail_bench.py > $O/${TAG}_ncu_tail.log 2>&1
+fi
 if [[ $WHAT == *onetest* ]]; then
-  timeout 600 python -m pytest tests/test_ppo_gpu.py -q -x -k "${ONETEST:-fused}" 2>&1 | tail -40 > $O/${TAG}_onetest.txt
+  timeout ${ONETEST_TIMEOUT:-200} python -m pytest tests/test_ppo_gpu.py -q -x -k "${ONETEST:-fused}" 2>&1 | tail -40 > $O/${TAG}_onetest.txt
 fi
 if [[ $WHAT == *blocks* ]]; then
   GO1_SWEEP_BLOCKS=32,64,128 GO1_SWEEP_ENVS=4096,16384 timeout 300 python walk-these-ways_b200/tools/sim_sweep.py > $O/${TAG}_sim_blocks.txt 2>&1
