@@ -350,6 +350,9 @@ int go1_mlp_extra_forward(float* y, int ldy, const float* extra, int ldex, const
  *   g_w_extra[j][t] (+)= sum_m dz[m][j] extra[m][t];   dextra[m][t] = sum_j dz[m][j] w_extra[j][t] (if dextra != NULL). */
 int go1_mlp_extra_backward(const float* dz, int lddz, const float* extra, int ldex, const float* w_extra, int ldw, float* g_w_extra, int ldgw,
                            float* dextra, int ldde, int M, int o, int E, int accumulate, void* stream);
+/* Forward of a narrow (o <= 16) output layer, the 12 / 2 / 1-wide heads of ActorCritic (actor_critic.py:52,64,76):
+ *   out[m][t] = b[t] + sum_k x[m][k] W[t][k]   (W row-major [o][K], K % 4 == 0, x rows 16-byte aligned; b may be NULL). */
+int go1_skinny_forward(const float* x, int ldx, const float* W, int ldw, const float* b, float* out, int ldo, int M, int o, int K, void* stream);
 /* dgrad through a narrow (o <= 16) output layer, with the previous layer's ELU' fused (y_prev may be NULL):
  *   dprev[m][c] = (sum_t dz[m][t] W[t][c]) * ELU'(y_prev[m][c]),  W row-major [o][n]. */
 int go1_skinny_dgrad(const float* dz, int lddz, const float* W, int ldw, const float* y_prev, int ldy, float* dprev, int lddp,

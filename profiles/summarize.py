@@ -51,8 +51,54 @@ def kernel(src, dst):
             f.write("\n")
 
 
+def traffic(dst, pairs):
+    """profiles/ncu_traffic.json: for each (kernel-name substring, .ncu-rep) pair the DRAM bytes per launch (mean over the captured
+    launches of that kernel) that bench.py reports as roofline.traffic, plus pipe utilisation figures of the same launches."""
+    import json
+    out = {}
+    try:
+        out = json.load(open(dst))
+    except Exception:
+        pass
+    for key, src in pairs:
+        raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        hdr, units = rows[0], rows[1]
+        idx = {h: i for i, h in enumerate(hdr)}
+        sel = [r for r in rows[2:] if key in r[idx["Kernel Name"]]]
+        if not sel:
+            continue
+
+        def col(name, scale_units=True):
+            vals = []
+            for r in sel:
+                v = float(r[idx[name]].replace(",", "") or 0)
+                u = units[idx[name]]
+                if scale_units:
+                    v *= {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
+                vals.append(v)
+            return vals
+        rd, wr = col("dram__bytes_read.sum"), col("dram__bytes_write.sum")
+        dur = col("gpu__time_duration.sum", False)
+        e = {"dram_bytes_per_launch": (sum(rd) + sum(wr)) / len(sel), "launches_captured": len(sel), "source": src.split("/")[-1],
+             "mean_duration_" + units[idx["gpu__time_duration.sum"]]: sum(dur) / len(dur)}
+        for name, short in (("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "fma_pipe_pct"),
+                            ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe_pct"),
+                            ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
+                            ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct")):
+            if name in idx:
+                v = col(name, False)
+                w = [a * b for a, b in zip(v, dur)]
+                e[short] = sum(w) / sum(dur)          # duration-weighted
+        out[key] = e
+    with open(dst, "w") as f:
+        json.dump(out, f, indent=1)
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "launches":
+    if sys.argv[1] == "traffic":         # traffic profiles/ncu_traffic.json key=file.ncu-rep ...
+        traffic(sys.argv[2], [a.split("=", 1) for a in sys.argv[3:]])
+    elif sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else sys.argv[2])
     else:
         kernel(sys.argv[2], sys.argv[3])

@@ -212,6 +212,58 @@ def test_gemm_tcgen05_tf32(M, N, K):
     assert ((C2.double() - want).abs() <= bound + 1e-5).all()
 
 
+# Staged epilogue of the BN <= 128 kernels: 32 x 32 output blocks leave through shared memory + one TMA store per warp, the ELU' operand
+# arrives through TMA loads (taken when C / dact_y are 16-byte aligned with row strides that are multiples of 4 floats, no accumulate, no split-K).
+# Ragged M and N exercise the TMA clipping; the guard columns behind N and guard rows behind M must stay untouched.
+@pytest.mark.parametrize("tb", [1, 0])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (24576, 512, 256), (24576, 256, 128), (1000, 200, 96), (4096 + 37, 128, 256), (300, 72, 40), (5000, 48, 512),
+                                   (24576, 128, 12)])
+def test_gemm_tcgen05_staged_epilogue(M, N, K, tb):
+    import ctypes as C
+    from go1_b200 import capi
+    torch.manual_seed(M + 3 * N + 5 * K + tb)
+    pad4 = lambda n: (n + 3) // 4 * 4
+    A = torch.randn(M, pad4(K), device="cuda")[:, :K]
+    if tb:
+        Bs = torch.randn(N, pad4(K), device="cuda"); B = Bs[:, :K]
+    else:
+        Bs = torch.randn(K, pad4(N), device="cuda"); B = Bs[:, :N].t()
+    ldc = pad4(N) + 8
+    ref = A.double() @ B.double().t()
+    bound = (A.abs().double() @ B.abs().double().t()) * 2.0 ** -9 + 1e-6
+    bias = torch.randn(N, device="cuda")
+    L = capi.lib()
+
+    def call(ep, Cbuf):
+        capi.check(L.go1_gemm_ex(0, tb, M, N, K, capi.ptr(A), A.stride(0), capi.ptr(Bs), Bs.stride(0), capi.ptr(Cbuf), ldc, C.byref(ep), 1, capi.stream_ptr()), "gemm_ex")
+        torch.cuda.synchronize()
+
+    # forward flavour: bias + ELU
+    Cb = torch.full((M + 3, ldc), 3.0, device="cuda")
+    ep = capi.Go1GemmEpilogue(); ep.bias = bias.data_ptr(); ep.act = 1
+    call(ep, Cb)
+    want = torch.nn.functional.elu(ref + bias.double())
+    assert ((Cb[:M, :N].double() - want).abs() <= bound + 1e-5).all()
+    assert (Cb[:M, N:] == 3.0).all() and (Cb[M:] == 3.0).all()
+    # dgrad flavour: ELU' operand (row stride a multiple of 4 floats) + column sums
+    y = torch.randn(M, pad4(N) + 4, device="cuda")
+    cs = torch.zeros(N, device="cuda")
+    Cb2 = torch.full((M + 3, ldc), 3.0, device="cuda")
+    ep2 = capi.Go1GemmEpilogue(); ep2.act = 2; ep2.dact_y, ep2.ld_dact_y = y.data_ptr(), y.stride(0); ep2.colsum = cs.data_ptr()
+    call(ep2, Cb2)
+    fac = torch.where(y[:, :N] > 0, torch.ones_like(y[:, :N]), y[:, :N] + 1).double()
+    want2 = ref * fac
+    assert ((Cb2[:M, :N].double() - want2).abs() <= bound * fac.abs() + 1e-5).all()
+    assert (Cb2[:M, N:] == 3.0).all() and (Cb2[M:] == 3.0).all()
+    cs_ref = Cb2[:M, :N].double().sum(0)
+    assert float((cs.double() - cs_ref).abs().max()) <= 1e-4 * float(Cb2[:M, :N].abs().double().sum(0).max()) + 1e-5
+    # repeated launches reuse the staging buffers and barriers: same answer
+    Cb3 = torch.full((M + 3, ldc), 3.0, device="cuda")
+    ep2.colsum = None
+    call(ep2, Cb3)
+    assert torch.equal(Cb3[:M, :N], Cb2[:M, :N])
+
+
 # MN-major operands (dgrad: B = W as [K][N]; wgrad: A = dz as [K][M], B = activations as [K][N]) read straight from HBM
 @pytest.mark.parametrize("ta,tb", [(0, 0), (1, 0), (1, 1)])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 32, 64), (300, 200, 72), (24576, 128, 12), (12, 128, 24576), (1280, 2100, 4096),
@@ -261,6 +313,21 @@ def test_gemm_tcgen05_rejects_unsupported_layouts():
 # ----------------------------------------------------------------------------------------------------------------
 # pieces of the fused first-layer forward and of the narrow-head backward
 # ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,o,K", [(4, 12, 128), (4096, 1, 128), (24576 + 5, 2, 128), (1000, 16, 256)])
+def test_skinny_forward_matches_fp64(M, o, K):
+    """go1_skinny_forward (the 12 / 2 / 1-wide heads) against an fp64 matmul; x with a padded row stride, guard column in the output."""
+    from go1_b200 import capi
+    torch.manual_seed(M + o + K)
+    xs = torch.randn(M, K + 8, device="cuda"); x = xs[:, :K]
+    W = torch.randn(o, K, device="cuda"); b = torch.randn(o, device="cuda")
+    out = torch.full((M, o + 1), 7.0, device="cuda")
+    capi.check(capi.lib().go1_skinny_forward(capi.ptr(xs), xs.stride(0), capi.ptr(W), K, capi.ptr(b), capi.ptr(out), o + 1, M, o, K, capi.stream_ptr()), "skinny_forward")
+    torch.cuda.synchronize()
+    ref = x.double() @ W.double().t() + b.double()
+    assert float((out[:, :o].double() - ref).abs().max()) < 1e-4
+    assert (out[:, o] == 7.0).all()
+
+
 @pytest.mark.parametrize("M,o,K", [(24576, 1, 128), (24576, 2, 128), (4097, 12, 128), (300, 16, 257)])
 def test_skinny_wgrad_matches_fp64(M, o, K):
     from go1_b200 import capi

@@ -20,6 +20,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <mutex>
+#include <unordered_map>
 #include <stdlib.h>
 #include "../../include/go1_b200.h"
 
@@ -103,6 +104,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ELU(v) = v > 0 ? v : expm1(v), branch-free: a degree-7 Taylor polynomial on (-0.35, 0] (truncation error < 2e-8 relative) and
+// ex2.approx(v log2 e) - 1 below it (absolute error ~1e-7 on a value >= 0.29); 13 instructions instead of expm1f's ~28 plus a
+// divergent branch.  The result feeds a TF32 product (relative operand rounding 5e-4) and ELU' = y + 1 in the backward pass.
+__device__ __forceinline__ float elu_fast(float v) {
+    float p = fmaf(v, 1.f / 5040.f, 1.f / 720.f);
+    p = fmaf(p, v, 1.f / 120.f); p = fmaf(p, v, 1.f / 24.f); p = fmaf(p, v, 1.f / 6.f); p = fmaf(p, v, 0.5f);
+    p = fmaf(p * v, v, v);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 1.4426950408889634f));
+    const float n = v > -0.35f ? p : e - 1.0f;
+    return v > 0.f ? v : n;
+}
+
 struct GemmArgs {
     float* C; const float* bias;
     int M, N, K, ldc, act, accumulate, kb_per_split;
@@ -113,12 +127,28 @@ struct GemmArgs {
     float* colsum;           // optional [N]: += column sums of the values written (bias gradient fused into the dgrad epilogue)
     const float* bx; const float* bwx; float* gwx; float* dx;     // fused trailing-input backward (see Go1GemmEpilogue)
     int ldbx, ldbwx, ldgwx, lddx, nbx;
+    int tma_store, tma_aux;  // staged epilogue (persistent kernel, STAGED): C blocks leave / ELU' operand blocks arrive through shared memory by TMA
 };
+
+// Per-warp shared-memory staging of the staged epilogue.  A row-per-lane float4 store touches 32 different 128-byte lines per
+// instruction (8 x the LSU wavefronts of a coalesced store); measured, that -- not the tensor core -- bounded every short-K product
+// (dgrad 24576 x 512 x 256: 37 us with nothing fused, 56 us with the ELU' operand, against 19 us of HBM time).  Staged: the warp's
+// 32 x 32 block is written to shared memory (128B-swizzled: conflict-free 16-byte accesses) and ONE thread hands it to the TMA unit.
+struct EpiStage {
+    uint8_t* out;            // 4 KB, 1024-byte aligned, or nullptr: direct global stores
+    const CUtensorMap* mapC;
+    const uint8_t* aux;      // 4 KB block of the ELU' operand, fetched by TMA and already waited for, or nullptr
+};
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
 
 // Epilogue of one 32-column chunk held in registers (thread = output row, r[j] = column col0 + j).  Called by all 32 lanes
 // of an epilogue warp (the per-column operands -- bias, extra-input weights -- are loaded once per lane and broadcast
 // with shuffles instead of 32 x per-thread global loads, which made the rank-2 term the slowest part of the kernel).
-__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, uint32_t (&r)[32], const int row, const int col0, const bool split, const int lane) {
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, uint32_t (&r)[32], const int row, const int col0, const bool split, const int lane,
+                                               const float4 (&ypre)[8], const bool have_pre, const EpiStage& es) {
     if (col0 >= g.N) return;                                    // warp-uniform
     const int ncols = min(32, g.N - col0);
     const bool row_ok = row < g.M;
@@ -182,10 +212,25 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, uint32_t (&r)[
     if (g.act == 1) {
         const int nlead = g.lead <= 0 ? 32 : max(0, min(32, g.lead - col0));      // leading columns of this chunk that get the ELU
 #pragma unroll
-        for (int j = 0; j < 32; j++) if (j < nlead) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
+        for (int j = 0; j < 32; j++) if (j < nlead) v[j] = elu_fast(v[j]);
     } else if (g.act == 2) {   // multiply by ELU'(z) from the saved activation y: 1 if y > 0 else y + 1
         const float* arow = g.aux + (size_t)row * g.ldaux + col0;
-        if (ncols == 32 && (g.ldaux & 3) == 0 && ((((uintptr_t)g.aux) & 15) == 0) && ((col0 & 3) == 0)) {
+        if (es.aux) {          // the operand block sits in shared memory (TMA, 128B swizzle: 16-byte chunk j of row l at (j ^ (l & 7)))
+            const uint8_t* srow = es.aux + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float4 y = *reinterpret_cast<const float4*>(srow + ((j ^ (lane & 7)) << 4));
+                v[4 * j] *= (y.x > 0.f ? 1.0f : y.x + 1.0f); v[4 * j + 1] *= (y.y > 0.f ? 1.0f : y.y + 1.0f);
+                v[4 * j + 2] *= (y.z > 0.f ? 1.0f : y.z + 1.0f); v[4 * j + 3] *= (y.w > 0.f ? 1.0f : y.w + 1.0f);
+            }
+        } else if (have_pre) { // the operand was fetched before the accumulator was ready (epilogue_prefetch)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float4 y = ypre[j];
+                v[4 * j] *= (y.x > 0.f ? 1.0f : y.x + 1.0f); v[4 * j + 1] *= (y.y > 0.f ? 1.0f : y.y + 1.0f);
+                v[4 * j + 2] *= (y.z > 0.f ? 1.0f : y.z + 1.0f); v[4 * j + 3] *= (y.w > 0.f ? 1.0f : y.w + 1.0f);
+            }
+        } else if (ncols == 32 && (g.ldaux & 3) == 0 && ((((uintptr_t)g.aux) & 15) == 0) && ((col0 & 3) == 0)) {
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const float4 y = __ldg(reinterpret_cast<const float4*>(arow) + j);
@@ -243,6 +288,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, uint32_t (&r)[
                 }
             }
         }
+    }
+    if (es.out) {           // warp-uniform: all 32 lanes stage their row (rows / columns beyond M / N are clipped by the TMA store)
+        uint8_t* srow = es.out + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            *reinterpret_cast<float4*>(srow + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the TMA (async proxy) read
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_2d(es.mapC, es.out, col0, row);                    // lane 0's row is the block's first row
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        return;
     }
     if (!row_ok) return;
     if (vec) {
@@ -334,7 +392,9 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_kernel(const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 32; j++) r[j] = 0u;
             }
-            epilogue_chunk(g, r, row, n0 + 32 * c, split, lane);
+            const float4 nopre[8] = {};
+            const EpiStage nostage = {nullptr, nullptr, nullptr};
+            epilogue_chunk(g, r, row, n0 + 32 * c, split, lane, nopre, false, nostage);
         }
     }
     // ===== teardown =====
@@ -346,24 +406,56 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_kernel(const __grid_constant
 }
 
 
+// ELU' operand of one 32-column chunk (act == 2), fetched into registers BEFORE the wait on the accumulator so that the HBM / L2
+// latency of these row-per-lane loads overlaps the main loop of the tile.  Warp-uniform result; rows beyond M read row 0 (ignored).
+__device__ __forceinline__ bool epilogue_prefetch(const GemmArgs& g, const int row, const int col0, const bool split, float4 (&ypre)[8]) {
+    if (g.act != 2 || split || col0 + 32 > g.N || (g.ldaux & 3) != 0 || ((((uintptr_t)g.aux) & 15) != 0) || (col0 & 3) != 0) return false;
+    const float4* arow = reinterpret_cast<const float4*>(g.aux + (size_t)(row < g.M ? row : 0) * g.ldaux + col0);
+#pragma unroll
+    for (int j = 0; j < 8; j++) ypre[j] = __ldg(arow + j);
+    return true;
+}
+
+// One accumulator tile (128 lanes x BN columns at tmem_d) drained by the epilogue warps: NEPI = 4 G warps, warp = (TMEM lane quarter
+// q = warp id % 4, column group grp): group grp takes the 32-column chunks grp, grp + G, ...  With G = 4 sixteen warps work on a tile:
+// the epilogue (activation, column sums, row-per-lane global traffic) is latency bound per warp, so its throughput scales with warps.
+template <int BN, int G>
+__device__ __forceinline__ void epilogue_tile(const GemmArgs& g, const uint32_t tmem_d, const int q, const int grp, const int row, const int n0,
+                                              const bool split, const int lane, const float4 (&ypre)[8], const bool have_pre) {
+#pragma unroll 1
+    for (int c = grp; c < BN / 32; c += G) {
+        uint32_t r[32];
+        tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), r);
+        const EpiStage nostage = {nullptr, nullptr, nullptr};
+        epilogue_chunk(g, r, row, n0 + 32 * c, split, lane, ypre, have_pre && c == grp, nostage);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Persistent variant: grid = min(#tiles, 2 x #SMs); every CTA walks tiles t = blockIdx.x + i * gridDim.x (n fastest, so the
 // CTAs of one wave share A tiles through L2).  The accumulator is double-buffered in TMEM (2 x BN columns): while the
 // epilogue warps drain tile i from buffer i&1, the MMA warp already accumulates tile i+1 into the other buffer, and the
 // per-CTA set-up (TMEM allocation, barrier init, tensormap prefetch) is paid once instead of once per tile.
 // ---------------------------------------------------------------------------------------------------------------
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1) gemm_tf32_persistent(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmArgs g,
-                                                                const int tiles_m, const int tiles_n, const int total_tiles) {
+template <int BN, int G, bool STAGED>
+__global__ void __launch_bounds__(64 + 128 * G, 1) gemm_tf32_persistent(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                                                                        const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapY, const GemmArgs g,
+                                                                        const int tiles_m, const int tiles_n, const int total_tiles, const int stages) {
+    constexpr int NEPI = 4 * G;                  // epilogue warps
+    constexpr int STAGE_BYTES = (BM + BN) * BK * 4;
+    constexpr int MAX_STAGES = 8;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [ring: stages x (A | B)][out staging NEPI x 4 KB][ELU' operand staging NEPI x 4 KB][barriers]   (staging only if STAGED)
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    float* sA = (float*)base;
-    float* sB = (float*)(base + (size_t)STAGES * BM * BK * 4);
-    uint64_t* full = (uint64_t*)(base + (size_t)STAGES * (BM + BN) * BK * 4);
-    uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;        // [2]
+    uint8_t* ring = base;
+    uint8_t* stage_out = base + (size_t)stages * STAGE_BYTES;
+    uint8_t* stage_aux = stage_out + (STAGED ? NEPI * 4096 : 0);
+    uint64_t* full = (uint64_t*)(stage_aux + ((STAGED && g.tma_aux) ? NEPI * 4096 : 0));
+    uint64_t* empty = full + MAX_STAGES;
+    uint64_t* tmem_full = empty + MAX_STAGES;    // [2]
     uint64_t* tmem_empty = tmem_full + 2;        // [2]
-    uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+    uint64_t* aux_bar = tmem_empty + 2;          // [NEPI]
+    uint32_t* tmem_slot = (uint32_t*)(aux_bar + NEPI);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb_total = (g.K + BK - 1) / BK;
@@ -371,8 +463,11 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_persistent(const __grid_cons
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+        if (STAGED && g.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapC) : "memory");
+        if (STAGED && g.tma_aux) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapY) : "memory");
+        for (int s = 0; s < stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128 * G); }
+        for (int w = 0; w < NEPI; w++) mbar_init(&aux_bar[w], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -393,15 +488,14 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_persistent(const __grid_cons
 
     if (warp == 0) {
         if (elect_one()) {
-            int it = 0;      // global k-block counter of this CTA: stage = it % STAGES, phase = (it / STAGES) & 1
+            int s = 0, ph = 0;      // ring position of this CTA's k-block stream
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 int m0, n0, kb0, nkb; tile_coords(t, m0, n0, kb0, nkb);
-                for (int i = 0; i < nkb; i++, it++) {
-                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                for (int i = 0; i < nkb; i++) {
                     mbar_wait(&empty[s], ph ^ 1);
-                    mbar_expect_tx(&full[s], (BM + BN) * BK * 4);
-                    float* a = sA + (size_t)s * BM * BK;
-                    float* b = sB + (size_t)s * BN * BK;
+                    mbar_expect_tx(&full[s], STAGE_BYTES);
+                    float* a = (float*)(ring + (size_t)s * STAGE_BYTES);
+                    float* b = a + BM * BK;
                     if (g.amn) {
 #pragma unroll
                         for (int x = 0; x < BM / 32; x++) tma_load_2d(&mapA, &full[s], a + x * 32 * BK, m0 + 32 * x, (kb0 + i) * BK);
@@ -410,6 +504,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_persistent(const __grid_cons
 #pragma unroll
                         for (int x = 0; x < BN / 32; x++) tma_load_2d(&mapB, &full[s], b + x * 32 * BK, n0 + 32 * x, (kb0 + i) * BK);
                     } else tma_load_2d(&mapB, &full[s], b, (kb0 + i) * BK, n0);
+                    if (++s == stages) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -418,56 +513,94 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_persistent(const __grid_cons
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.amn ? 1 : 0) << 15) | ((uint32_t)(g.bmn ? 1 : 0) << 16) |
                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
         const uint32_t ka = g.amn ? (1024 >> 4) : 2, kb = g.bmn ? (1024 >> 4) : 2;     // per-instruction K advance of the descriptors
-        int it = 0, j = 0;
+        int s = 0, ph = 0, j = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, j++) {
             int m0, n0, kb0, nkb; tile_coords(t, m0, n0, kb0, nkb);
             const int buf = j & 1;
             mbar_wait(&tmem_empty[buf], ((j >> 1) & 1) ^ 1);          // epilogue has drained this accumulator buffer
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
-            for (int i = 0; i < nkb; i++, it++) {
-                const int s = it % STAGES, ph = (it / STAGES) & 1;
+            for (int i = 0; i < nkb; i++) {
                 mbar_wait(&full[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
-                    const uint64_t da = g.amn ? make_desc_mn(sA + (size_t)s * BM * BK) : make_desc(sA + (size_t)s * BM * BK);
-                    const uint64_t db = g.bmn ? make_desc_mn(sB + (size_t)s * BN * BK) : make_desc(sB + (size_t)s * BN * BK);
+                    const float* a = (const float*)(ring + (size_t)s * STAGE_BYTES);
+                    const float* b = a + BM * BK;
+                    const uint64_t da = g.amn ? make_desc_mn(a) : make_desc(a);
+                    const uint64_t db = g.bmn ? make_desc_mn(b) : make_desc(b);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; k++) umma_tf32(tmem_d, da + ka * k, db + kb * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
                     umma_commit(&empty[s]);
                     if (i == nkb - 1) umma_commit(&tmem_full[buf]);
                 }
                 __syncwarp();
+                if (++s == stages) { s = 0; ph ^= 1; }
             }
         }
     } else {
-        const int q = warp & 3;
+        // ===== epilogue: NEPI warps; warp = (TMEM lane quarter q = warp id % 4, column group grp); group grp takes chunks grp, grp + G, ...
+        const int ew = warp - 2, q = warp & 3, grp = ew >> 2;
         const bool split = g.kb_per_split < num_kb_total;
+        const bool st_out = STAGED && g.tma_store, st_aux = STAGED && g.tma_aux;
+        uint8_t* my_out = stage_out + ew * 4096;
+        uint8_t* my_aux = stage_aux + ew * 4096;
+        uint64_t* my_bar = &aux_bar[ew];
+        EpiStage es;
+        es.out = st_out ? my_out : nullptr; es.mapC = &mapC; es.aux = st_aux ? my_aux : nullptr;
+        // ELU' operand blocks run one chunk ahead of the epilogue: cursor (pt, pc) = the next chunk of this warp whose block has not been requested yet
+        int pt = blockIdx.x, pc = grp - G;
+        auto next_chunk = [&]() -> bool {
+            for (;;) {
+                pc += G;
+                if (pc >= BN / 32) { pt += gridDim.x; pc = grp; }
+                if (pt >= total_tiles) return false;
+                if ((pt % tiles_n) * BN + 32 * pc < g.N) return true;
+            }
+        };
+        auto request_aux = [&]() {
+            if (next_chunk() && lane == 0) {
+                int m0, n0, kb0, nkb; tile_coords(pt, m0, n0, kb0, nkb);
+                mbar_expect_tx(my_bar, 4096);
+                tma_load_2d(&mapY, my_bar, my_aux, n0 + 32 * pc, m0 + 32 * q);
+            }
+        };
+        if (st_aux) request_aux();
+        uint32_t aux_phase = 0;
         int j = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, j++) {
             int m0, n0, kb0, nkb; tile_coords(t, m0, n0, kb0, nkb);
             const int buf = j & 1;
             const int row = m0 + 32 * q + lane;
-            // ELU'(y) operand of this tile (act == 2): one L1 prefetch per 128-byte row chunk, issued while the main loop of the tile is
-            // still running, so that the epilogue's loads below hit the cache instead of stalling on HBM / L2 (no registers held)
-            if (g.act == 2 && !split && row < g.M) {
-#pragma unroll
-                for (int c = 0; c < BN / 32; c++)
-                    if (n0 + 32 * c < g.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(g.aux + (size_t)row * g.ldaux + n0 + 32 * c));
-            }
+            float4 ypre[8];
+            const bool have_pre = !st_aux && (grp < BN / 32) && epilogue_prefetch(g, row, n0 + 32 * grp, split, ypre);
             mbar_wait(&tmem_full[buf], (j >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+            bool released = false;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; c++) {
+            for (int c = grp; c < BN / 32; c += G) {
+                if (n0 + 32 * c >= g.N) break;                           // warp-uniform
                 uint32_t r[32];
                 tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), r);
-                epilogue_chunk(g, r, row, n0 + 32 * c, split, lane);
+                if (c + G >= BN / 32 || n0 + 32 * (c + G) >= g.N) {      // last chunk of this warp in the tile: the accumulator is in registers, hand the buffer back now
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(&tmem_empty[buf]);
+                    released = true;
+                }
+                if (st_out) {                                            // the previous block must have left the staging buffer
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+                }
+                if (st_aux) { mbar_wait(my_bar, aux_phase); aux_phase ^= 1; }
+                epilogue_chunk(g, r, row, n0 + 32 * c, split, lane, ypre, have_pre && c == grp, es);
+                if (st_aux) { __syncwarp(); request_aux(); }             // every lane has read the operand block: fetch the next one into it
             }
-            // this thread's TMEM reads of the buffer are complete (tcgen05.wait::ld inside tmem_ld32): hand it back
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(&tmem_empty[buf]);
+            if (!released) {
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(&tmem_empty[buf]);
+            }
         }
+        if (st_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all stores of this warp have completed
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -481,7 +614,27 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode = nullptr;
 std::once_flag g_once;
 
+int make_map_uncached(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_rows, CUtensorMapSwizzle swz);
+// Encoding a tensor map costs about a microsecond of host time and the learner issues the same few hundred (pointer, shape) combinations
+// every update: keep them.
+struct MapKey { const float* ptr; int rows, cols, ld, box_rows, swz; bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && swz == o.swz; } };
+struct MapKeyHash { size_t operator()(const MapKey& k) const { size_t h = (size_t)k.ptr; h = h * 1000003u ^ (size_t)k.rows; h = h * 1000003u ^ (size_t)k.cols; h = h * 1000003u ^ (size_t)k.ld; h = h * 1000003u ^ (size_t)(k.box_rows * 8 + k.swz); return h; } };
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+std::mutex g_map_mutex;
 int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_rows, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+    const MapKey key{ptr, rows, cols, ld, box_rows, (int)swz};
+    {
+        std::lock_guard<std::mutex> lk(g_map_mutex);
+        auto it = g_map_cache.find(key);
+        if (it != g_map_cache.end()) { *map = it->second; return 0; }
+    }
+    if (int e = make_map_uncached(map, ptr, rows, cols, ld, box_rows, swz)) return e;
+    std::lock_guard<std::mutex> lk(g_map_mutex);
+    if (g_map_cache.size() > 8192) g_map_cache.clear();
+    g_map_cache.emplace(key, *map);
+    return 0;
+}
+int make_map_uncached(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_rows, CUtensorMapSwizzle swz) {
     std::call_once(g_once, [] {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult q;
@@ -528,21 +681,27 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, int 
     return 0;
 }
 
-template <int BN, int STAGES>
-int launch_persistent(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, int splits, cudaStream_t st) {
-    const size_t smem = (size_t)STAGES * (BM + BN) * BK * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
+template <int BN, int G, bool STAGED>
+int launch_persistent(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& my, const GemmArgs& g, int splits, cudaStream_t st) {
+    constexpr int NEPI = 4 * G, STAGE_BYTES = (BM + BN) * BK * 4;
+    const size_t staging = STAGED ? (size_t)NEPI * 4096 * (g.tma_aux ? 2 : 1) : 0;
+    const size_t fixed = staging + (2 * 8 + 4 + NEPI) * 8 + 16 + 1024;
+    const size_t budget = 227 * 1024;
+    int stages = (int)((budget - fixed) / STAGE_BYTES);
+    if (stages > 8) stages = 8;
+    if (stages < 2) return go1_set_error("go1_gemm impl=1: no room for the operand ring");
+    const size_t smem = (size_t)stages * STAGE_BYTES + fixed;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_persistent<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_persistent<BN, G, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
         if (e != cudaSuccess) return go1_set_error(cudaGetErrorString(e));
         configured = true;
     }
     const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN, total = tiles_m * tiles_n * splits;
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-    const int per_sm = (smem > 113 * 1024) ? 1 : 2;      // CTAs that fit one SM (shared memory bound)
-    const int grid = total < per_sm * sms ? total : per_sm * sms;
-    gemm_tf32_persistent<BN, STAGES><<<grid, 192, smem, st>>>(ma, mb, g, tiles_m, tiles_n, total);
+    const int grid = total < sms ? total : sms;          // one CTA per SM (the ring and the staging fill its shared memory)
+    gemm_tf32_persistent<BN, G, STAGED><<<grid, 64 + 128 * G, smem, st>>>(ma, mb, mc, my, g, tiles_m, tiles_n, total, stages);
     go1_count_launch(1);
     return 0;
 }
@@ -578,8 +737,8 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
                  ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int STAGES>
-__global__ void __launch_bounds__(192, 1) gemm_tf32_2cta(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmArgs g,
+template <int STAGES, int G>
+__global__ void __launch_bounds__(64 + 128 * G, 1) gemm_tf32_2cta(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmArgs g,
                                                           const int tiles_m2, const int tiles_n, const int total_tiles) {
     constexpr int BN = 256, HB = 128;              // cluster tile 256 x 256; each CTA stages 128 rows of A and 128 columns of B
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -601,7 +760,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_2cta(const __grid_constant__
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
         for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 256); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 2 * 128 * G); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {     // both CTAs of the pair allocate together (same warp id, same slot address)
@@ -672,22 +831,18 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_2cta(const __grid_constant__
             }
         }
     } else {
-        const int q = warp & 3;
+        const int q = warp & 3, grp = (warp - 2) >> 2;
         const bool split = g.kb_per_split < num_kb_total;
         int j = 0;
         for (int t = cluster_id; t < total_tiles; t += num_clusters, j++) {
             int m0, n0, kb0, nkb; tile_coords(t, m0, n0, kb0, nkb);
             const int buf = j & 1;
             const int row = m0 + 32 * q + lane;
+            float4 ypre[8];
+            const bool have_pre = epilogue_prefetch(g, row, n0 + 32 * grp, split, ypre);
             mbar_wait(&tmem_full[buf], (j >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; c++) {
-                uint32_t r[32];
-                tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), r);
-                epilogue_chunk(g, r, row, n0 + 32 * c, split, lane);
-            }
+            epilogue_tile<BN, G>(g, tmem_base + (uint32_t)(buf * BN), q, grp, row, n0, split, lane, ypre, have_pre);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive_leader(&tmem_empty[buf]);
         }
@@ -700,12 +855,12 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32_2cta(const __grid_constant__
     }
 }
 
-template <int STAGES>
+template <int STAGES, int G>
 int launch_2cta(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, int splits, cudaStream_t st) {
     const size_t smem = (size_t)STAGES * (BM + 128) * BK * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_2cta<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_2cta<STAGES, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return go1_set_error(cudaGetErrorString(e));
         configured = true;
     }
@@ -714,12 +869,12 @@ int launch_2cta(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g,
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
     const int clusters = total < sms / 2 ? total : sms / 2;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(64 + 128 * G); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32_2cta<STAGES>, ma, mb, g, tiles_m2, tiles_n, total);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tf32_2cta<STAGES, G>, ma, mb, g, tiles_m2, tiles_n, total);
     if (e != cudaSuccess) return go1_set_error(cudaGetErrorString(e));
     go1_count_launch(1);
     return 0;
@@ -1073,10 +1228,23 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
         g_time_recs.push_back({M, N, K, amn, bmn, act, g.nex, splits, two_cta ? 2 : BN, g.colsum ? 1 : 0});
     }
     int e;
-    if (two_cta) e = launch_2cta<6>(ma, mb, g, splits, st);
-    else if (BN == 256) e = launch_persistent<256, 4>(ma, mb, g, splits, st);
-    else if (g_tf32_persistent) e = (BN == 128) ? launch_persistent<128, 3>(ma, mb, g, splits, st) : (BN == 64 ? launch_persistent<64, 4>(ma, mb, g, splits, st) : launch_persistent<32, 4>(ma, mb, g, splits, st));
-    else e = (BN == 128) ? launch<128, 3>(ma, mb, g, splits, st) : (BN == 64 ? launch<64, 4>(ma, mb, g, splits, st) : launch<32, 4>(ma, mb, g, splits, st));
+    // staged epilogue (BN <= 128 kernels): C blocks through shared memory + TMA store, the ELU' operand through TMA loads
+    static const int use_staged = getenv("GO1_TF32_STAGED") ? atoi(getenv("GO1_TF32_STAGED")) : 1;
+    CUtensorMap mc = ma, my = ma;
+    g.tma_store = g.tma_aux = 0;
+    if (use_staged && !two_cta && BN <= 128 && splits == 1 && !accumulate && N >= 32 && (ldc & 3) == 0 && (((uintptr_t)Cm) & 15) == 0) {
+        if (int e2 = make_map(&mc, Cm, M, N, ldc, 32)) return e2;
+        g.tma_store = 1;
+        if (g.act == 2 && (g.ldaux & 3) == 0 && (((uintptr_t)g.aux) & 15) == 0) {
+            if (int e2 = make_map(&my, g.aux, M, N, g.ldaux, 32)) return e2;
+            g.tma_aux = 1;
+        }
+    }
+    if (two_cta) e = launch_2cta<6, 4>(ma, mb, g, splits, st);
+    else if (BN == 256) e = launch_persistent<256, 4, false>(ma, mb, mc, my, g, splits, st);
+    else if (BN == 128) e = launch_persistent<128, 4, true>(ma, mb, mc, my, g, splits, st);
+    else if (BN == 64) e = launch_persistent<64, 2, true>(ma, mb, mc, my, g, splits, st);
+    else e = launch_persistent<32, 1, true>(ma, mb, mc, my, g, splits, st);
     if (e) return e;
     if (splits > 1 && (bias || act)) { const size_t tot = (size_t)M * N; bias_act_strided<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cm, ldc, bias, M, N, act); go1_count_launch(1); }
     if (timed) cudaEventRecord(timing_event(), st);

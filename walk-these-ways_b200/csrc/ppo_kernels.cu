@@ -815,6 +815,52 @@ extern "C" int go1_skinny_dgrad(const float* dz, int lddz, const float* W, int l
     return cuda_rc("go1_skinny_dgrad");
 }
 
+// Forward of a narrow output layer (the 12 / 2 / 1-wide heads, actor_critic.py:52,64,76): out[m][t] = b[t] + sum_k x[m][k] W[t][k], o <= 16.
+// One bandwidth-bound pass over x (8 lanes per row, 16-byte loads; W and b in shared memory) instead of a padded 128 x 32 tensor-core tile.
+__global__ void __launch_bounds__(256) skinny_forward_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W, int ldw, const float* __restrict__ b,
+                                                             float* __restrict__ out, int ldo, int M, int o, int K) {
+    extern __shared__ float s_w[];              // [o][K] then [16] bias
+    float* s_b = s_w + (size_t)o * K;
+    for (int i = threadIdx.x; i < o * K; i += blockDim.x) s_w[i] = __ldg(W + (size_t)(i / K) * ldw + (i % K));
+    if (threadIdx.x < 16) s_b[threadIdx.x] = (threadIdx.x < o && b) ? __ldg(b + threadIdx.x) : 0.f;
+    __syncthreads();
+    const int sub = threadIdx.x & 7;            // lane within the row's group of 8
+    const int K4 = K >> 2;
+    for (int m = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); m < M; m += gridDim.x * (blockDim.x >> 3)) {
+        float acc[16];
+#pragma unroll
+        for (int t = 0; t < 16; t++) acc[t] = 0.f;
+        const float4* xr = reinterpret_cast<const float4*>(x + (size_t)m * ldx);
+        for (int c = sub; c < K4; c += 8) {
+            const float4 v = __ldg(xr + c);
+#pragma unroll
+            for (int t = 0; t < 16; t++) {
+                if (t < o) {
+                    const float4 w = *reinterpret_cast<const float4*>(s_w + (size_t)t * K + 4 * c);
+                    acc[t] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[t]))));
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 16; t++) {
+            if (t < o) {
+                float a = acc[t];
+                a += __shfl_xor_sync(0xffffffffu, a, 1); a += __shfl_xor_sync(0xffffffffu, a, 2); a += __shfl_xor_sync(0xffffffffu, a, 4);
+                if (sub == (t & 7)) out[(size_t)m * ldo + t] = a + s_b[t];
+            }
+        }
+    }
+}
+extern "C" int go1_skinny_forward(const float* x, int ldx, const float* W, int ldw, const float* b, float* out, int ldo, int M, int o, int K, void* stream) {
+    if (!x || !W || !out || M <= 0 || o <= 0 || o > 16 || K <= 0 || (K & 3) || (ldx & 3) || (((uintptr_t)x) & 15) || (size_t)(o * K + 16) * 4 > 48 * 1024)
+        return go1_set_error("go1_skinny_forward: bad arguments (o <= 16, K % 4 == 0, x 16-byte aligned rows)");
+    const int rows_per_block = 32;
+    int grid = (M + rows_per_block - 1) / rows_per_block;
+    if (grid > 148 * 8) grid = 148 * 8;
+    skinny_forward_kernel<<<grid, 256, (size_t)(o * K + 16) * 4, (cudaStream_t)stream>>>(x, ldx, W, ldw, b, out, ldo, M, o, K); go1_count_launch(1);
+    return cuda_rc("go1_skinny_forward");
+}
+
 // ---------------------------------------------------------------------------------------------
 // RolloutStorage.add_transitions (rollout_storage.py:55-69) + the time-out bootstrap of PPO.process_env_step
 // (ppo.py:84-86) in one launch: the 2100-wide history row is the bulk (float4 copy), the small fields ride along.

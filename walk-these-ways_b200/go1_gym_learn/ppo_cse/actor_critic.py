@@ -138,13 +138,21 @@ class _Net:
             b = self.flat[bo:bo + o]
             act = 1 if li < n - 1 else 0
             first_extra = li == 0 and extra is not None
+            if impl == 1 and li == n - 1 and li > 0 and o <= 16 and i % 4 == 0 and i <= 512 and self._tma_ok(inp, ld_in):
+                # the narrow head: one bandwidth-bound pass instead of a padded tensor-core tile
+                capi.check(capi.lib().go1_skinny_forward(self._p(inp), ld_in, W.data_ptr(), i, b.data_ptr(), capi.ptr(y), o, M, o, i, capi.stream_ptr()), "skinny_forward")
+                outs.append(y)
+                continue
             K = K0 if first_extra else i
             Wm, ldw = W, i
             tc = impl == 1 and self._tma_ok(inp, ld_in)
-            if tc and not self._tma_ok(W, i):      # pack W[:, :K] into a TMA-readable copy (rows of K floats, K % 4 == 0)
+            if tc and (not self._tma_ok(W, i) or (li == 0 and K >= 1024 and i % 32 != 0)):
+                # pack W[:, :K] into a TMA-readable copy whose row pitch is a multiple of 128 bytes (K % 4 == 0); for the long first-layer
+                # rows the aligned pitch alone is worth 30 % (misaligned 128-byte box rows cost an extra L2 sector each)
                 if K % 4 == 0:
-                    Wm = self._cached(("pack", li), lambda old: (old if old is not None else _empty(o, K, device=W.device)).copy_(W.view(o, i)[:, :K]))
-                    ldw = K
+                    KPk = (K + 31) // 32 * 32
+                    Wm = self._cached(("pack", li), lambda old: (old if old is not None else _empty(o, KPk, device=W.device)[:, :K]).copy_(W.view(o, i)[:, :K]))
+                    ldw = KPk
                 else:
                     tc = False
             if first_extra:     # y = act(x W[:, :K0]^T + extra W[:, K0:]^T + b): the 2 trailing columns ride in the epilogue
@@ -291,7 +299,7 @@ class ActorCritic(nn.Module):
         self.fuse_bias_grad = os.environ.get("GO1_FUSE_BIAS_GRAD", "1") != "0"     # bias gradients reduced in the dgrad GEMM epilogues
         self.update_streams = os.environ.get("GO1_UPDATE_STREAMS", "1") != "0"     # critic chain on a second stream during the update (measured -1.3 ms / iteration)
         self._side = None
-        self.fuse_tail = os.environ.get("GO1_FUSE_TAIL", "1") != "0"     # layers behind a first layer in one tcgen05 launch (go1_mlp_tail_forward)
+        self.fuse_tail = os.environ.get("GO1_FUSE_TAIL", "0") != "0"     # layers behind a first layer in one tcgen05 launch (go1_mlp_tail_forward); off: measured slower than layer by layer (130 vs 70 us at M = 24576)
         self.grads_prezeroed = False  # PPO.update zeroes the flat gradient buffer once per optimizer step (one fill instead of one per layer)
 
     # ------------------------------------------------------------------ flat storage
@@ -419,8 +427,10 @@ class ActorCritic(nn.Module):
 
         (Wa, ba), (Wp, bp), (Wc, bc) = w1(na), w1(npol), w1(ncr)
 
+        KP = (K0 + 31) // 32 * 32      # 128-byte row pitch of the packed weights (aligned TMA box rows, see RolloutStorage.hist_pitch)
+
         def build_w(old):
-            W = old if old is not None else _empty(oa + oc + op, K0, device=flat.device)
+            W = old if old is not None else _empty(oa + oc + op, KP, device=flat.device)[:, :K0]
             W[:oa].copy_(Wa); W[oa:oa + oc].copy_(Wc[:, :K0]); W[oa + oc:].copy_(Wp[:, :K0])
             return W
 
@@ -436,7 +446,7 @@ class ActorCritic(nn.Module):
 
         Wcat, bcat, xcat = na._cached(("l1cat", "W"), build_w), na._cached(("l1cat", "b"), build_b), na._cached(("l1cat", "x"), build_x)
         y = na._buf((tag, "y1cat"), M, oa + oc + op)
-        na._gemm(0, 1, M, oa + oc + op, K0, h, h.stride(0), Wcat, K0, y, y.stride(0), bcat, 1, 0, 1,
+        na._gemm(0, 1, M, oa + oc + op, K0, h, h.stride(0), Wcat, Wcat.stride(0), y, y.stride(0), bcat, 1, 0, 1,
                  extra=priv, w_extra=xcat.data_ptr(), ld_w_extra=E, lead_cols=oa + oc)
         ya, yc, yp = y[:, :oa], y[:, oa:oa + oc], y[:, oa + oc:]
         side = self._side_stream(M)
