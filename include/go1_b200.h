@@ -357,6 +357,12 @@ int go1_skinny_forward(const float* x, int ldx, const float* W, int ldw, const f
  *   dprev[m][c] = (sum_t dz[m][t] W[t][c]) * ELU'(y_prev[m][c]),  W row-major [o][n]. */
 int go1_skinny_dgrad(const float* dz, int lddz, const float* W, int ldw, const float* y_prev, int ldy, float* dprev, int lddp,
                      int M, int o, int n, void* stream);
+/* go1_skinny_dgrad + the column sums of the values written, colsum[c] += sum_m dprev[m][c] (atomics into a zeroed buffer; may be NULL):
+ * the bias gradient of the layer below (nn.Linear backward), reduced while dprev is produced. */
+int go1_skinny_dgrad_ex(const float* dz, int lddz, const float* W, int ldw, const float* y_prev, int ldy, float* dprev, int lddp,
+                        float* colsum, int M, int o, int n, void* stream);
+/* go1_skinny_wgrad + the layer's bias gradient gb[j] (+)= sum_m dz[m][j] (may be NULL; needs K % 4 == 0 and 16-byte aligned x rows). */
+int go1_skinny_wgrad_ex(const float* dz, int lddz, const float* x, int ldx, float* gW, int ldg, float* gb, int M, int o, int K, int accumulate, void* stream);
 /* wgrad of a narrow (o <= 16) output layer (the 12 / 2 / 1-wide heads): gW[j][k] (+)= sum_m dz[m][j] x[m][k]. */
 int go1_skinny_wgrad(const float* dz, int lddz, const float* x, int ldx, float* gW, int ldg, int M, int o, int K, int accumulate, void* stream);
 /* out[n] (+)= sum_m x[m][n]: bias gradient of nn.Linear. */

@@ -283,8 +283,56 @@ extern "C" int go1_gemm(int transA, int transB, int M, int N, int K, const float
     return go1_gemm_ex(transA, transB, M, N, K, A, lda, B, ldb, Cm, ldc, &ep, impl, stream);
 }
 
-// y = act(y + extra . w_extra^T) in place: the deferred trailing-input term + activation of a first layer
-// grid (column blocks of 256, row blocks of 8): each thread keeps its column's E weights in registers and walks 8 rows
+// ELU, branch-free (the same polynomial / ex2 split as the tcgen05 epilogue, gemm_tf32.cu: absolute error ~1e-7)
+__device__ __forceinline__ float elu_fast(float v) {
+    float p = fmaf(v, 1.f / 5040.f, 1.f / 720.f);
+    p = fmaf(p, v, 1.f / 120.f); p = fmaf(p, v, 1.f / 24.f); p = fmaf(p, v, 1.f / 6.f); p = fmaf(p, v, 0.5f);
+    p = fmaf(p * v, v, v);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 1.4426950408889634f));
+    const float n = v > -0.35f ? p : e - 1.0f;
+    return v > 0.f ? v : n;
+}
+// y = act(y + extra . w_extra^T) in place: the deferred trailing-input term + activation of a first layer.
+// float4 variant (o % 4 == 0, 16-byte aligned rows): one thread = 4 consecutive columns, 4 row-strided elements in flight per thread.
+__global__ void __launch_bounds__(256) extra_fwd4_kernel(float* __restrict__ y, int ldy, const float* __restrict__ ex, int ldex, const float* __restrict__ wex, int ldw,
+                                                         int M, int o4, int E, int act, int rows_per_pass) {
+    // blockDim.x = 256 threads = (256 / o4) rows x o4 column groups (o4 divides 256) or one row segment
+    const int cg = threadIdx.x % o4, rsub = threadIdx.x / o4, rpb = blockDim.x / o4;
+    float w[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int t = 0; t < 4; t++) w[c][t] = t < E ? __ldg(wex + (size_t)(4 * cg + c) * ldw + t) : 0.f;
+    for (int m0 = blockIdx.x * rpb * 4 + rsub; m0 < M; m0 += gridDim.x * rpb * 4) {
+        float4 v[4]; float e[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int m = m0 + u * rpb;
+            if (m < M) {
+                v[u] = *reinterpret_cast<const float4*>(y + (size_t)m * ldy + 4 * cg);
+#pragma unroll
+                for (int t = 0; t < 4; t++) e[u][t] = t < E ? __ldg(ex + (size_t)m * ldex + t) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int m = m0 + u * rpb;
+            if (m < M) {
+                float r[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    float a = r[c];
+#pragma unroll
+                    for (int t = 0; t < 4; t++) a = fmaf(e[u][t], w[c][t], a);
+                    r[c] = act == 1 ? elu_fast(a) : a;
+                }
+                *reinterpret_cast<float4*>(y + (size_t)m * ldy + 4 * cg) = make_float4(r[0], r[1], r[2], r[3]);
+            }
+        }
+    }
+}
+// generic variant: grid (column blocks of 256, row blocks of 8): each thread keeps its column's E weights in registers and walks 8 rows
 __global__ void __launch_bounds__(256) extra_fwd_kernel(float* __restrict__ y, int ldy, const float* __restrict__ ex, int ldex, const float* __restrict__ wex, int ldw,
                                                         int M, int o, int E, int act) {
     const int n = blockIdx.x * 256 + threadIdx.x;
@@ -306,6 +354,14 @@ __global__ void __launch_bounds__(256) extra_fwd_kernel(float* __restrict__ y, i
 extern "C" int go1_mlp_extra_forward(float* y, int ldy, const float* extra, int ldex, const float* w_extra, int ldw, int M, int o, int E, int act,
                                      void* stream) {
     if (!y || !extra || !w_extra || M <= 0 || o <= 0 || E < 1 || E > 4 || act < 0 || act > 1) return go1_set_error("go1_mlp_extra_forward: bad arguments");
+    const int o4 = o / 4;
+    if ((o & 3) == 0 && (ldy & 3) == 0 && (((uintptr_t)y) & 15) == 0 && o4 <= 256 && 256 % o4 == 0) {
+        const int rpb = 256 / o4;
+        int grid = (M + 4 * rpb - 1) / (4 * rpb);
+        if (grid > 148 * 16) grid = 148 * 16;
+        extra_fwd4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, ldy, extra, ldex, w_extra, ldw, M, o4, E, act, 4 * rpb); go1_count_launch(1);
+        return cuda_rc("go1_mlp_extra_forward");
+    }
     dim3 grid((o + 255) / 256, (M + 7) / 8);
     extra_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, ldy, extra, ldex, w_extra, ldw, M, o, E, act); go1_count_launch(1);
     return cuda_rc("go1_mlp_extra_forward");
@@ -351,7 +407,7 @@ __global__ void __launch_bounds__(128) skinny_wgrad_kernel(const float* __restri
 // set of global atomics per block.
 template <int O>
 __global__ void __launch_bounds__(256) skinny_wgrad4_kernel(const float* __restrict__ dz, int lddz, const float* __restrict__ x, int ldx,
-                                                            float* __restrict__ gW, int ldg, int M, int o, int K, int rows_per_block) {
+                                                            float* __restrict__ gW, int ldg, float* __restrict__ gb, int M, int o, int K, int rows_per_block) {
     __shared__ float s_acc[O][128];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int k = blockIdx.x * 128 + lane * 4;
@@ -361,10 +417,12 @@ __global__ void __launch_bounds__(256) skinny_wgrad4_kernel(const float* __restr
     float acc[O][4];
 #pragma unroll
     for (int j = 0; j < O; j++) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+    float dsum = 0.f;          // lane j < o: sum over this warp's rows of dz[m][j] (the layer's bias gradient, reduced by the column-block-0 CTAs)
 #pragma unroll 2
     for (int m = r0 + w; m < r1; m += 8) {
         const float4 xv = k < K ? *reinterpret_cast<const float4*>(x + (size_t)m * ldx + k) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float dl = lane < o ? __ldg(dz + (size_t)m * lddz + lane) : 0.f;
+        dsum += dl;
 #pragma unroll
         for (int j = 0; j < O; j++) {
             const float d = __shfl_sync(0xffffffffu, dl, j);
@@ -381,22 +439,25 @@ __global__ void __launch_bounds__(256) skinny_wgrad4_kernel(const float* __restr
         const int j = i >> 7, kk = blockIdx.x * 128 + (i & 127);
         if (kk < K) atomicAdd(gW + (size_t)j * ldg + kk, s_acc[j][i & 127]);
     }
+    if (gb && blockIdx.x == 0 && lane < o) atomicAdd(gb + lane, dsum);
 }
-extern "C" int go1_skinny_wgrad(const float* dz, int lddz, const float* x, int ldx, float* gW, int ldg, int M, int o, int K, int accumulate, void* stream) {
+extern "C" int go1_skinny_wgrad_ex(const float* dz, int lddz, const float* x, int ldx, float* gW, int ldg, float* gb, int M, int o, int K, int accumulate, void* stream) {
     if (!dz || !x || !gW || M <= 0 || o < 1 || o > 16 || K <= 0 || ldg < K) return go1_set_error("go1_skinny_wgrad: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
+    if (gb && !((K & 3) == 0 && (ldx & 3) == 0 && (((uintptr_t)x) & 15) == 0)) return go1_set_error("go1_skinny_wgrad_ex: the fused bias gradient needs K % 4 == 0 and 16-byte aligned x rows");
     if (!accumulate) {
         if (ldg == K) cudaMemsetAsync(gW, 0, sizeof(float) * (size_t)o * K, st);
         else cudaMemset2DAsync(gW, sizeof(float) * ldg, 0, sizeof(float) * K, o, st);
+        if (gb) cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)o, st);
     }
     if ((K & 3) == 0 && (ldx & 3) == 0 && (((uintptr_t)x) & 15) == 0) {
         const int kb = (K + 127) / 128;
         int rpb4 = (M * kb + 147) / 148;                 // about one block per SM
         rpb4 = (rpb4 + 7) / 8 * 8; if (rpb4 < 8) rpb4 = 8;
         dim3 grid4(kb, (M + rpb4 - 1) / rpb4);
-        if (o <= 2) skinny_wgrad4_kernel<2><<<grid4, 256, 0, st>>>(dz, lddz, x, ldx, gW, ldg, M, o, K, rpb4);
-        else if (o <= 4) skinny_wgrad4_kernel<4><<<grid4, 256, 0, st>>>(dz, lddz, x, ldx, gW, ldg, M, o, K, rpb4);
-        else skinny_wgrad4_kernel<16><<<grid4, 256, 0, st>>>(dz, lddz, x, ldx, gW, ldg, M, o, K, rpb4);
+        if (o <= 2) skinny_wgrad4_kernel<2><<<grid4, 256, 0, st>>>(dz, lddz, x, ldx, gW, ldg, gb, M, o, K, rpb4);
+        else if (o <= 4) skinny_wgrad4_kernel<4><<<grid4, 256, 0, st>>>(dz, lddz, x, ldx, gW, ldg, gb, M, o, K, rpb4);
+        else skinny_wgrad4_kernel<16><<<grid4, 256, 0, st>>>(dz, lddz, x, ldx, gW, ldg, gb, M, o, K, rpb4);
         go1_count_launch(1);
         return cuda_rc("go1_skinny_wgrad");
     }
@@ -407,6 +468,10 @@ extern "C" int go1_skinny_wgrad(const float* dz, int lddz, const float* x, int l
     else skinny_wgrad_kernel<16><<<grid, 128, 0, st>>>(dz, lddz, x, ldx, gW, ldg, M, o, K, rpb);
     go1_count_launch(1);
     return cuda_rc("go1_skinny_wgrad");
+}
+
+extern "C" int go1_skinny_wgrad(const float* dz, int lddz, const float* x, int ldx, float* gW, int ldg, int M, int o, int K, int accumulate, void* stream) {
+    return go1_skinny_wgrad_ex(dz, lddz, x, ldx, gW, ldg, nullptr, M, o, K, accumulate, stream);
 }
 
 // out[n] (+)= sum_m x[m][n]   (bias gradients)
@@ -807,12 +872,76 @@ __global__ void skinny_dgrad_kernel(const float* __restrict__ dz, int lddz, cons
     if (y) { const float yy = y[(size_t)m * ldy + c]; v *= (yy > 0.f ? 1.0f : yy + 1.0f); }
     dprev[(size_t)m * lddp + c] = v;
 }
+// float4 variant: a warp owns rows (stride 8 inside the block's row slab), a lane owns 4 consecutive columns of a 128-column group and keeps
+// its O x 4 weights in registers; the row's o output gradients are fetched by the first o lanes and shuffle-broadcast.  Optionally the
+// column sums of the values written (= the bias gradient of the layer below) are reduced here as well: per-lane partial sums, one
+// shared-memory reduction per block, one set of atomics per block.
+template <int O>
+__global__ void __launch_bounds__(256) skinny_dgrad4_kernel(const float* __restrict__ dz, int lddz, const float* __restrict__ W, int ldw, const float* __restrict__ y, int ldy,
+                                                            float* __restrict__ dprev, int lddp, float* __restrict__ colsum, int M, int o, int n, int rows_per_block) {
+    __shared__ float4 s_sum[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * 128 + lane * 4;
+    const bool col_ok = c < n;
+    float wr[O][4];
+#pragma unroll
+    for (int t = 0; t < O; t++) {
+        const float4 ww = (t < o && col_ok) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)t * ldw + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        wr[t][0] = ww.x; wr[t][1] = ww.y; wr[t][2] = ww.z; wr[t][3] = ww.w;
+    }
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+    for (int m = r0 + w; m < r1; m += 8) {
+        const float dl = lane < o ? __ldg(dz + (size_t)m * lddz + lane) : 0.f;
+        float4 yy = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (y && col_ok) yy = __ldg(reinterpret_cast<const float4*>(y + (size_t)m * ldy + c));
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+#pragma unroll
+        for (int t = 0; t < O; t++) {
+            const float d = __shfl_sync(0xffffffffu, dl, t);
+            v0 = fmaf(d, wr[t][0], v0); v1 = fmaf(d, wr[t][1], v1); v2 = fmaf(d, wr[t][2], v2); v3 = fmaf(d, wr[t][3], v3);
+        }
+        if (y) { v0 *= (yy.x > 0.f ? 1.0f : yy.x + 1.0f); v1 *= (yy.y > 0.f ? 1.0f : yy.y + 1.0f); v2 *= (yy.z > 0.f ? 1.0f : yy.z + 1.0f); v3 *= (yy.w > 0.f ? 1.0f : yy.w + 1.0f); }
+        if (col_ok) *reinterpret_cast<float4*>(dprev + (size_t)m * lddp + c) = make_float4(v0, v1, v2, v3);
+        cs.x += v0; cs.y += v1; cs.z += v2; cs.w += v3;
+    }
+    if (colsum) {
+        s_sum[w][lane] = cs;
+        __syncthreads();
+        if (w == 0 && col_ok) {
+            float4 t = s_sum[0][lane];
+#pragma unroll
+            for (int k = 1; k < 8; k++) { t.x += s_sum[k][lane].x; t.y += s_sum[k][lane].y; t.z += s_sum[k][lane].z; t.w += s_sum[k][lane].w; }
+            atomicAdd(colsum + c, t.x); atomicAdd(colsum + c + 1, t.y); atomicAdd(colsum + c + 2, t.z); atomicAdd(colsum + c + 3, t.w);
+        }
+    }
+}
+extern "C" int go1_skinny_dgrad_ex(const float* dz, int lddz, const float* W, int ldw, const float* y_prev, int ldy, float* dprev, int lddp,
+                                   float* colsum, int M, int o, int n, void* stream) {
+    if (!dz || !W || !dprev || M <= 0 || o <= 0 || o > 16 || n <= 0) return go1_set_error("go1_skinny_dgrad: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (n & 3) == 0 && (ldw & 3) == 0 && (lddp & 3) == 0 && (!y_prev || (ldy & 3) == 0) &&
+                     ((((uintptr_t)W) | ((uintptr_t)dprev) | ((uintptr_t)(y_prev ? y_prev : W))) & 15) == 0;
+    if (vec) {
+        const int cb = (n + 127) / 128;
+        int rpb = (M * cb + 2 * 148 - 1) / (2 * 148);           // about two blocks per SM
+        rpb = (rpb + 7) / 8 * 8; if (rpb < 8) rpb = 8;
+        dim3 grid(cb, (M + rpb - 1) / rpb);
+        if (o <= 2) skinny_dgrad4_kernel<2><<<grid, 256, 0, st>>>(dz, lddz, W, ldw, y_prev, ldy, dprev, lddp, colsum, M, o, n, rpb);
+        else if (o <= 4) skinny_dgrad4_kernel<4><<<grid, 256, 0, st>>>(dz, lddz, W, ldw, y_prev, ldy, dprev, lddp, colsum, M, o, n, rpb);
+        else skinny_dgrad4_kernel<16><<<grid, 256, 0, st>>>(dz, lddz, W, ldw, y_prev, ldy, dprev, lddp, colsum, M, o, n, rpb);
+        go1_count_launch(1);
+        return cuda_rc("go1_skinny_dgrad");
+    }
+    if (colsum) return go1_set_error("go1_skinny_dgrad_ex: the fused column sum needs 16-byte aligned operands with n % 4 == 0");
+    const size_t tot = (size_t)M * n;
+    skinny_dgrad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(dz, lddz, W, ldw, y_prev, ldy, dprev, lddp, M, o, n); go1_count_launch(1);
+    return cuda_rc("go1_skinny_dgrad");
+}
 extern "C" int go1_skinny_dgrad(const float* dz, int lddz, const float* W, int ldw, const float* y_prev, int ldy, float* dprev, int lddp,
                                 int M, int o, int n, void* stream) {
-    if (!dz || !W || !dprev || M <= 0 || o <= 0 || o > 16 || n <= 0) return go1_set_error("go1_skinny_dgrad: bad arguments");
-    const size_t tot = (size_t)M * n;
-    skinny_dgrad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dz, lddz, W, ldw, y_prev, ldy, dprev, lddp, M, o, n); go1_count_launch(1);
-    return cuda_rc("go1_skinny_dgrad");
+    return go1_skinny_dgrad_ex(dz, lddz, W, ldw, y_prev, ldy, dprev, lddp, nullptr, M, o, n, stream);
 }
 
 // Forward of a narrow output layer (the 12 / 2 / 1-wide heads, actor_critic.py:52,64,76): out[m][t] = b[t] + sum_k x[m][k] W[t][k], o <= 16.

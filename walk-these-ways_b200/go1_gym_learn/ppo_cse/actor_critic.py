@@ -214,18 +214,25 @@ class _Net:
             W = self.flat[wo:wo + o * i]
             gW, gb = self.grad[wo:wo + o * i], self.grad[bo:bo + o]
             ldz = dz.stride(0)
-            if not bias_done:
-                capi.check(L.go1_colsum(capi.ptr(dz), ldz, capi.ptr(gb), M, o, accumulate, st), "colsum")
-            bias_done = False
             if li == 0:
                 inp, ld_in, K = x, ldx, (K0 if extra is not None else i)
             else:
                 inp, ld_in, K = outs[li - 1], outs[li - 1].stride(0), i
+            prez = 1 if (accumulate or self.owner.grads_prezeroed) else 0      # the caller zeroed the gradient buffer: accumulate, no memsets
+            skinny_w = not (li == 0 and dz1_out is not None) and o <= 16 and K >= 32
+            if not bias_done and skinny_w and K % 4 == 0 and self._tma_ok(inp, ld_in):
+                # the narrow heads: weight AND bias gradient in one bandwidth-bound pass over the layer input
+                capi.check(L.go1_skinny_wgrad_ex(capi.ptr(dz), ldz, capi.ptr(inp), ld_in, gW.data_ptr(), i, gb.data_ptr(), M, o, K, prez, st), "skinny_wgrad")
+                skinny_w, bias_done = False, True
+            if not bias_done:
+                capi.check(L.go1_colsum(capi.ptr(dz), ldz, capi.ptr(gb), M, o, accumulate, st), "colsum")
+            bias_done = False
             # ---- wgrad: dW[o][K] = dz^T[o][M] inp[M][K]
             if li == 0 and dz1_out is not None:
                 pass                                    # fused by the caller
             elif o <= 16 and K >= 32:   # the narrow heads: one bandwidth-bound pass instead of a padded GEMM tile
-                capi.check(L.go1_skinny_wgrad(capi.ptr(dz), ldz, capi.ptr(inp), ld_in, gW.data_ptr(), i, M, o, K, accumulate, st), "skinny_wgrad")
+                if skinny_w:
+                    capi.check(L.go1_skinny_wgrad(capi.ptr(dz), ldz, capi.ptr(inp), ld_in, gW.data_ptr(), i, M, o, K, prez, st), "skinny_wgrad")
             else:       # impl 1: both operands MN-major, read in place by the tcgen05 kernel
                 tc = impl == 1 and M >= 64 and K >= 8 and self._tma_ok(dz, ldz) and self._tma_ok(inp, ld_in)
                 # into a gradient buffer the caller has already zeroed the split-K partial tiles can accumulate directly (no zeroing pass)
@@ -263,7 +270,15 @@ class _Net:
                     self._gemm(0, 0, M, i, o, dz, ldz, W, i, dprev, ldp, None, 2, 0, 1, dact_y=yprev, colsum=gb_prev if fuse else None, bwd_extra=bx)
                     bias_done = bool(fuse)
                 elif o <= 16:
-                    capi.check(L.go1_skinny_dgrad(capi.ptr(dz), ldz, capi.ptr(W), i, capi.ptr(yprev), yprev.stride(0), capi.ptr(dprev), ldp, M, o, i, st), "skinny_dgrad")
+                    pwo, pbo, po, pi = self.specs[li - 1]
+                    gb_prev = self.grad[pbo:pbo + po]
+                    fuse = impl == 1 and self.owner.fuse_bias_grad and i % 4 == 0 and self._tma_ok(W, i) and self._tma_ok(dprev, ldp) and self._tma_ok(yprev, yprev.stride(0))
+                    if fuse and not accumulate and not self.owner.grads_prezeroed:
+                        gb_prev.zero_()
+                    # the bias gradient of layer li-1 (column sums of dprev) is reduced in the same pass
+                    capi.check(L.go1_skinny_dgrad_ex(capi.ptr(dz), ldz, capi.ptr(W), i, capi.ptr(yprev), yprev.stride(0), capi.ptr(dprev), ldp,
+                                                     gb_prev.data_ptr() if fuse else None, M, o, i, st), "skinny_dgrad")
+                    bias_done = bool(fuse)
                 else:
                     self._gemm(0, 0, M, i, o, dz, ldz, W, i, dprev, ldp, None, 2, 0, 0, dact_y=yprev)
                 dz = dprev
