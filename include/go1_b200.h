@@ -330,6 +330,13 @@ int go1_gemm_ex(int transA, int transB, int M, int N, int K, const float* A, int
 int go1_mlp_tail_forward(const float* x, int ldx, int M, int K1, const float* W2, const float* b2, int N2, float* y2, int ldy2,
                          const float* W3, const float* b3, int N3, float* y3, int ldy3, const float* Wh, const float* bh, int nh,
                          float* out, int ldout, void* stream);
+/* The same for up to two problems of equal shape in ONE grid (the actor and critic bodies: 2 x 192 row blocks fill the 148 SMs in 3 even
+ * rounds instead of 2 x 2 ragged ones).  nh <= 12 per problem. */
+typedef struct Go1TailProblem {
+    const float* x; int32_t ldx; const float* W2; const float* b2; float* y2; int32_t ldy2;
+    const float* W3; const float* b3; float* y3; int32_t ldy3; const float* Wh; const float* bh; int32_t nh; float* out; int32_t ldout;
+} Go1TailProblem;
+int go1_mlp_tail_forward_grouped(const Go1TailProblem* probs, int nprob, int M, int K1, int N2, int N3, void* stream);
 
 /* Per-launch timing of the impl-1 (tcgen05) products for the roofline report: on = 1 starts collecting (CUDA events on the launch
  * stream around every call that is not being graph-captured), on = 0 stops and returns the summed kernel time, flops and count. */

@@ -885,70 +885,96 @@ int launch_2cta(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g,
 // Fused MLP tail, forward: the layers behind a first layer of ActorCritic's MLPs (actor_critic.py:38-77) in ONE launch,
 //     y2 = ELU(x W2^T + b2)   [M][N2]        x = the first layer's activated output, K1 wide (a column slice of the fused first-layer product)
 //     y3 = ELU(y2 W3^T + b3)  [M][N3]        (N3 = 0: two-layer tail, the head reads y2)
-//     out = y_last Wh^T + bh  [M][nh]        nh <= 16 (12 action means / 1 value / 2 latents): CUDA cores, from registers
-// One CTA owns a 128-row block.  Product 1 streams x and W2 through a TMA ring into tcgen05 (accumulator in TMEM columns 0..N2);
-// its epilogue writes y2 to global memory (the backward pass needs it) AND, 128B-swizzled, into the (now idle) ring as the K-major A
-// operand of product 2, whose B operand (W3) arrives through a second small ring; accumulator 2 lives in TMEM columns 256..256+N3.
-// The separate launches this replaces ran at 50-120 TFLOP/s (one short tile per CTA, activations re-read from HBM / L2 in between).
+//     out = y_last Wh^T + bh  [M][nh]        nh <= 12 (12 action means / 1 value / 2 latents): CUDA cores, from registers
+// for up to two problems of the same shape (actor and critic bodies) in one grid.  One CTA (576 threads) owns a 128-row block:
+//   warp 0   TMA producer: ring 1 streams x and W2 k-blocks, ring 2 the W3 k-blocks
+//   warp 1   tcgen05 issuer: product 1 -> TMEM columns [0, N2); product 2 -> TMEM columns [256, 256 + N3), its A operand is the y2 tile
+//            the epilogue warps laid out in shared memory (K-major, 128B-swizzled, overlaying ring 1)
+//   warps 2-17  epilogue, warp = (TMEM lane quarter, column group): bias + ELU on the accumulator chunks; y2 goes to shared memory once
+//            and from there BOTH to the tensor core (product 2) and to global memory (one TMA store per warp and 32 x 32 block: the
+//            backward pass needs y2); y3 is stored from registers; the head's partial dot products of the four column groups meet
+//            in shared memory.
+// Product 1 of tile t+1 (operand loads included: the L2 -> SM stream of x and W2 bounds the kernel) overlaps the second epilogue of tile t.
+// Barriers, all flipping once per tile: acc1_full (commit of product 1), y2_ready (512 epilogue threads: the y2 tile is in ring 1 and
+// accumulator 1 has been read), acc2_full (commit of product 2), r1_free (commit of product 2: the tensor core is done with ring 1),
+// y2_stored (16 lanes: the TMA stores have read ring 1).  The producer refills ring 1 after r1_free and y2_stored.
 // ---------------------------------------------------------------------------------------------------------------
-struct TailArgs {
-    const float* b2; const float* b3; const float* Wh; const float* bh;
-    float* y2; float* y3; float* out;
-    int ldy2, ldy3, ldwh, ldout, nh, M;
-};
-
-__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
+constexpr int TAIL_MAXP = 2, TAIL_G = 4, TAIL_NEPI = 16, TAIL_HPW = 12;
+struct TailProb { const float* b2; const float* b3; const float* Wh; const float* bh; float* y3; float* out; int ldy3, ldout, nh, wh_row0; };
+struct TailArgs { TailProb p[TAIL_MAXP]; int nprob, M, tiles_per_prob, tiles; };
+struct TailMaps { CUtensorMap x[TAIL_MAXP], w2[TAIL_MAXP], w3[TAIL_MAXP], y2[TAIL_MAXP]; };
 
 template <int K1, int N2, int N3>
-__global__ void __launch_bounds__(192, 1) mlp_tail_fwd_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW2,
-                                                              const __grid_constant__ CUtensorMap mapW3, const TailArgs g, const int tiles) {
-    constexpr int S1 = 3, S2 = (N3 > 0) ? 4 : 1;
-    constexpr int KB1 = K1 / BK, KB2 = N2 / BK;
-    constexpr int STAGE1 = (BM + N2) * BK * 4;
-    constexpr int Y2TILE = KB2 * BM * BK * 4;
-    constexpr int R1 = (N3 > 0 && Y2TILE > S1 * STAGE1) ? Y2TILE : S1 * STAGE1;      // ring 1; later overlaid by the y2 tile
-    constexpr int STAGE2 = (N3 > 0 ? N3 : 8) * BK * 4;
-    constexpr int R2 = (N3 > 0) ? S2 * STAGE2 : 0;
-    constexpr int NL = (N3 > 0) ? N3 : N2;
+struct TailSmem {
+    static constexpr int S1 = 3, S2 = (N3 > 0) ? 3 : 0;
+    static constexpr int KB1 = K1 / BK, KB2 = N2 / BK;
+    static constexpr int STAGE1 = (BM + N2) * BK * 4;
+    static constexpr int Y2TILE = KB2 * BM * BK * 4;
+    static constexpr int R1 = (N3 > 0 && Y2TILE > S1 * STAGE1) ? Y2TILE : S1 * STAGE1;      // ring 1; in the three-layer tail overlaid by the y2 tile
+    static constexpr int STAGE2 = (N3 > 0 ? N3 : 8) * BK * 4;
+    static constexpr int R2 = S2 * STAGE2;
+    static constexpr int YSTG = (N3 > 0) ? 0 : TAIL_NEPI * 4096;        // two-layer tail: per-warp staging of the y2 blocks for their TMA stores
+    static constexpr int NL = (N3 > 0) ? N3 : N2;
+    static constexpr int PARAMS = (TAIL_MAXP * (N2 + N3) + 16 * NL + TAIL_MAXP * 16) * 4;
+    static constexpr int HP = (TAIL_G - 1) * TAIL_HPW * BM * 4;
+    static constexpr int BARS = (2 * S1 + 2 * (S2 > 0 ? S2 : 1) + 5) * 8 + 16;
+    static constexpr int TOTAL = R1 + R2 + YSTG + PARAMS + HP + BARS + 1024;
+};
+
+template <int K1, int N2, int N3>
+__global__ void __launch_bounds__(64 + 128 * TAIL_G, 1) mlp_tail_fwd_kernel(const __grid_constant__ TailMaps maps, const TailArgs g) {
+    using L = TailSmem<K1, N2, N3>;
+    constexpr int S1 = L::S1, S2 = (L::S2 > 0 ? L::S2 : 1), KB1 = L::KB1, KB2 = L::KB2, STAGE1 = L::STAGE1, STAGE2 = L::STAGE2, NL = L::NL;
     constexpr uint32_t TMEM_COLS = (N3 > 0) ? 512u : (uint32_t)N2;
+    constexpr int G = TAIL_G;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* r1 = base;
-    uint8_t* r2 = base + R1;
-    float* s_b2 = (float*)(base + R1 + R2);
-    float* s_b3 = s_b2 + N2;
-    float* s_wh = s_b3 + (N3 > 0 ? N3 : 0);          // [16][NL]
-    float* s_bh = s_wh + 16 * NL;
-    uint64_t* full1 = (uint64_t*)(s_bh + 16);
+    uint8_t* r2 = base + L::R1;
+    uint8_t* ystg = r2 + L::R2;
+    float* s_b2 = (float*)(ystg + L::YSTG);                 // [MAXP][N2]
+    float* s_b3 = s_b2 + TAIL_MAXP * N2;                     // [MAXP][N3]
+    float* s_wh = s_b3 + TAIL_MAXP * N3;                     // [16][NL]: the head rows of all problems (problem p starts at row wh_row0)
+    float* s_bh = s_wh + 16 * NL;                            // [MAXP][16]
+    float* s_hp = s_bh + TAIL_MAXP * 16;                     // [G-1][HPW][128]: head partial sums of column groups 1..G-1
+    uint64_t* full1 = (uint64_t*)(s_hp + (G - 1) * TAIL_HPW * BM);
     uint64_t* empty1 = full1 + S1;
     uint64_t* full2 = empty1 + S1;
     uint64_t* empty2 = full2 + S2;
     uint64_t* acc1_full = empty2 + S2;
     uint64_t* acc2_full = acc1_full + 1;
     uint64_t* y2_ready = acc2_full + 1;
-    uint64_t* acc_free = y2_ready + 1;
-    uint64_t* r1_free = acc_free + 1;
-    uint32_t* tmem_slot = (uint32_t*)(r1_free + 1);
+    uint64_t* r1_free = y2_ready + 1;
+    uint64_t* y2_stored = r1_free + 1;
+    uint32_t* tmem_slot = (uint32_t*)(y2_stored + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW2) : "memory");
-        if (N3 > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW3) : "memory");
+        for (int p = 0; p < g.nprob; p++) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x[p]) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w2[p]) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.y2[p]) : "memory");
+            if (N3 > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w3[p]) : "memory");
+        }
         for (int s = 0; s < S1; s++) { mbar_init(&full1[s], 1); mbar_init(&empty1[s], 1); }
         for (int s = 0; s < S2; s++) { mbar_init(&full2[s], 1); mbar_init(&empty2[s], 1); }
-        mbar_init(acc1_full, 1); mbar_init(acc2_full, 1); mbar_init(y2_ready, 128); mbar_init(acc_free, 128); mbar_init(r1_free, 1);
+        mbar_init(acc1_full, 1); mbar_init(acc2_full, 1); mbar_init(y2_ready, 128 * G); mbar_init(r1_free, 1); mbar_init(y2_stored, TAIL_NEPI);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // biases and head weights: read by every epilogue thread for every row -> shared memory (zero rows beyond nh)
-    for (int i = threadIdx.x; i < N2; i += blockDim.x) s_b2[i] = g.b2 ? __ldg(g.b2 + i) : 0.f;
-    if (N3 > 0) for (int i = threadIdx.x; i < N3; i += blockDim.x) s_b3[i] = g.b3 ? __ldg(g.b3 + i) : 0.f;
-    for (int i = threadIdx.x; i < 16 * NL; i += blockDim.x) { const int n = i / NL, k = i - n * NL; s_wh[i] = n < g.nh ? __ldg(g.Wh + (size_t)n * g.ldwh + k) : 0.f; }
-    if (threadIdx.x < 16) s_bh[threadIdx.x] = (threadIdx.x < g.nh && g.bh) ? __ldg(g.bh + threadIdx.x) : 0.f;
+    // biases and head weights: read by every epilogue thread for every row -> shared memory
+    for (int i = threadIdx.x; i < TAIL_MAXP * N2; i += blockDim.x) { const int p = i / N2; s_b2[i] = (p < g.nprob && g.p[p].b2) ? __ldg(g.p[p].b2 + (i - p * N2)) : 0.f; }
+    if (N3 > 0) for (int i = threadIdx.x; i < TAIL_MAXP * N3; i += blockDim.x) { const int p = i / (N3 > 0 ? N3 : 1); s_b3[i] = (p < g.nprob && g.p[p].b3) ? __ldg(g.p[p].b3 + (i - p * N3)) : 0.f; }
+    for (int i = threadIdx.x; i < 16 * NL; i += blockDim.x) {
+        const int n = i / NL, k = i - n * NL;
+        float v = 0.f;
+        for (int p = 0; p < g.nprob; p++) { const int r = n - g.p[p].wh_row0; if (r >= 0 && r < g.p[p].nh) v = __ldg(g.p[p].Wh + (size_t)r * NL + k); }
+        s_wh[i] = v;
+    }
+    if (threadIdx.x < TAIL_MAXP * 16) { const int p = threadIdx.x >> 4, n = threadIdx.x & 15; s_bh[threadIdx.x] = (p < g.nprob && n < g.p[p].nh && g.p[p].bh) ? __ldg(g.p[p].bh + n) : 0.f; }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -958,22 +984,22 @@ __global__ void __launch_bounds__(192, 1) mlp_tail_fwd_kernel(const __grid_const
         // ===== TMA producer =====
         if (elect_one()) {
             int it1 = 0, it2 = 0, tl = 0;
-            for (int t = blockIdx.x; t < tiles; t += gridDim.x, tl++) {
-                const int m0 = t * BM;
-                if (N3 > 0 && tl > 0) mbar_wait(r1_free, (tl - 1) & 1);       // product 2 of the previous tile is done with the y2 tile in ring 1
+            for (int t = blockIdx.x; t < g.tiles; t += gridDim.x, tl++) {
+                const int p = t / g.tiles_per_prob, m0 = (t - p * g.tiles_per_prob) * BM;
+                if (N3 > 0 && tl > 0) { mbar_wait(r1_free, (tl - 1) & 1); mbar_wait(y2_stored, (tl - 1) & 1); }   // ring 1 held the previous tile's y2
                 for (int i = 0; i < KB1; i++, it1++) {
                     const int s = it1 % S1, ph = (it1 / S1) & 1;
                     mbar_wait(&empty1[s], ph ^ 1);
                     mbar_expect_tx(&full1[s], STAGE1);
-                    tma_load_2d(&mapX, &full1[s], r1 + (size_t)s * STAGE1, i * BK, m0);
-                    tma_load_2d(&mapW2, &full1[s], r1 + (size_t)s * STAGE1 + BM * BK * 4, i * BK, 0);
+                    tma_load_2d(&maps.x[p], &full1[s], r1 + (size_t)s * STAGE1, i * BK, m0);
+                    tma_load_2d(&maps.w2[p], &full1[s], r1 + (size_t)s * STAGE1 + BM * BK * 4, i * BK, 0);
                 }
                 if (N3 > 0) {
                     for (int i = 0; i < KB2; i++, it2++) {
                         const int s = it2 % S2, ph = (it2 / S2) & 1;
                         mbar_wait(&empty2[s], ph ^ 1);
                         mbar_expect_tx(&full2[s], STAGE2);
-                        tma_load_2d(&mapW3, &full2[s], r2 + (size_t)s * STAGE2, i * BK, 0);
+                        tma_load_2d(&maps.w3[p], &full2[s], r2 + (size_t)s * STAGE2, i * BK, 0);
                     }
                 }
             }
@@ -983,8 +1009,10 @@ __global__ void __launch_bounds__(192, 1) mlp_tail_fwd_kernel(const __grid_const
         const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N2 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
         const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((N3 > 0 ? N3 : 8) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
         int it1 = 0, it2 = 0, tl = 0;
-        for (int t = blockIdx.x; t < tiles; t += gridDim.x, tl++) {
-            if (tl > 0) { mbar_wait(acc_free, (tl - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+        for (int t = blockIdx.x; t < g.tiles; t += gridDim.x, tl++) {
+            // accumulator 1 is free: the epilogue read it before y2_ready of the previous tile, which product 2 of that tile (issued by
+            // this warp, in order) waited for.  The two-layer tail has no product 2: wait for y2_ready of the previous tile here.
+            if (N3 == 0 && tl > 0) { mbar_wait(y2_ready, (tl - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
             for (int i = 0; i < KB1; i++, it1++) {
                 const int s = it1 % S1, ph = (it1 / S1) & 1;
                 mbar_wait(&full1[s], ph);
@@ -1017,42 +1045,49 @@ __global__ void __launch_bounds__(192, 1) mlp_tail_fwd_kernel(const __grid_const
             }
         }
     } else {
-        // ===== epilogue: thread = one row of the block =====
-        const int q = warp & 3, rl = 32 * q + lane;
+        // ===== epilogue: 16 warps; warp = (TMEM lane quarter q, column group grp); thread = one row of the block =====
+        const int ew = warp - 2, q = warp & 3, grp = ew >> 2, rl = 32 * q + lane;
         int tl = 0;
-        for (int t = blockIdx.x; t < tiles; t += gridDim.x, tl++) {
-            const int row = t * BM + rl;
+        for (int t = blockIdx.x; t < g.tiles; t += gridDim.x, tl++) {
+            const int p = t / g.tiles_per_prob, m0 = (t - p * g.tiles_per_prob) * BM;
+            const TailProb& pr = g.p[p];
+            const int row = m0 + rl;
             const bool row_ok = row < g.M;
-            float h[16];
+            const float* b2 = s_b2 + p * N2;
+            float h[TAIL_HPW];
 #pragma unroll
-            for (int n = 0; n < 16; n++) h[n] = s_bh[n];
+            for (int n = 0; n < TAIL_HPW; n++) h[n] = 0.f;
             mbar_wait(acc1_full, tl & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (N3 == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the previous tile's block has left the staging buffer
+            if (N3 == 0) __syncwarp();
 #pragma unroll 1
-            for (int c = 0; c < N2 / 32; c++) {
+            for (int c = grp; c < N2 / 32; c += G) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), r);
                 float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; j++) v[j] = elu1(__uint_as_float(r[j]) + s_b2[32 * c + j]);
-                if (row_ok) {
-                    float4* dst = reinterpret_cast<float4*>(g.y2 + (size_t)row * g.ldy2 + 32 * c);
+                for (int j = 0; j < 32; j++) v[j] = elu_fast(__uint_as_float(r[j]) + b2[32 * c + j]);
+                // the warp's 32 x 32 block, 128-byte rows, 16-byte chunks XOR-swizzled by row % 8: the layout TMA reads / writes with
+                // CU_TENSOR_MAP_SWIZZLE_128B and the K-major UMMA descriptor expects.  Three-layer tail: k-block c of product 2's A operand.
+                uint8_t* blk = (N3 > 0) ? (r1 + (size_t)c * (BM * BK * 4) + (size_t)(32 * q) * 128) : (ystg + (size_t)ew * 4096);
+                uint8_t* trow = blk + (size_t)lane * 128;
 #pragma unroll
-                    for (int j = 0; j < 8; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                for (int j = 0; j < 8; j++)
+                    *reinterpret_cast<float4*>(trow + ((j ^ (lane & 7)) << 4)) = row_ok ? make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3])
+                                                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the async proxy (tensor core, TMA store)
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&maps.y2[p], blk, 32 * c, m0 + 32 * q);           // rows beyond M are clipped
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-                if (N3 > 0) {
-                    // k-block c of product 2's A operand: [128 rows][32 floats], 128-byte rows, 16-byte chunks XOR-swizzled by row % 8
-                    // (the layout TMA writes with CU_TENSOR_MAP_SWIZZLE_128B, which the K-major UMMA descriptor expects)
-                    uint8_t* trow = r1 + (size_t)c * (BM * BK * 4) + (size_t)rl * 128;
+                if (N3 == 0) {      // two-layer tail: the head reads y2 from registers
+                    const float* wh = s_wh + (size_t)pr.wh_row0 * NL + 32 * c;
 #pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        *reinterpret_cast<float4*>(trow + ((j ^ (rl & 7)) << 4)) = row_ok ? make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3])
-                                                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-                } else {
-#pragma unroll
-                    for (int n = 0; n < 16; n++) {
-                        if (n < g.nh) {
-                            const float4* w = reinterpret_cast<const float4*>(s_wh + n * NL + 32 * c);
+                    for (int n = 0; n < TAIL_HPW; n++) {
+                        if (n < pr.nh) {
+                            const float4* w = reinterpret_cast<const float4*>(wh + n * NL);
                             float a = h[n];
 #pragma unroll
                             for (int j = 0; j < 8; j++) { const float4 ww = w[j]; a = fmaf(v[4 * j], ww.x, a); a = fmaf(v[4 * j + 1], ww.y, a); a = fmaf(v[4 * j + 2], ww.z, a); a = fmaf(v[4 * j + 3], ww.w, a); }
@@ -1061,28 +1096,30 @@ __global__ void __launch_bounds__(192, 1) mlp_tail_fwd_kernel(const __grid_const
                     }
                 }
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(y2_ready);
             if (N3 > 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores above -> visible to the tensor core's async proxy
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                mbar_arrive(y2_ready);
                 mbar_wait(acc2_full, tl & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); mbar_arrive(y2_stored); }      // the y2 stores have read ring 1
+                const float* b3 = s_b3 + p * N3;
 #pragma unroll 1
-                for (int c = 0; c < (N3 > 0 ? N3 : 32) / 32; c++) {
+                for (int c = grp; c < (N3 > 0 ? N3 : 32) / 32; c += G) {
                     uint32_t r[32];
                     tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + 256u + (uint32_t)(32 * c), r);
                     float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] = elu1(__uint_as_float(r[j]) + s_b3[32 * c + j]);
+                    for (int j = 0; j < 32; j++) v[j] = elu_fast(__uint_as_float(r[j]) + b3[32 * c + j]);
                     if (row_ok) {
-                        float4* dst = reinterpret_cast<float4*>(g.y3 + (size_t)row * g.ldy3 + 32 * c);
+                        float4* dst = reinterpret_cast<float4*>(pr.y3 + (size_t)row * pr.ldy3 + 32 * c);
 #pragma unroll
                         for (int j = 0; j < 8; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     }
+                    const float* wh = s_wh + (size_t)pr.wh_row0 * NL + 32 * c;
 #pragma unroll
-                    for (int n = 0; n < 16; n++) {
-                        if (n < g.nh) {
-                            const float4* w = reinterpret_cast<const float4*>(s_wh + n * NL + 32 * c);
+                    for (int n = 0; n < TAIL_HPW; n++) {
+                        if (n < pr.nh) {
+                            const float4* w = reinterpret_cast<const float4*>(wh + n * NL);
                             float a = h[n];
 #pragma unroll
                             for (int j = 0; j < 8; j++) { const float4 ww = w[j]; a = fmaf(v[4 * j], ww.x, a); a = fmaf(v[4 * j + 1], ww.y, a); a = fmaf(v[4 * j + 2], ww.z, a); a = fmaf(v[4 * j + 3], ww.w, a); }
@@ -1091,13 +1128,29 @@ __global__ void __launch_bounds__(192, 1) mlp_tail_fwd_kernel(const __grid_const
                     }
                 }
             }
-            if (row_ok) {
+            // the head: partial sums of column groups 1..G-1 meet group 0's in shared memory ([group][output][row]: conflict-free)
+            if (grp > 0) {
 #pragma unroll
-                for (int n = 0; n < 16; n++) if (n < g.nh) g.out[(size_t)row * g.ldout + n] = h[n];
+                for (int n = 0; n < TAIL_HPW; n++) if (n < pr.nh) s_hp[((grp - 1) * TAIL_HPW + n) * BM + rl] = h[n];
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(acc_free);
+            asm volatile("bar.sync 1, %0;" ::"r"(128 * G) : "memory");
+            if (grp == 0 && row_ok) {
+                const float* bh = s_bh + p * 16;
+#pragma unroll
+                for (int n = 0; n < TAIL_HPW; n++) {
+                    if (n < pr.nh) {
+                        float a = h[n] + bh[n];
+#pragma unroll
+                        for (int gg = 0; gg < G - 1; gg++) a += s_hp[(gg * TAIL_HPW + n) * BM + rl];
+                        pr.out[(size_t)row * pr.ldout + n] = a;
+                    }
+                }
+            }
+            // Three-layer tail: s_hp is rewritten only after the next tile's acc2_full, i.e. after y2_ready of that tile, which group 0's threads
+            // reach after these reads.  Two-layer tail: the next tile's partial sums can be ready sooner, so hold everybody until they are read.
+            if (N3 == 0) asm volatile("bar.sync 1, %0;" ::"r"(128 * G) : "memory");
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -1107,25 +1160,20 @@ __global__ void __launch_bounds__(192, 1) mlp_tail_fwd_kernel(const __grid_const
 }
 
 template <int K1, int N2, int N3>
-int launch_tail(const CUtensorMap& mx, const CUtensorMap& mw2, const CUtensorMap& mw3, const TailArgs& g, cudaStream_t st) {
-    constexpr int S1 = 3, S2 = (N3 > 0) ? 4 : 1;
-    constexpr int STAGE1 = (BM + N2) * BK * 4, Y2TILE = (N2 / BK) * BM * BK * 4;
-    constexpr int R1 = (N3 > 0 && Y2TILE > S1 * STAGE1) ? Y2TILE : S1 * STAGE1;
-    constexpr int R2 = (N3 > 0) ? S2 * N3 * BK * 4 : 0;
-    constexpr int NL = (N3 > 0) ? N3 : N2;
-    const size_t smem = (size_t)R1 + R2 + (size_t)(N2 + N3 + 16 * NL + 16) * 4 + (2 * S1 + 2 * S2 + 5) * 8 + 16 + 1024;
+int launch_tail(const TailMaps& maps, const TailArgs& g, cudaStream_t st) {
+    using L = TailSmem<K1, N2, N3>;
+    static_assert(L::TOTAL <= 227 * 1024, "fused tail: shared memory budget");
+    const size_t smem = L::TOTAL;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(mlp_tail_fwd_kernel<K1, N2, N3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return go1_set_error(cudaGetErrorString(e));
         configured = true;
     }
-    const int tiles = (g.M + BM - 1) / BM;
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-    const int per_sm = (smem > 113 * 1024) ? 1 : 2;
-    const int grid = tiles < per_sm * sms ? tiles : per_sm * sms;
-    mlp_tail_fwd_kernel<K1, N2, N3><<<grid, 192, smem, st>>>(mx, mw2, mw3, g, tiles);
+    const int grid = g.tiles < sms ? g.tiles : sms;
+    mlp_tail_fwd_kernel<K1, N2, N3><<<grid, 64 + 128 * TAIL_G, smem, st>>>(maps, g);
     go1_count_launch(1);
     return 0;
 }
@@ -1279,35 +1327,53 @@ extern "C" int go1_transpose(const float* src, int lds, float* dst, int ldd, int
 
 
 // ---- fused MLP tail (forward), see mlp_tail_fwd_kernel
-extern "C" int go1_mlp_tail_forward(const float* x, int ldx, int M, int K1, const float* W2, const float* b2, int N2, float* y2, int ldy2,
-                                    const float* W3, const float* b3, int N3, float* y3, int ldy3, const float* Wh, const float* bh, int nh,
-                                    float* out, int ldout, void* stream) {
+extern "C" int go1_mlp_tail_forward_grouped(const Go1TailProblem* probs, int nprob, int M, int K1, int N2, int N3, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (!x || !W2 || !y2 || !Wh || !out || M <= 0 || nh < 1 || nh > 16 || ldout < nh) return go1_set_error("go1_mlp_tail_forward: bad arguments");
-    if (N3 > 0 && (!W3 || !y3)) return go1_set_error("go1_mlp_tail_forward: the three-layer tail needs W3 / y3");
+    if (!probs || nprob < 1 || nprob > TAIL_MAXP || M <= 0) return go1_set_error("go1_mlp_tail_forward: 1 or 2 problems of the same shape");
     const bool shape_a = (K1 == 512 && N2 == 256 && N3 == 128), shape_b = (K1 == 256 && N2 == 128 && N3 == 0);
     if (!shape_a && !shape_b) return go1_set_error("go1_mlp_tail_forward: supported tails are 512-256-128-head and 256-128-head");
-    if ((ldx & 3) || (ldy2 & 3) || (N3 > 0 && (ldy3 & 3)) || ((((uintptr_t)x | (uintptr_t)W2 | (uintptr_t)y2 | (uintptr_t)(N3 > 0 ? (const void*)W3 : (const void*)W2) |
-                                                                 (uintptr_t)(N3 > 0 ? (const void*)y3 : (const void*)y2)) & 15) != 0))
-        return go1_set_error("go1_mlp_tail_forward: operands must be 16-byte aligned with row strides that are multiples of 4 floats");
-    CUtensorMap mx, mw2, mw3;
-    if (int e = make_map(&mx, x, M, K1, ldx, BM)) return e;
-    if (int e = make_map(&mw2, W2, N2, K1, K1, N2)) return e;
-    if (N3 > 0) { if (int e = make_map(&mw3, W3, N3, N2, N2, N3)) return e; } else mw3 = mw2;
+    TailMaps maps;
     TailArgs g;
-    g.b2 = b2; g.b3 = b3; g.Wh = Wh; g.bh = bh; g.y2 = y2; g.y3 = y3; g.out = out;
-    g.ldy2 = ldy2; g.ldy3 = ldy3; g.ldwh = (N3 > 0 ? N3 : N2); g.ldout = ldout; g.nh = nh; g.M = M;
+    g.nprob = nprob; g.M = M; g.tiles_per_prob = (M + BM - 1) / BM; g.tiles = g.tiles_per_prob * nprob;
+    int rows = 0;
+    for (int p = 0; p < nprob; p++) {
+        const Go1TailProblem& q = probs[p];
+        if (!q.x || !q.W2 || !q.y2 || !q.Wh || !q.out || q.nh < 1 || q.nh > TAIL_HPW || q.ldout < q.nh) return go1_set_error("go1_mlp_tail_forward: bad arguments (head width 1..12)");
+        if (N3 > 0 && (!q.W3 || !q.y3)) return go1_set_error("go1_mlp_tail_forward: the three-layer tail needs W3 / y3");
+        if ((q.ldx & 3) || (q.ldy2 & 3) || (N3 > 0 && (q.ldy3 & 3)) ||
+            ((((uintptr_t)q.x | (uintptr_t)q.W2 | (uintptr_t)q.y2 | (uintptr_t)(N3 > 0 ? (const void*)q.W3 : (const void*)q.W2) |
+               (uintptr_t)(N3 > 0 ? (const void*)q.y3 : (const void*)q.y2)) & 15) != 0))
+            return go1_set_error("go1_mlp_tail_forward: operands must be 16-byte aligned with row strides that are multiples of 4 floats");
+        if (int e = make_map(&maps.x[p], q.x, M, K1, q.ldx, BM)) return e;
+        if (int e = make_map(&maps.w2[p], q.W2, N2, K1, K1, N2)) return e;
+        if (N3 > 0) { if (int e = make_map(&maps.w3[p], q.W3, N3, N2, N2, N3)) return e; } else maps.w3[p] = maps.w2[p];
+        if (int e = make_map(&maps.y2[p], q.y2, M, N2, q.ldy2, 32)) return e;
+        TailProb& d = g.p[p];
+        d.b2 = q.b2; d.b3 = q.b3; d.Wh = q.Wh; d.bh = q.bh; d.y3 = q.y3; d.out = q.out; d.ldy3 = q.ldy3; d.ldout = q.ldout; d.nh = q.nh; d.wh_row0 = rows;
+        rows += q.nh;
+    }
+    if (rows > 16) return go1_set_error("go1_mlp_tail_forward: the head rows of all problems must fit 16");
+    for (int p = nprob; p < TAIL_MAXP; p++) { maps.x[p] = maps.x[0]; maps.w2[p] = maps.w2[0]; maps.w3[p] = maps.w3[0]; maps.y2[p] = maps.y2[0]; g.p[p] = g.p[0]; }
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     const bool timed = g_time_on && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone;
     if (timed) {
         cudaEventRecord(timing_event(), st);
-        g_time_flop += 2.0 * (double)M * ((double)K1 * N2 + (double)N2 * N3 + (double)(N3 > 0 ? N3 : N2) * nh);
-        g_time_recs.push_back({M, N2, K1, 0, 0, 1, 0, 1, shape_a ? 1003 : 1002, 0});
+        double fl = 0.0;
+        for (int p = 0; p < nprob; p++) fl += 2.0 * (double)M * ((double)K1 * N2 + (double)N2 * N3 + (double)(N3 > 0 ? N3 : N2) * probs[p].nh);
+        g_time_flop += fl;
+        g_time_recs.push_back({M * nprob, N2, K1, 0, 0, 1, 0, 1, shape_a ? 1003 : 1002, 0});
     }
-    int e = shape_a ? launch_tail<512, 256, 128>(mx, mw2, mw3, g, st) : launch_tail<256, 128, 0>(mx, mw2, mw3, g, st);
+    int e = shape_a ? launch_tail<512, 256, 128>(maps, g, st) : launch_tail<256, 128, 0>(maps, g, st);
     if (e) return e;
     if (timed) cudaEventRecord(timing_event(), st);
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return go1_set_error(cudaGetErrorString(ce));
     return 0;
+}
+extern "C" int go1_mlp_tail_forward(const float* x, int ldx, int M, int K1, const float* W2, const float* b2, int N2, float* y2, int ldy2,
+                                    const float* W3, const float* b3, int N3, float* y3, int ldy3, const float* Wh, const float* bh, int nh,
+                                    float* out, int ldout, void* stream) {
+    Go1TailProblem q;
+    q.x = x; q.ldx = ldx; q.W2 = W2; q.b2 = b2; q.y2 = y2; q.ldy2 = ldy2; q.W3 = W3; q.b3 = b3; q.y3 = y3; q.ldy3 = ldy3; q.Wh = Wh; q.bh = bh; q.nh = nh; q.out = out; q.ldout = ldout;
+    return go1_mlp_tail_forward_grouped(&q, 1, M, K1, N2, N3, stream);
 }

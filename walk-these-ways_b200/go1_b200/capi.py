@@ -116,6 +116,12 @@ class Go1GemmEpilogue(C.Structure):
                 ("ld_bwd_extra", _i), ("ld_bwd_w_extra", _i), ("ld_g_w_extra", _i), ("ld_d_extra", _i), ("num_bwd_extra", _i)]
 
 
+class Go1TailProblem(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("ldx", _i), ("W2", C.c_void_p), ("b2", C.c_void_p), ("y2", C.c_void_p), ("ldy2", _i),
+                ("W3", C.c_void_p), ("b3", C.c_void_p), ("y3", C.c_void_p), ("ldy3", _i), ("Wh", C.c_void_p), ("bh", C.c_void_p), ("nh", _i),
+                ("out", C.c_void_p), ("ldout", _i)]
+
+
 class Go1Error(RuntimeError):
     pass
 
@@ -156,6 +162,7 @@ def lib():
         "go1_gemm": ([ip, ip, ip, ip, ip, vp, ip, vp, ip, vp, ip, vp, ip, ip, ip, vp], ip),
         "go1_gemm_ex": ([ip, ip, ip, ip, ip, vp, ip, vp, ip, vp, ip, C.POINTER(Go1GemmEpilogue), ip, vp], ip),
         "go1_gemm_tf32_set_persistent": ([ip], None),
+        "go1_mlp_tail_forward_grouped": ([C.POINTER(Go1TailProblem), ip, ip, ip, ip, ip, vp], ip),
         "go1_mlp_tail_forward": ([vp, ip, ip, ip, vp, vp, ip, vp, ip, vp, vp, ip, vp, ip, vp, vp, ip, vp, ip, vp], ip),
         "go1_gemm_tf32_set_wide": ([ip], None),
         "go1_transpose": ([vp, ip, vp, ip, ip, ip, vp], ip),

@@ -170,33 +170,42 @@ class _Net:
         if not self.owner.fuse_tail:
             return False
         widths = tuple(sp[2] for sp in self.specs[:-1])
-        if self._TAILS.get(widths) != len(self.specs) - 1 or self.specs[-1][2] > 16:
+        if self._TAILS.get(widths) != len(self.specs) - 1 or self.specs[-1][2] > 12:
             return False
         ok = self._tma_ok(x1, ldx1)
         for wo, bo, o, i in self.specs[1:-1]:
             ok = ok and ((self.flat.data_ptr() + 4 * wo) & 15) == 0 and i % 4 == 0
         return ok
 
-    def _forward_tail(self, x1, ldx1, M, tag):
-        """Layers 1.. (and the head) in ONE launch; returns their outputs in layer order."""
-        L = capi.lib()
-        sp = self.specs
-        flat = self.flat
+    def _tail_problem(self, x1, ldx1, M, tag):
+        """(Go1TailProblem, [outputs of layers 1..]) of this net's tail for go1_mlp_tail_forward_grouped."""
+        sp, flat = self.specs, self.flat
         ptr = lambda off: flat.data_ptr() + 4 * off
+        q = capi.Go1TailProblem()
         (w2, b2, n2, k1) = sp[1]
         y2 = self._buf((tag, 1), M, n2)
+        q.x, q.ldx, q.W2, q.b2, q.y2, q.ldy2 = self._p(x1), ldx1, ptr(w2), ptr(b2), y2.data_ptr(), y2.stride(0)
         if len(sp) == 4:
             (w3, b3, n3, _), (wh, bh, nh, _) = sp[2], sp[3]
             y3 = self._buf((tag, 2), M, n3)
             out = self._buf((tag, 3), M, nh)
-            capi.check(L.go1_mlp_tail_forward(capi.ptr(x1), ldx1, M, k1, ptr(w2), ptr(b2), n2, capi.ptr(y2), y2.stride(0), ptr(w3), ptr(b3), n3, capi.ptr(y3),
-                                              y3.stride(0), ptr(wh), ptr(bh), nh, capi.ptr(out), out.stride(0), capi.stream_ptr()), "go1_mlp_tail_forward")
-            return [y2, y3, out]
-        (wh, bh, nh, _) = sp[2]
-        out = self._buf((tag, 2), M, nh)
-        capi.check(L.go1_mlp_tail_forward(capi.ptr(x1), ldx1, M, k1, ptr(w2), ptr(b2), n2, capi.ptr(y2), y2.stride(0), None, None, 0, None, 0,
-                                          ptr(wh), ptr(bh), nh, capi.ptr(out), out.stride(0), capi.stream_ptr()), "go1_mlp_tail_forward")
-        return [y2, out]
+            q.W3, q.b3, q.y3, q.ldy3 = ptr(w3), ptr(b3), y3.data_ptr(), y3.stride(0)
+            outs = [y2, y3, out]
+        else:
+            (wh, bh, nh, _) = sp[2]
+            n3 = 0
+            out = self._buf((tag, 2), M, nh)
+            q.W3, q.b3, q.y3, q.ldy3 = None, None, None, 0
+            outs = [y2, out]
+        q.Wh, q.bh, q.nh, q.out, q.ldout = ptr(wh), ptr(bh), nh, out.data_ptr(), out.stride(0)
+        return q, outs, (k1, n2, n3)
+
+    def _forward_tail(self, x1, ldx1, M, tag):
+        """Layers 1.. (and the head) in ONE launch; returns their outputs in layer order."""
+        q, outs, (k1, n2, n3) = self._tail_problem(x1, ldx1, M, tag)
+        arr = (capi.Go1TailProblem * 1)(q)
+        capi.check(capi.lib().go1_mlp_tail_forward_grouped(arr, 1, M, k1, n2, n3, capi.stream_ptr()), "go1_mlp_tail_forward")
+        return outs
 
     def backward(self, x, ldx, K0, extra, outs, dout, M, impl, accumulate, want_dextra=False, tag="a", dz1_out=None):
         """dout: gradient w.r.t. the network output [M][out] (the last layer has no activation).  Writes weight/bias grads
@@ -314,7 +323,7 @@ class ActorCritic(nn.Module):
         self.fuse_bias_grad = os.environ.get("GO1_FUSE_BIAS_GRAD", "1") != "0"     # bias gradients reduced in the dgrad GEMM epilogues
         self.update_streams = os.environ.get("GO1_UPDATE_STREAMS", "1") != "0"     # critic chain on a second stream during the update (measured -1.3 ms / iteration)
         self._side = None
-        self.fuse_tail = os.environ.get("GO1_FUSE_TAIL", "0") != "0"     # layers behind a first layer in one tcgen05 launch (go1_mlp_tail_forward); off: measured slower than layer by layer (130 vs 70 us at M = 24576)
+        self.fuse_tail = os.environ.get("GO1_FUSE_TAIL", "1") != "0"     # layers behind a first layer in one tcgen05 launch (go1_mlp_tail_forward_grouped: actor + critic bodies in one grid)
         self.grads_prezeroed = False  # PPO.update zeroes the flat gradient buffer once per optimizer step (one fill instead of one per layer)
 
     # ------------------------------------------------------------------ flat storage
@@ -464,7 +473,9 @@ class ActorCritic(nn.Module):
         na._gemm(0, 1, M, oa + oc + op, K0, h, h.stride(0), Wcat, Wcat.stride(0), y, y.stride(0), bcat, 1, 0, 1,
                  extra=priv, w_extra=xcat.data_ptr(), ld_w_extra=E, lead_cols=oa + oc)
         ya, yc, yp = y[:, :oa], y[:, oa:oa + oc], y[:, oa + oc:]
-        side = self._side_stream(M)
+        pair = self.fuse_tail and npol._tail_ok(yp, yp.stride(0), M) and ncr._tail_ok(yc, yc.stride(0), M) and \
+            [sp[2:] for sp in npol.specs[1:-1]] == [sp[2:] for sp in ncr.specs[1:-1]] and npol.specs[-1][2] + ncr.specs[-1][2] <= 16
+        side = None if pair else self._side_stream(M)
         if side is not None:        # the critic's tail does not depend on the adaptation module: it runs beside adapt -> actor
             self._fork(side)
             with torch.cuda.stream(side):
@@ -473,6 +484,14 @@ class ActorCritic(nn.Module):
         latent = self._latent = self._a_out[-1]
         capi.check(capi.lib().go1_mlp_extra_forward(capi.ptr(yp), yp.stride(0), capi.ptr(latent), latent.stride(0), Wp.data_ptr() + 4 * K0, K0 + E,
                                                     M, op, E, 1, capi.stream_ptr()), "go1_mlp_extra_forward")
+        if pair:                    # the equal-shape tails of the actor and critic bodies in ONE grid
+            qp, outs_p, shape = npol._tail_problem(yp, yp.stride(0), M, tag)
+            qc, outs_c, _ = ncr._tail_problem(yc, yc.stride(0), M, tag)
+            arr = (capi.Go1TailProblem * 2)(qp, qc)
+            capi.check(capi.lib().go1_mlp_tail_forward_grouped(arr, 2, M, shape[0], shape[1], shape[2], capi.stream_ptr()), "go1_mlp_tail_forward")
+            self._p_out, self._c_out = [yp] + outs_p, [yc] + outs_c
+            self._mean, self._value = self._p_out[-1], self._c_out[-1]
+            return self._mean, self._value
         self._p_out = npol.forward(h, h.stride(0), K0, latent, M, impl, tag, first_out=yp)
         self._mean = self._p_out[-1]
         if side is not None:

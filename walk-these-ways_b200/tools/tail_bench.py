@@ -31,6 +31,23 @@ def main():
                 e1.record(); torch.cuda.synchronize()
                 if it >= 2:
                     ts.append(e0.elapsed_time(e1) * 1e3)
+            # two problems of this shape in one grid (actor + critic bodies)
+            tsg = []
+            x2 = torch.randn(M, 1280, device="cuda")[:, :K1]
+            y2b, y3b, outb = torch.empty_like(y2), torch.empty_like(y3), torch.empty(M, 1, device="cuda")
+            qs = (capi.Go1TailProblem * 2)()
+            for q, (xx, yy2, yy3, oo, hh) in zip(qs, ((x, y2, y3, out, nh), (x2, y2b, y3b, outb, 1))):
+                q.x, q.ldx, q.W2, q.b2, q.y2, q.ldy2 = xx.data_ptr(), xx.stride(0), W2.data_ptr(), b2.data_ptr(), yy2.data_ptr(), N2
+                q.W3, q.b3, q.y3, q.ldy3 = (W3.data_ptr(), b3.data_ptr(), yy3.data_ptr(), N3) if N3 else (None, None, None, 0)
+                q.Wh, q.bh, q.nh, q.out, q.ldout = Wh.data_ptr(), bh.data_ptr(), hh, oo.data_ptr(), hh
+            for it in range(6):
+                flush.fill_(it)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                capi.check(L.go1_mlp_tail_forward_grouped(qs, 2, M, K1, N2, N3, capi.stream_ptr()), "tail2")
+                e1.record(); torch.cuda.synchronize()
+                if it >= 2:
+                    tsg.append(e0.elapsed_time(e1) * 1e3)
             # the separate products
             ts2 = []
             for it in range(6):
@@ -45,7 +62,7 @@ def main():
                 e1.record(); torch.cuda.synchronize()
                 if it >= 2:
                     ts2.append(e0.elapsed_time(e1) * 1e3)
-            print(f"M={M} tail {K1}-{N2}-{N3}-{nh}: fused {sum(ts) / len(ts):.1f} us, layer by layer {sum(ts2) / len(ts2):.1f} us", flush=True)
+            print(f"M={M} tail {K1}-{N2}-{N3}-{nh}: fused {sum(ts) / len(ts):.1f} us, two problems in one grid {sum(tsg) / len(tsg):.1f} us, layer by layer {sum(ts2) / len(ts2):.1f} us", flush=True)
 
 
 if __name__ == "__main__":
