@@ -267,7 +267,7 @@ def test_gemm_tcgen05_staged_epilogue(M, N, K, tb):
 # MN-major operands (dgrad: B = W as [K][N]; wgrad: A = dz as [K][M], B = activations as [K][N]) read straight from HBM
 @pytest.mark.parametrize("ta,tb", [(0, 0), (1, 0), (1, 1)])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 32, 64), (300, 200, 72), (24576, 128, 12), (12, 128, 24576), (1280, 2100, 4096),
-                                   (512, 256, 24576), (4096, 512, 256)])
+                                   (512, 256, 24576), (4096, 512, 256), (256, 2100, 24576), (256, 2100, 3000), (384, 1100, 2048)])
 def test_gemm_tcgen05_tf32_mn_major(ta, tb, M, N, K):
     torch.manual_seed(M * 7 + N * 3 + K + ta * 2 + tb)
     pad = lambda n: (n + 3) // 4 * 4 + 4

@@ -1245,11 +1245,12 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
     // products sit at the chip's TMA/L2 throughput cap (ncu: 11.4 TB/s), so that is what they are worth -- when the tile count
     // still fills the 148 SMs evenly (a 160-tile product would run two half-empty rounds) and K is long enough to hide the epilogue
     static const int wide_min_k = getenv("GO1_TF32_WIDE_MINK") ? atoi(getenv("GO1_TF32_WIDE_MINK")) : 1024;
-    static const int wide_min_tiles = getenv("GO1_TF32_WIDE_MINTILES") ? atoi(getenv("GO1_TF32_WIDE_MINTILES")) : 60;
+    static const int wide_min_tiles = getenv("GO1_TF32_WIDE_MINTILES") ? atoi(getenv("GO1_TF32_WIDE_MINTILES")) : 9;      // 9: the 256 x 2100 x 24576 adaptation wgrad takes cta_group::2 pairs + split-K (74 -> 62 us)
     static const int split_ctas = getenv("GO1_TF32_SPLIT_CTAS") ? atoi(getenv("GO1_TF32_SPLIT_CTAS")) : 2 * 148;
     static const int split_min_kb = getenv("GO1_TF32_SPLIT_MINKB") ? atoi(getenv("GO1_TF32_SPLIT_MINKB")) : 16;
     const int wtiles = ((M + BM - 1) / BM) * ((N + 255) / 256);
-    const bool fills = wtiles < 148 ? wtiles >= wide_min_tiles : (double)wtiles / (148.0 * ((wtiles + 147) / 148)) >= 0.85;
+    static const double wide_min_fill = getenv("GO1_TF32_WIDE_MINFILL") ? atof(getenv("GO1_TF32_WIDE_MINFILL")) : 0.85;
+    const bool fills = wtiles < 148 ? wtiles >= wide_min_tiles : (double)wtiles / (148.0 * ((wtiles + 147) / 148)) >= wide_min_fill;
     const bool wide = g_tf32_persistent && g_tf32_wide && K >= wide_min_k && N >= 256 && (N % 256 == 0 || N >= 1024) && fills;
     static const int use_2cta = getenv("GO1_TF32_2CTA") ? atoi(getenv("GO1_TF32_2CTA")) : 1;      // cta_group::2 pairs for the wide shapes
     const bool two_cta = use_2cta && wide && M >= 256;

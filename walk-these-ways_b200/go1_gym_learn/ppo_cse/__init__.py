@@ -198,7 +198,7 @@ class Runner:
                     for stale in [k for k in sg["graphs"] if k[1] != key[1]]:
                         del sg["graphs"][stale]
                     graph = torch.cuda.CUDAGraph()
-                    ac.force_repack = True
+                    ac.ensure_packed()
                     n0 = L.go1_kernel_launch_count()
                     try:
                         with torch.cuda.graph(graph):
@@ -211,6 +211,7 @@ class Runner:
                     g = sg["graphs"][key] = (graph, actions, n_kernels)
                 if g is not None:
                     graph, actions, n_kernels = g
+                    ac.ensure_packed()                                 # packed weight copies are refreshed once per weight version, outside the graph
                     graph.replay()
                     L.go1_kernel_launch_add(n_kernels)
                     env._cur = p ^ 1; env.obs_history = env._bufs[p ^ 1]

@@ -80,12 +80,23 @@ class _Net:
         return t[:M]
 
     def _cached(self, key, build):
+        """A packed copy of weights, rebuilt when the weights changed (weights_version).  The entry keeps its builder so that
+        ActorCritic.ensure_packed() can refresh every copy eagerly before a CUDA graph that reads them is replayed: the graphs contain
+        no packing kernels (the rollout replays one 24 times per weight version)."""
         ver = self.owner.weights_version
         hit = self._cache.get(key)
-        if hit is None or hit[0] != ver or self.owner.force_repack:
-            hit = (ver, build(hit[1] if hit else None))
+        if hit is None or hit[0] != ver:
+            if torch.cuda.is_current_stream_capturing():
+                raise capi.Go1Error("stale packed weights during graph capture: call ActorCritic.ensure_packed() first")
+            hit = (ver, build(hit[1] if hit else None), build)
             self._cache[key] = hit
         return hit[1]
+
+    def refresh_packed(self):
+        ver = self.owner.weights_version
+        for key, hit in list(self._cache.items()):
+            if hit[0] != ver:
+                self._cache[key] = (ver, hit[2](hit[1]), hit[2])
 
     @staticmethod
     def _p(x):
@@ -151,7 +162,7 @@ class _Net:
                 # rows the aligned pitch alone is worth 30 % (misaligned 128-byte box rows cost an extra L2 sector each)
                 if K % 4 == 0:
                     KPk = (K + 31) // 32 * 32
-                    Wm = self._cached(("pack", li), lambda old: (old if old is not None else _empty(o, KPk, device=W.device)[:, :K]).copy_(W.view(o, i)[:, :K]))
+                    Wm = self._cached(("pack", li), lambda old, W=W, o=o, i=i, K=K, KPk=KPk: (old if old is not None else _empty(o, KPk, device=W.device)[:, :K]).copy_(W.view(o, i)[:, :K]))
                     ldw = KPk
                 else:
                     tc = False
@@ -315,7 +326,8 @@ class ActorCritic(nn.Module):
         self._mean = self._value = self._logp = None
         self._sample_counter = 0
         self._counter_dev = None
-        self.force_repack = False     # set while a CUDA graph of the forward pass is captured: weight packing must be IN the graph
+        self.force_repack = False     # (kept for callers that set it; packing is never part of a graph any more, see ensure_packed)
+        self._packed_version = -1
         self.sample_seed = 0
         self.injected_eps = None      # parity tests inject the N(0,1) draws
         self.weights_version = 0      # bumped by every optimizer step / load: invalidates the packed first-layer weight copies
@@ -371,6 +383,15 @@ class ActorCritic(nn.Module):
             self._nets[name] = _Net(seq, self._flat, self._grad, offsets, self)
         self.n_adapt_params = (self._nets["adapt"].end + 3) // 4 * 4
         self.std_offset = offsets[id(self.std)]
+
+    def ensure_packed(self):
+        """Bring every packed weight copy (fused first-layer block, TMA-readable first-layer copies) up to date with the current weights.
+        Called before a captured forward pass is replayed; a no-op while the weights are unchanged."""
+        if self._flat is None or self._packed_version == self.weights_version:
+            return
+        for net in self._nets.values():
+            net.refresh_packed()
+        self._packed_version = self.weights_version
 
     @property
     def flat_params(self):

@@ -128,7 +128,7 @@ class PPO:
                     self._act_eager(h_in, p_in)             # allocates every scratch buffer, configures kernels
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
-            ac.force_repack = True
+            ac.ensure_packed()                                    # the graph reads the packed weight copies, it does not build them
             L = capi.lib()
             n0 = L.go1_kernel_launch_count()
             try:
@@ -142,6 +142,7 @@ class PPO:
         graph, h_in, p_in, outs, attrs, inplace, n_kernels = g
         if not inplace:
             h_in.copy_(obs_history); p_in.copy_(privileged_obs)
+        ac.ensure_packed()
         graph.replay()
         capi.lib().go1_kernel_launch_add(n_kernels)
         ac._mean, ac._logp, ac._last_actions, ac._value, ac._latent = attrs     # the graph's static outputs
