@@ -316,7 +316,7 @@ typedef struct Go1GemmEpilogue {
                           * of the layer whose dz this dgrad product produces, reduced in the epilogue (atomic adds: zero it first) */
     /* optional (impl 1): C is the dz of a first layer with `num_bwd_extra` (<= 4) trailing inputs (go1_mlp_extra_backward's job done in
      * this epilogue, atomic adds into zeroed outputs):  g_w_extra[n][t] += sum_m C[m][n] bwd_extra[m][t];
-     * d_extra[m][t] += sum_n C[m][n] bwd_w_extra[n][t]  (d_extra may be NULL) */
+     * d_extra[m][t] += sum_n C[m][n] bwd_w_extra[n][t]  (d_extra may be NULL; g_w_extra may be NULL when d_extra is given) */
     const float* bwd_extra; const float* bwd_w_extra; float* g_w_extra; float* d_extra;
     int32_t ld_bwd_extra, ld_bwd_w_extra, ld_g_w_extra, ld_d_extra, num_bwd_extra;
 } Go1GemmEpilogue;
@@ -372,6 +372,11 @@ int go1_skinny_dgrad_ex(const float* dz, int lddz, const float* W, int ldw, cons
 int go1_skinny_wgrad_ex(const float* dz, int lddz, const float* x, int ldx, float* gW, int ldg, float* gb, int M, int o, int K, int accumulate, void* stream);
 /* wgrad of a narrow (o <= 16) output layer (the 12 / 2 / 1-wide heads): gW[j][k] (+)= sum_m dz[m][j] x[m][k]. */
 int go1_skinny_wgrad(const float* dz, int lddz, const float* x, int ldx, float* gW, int ldg, int M, int o, int K, int accumulate, void* stream);
+/* Up to 8 strided 2-D copies dst[r][c] = src[r][c] in ONE launch: builds the packed first-layer weight block / bias / trailing-input
+ * weights that the fused first-layer product of ActorCritic reads (actor_critic.py:113-144 evaluates the three MLPs on the same
+ * obs_history), and brings the fused wgrad's output back into the flat gradient buffer. */
+typedef struct Go1CopySeg { const float* src; int32_t lds; float* dst; int32_t ldd; int32_t rows, cols; } Go1CopySeg;
+int go1_copy_segments(const Go1CopySeg* segs, int n, void* stream);
 /* out[n] (+)= sum_m x[m][n]: bias gradient of nn.Linear. */
 int go1_colsum(const float* x, int ldx, float* out, int M, int N, int accumulate, void* stream);
 

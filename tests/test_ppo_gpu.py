@@ -414,6 +414,22 @@ def test_fused_backward_epilogues_match_separate_kernels(M):
     a, b = grads[False], grads[True]
     scale = a.abs().max()
     assert float((a - b).abs().max()) <= 2e-5 * float(scale) + 1e-7, float((a - b).abs().max())
+    # augmented input columns: bias and trailing-input weight gradients of the first layers out of the fused first-layer wgrad
+    # (h lives in a row buffer with spare columns [1 | priv | latent slot] behind the history, as RolloutStorage builds it)
+    hb = torch.zeros(M, NH + 12, device="cuda")
+    hb[:, :NH] = h; hb[:, NH] = 1.0; hb[:, NH + 1:NH + 1 + NP] = priv
+    h2 = hb[:, :NH]
+    ac.fuse_bias_grad = True
+    ac.flat_grads.zero_(); ac.grads_prezeroed = True
+    ac.forward_all(h2, priv, tag="train")
+    ac.backward_ppo(h2, priv, dmean, dvalue, dstd, aug=True)
+    torch.cuda.synchronize()
+    c = ac.flat_grads.clone()
+    ac.grads_prezeroed = False
+    assert torch.equal(hb[:, NH + 1 + NP:NH + 1 + 2 * NP], ac._latent)          # the latent slot was filled
+    # TF32 products instead of fp32 reductions for these few gradients: compare at TF32 accuracy against the fp32-reduced ones
+    assert float((a - c).abs().max()) <= 3e-3 * float(scale) + 1e-7, float((a - c).abs().max())
+    b = c
     # fp64 autograd of sum(mean * dmean) + sum(value * dvalue) through plain torch modules holding the same weights
     import copy
     ref = {k: copy.deepcopy(getattr(ac, k)).double() for k in ("adaptation_module", "actor_body", "critic_body")}

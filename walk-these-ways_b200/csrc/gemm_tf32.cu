@@ -264,6 +264,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, uint32_t (&r)[
 #pragma unroll
         for (int t = 0; t < 4; t++) {
             if (t < g.nbx) {
+                if (g.gwx) {        // (NULL: the caller gets this weight gradient elsewhere -- from augmented input columns of the first-layer wgrad)
                 const float e = row_ok ? __ldg(g.bx + (size_t)row * g.ldbx + t) : 0.f;
                 float sred[32];
 #pragma unroll
@@ -279,6 +280,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, uint32_t (&r)[
                     }
                 }
                 if (lane < ncols) atomicAdd(g.gwx + (size_t)cjx * g.ldgwx + t, sred[0]);
+                }
                 if (g.dx) {
                     const float wl = lane < ncols ? __ldg(g.bwx + (size_t)cjx * g.ldbwx + t) : 0.f;
                     float acc = 0.f;
@@ -1236,7 +1238,7 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
     g.amn = amn; g.bmn = bmn; g.lead = ep->lead_cols; g.colsum = ep->colsum;
     g.nbx = ep->num_bwd_extra; g.bx = ep->bwd_extra; g.bwx = ep->bwd_w_extra; g.gwx = ep->g_w_extra; g.dx = ep->d_extra;
     g.ldbx = ep->ld_bwd_extra; g.ldbwx = ep->ld_bwd_w_extra; g.ldgwx = ep->ld_g_w_extra; g.lddx = ep->ld_d_extra;
-    if (g.nbx < 0 || g.nbx > 4 || (g.nbx > 0 && (!g.bx || !g.gwx || (g.dx && !g.bwx)))) return go1_set_error("go1_gemm_ex: bad fused trailing-input backward arguments");
+    if (g.nbx < 0 || g.nbx > 4 || (g.nbx > 0 && ((g.gwx && !g.bx) || (!g.gwx && !g.dx) || (g.dx && !g.bwx)))) return go1_set_error("go1_gemm_ex: bad fused trailing-input backward arguments");
     if (g.nex < 0 || g.nex > 4) return go1_set_error("go1_gemm_ex: num_extra must be 0..4");
     if (act == 2 && !g.aux) return go1_set_error("go1_gemm_ex: act 2 needs dact_y");
     const int num_kb = (K + BK - 1) / BK;

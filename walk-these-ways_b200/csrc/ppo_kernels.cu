@@ -474,6 +474,48 @@ extern "C" int go1_skinny_wgrad(const float* dz, int lddz, const float* x, int l
     return go1_skinny_wgrad_ex(dz, lddz, x, ldx, gW, ldg, nullptr, M, o, K, accumulate, stream);
 }
 
+// Up to 8 strided 2-D copies in ONE launch (dst[r][c] = src[r][c]): the packed first-layer weight block / bias / trailing-input
+// weights the fused first-layer product reads, and the way back from the fused wgrad's output into the flat gradient buffer.
+// Rows of the ActorCritic first layers are 2102 floats long (8-byte aligned), so the vector width is 8 bytes.
+struct CopySegs { Go1CopySeg s[8]; int n; };
+__global__ void __launch_bounds__(256) copy_segments_kernel(const CopySegs a) {
+    for (int si = 0; si < a.n; si++) {
+        const Go1CopySeg& sg = a.s[si];
+        const bool v2 = ((sg.cols & 1) == 0) && ((sg.lds & 1) == 0) && ((sg.ldd & 1) == 0) && (((uintptr_t)sg.src | (uintptr_t)sg.dst) & 7) == 0;
+        if (v2) {
+            const int c2 = sg.cols >> 1;
+            const long long total = (long long)sg.rows * c2;
+            for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+                const int r = (int)(i / c2), c = (int)(i - (long long)r * c2);
+                reinterpret_cast<float2*>(sg.dst + (size_t)r * sg.ldd)[c] = __ldg(reinterpret_cast<const float2*>(sg.src + (size_t)r * sg.lds) + c);
+            }
+        } else {
+            const long long total = (long long)sg.rows * sg.cols;
+            for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+                const int r = (int)(i / sg.cols), c = (int)(i - (long long)r * sg.cols);
+                sg.dst[(size_t)r * sg.ldd + c] = __ldg(sg.src + (size_t)r * sg.lds + c);
+            }
+        }
+    }
+}
+extern "C" int go1_copy_segments(const Go1CopySeg* segs, int n, void* stream) {
+    if (!segs || n < 1 || n > 8) return go1_set_error("go1_copy_segments: 1..8 segments");
+    CopySegs a; a.n = n;
+    long long work = 0;
+    for (int i = 0; i < n; i++) {
+        if (!segs[i].src || !segs[i].dst || segs[i].rows <= 0 || segs[i].cols <= 0 || segs[i].lds < segs[i].cols || segs[i].ldd < segs[i].cols)
+            return go1_set_error("go1_copy_segments: bad segment");
+        a.s[i] = segs[i];
+        const long long w = (long long)segs[i].rows * segs[i].cols / 2;
+        if (w > work) work = w;
+    }
+    long long blocks = (work + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    copy_segments_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a); go1_count_launch(1);
+    return cuda_rc("go1_copy_segments");
+}
+
 // out[n] (+)= sum_m x[m][n]   (bias gradients)
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int ldx, float* __restrict__ out, int M, int N, int rows_per_block) {
     __shared__ float s[8][33];

@@ -122,6 +122,20 @@ class Go1TailProblem(C.Structure):
                 ("out", C.c_void_p), ("ldout", _i)]
 
 
+class Go1CopySeg(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("lds", _i), ("dst", C.c_void_p), ("ldd", _i), ("rows", _i), ("cols", _i)]
+
+
+def copy_segments(pairs):
+    """dst.copy_(src) for up to 8 (dst, src) pairs of 2-D float32 CUDA tensors (unit inner stride) in ONE launch (go1_copy_segments)."""
+    n = len(pairs)
+    arr = (Go1CopySeg * n)()
+    for sg, (dst, src) in zip(arr, pairs):
+        assert dst.shape == src.shape and dst.dim() == 2 and dst.stride(1) == 1 and src.stride(1) == 1
+        sg.src, sg.lds, sg.dst, sg.ldd, sg.rows, sg.cols = src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), dst.shape[0], dst.shape[1]
+    check(lib().go1_copy_segments(arr, n, stream_ptr()), "go1_copy_segments")
+
+
 class Go1Error(RuntimeError):
     pass
 
@@ -172,6 +186,7 @@ def lib():
         "go1_skinny_dgrad": ([vp, ip, vp, ip, vp, ip, vp, ip, ip, ip, ip, vp], ip),
         "go1_skinny_dgrad_ex": ([vp, ip, vp, ip, vp, ip, vp, ip, vp, ip, ip, ip, vp], ip),
         "go1_skinny_wgrad_ex": ([vp, ip, vp, ip, vp, ip, vp, ip, ip, ip, ip, vp], ip),
+        "go1_copy_segments": ([C.POINTER(Go1CopySeg), ip, vp], ip),
         "go1_skinny_forward": ([vp, ip, vp, ip, vp, vp, ip, ip, ip, ip, vp], ip),
         "go1_skinny_wgrad": ([vp, ip, vp, ip, vp, ip, ip, ip, ip, ip, vp], ip),
         "go1_colsum": ([vp, ip, vp, ip, ip, ip, vp], ip),

@@ -110,7 +110,7 @@ class _Net:
         if bwd_extra is not None:      # (extra [M][E], w_extra ptr, ld, g_w_extra ptr, ld, dextra [M][E] or None)
             ex, wex, ldw, gw, ldg, dex = bwd_extra
             ep.bwd_extra, ep.ld_bwd_extra, ep.num_bwd_extra = ex.data_ptr(), ex.stride(0), ex.shape[1]
-            ep.bwd_w_extra, ep.ld_bwd_w_extra, ep.g_w_extra, ep.ld_g_w_extra = wex, ldw, gw, ldg
+            ep.bwd_w_extra, ep.ld_bwd_w_extra, ep.g_w_extra, ep.ld_g_w_extra = wex, ldw, gw, ldg      # gw None: no weight-gradient reduction
             ep.d_extra, ep.ld_d_extra = (dex.data_ptr(), dex.stride(0)) if dex is not None else (None, 0)
         else:
             ep.num_bwd_extra = 0
@@ -218,11 +218,13 @@ class _Net:
         capi.check(capi.lib().go1_mlp_tail_forward_grouped(arr, 1, M, k1, n2, n3, capi.stream_ptr()), "go1_mlp_tail_forward")
         return outs
 
-    def backward(self, x, ldx, K0, extra, outs, dout, M, impl, accumulate, want_dextra=False, tag="a", dz1_out=None):
+    def backward(self, x, ldx, K0, extra, outs, dout, M, impl, accumulate, want_dextra=False, tag="a", dz1_out=None, aug_first=False):
         """dout: gradient w.r.t. the network output [M][out] (the last layer has no activation).  Writes weight/bias grads
         into the flat grad buffer.  dz of every hidden layer comes out of the dgrad GEMM already multiplied by ELU'
         (fused epilogue).  dz1_out: optional [M][o1] strided view; when given the first layer's dz is written there and its wgrad is
-        left to the caller (ActorCritic fuses the three first-layer wgrads into one GEMM).  Returns d(extra) [M][E] if requested."""
+        left to the caller (ActorCritic fuses the three first-layer wgrads into one GEMM).  aug_first: the caller's fused wgrad also yields the first
+        layer's bias gradient and trailing-input weight gradients (augmented input columns), so the dgrad epilogue that produces the first layer's
+        dz reduces neither of them (only d(extra) if requested).  Returns d(extra) [M][E] if requested."""
         L, st = capi.lib(), capi.stream_ptr()
         n = len(self.specs)
         dz = dout
@@ -277,7 +279,17 @@ class _Net:
                     if fuse and not accumulate and not self.owner.grads_prezeroed:
                         gb_prev.zero_()
                     bx = None
-                    if fuse and li == 1 and extra is not None and self.owner.grads_prezeroed and not accumulate and 1 <= pi - K0 <= 4:
+                    aug = aug_first and li == 1
+                    if aug:
+                        # the first layer's bias and trailing-input weight gradients come out of the caller's fused wgrad; only d(extra) is left
+                        if extra is not None and want_dextra:
+                            E0 = pi - K0
+                            Wp = self.flat[pwo:pwo + po * pi]
+                            dextra = self._buf((tag, "dextra"), M, E0)
+                            dextra.zero_()
+                            bx = (extra, Wp.data_ptr() + 4 * K0, pi, None, 0, dextra)
+                        extra_done = True
+                    elif fuse and li == 1 and extra is not None and self.owner.grads_prezeroed and not accumulate and 1 <= pi - K0 <= 4:
                         # dprev is the first layer's dz: its trailing-input weight gradient (and d(extra)) are reduced in this epilogue too
                         E0 = pi - K0
                         Wp = self.flat[pwo:pwo + po * pi]
@@ -287,8 +299,10 @@ class _Net:
                             dextra.zero_()
                         bx = (extra, Wp.data_ptr() + 4 * K0, pi, gWp.data_ptr() + 4 * K0, pi, dextra if want_dextra else None)
                         extra_done = True
-                    self._gemm(0, 0, M, i, o, dz, ldz, W, i, dprev, ldp, None, 2, 0, 1, dact_y=yprev, colsum=gb_prev if fuse else None, bwd_extra=bx)
-                    bias_done = bool(fuse)
+                    self._gemm(0, 0, M, i, o, dz, ldz, W, i, dprev, ldp, None, 2, 0, 1, dact_y=yprev, colsum=gb_prev if (fuse and not aug) else None, bwd_extra=bx)
+                    bias_done = bool(fuse) or aug
+                elif aug_first and li == 1:
+                    raise capi.Go1Error("augmented first-layer wgrad: the dgrad that produces the first layer's dz must be a tcgen05 product")
                 elif o <= 16:
                     pwo, pbo, po, pi = self.specs[li - 1]
                     gb_prev = self.grad[pbo:pbo + po]
@@ -474,22 +488,16 @@ class ActorCritic(nn.Module):
 
         KP = (K0 + 31) // 32 * 32      # 128-byte row pitch of the packed weights (aligned TMA box rows, see RolloutStorage.hist_pitch)
 
-        def build_w(old):
-            W = old if old is not None else _empty(oa + oc + op, KP, device=flat.device)[:, :K0]
-            W[:oa].copy_(Wa); W[oa:oa + oc].copy_(Wc[:, :K0]); W[oa + oc:].copy_(Wp[:, :K0])
-            return W
+        def build_all(old):     # the packed block [adapt | critic | actor] x K0 (128-byte row pitch), its bias row and the trailing-input
+            if old is None:     # weights of the leading (adaptation | critic) columns (zeros | Wc[:, K0:]): ONE launch for all seven pieces
+                old = (_empty(oa + oc + op, KP, device=flat.device)[:, :K0], _empty(1, oa + oc + op, device=flat.device),
+                       _empty(oa + oc, E, device=flat.device).zero_())
+            W, b, x = old
+            capi.copy_segments([(W[:oa], Wa), (W[oa:oa + oc], Wc[:, :K0]), (W[oa + oc:], Wp[:, :K0]),
+                                (b[:, :oa], ba.view(1, -1)), (b[:, oa:oa + oc], bc.view(1, -1)), (b[:, oa + oc:], bp.view(1, -1)), (x[oa:], Wc[:, K0:])])
+            return old
 
-        def build_b(old):
-            b = old if old is not None else _empty(1, oa + oc + op, device=flat.device)
-            b[0, :oa].copy_(ba); b[0, oa:oa + oc].copy_(bc); b[0, oa + oc:].copy_(bp)
-            return b
-
-        def build_x(old):       # trailing-input weights of the leading (adaptation | critic) columns: zeros | Wc[:, K0:]
-            x = old if old is not None else _empty(oa + oc, E, device=flat.device).zero_()
-            x[oa:].copy_(Wc[:, K0:])
-            return x
-
-        Wcat, bcat, xcat = na._cached(("l1cat", "W"), build_w), na._cached(("l1cat", "b"), build_b), na._cached(("l1cat", "x"), build_x)
+        Wcat, bcat, xcat = na._cached(("l1cat", "all"), build_all)
         y = na._buf((tag, "y1cat"), M, oa + oc + op)
         na._gemm(0, 1, M, oa + oc + op, K0, h, h.stride(0), Wcat, Wcat.stride(0), y, y.stride(0), bcat, 1, 0, 1,
                  extra=priv, w_extra=xcat.data_ptr(), ld_w_extra=E, lead_cols=oa + oc)
@@ -617,9 +625,14 @@ class ActorCritic(nn.Module):
         return self._nets["adapt"].forward(h, h.stride(0), self.num_obs_history, None, h.shape[0], self._impl(), "latent")[-1]
 
     # ------------------------------------------------------------------ explicit backward passes (ppo.py:154-189)
-    def backward_ppo(self, h, priv, dmean, dvalue, dstd):
+    def backward_ppo(self, h, priv, dmean, dvalue, dstd, aug=False):
         """Gradients of the PPO loss into flat_grads (overwrites). h/priv are the minibatch inputs of the forward
-        pass just run with tag='train'; dmean [M,A], dvalue [M,1], dstd [A]."""
+        pass just run with tag='train'; dmean [M,A], dvalue [M,1], dstd [A].
+        aug: h is a view of a row buffer with spare columns behind the K0 history columns that the caller has filled with
+        [1 | priv (E) | anything (E)] (RolloutStorage.mini_batch_generator does).  The latent is copied into the last E and the fused
+        first-layer wgrad runs over K0 + 1 + 2E input columns: its extra output columns ARE the three first-layer bias gradients and the
+        trailing-input weight gradients of the critic (priv columns) and the actor (latent columns), for free on the tensor core, so the
+        dgrad epilogues that produce the first-layer dz skip those reductions."""
         M, K0, impl = h.shape[0], self.num_obs_history, self._impl()
         nets = self._nets
         if impl == 1 and M >= 64 and _Net._tma_ok(h, h.stride(0)):
@@ -628,25 +641,40 @@ class ActorCritic(nn.Module):
             # column slice of `dz1` by that net's layer-2 dgrad)
             oa, op, oc = nets["adapt"].specs[0][2], nets["actor"].specs[0][2], nets["critic"].specs[0][2]
             dz1 = nets["adapt"]._buf(("train", "dz1cat"), M, oa + op + oc)
+            E = self.num_privileged_obs
+            aug = bool(aug) and self.fuse_bias_grad and self.grads_prezeroed and h.stride(0) >= K0 + 1 + 2 * E and 1 <= E <= 4 and \
+                nets["actor"].specs[0][3] == K0 + E and nets["critic"].specs[0][3] == K0 + E and priv.shape[1] == E
+            KA = K0 + 1 + 2 * E if aug else K0          # input columns of the fused wgrad
+            if aug:
+                h_ext = h.as_strided((M, KA), (h.stride(0), 1))
+                capi.copy_segments([(h_ext[:, K0 + 1 + E:], self._latent)])
             side = self._side_stream(M)
             if side is not None:    # critic chain beside actor -> adaptation chain
                 self._fork(side)
                 with torch.cuda.stream(side):
-                    nets["critic"].backward(h, h.stride(0), K0, priv, self._c_out, dvalue, M, impl, 0, tag="train", dz1_out=dz1[:, oa + op:])
-            dlat = nets["actor"].backward(h, h.stride(0), K0, self._latent, self._p_out, dmean, M, impl, 0, want_dextra=True, tag="train", dz1_out=dz1[:, oa:oa + op])
+                    nets["critic"].backward(h, h.stride(0), K0, priv, self._c_out, dvalue, M, impl, 0, tag="train", dz1_out=dz1[:, oa + op:], aug_first=aug)
+            dlat = nets["actor"].backward(h, h.stride(0), K0, self._latent, self._p_out, dmean, M, impl, 0, want_dextra=True, tag="train", dz1_out=dz1[:, oa:oa + op],
+                                          aug_first=aug)
             if side is None:
-                nets["critic"].backward(h, h.stride(0), K0, priv, self._c_out, dvalue, M, impl, 0, tag="train", dz1_out=dz1[:, oa + op:])
-            nets["adapt"].backward(h, h.stride(0), K0, None, self._a_out, dlat, M, impl, 0, tag="train", dz1_out=dz1[:, :oa])
+                nets["critic"].backward(h, h.stride(0), K0, priv, self._c_out, dvalue, M, impl, 0, tag="train", dz1_out=dz1[:, oa + op:], aug_first=aug)
+            nets["adapt"].backward(h, h.stride(0), K0, None, self._a_out, dlat, M, impl, 0, tag="train", dz1_out=dz1[:, :oa], aug_first=aug)
             if side is not None:
                 self._join(side)
             n0 = nets["adapt"]
-            gcat = n0._buf(("train", "gWcat"), oa + op + oc, K0)
-            n0._gemm(1, 0, oa + op + oc, K0, M, dz1, dz1.stride(0), h, h.stride(0), gcat, K0, None, 0, 0, 1)
-            row = 0
-            for name in ("adapt", "actor", "critic"):
+            KP = (KA + 31) // 32 * 32
+            gcat = n0._buf(("train", "gWcat"), oa + op + oc, KP)
+            n0._gemm(1, 0, oa + op + oc, KA, M, dz1, dz1.stride(0), h_ext if aug else h, h.stride(0), gcat, KP, None, 0, 0, 1)
+            row, pairs = 0, []
+            for name, xcol in (("adapt", None), ("actor", K0 + 1 + E), ("critic", K0 + 1)):
                 wo, bo, o, i = nets[name].specs[0]
-                self._grad[wo:wo + o * i].view(o, i)[:, :K0].copy_(gcat[row:row + o])
+                gW = self._grad[wo:wo + o * i].view(o, i)
+                pairs.append((gW[:, :K0], gcat[row:row + o, :K0]))
+                if aug:     # column K0: the bias gradient; columns xcol..xcol+E: the trailing-input weight gradient of this net
+                    pairs.append((self._grad[bo:bo + o].view(o, 1), gcat[row:row + o, K0:K0 + 1]))
+                    if xcol is not None:
+                        pairs.append((gW[:, K0:K0 + E], gcat[row:row + o, xcol:xcol + E]))
                 row += o
+            capi.copy_segments(pairs)
         else:
             dlat = nets["actor"].backward(h, h.stride(0), K0, self._latent, self._p_out, dmean, M, impl, 0, want_dextra=True, tag="train")
             nets["critic"].backward(h, h.stride(0), K0, priv, self._c_out, dvalue, M, impl, 0, tag="train")

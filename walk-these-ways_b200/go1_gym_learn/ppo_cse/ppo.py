@@ -222,7 +222,7 @@ class PPO:
                                       capi.ptr(dmean), ac.num_actions, capi.ptr(dvalue), capi.ptr(self._dstd), capi.ptr(self._scalars), M, ac.num_actions,
                                       PPO_Args.clip_param, PPO_Args.value_loss_coef, PPO_Args.entropy_coef, int(PPO_Args.use_clipped_value_loss),
                                       1.0 / (M * world), st()), "ppo_loss")
-            ac.backward_ppo(hist_b, priv_b, dmean, dvalue, self._dstd)
+            ac.backward_ppo(hist_b, priv_b, dmean, dvalue, self._dstd, aug=getattr(hist_b, "aug", False))
             # ONE collective per optimizer step: gradients (already scaled by 1/global batch) + the 8 loss scalars in the buffer head
             self._allreduce(ac.flat_grads)
             if PPO_Args.desired_kl is not None and PPO_Args.schedule == 'adaptive':   # ppo.py:118-132, on the device, from the global KL

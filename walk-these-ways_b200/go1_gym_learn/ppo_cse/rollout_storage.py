@@ -158,7 +158,19 @@ class RolloutStorage:
             for i in range(num_mini_batches):
                 idx = indices[i * mini_batch_size:(i + 1) * mini_batch_size].contiguous()
                 obs = self.gather(self.observations, idx)
-                yield (obs, obs, self.gather(self.privileged_observations, idx), self.gather(self.observation_histories, idx, key=("hist", i), ldd=self.hist_pitch),
+                priv_b = self.gather(self.privileged_observations, idx)
+                hist_b = self.gather(self.observation_histories, idx, key=("hist", i), ldd=self.hist_pitch)
+                w, P = hist_b.shape[1], priv_b.shape[1]
+                hist_b.aug = False
+                if hist_b.stride(0) >= w + 1 + 2 * P and P >= 1:
+                    # spare columns behind the history: [1 | privileged obs | (latent slot)], the augmented inputs of ActorCritic.backward_ppo's
+                    # fused first-layer wgrad (bias and trailing-input weight gradients come out of the tensor core with the weight gradient)
+                    pad = hist_b.as_strided((hist_b.shape[0], hist_b.stride(0) - w), (hist_b.stride(0), 1), hist_b.storage_offset() + w)
+                    pad.zero_()
+                    pad[:, 0] = 1.0
+                    pad[:, 1:1 + P] = priv_b
+                    hist_b.aug = True
+                yield (obs, obs, priv_b, hist_b,
                        self.gather(self.actions, idx), self.gather(self.values, idx), self.gather(self.advantages, idx),
                        self.gather(self.returns, idx), self.gather(self.actions_log_prob, idx), self.gather(self.mu, idx),
                        self.gather(self.sigma, idx), dones8, self.gather(self.env_bins, idx))
