@@ -296,10 +296,8 @@ int go1_ppo_normalize_advantages(float* advantages, const double* stats, int64_t
  * impl: 0 = fp32 CUDA cores (exact-fp32 path), 1 = tcgen05 TF32 tensor cores with fp32 accumulation. */
 int go1_gemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
              float* C, int ldc, const float* bias, int act, int accumulate, int impl, void* stream);
-/* impl=1 kernel selection: 1 (default) = persistent tile loop with double-buffered TMEM accumulators, 0 = one tile per CTA. */
-void go1_gemm_tf32_set_persistent(int on);
-/* opt-in (default 0): products with N >= 512 and enough tiles use 128 x 256 output tiles (one CTA per SM); measured +25% on the isolated
- * product but -8% on the whole PPO update (no co-residency with the neighbouring kernels), see profiles/. */
+/* impl=1 tile selection (default 1): products with K >= 1024, N >= 256 and enough tiles run as cta_group::2 256 x 256 tile pairs
+ * (128 x 256 single-CTA tiles when M < 256); 0 forces the 128 x 128 persistent kernel everywhere (a tuning / bisecting switch). */
 void go1_gemm_tf32_set_wide(int on);
 /* Same product with the full fused epilogue, applied in this order to each output element v = sum_k a*b:
  *   v += C_old (accumulate);  v += sum_e extra[m][e] * w_extra[n][e]  (num_extra <= 4: the 2 trailing input columns of

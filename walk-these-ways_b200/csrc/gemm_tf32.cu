@@ -5,16 +5,17 @@
 // The forward products read both operands K-major (A = activations row-major, B = torch.nn.Linear weight [out][in]);
 // dgrad (B = W as [K][N]) and wgrad (A = dz as [K][M], B = activations as [K][N]) read MN-major operands straight from
 // HBM: the TMA boxes become [32 k-rows][32 mn-floats] and the UMMA descriptors / instruction descriptor switch to the
-// MN-major canonical layout, so no transposed copies exist anywhere.  Structure (one 128 x BN output tile per
-// CTA, 192 threads):
-//   warp 0   TMA producer: cp.async.bulk.tensor 2D loads of 128x32 (A) and BNx32 (B) fp32 boxes, 128B swizzle,
-//            S-stage ring guarded by full/empty mbarriers
-//   warp 1   TMEM allocator + single-thread tcgen05.mma.cta_group::1.kind::tf32 issuer (M=128, N=BN, K=8 per
-//            instruction, 4 per k-block), tcgen05.commit to release smem stages and to publish the accumulator
-//   warps 2-5 epilogue: tcgen05.ld 32x32b from TMEM -> registers -> bias / ELU / accumulate -> global
-//            (red.global.add when split-K partitions the reduction)
-// Accumulators live in TMEM (BN fp32 columns x 128 lanes); 2 CTAs fit per SM so one CTA's epilogue overlaps the
-// other's main loop.
+// MN-major canonical layout, so no transposed copies exist anywhere.  Structure (persistent CTAs, one per SM, 576 threads,
+// walking 128 x BN output tiles; gemm_tf32_2cta pairs two CTAs on 256 x 256 tiles):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of 128x32 (A) and BNx32 (B) fp32 boxes, 128B swizzle,
+//               ring of 3-8 stages guarded by full/empty mbarriers
+//   warp 1      TMEM allocator + single-thread tcgen05.mma.cta_group::1.kind::tf32 issuer (M=128, N=BN, K=8 per
+//               instruction, 4 per k-block), tcgen05.commit to release smem stages and to publish the accumulator
+//   warps 2-17  epilogue (TMEM lane quarter x column group): tcgen05.ld 32x32b -> registers -> bias / ELU / ELU' / column sums /
+//               trailing-input terms -> swizzled shared memory -> one TMA store per warp and 32 x 32 block (staged epilogue),
+//               red.global.add.v4 when split-K partitions the reduction
+// Accumulators live in TMEM, double-buffered (2 x BN fp32 columns x 128 lanes): the epilogue of tile i overlaps the main loop of
+// tile i+1.  mlp_tail_fwd_kernel chains two such products and a CUDA-core head for the layers behind a first layer.
 #include <cuda_runtime.h>
 #include <cuda.h>
 #include <stdint.h>
@@ -314,100 +315,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, uint32_t (&r)[
     }
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1) gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmArgs g) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: [A stages][B stages][barriers]
-    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    float* sA = (float*)base;                                   // STAGES x 128 x 32
-    float* sB = (float*)(base + (size_t)STAGES * BM * BK * 4);  // STAGES x BN x 32
-    uint64_t* full = (uint64_t*)(base + (size_t)STAGES * (BM + BN) * BK * 4);
-    uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;
-    uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int num_kb_total = (g.K + BK - 1) / BK;
-    const int kb0 = blockIdx.z * g.kb_per_split;
-    const int num_kb = min(g.kb_per_split, num_kb_total - kb0);
-
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {   // TMEM allocation: BN fp32 accumulator columns (power of two >= 32)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_d = *tmem_slot;
-
-    if (warp == 0) {
-        // ===== TMA producer =====
-        if (elect_one()) {
-            for (int i = 0; i < num_kb; i++) {
-                const int s = i % STAGES, ph = (i / STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], (BM + BN) * BK * 4);
-                tma_load_2d(&mapA, &full[s], sA + (size_t)s * BM * BK, (kb0 + i) * BK, m0);
-                tma_load_2d(&mapB, &full[s], sB + (size_t)s * BN * BK, (kb0 + i) * BK, n0);
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        // instruction descriptor: D=F32 (bits 4-5 = 1), A/B = TF32 (2 at bits 7-9 / 10-12), K-major both, N>>3 at 17, M>>4 at 24
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        for (int i = 0; i < num_kb; i++) {
-            const int s = i % STAGES, ph = (i / STAGES) & 1;
-            mbar_wait(&full[s], ph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (elect_one()) {
-                const uint64_t da = make_desc(sA + (size_t)s * BM * BK), db = make_desc(sB + (size_t)s * BN * BK);
-#pragma unroll
-                for (int k = 0; k < BK / UMMA_K; k++)      // advance 32 B along K inside the 128 B swizzle row: +2 in 16-byte units
-                    umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
-                umma_commit(&empty[s]);                    // stage reusable once these MMAs have read it
-                if (i == num_kb - 1) umma_commit(tmem_full);
-            }
-            __syncwarp();
-        }
-    } else {
-        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-        const int q = warp & 3;
-        const int row = m0 + 32 * q + lane;
-        if (num_kb > 0) {
-            mbar_wait(tmem_full, 0);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-        const bool split = gridDim.z > 1;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; c++) {
-            uint32_t r[32];
-            if (num_kb > 0) tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), r);
-            else {
-#pragma unroll
-                for (int j = 0; j < 32; j++) r[j] = 0u;
-            }
-            const float4 nopre[8] = {};
-            const EpiStage nostage = {nullptr, nullptr, nullptr};
-            epilogue_chunk(g, r, row, n0 + 32 * c, split, lane, nopre, false, nostage);
-        }
-    }
-    // ===== teardown =====
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)BN) : "memory");
-    }
-}
-
-
 // ELU' operand of one 32-column chunk (act == 2), fetched into registers BEFORE the wait on the accumulator so that the HBM / L2
 // latency of these row-per-lane loads overlaps the main loop of the tile.  Warp-uniform result; rows beyond M read row 0 (ignored).
 __device__ __forceinline__ bool epilogue_prefetch(const GemmArgs& g, const int row, const int col0, const bool split, float4 (&ypre)[8]) {
@@ -666,21 +573,6 @@ __global__ void bias_act_strided(float* C, int ldc, const float* bias, int M, in
     if (bias) v += bias[i % N];
     if (act == 1) v = v > 0.f ? v : expm1f(v);
     *c = v;
-}
-
-template <int BN, int STAGES>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, int splits, cudaStream_t st) {
-    const size_t smem = (size_t)STAGES * (BM + BN) * BK * 4 + (2 * STAGES + 1) * 8 + 16 + 1024;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return go1_set_error(cudaGetErrorString(e));
-        configured = true;
-    }
-    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, splits);
-    gemm_tf32_kernel<BN, STAGES><<<grid, 192, smem, st>>>(ma, mb, g);
-    go1_count_launch(1);
-    return 0;
 }
 
 template <int BN, int G, bool STAGED>
@@ -1182,7 +1074,7 @@ int launch_tail(const TailMaps& maps, const TailArgs& g, cudaStream_t st) {
 
 }  // namespace
 
-static int g_tf32_persistent = 1, g_tf32_wide = 1;   // wide = 128 x 256 tiles where the heuristic in go1_gemm_tf32 says they pay
+static int g_tf32_wide = 1;   // wide = 128 x 256 tiles / cta_group::2 pairs where the heuristic in go1_gemm_tf32 says they pay
 extern "C" void go1_gemm_tf32_set_wide(int on) { g_tf32_wide = on; }
 
 // ---- optional per-launch timing of the tensor-core GEMM (bench.py's roofline): CUDA events on the launch stream around every
@@ -1221,14 +1113,11 @@ extern "C" int go1_gemm_timing(int on, double* total_ms, double* total_flop, lon
     if (launches) *launches = (long long)(g_time_used / 2);
     return 0;
 }
-extern "C" void go1_gemm_tf32_set_persistent(int on) { g_tf32_persistent = on; }
 
 extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                              float* Cm, int ldc, const Go1GemmEpilogue* ep, cudaStream_t st) {
     const float* bias = ep->bias; const int act = ep->act, accumulate = ep->accumulate;
     const int amn = transA ? 1 : 0, bmn = transB ? 0 : 1;     // A given as [K][M] / B given as [K][N]: MN-major operands
-    if ((amn || bmn) && !g_tf32_persistent)
-        return go1_set_error("go1_gemm impl=1: MN-major operands (transA=1 / transB=0) need the persistent kernel");
     if ((lda & 3) || (ldb & 3) || (((uintptr_t)A | (uintptr_t)B) & 15))
         return go1_set_error("go1_gemm impl=1: A/B must be 16-byte aligned with row strides that are multiples of 4 floats (TMA)");
     GemmArgs g;
@@ -1253,7 +1142,7 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
     const int wtiles = ((M + BM - 1) / BM) * ((N + 255) / 256);
     static const double wide_min_fill = getenv("GO1_TF32_WIDE_MINFILL") ? atof(getenv("GO1_TF32_WIDE_MINFILL")) : 0.85;
     const bool fills = wtiles < 148 ? wtiles >= wide_min_tiles : (double)wtiles / (148.0 * ((wtiles + 147) / 148)) >= wide_min_fill;
-    const bool wide = g_tf32_persistent && g_tf32_wide && K >= wide_min_k && N >= 256 && (N % 256 == 0 || N >= 1024) && fills;
+    const bool wide = g_tf32_wide && K >= wide_min_k && N >= 256 && (N % 256 == 0 || N >= 1024) && fills;
     static const int use_2cta = getenv("GO1_TF32_2CTA") ? atoi(getenv("GO1_TF32_2CTA")) : 1;      // cta_group::2 pairs for the wide shapes
     const bool two_cta = use_2cta && wide && M >= 256;
     const int BN = wide ? 256 : ((N > 64) ? 128 : (N > 32 ? 64 : 32));

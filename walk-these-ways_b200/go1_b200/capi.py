@@ -175,7 +175,6 @@ def lib():
         "go1_ppo_normalize_advantages": ([vp, vp, i64, i64, vp], ip),
         "go1_gemm": ([ip, ip, ip, ip, ip, vp, ip, vp, ip, vp, ip, vp, ip, ip, ip, vp], ip),
         "go1_gemm_ex": ([ip, ip, ip, ip, ip, vp, ip, vp, ip, vp, ip, C.POINTER(Go1GemmEpilogue), ip, vp], ip),
-        "go1_gemm_tf32_set_persistent": ([ip], None),
         "go1_mlp_tail_forward_grouped": ([C.POINTER(Go1TailProblem), ip, ip, ip, ip, ip, vp], ip),
         "go1_mlp_tail_forward": ([vp, ip, ip, ip, vp, vp, ip, vp, ip, vp, vp, ip, vp, ip, vp, vp, ip, vp, ip, vp], ip),
         "go1_gemm_tf32_set_wide": ([ip], None),
