@@ -264,6 +264,30 @@ def test_gemm_tcgen05_staged_epilogue(M, N, K, tb):
     assert torch.equal(Cb3[:M, :N], Cb2[:M, :N])
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 4])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 24576), (256, 512, 8192), (100, 72, 500)])
+def test_gemm_grouped_wgrads(M, N, K, n):
+    """go1_gemm_grouped: n products of one shape in one grid (the equal-shape split-K wgrads of the three MLPs), accumulating into
+    pre-filled outputs; each against its own fp64 reference."""
+    import ctypes as C
+    from go1_b200 import capi
+    torch.manual_seed(M + N + K + n)
+    pad = lambda v: (v + 3) // 4 * 4
+    As = [torch.randn(K, pad(M), device="cuda") for _ in range(n)]      # dz as [K][M]
+    Bs = [torch.randn(K, pad(N), device="cuda") for _ in range(n)]      # activations as [K][N]
+    ldc = pad(N) + 4
+    Cs = [torch.full((M, ldc), 0.5, device="cuda") for _ in range(n)]
+    arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+    capi.check(capi.lib().go1_gemm_grouped(1, 0, M, N, K, n, arr(As), pad(M), arr(Bs), pad(N), arr(Cs), ldc, 1, capi.stream_ptr()), "go1_gemm_grouped")
+    torch.cuda.synchronize()
+    for a, b, c in zip(As, Bs, Cs):
+        A, B = a[:, :M].t().double(), b[:, :N].double()
+        ref = 0.5 + A @ B
+        bound = (A.abs() @ B.abs()) * 2.0 ** -9 + 1e-5
+        assert ((c[:, :N].double() - ref).abs() <= bound).all()
+        assert (c[:, N:] == 0.5).all()
+
+
 # MN-major operands (dgrad: B = W as [K][N]; wgrad: A = dz as [K][M], B = activations as [K][N]) read straight from HBM
 @pytest.mark.parametrize("ta,tb", [(0, 0), (1, 0), (1, 1)])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 32, 64), (300, 200, 72), (24576, 128, 12), (12, 128, 24576), (1280, 2100, 4096),

@@ -129,7 +129,12 @@ struct GemmArgs {
     const float* bx; const float* bwx; float* gwx; float* dx;     // fused trailing-input backward (see Go1GemmEpilogue)
     int ldbx, ldbwx, ldgwx, lddx, nbx;
     int tma_store, tma_aux;  // staged epilogue (persistent kernel, STAGED): C blocks leave / ELU' operand blocks arrive through shared memory by TMA
+    // grouped launch (persistent kernel): nprob problems of the same shape and operand strides in one grid; tile t belongs to problem
+    // t / tiles_per_prob, whose operands are maps.a/b[p] and whose output is Cg[p] (no per-problem epilogue operands: split-K wgrads)
+    float* Cg[4]; int nprob, tiles_per_prob;
 };
+constexpr int GEMM_MAXP = 4;
+struct GemmMaps { CUtensorMap a[GEMM_MAXP], b[GEMM_MAXP]; };
 
 // Per-warp shared-memory staging of the staged epilogue.  A row-per-lane float4 store touches 32 different 128-byte lines per
 // instruction (8 x the LSU wavefronts of a coalesced store); measured, that -- not the tensor core -- bounded every short-K product
@@ -148,15 +153,15 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 // Epilogue of one 32-column chunk held in registers (thread = output row, r[j] = column col0 + j).  Called by all 32 lanes
 // of an epilogue warp (the per-column operands -- bias, extra-input weights -- are loaded once per lane and broadcast
 // with shuffles instead of 32 x per-thread global loads, which made the rank-2 term the slowest part of the kernel).
-__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, uint32_t (&r)[32], const int row, const int col0, const bool split, const int lane,
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, float* const Cbase, uint32_t (&r)[32], const int row, const int col0, const bool split, const int lane,
                                                const float4 (&ypre)[8], const bool have_pre, const EpiStage& es) {
     if (col0 >= g.N) return;                                    // warp-uniform
     const int ncols = min(32, g.N - col0);
     const bool row_ok = row < g.M;
-    float* crow = g.C + (size_t)(row_ok ? row : 0) * g.ldc + col0;
+    float* crow = Cbase + (size_t)(row_ok ? row : 0) * g.ldc + col0;
     if (split) {            // split-K partial tile: reduce into C; 16-byte vector reductions cut the L2 atomic operations 4x
         if (row_ok) {
-            if ((ncols == 32) && ((g.ldc & 3) == 0) && ((((uintptr_t)g.C) & 15) == 0) && ((col0 & 3) == 0)) {
+            if ((ncols == 32) && ((g.ldc & 3) == 0) && ((((uintptr_t)Cbase) & 15) == 0) && ((col0 & 3) == 0)) {
 #pragma unroll
                 for (int j = 0; j < 8; j++)
                     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + 4 * j), "f"(__uint_as_float(r[4 * j])), "f"(__uint_as_float(r[4 * j + 1])),
@@ -168,7 +173,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, uint32_t (&r)[
         }
         return;
     }
-    const bool vec = (ncols == 32) && ((g.ldc & 3) == 0) && ((((uintptr_t)g.C) & 15) == 0) && ((col0 & 3) == 0);
+    const bool vec = (ncols == 32) && ((g.ldc & 3) == 0) && ((((uintptr_t)Cbase) & 15) == 0) && ((col0 & 3) == 0);
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
@@ -336,7 +341,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, const uint32_t 
         uint32_t r[32];
         tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), r);
         const EpiStage nostage = {nullptr, nullptr, nullptr};
-        epilogue_chunk(g, r, row, n0 + 32 * c, split, lane, ypre, have_pre && c == grp, nostage);
+        epilogue_chunk(g, g.C, r, row, n0 + 32 * c, split, lane, ypre, have_pre && c == grp, nostage);
     }
 }
 
@@ -347,7 +352,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, const uint32_t 
 // per-CTA set-up (TMEM allocation, barrier init, tensormap prefetch) is paid once instead of once per tile.
 // ---------------------------------------------------------------------------------------------------------------
 template <int BN, int G, bool STAGED>
-__global__ void __launch_bounds__(64 + 128 * G, 1) gemm_tf32_persistent(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+__global__ void __launch_bounds__(64 + 128 * G, 1) gemm_tf32_persistent(const __grid_constant__ GemmMaps gm,
                                                                         const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapY, const GemmArgs g,
                                                                         const int tiles_m, const int tiles_n, const int total_tiles, const int stages) {
     constexpr int NEPI = 4 * G;                  // epilogue warps
@@ -370,8 +375,10 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) gemm_tf32_persistent(const __
     const int num_kb_total = (g.K + BK - 1) / BK;
 
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+        for (int p = 0; p < g.nprob; p++) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&gm.a[p]) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&gm.b[p]) : "memory");
+        }
         if (STAGED && g.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapC) : "memory");
         if (STAGED && g.tma_aux) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapY) : "memory");
         for (int s = 0; s < stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -388,8 +395,9 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) gemm_tf32_persistent(const __
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    // tile -> (m0, n0, k-block range)
+    // tile -> (m0, n0, k-block range); grouped launches: tile t of problem t / tiles_per_prob
     auto tile_coords = [&](int t, int& m0, int& n0, int& kb0, int& nkb) {
+        if (g.nprob > 1) t %= g.tiles_per_prob;
         const int tn = t % tiles_n; t /= tiles_n;
         const int tm = t % tiles_m; const int z = t / tiles_m;
         m0 = tm * BM; n0 = tn * BN; kb0 = z * g.kb_per_split; nkb = min(g.kb_per_split, num_kb_total - kb0);
@@ -400,6 +408,9 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) gemm_tf32_persistent(const __
             int s = 0, ph = 0;      // ring position of this CTA's k-block stream
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 int m0, n0, kb0, nkb; tile_coords(t, m0, n0, kb0, nkb);
+                const int p = g.nprob > 1 ? t / g.tiles_per_prob : 0;
+                const CUtensorMap* mapA = &gm.a[p];
+                const CUtensorMap* mapB = &gm.b[p];
                 for (int i = 0; i < nkb; i++) {
                     mbar_wait(&empty[s], ph ^ 1);
                     mbar_expect_tx(&full[s], STAGE_BYTES);
@@ -407,12 +418,12 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) gemm_tf32_persistent(const __
                     float* b = a + BM * BK;
                     if (g.amn) {
 #pragma unroll
-                        for (int x = 0; x < BM / 32; x++) tma_load_2d(&mapA, &full[s], a + x * 32 * BK, m0 + 32 * x, (kb0 + i) * BK);
-                    } else tma_load_2d(&mapA, &full[s], a, (kb0 + i) * BK, m0);
+                        for (int x = 0; x < BM / 32; x++) tma_load_2d(mapA, &full[s], a + x * 32 * BK, m0 + 32 * x, (kb0 + i) * BK);
+                    } else tma_load_2d(mapA, &full[s], a, (kb0 + i) * BK, m0);
                     if (g.bmn) {
 #pragma unroll
-                        for (int x = 0; x < BN / 32; x++) tma_load_2d(&mapB, &full[s], b + x * 32 * BK, n0 + 32 * x, (kb0 + i) * BK);
-                    } else tma_load_2d(&mapB, &full[s], b, (kb0 + i) * BK, n0);
+                        for (int x = 0; x < BN / 32; x++) tma_load_2d(mapB, &full[s], b + x * 32 * BK, n0 + 32 * x, (kb0 + i) * BK);
+                    } else tma_load_2d(mapB, &full[s], b, (kb0 + i) * BK, n0);
                     if (++s == stages) { s = 0; ph ^= 1; }
                 }
             }
@@ -480,6 +491,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) gemm_tf32_persistent(const __
             int m0, n0, kb0, nkb; tile_coords(t, m0, n0, kb0, nkb);
             const int buf = j & 1;
             const int row = m0 + 32 * q + lane;
+            float* const Cbase = g.nprob > 1 ? g.Cg[t / g.tiles_per_prob] : g.C;
             float4 ypre[8];
             const bool have_pre = !st_aux && (grp < BN / 32) && epilogue_prefetch(g, row, n0 + 32 * grp, split, ypre);
             mbar_wait(&tmem_full[buf], (j >> 1) & 1);
@@ -501,7 +513,7 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) gemm_tf32_persistent(const __
                     __syncwarp();
                 }
                 if (st_aux) { mbar_wait(my_bar, aux_phase); aux_phase ^= 1; }
-                epilogue_chunk(g, r, row, n0 + 32 * c, split, lane, ypre, have_pre && c == grp, es);
+                epilogue_chunk(g, Cbase, r, row, n0 + 32 * c, split, lane, ypre, have_pre && c == grp, es);
                 if (st_aux) { __syncwarp(); request_aux(); }             // every lane has read the operand block: fetch the next one into it
             }
             if (!released) {
@@ -576,7 +588,7 @@ __global__ void bias_act_strided(float* C, int ldc, const float* bias, int M, in
 }
 
 template <int BN, int G, bool STAGED>
-int launch_persistent(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& my, const GemmArgs& g, int splits, cudaStream_t st) {
+int launch_persistent(const GemmMaps& gm, const CUtensorMap& mc, const CUtensorMap& my, GemmArgs& g, int splits, cudaStream_t st) {
     constexpr int NEPI = 4 * G, STAGE_BYTES = (BM + BN) * BK * 4;
     const size_t staging = STAGED ? (size_t)NEPI * 4096 * (g.tma_aux ? 2 : 1) : 0;
     const size_t fixed = staging + (2 * 8 + 4 + NEPI) * 8 + 16 + 1024;
@@ -591,11 +603,13 @@ int launch_persistent(const CUtensorMap& ma, const CUtensorMap& mb, const CUtens
         if (e != cudaSuccess) return go1_set_error(cudaGetErrorString(e));
         configured = true;
     }
-    const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN, total = tiles_m * tiles_n * splits;
+    const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
+    g.tiles_per_prob = tiles_m * tiles_n * splits;
+    const int total = g.tiles_per_prob * (g.nprob > 1 ? g.nprob : 1);
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
     const int grid = total < sms ? total : sms;          // one CTA per SM (the ring and the staging fill its shared memory)
-    gemm_tf32_persistent<BN, G, STAGED><<<grid, 64 + 128 * G, smem, st>>>(ma, mb, mc, my, g, tiles_m, tiles_n, total, stages);
+    gemm_tf32_persistent<BN, G, STAGED><<<grid, 64 + 128 * G, smem, st>>>(gm, mc, my, g, tiles_m, tiles_n, total, stages);
     go1_count_launch(1);
     return 0;
 }
@@ -1114,13 +1128,17 @@ extern "C" int go1_gemm_timing(int on, double* total_ms, double* total_flop, lon
     return 0;
 }
 
-extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
-                             float* Cm, int ldc, const Go1GemmEpilogue* ep, cudaStream_t st) {
+static int gemm_tf32_impl(int transA, int transB, int M, int N, int K, int nprob, const float* const* As, int lda, const float* const* Bs, int ldb,
+                          float* const* Cs, int ldc, const Go1GemmEpilogue* ep, cudaStream_t st) {
+    float* Cm = Cs[0];
     const float* bias = ep->bias; const int act = ep->act, accumulate = ep->accumulate;
     const int amn = transA ? 1 : 0, bmn = transB ? 0 : 1;     // A given as [K][M] / B given as [K][N]: MN-major operands
-    if ((lda & 3) || (ldb & 3) || (((uintptr_t)A | (uintptr_t)B) & 15))
-        return go1_set_error("go1_gemm impl=1: A/B must be 16-byte aligned with row strides that are multiples of 4 floats (TMA)");
+    for (int p = 0; p < nprob; p++)
+        if ((lda & 3) || (ldb & 3) || (((uintptr_t)As[p] | (uintptr_t)Bs[p]) & 15) || !Cs[p])
+            return go1_set_error("go1_gemm impl=1: A/B must be 16-byte aligned with row strides that are multiples of 4 floats (TMA)");
     GemmArgs g;
+    g.nprob = nprob; g.tiles_per_prob = 0;
+    for (int p = 0; p < GEMM_MAXP; p++) g.Cg[p] = Cs[p < nprob ? p : 0];
     g.C = Cm; g.bias = bias; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.act = act; g.accumulate = accumulate;
     g.ex = ep->extra; g.ldex = ep->ld_extra; g.wex = ep->w_extra; g.ldwex = ep->ld_w_extra; g.nex = ep->extra ? ep->num_extra : 0;
     g.aux = ep->dact_y; g.ldaux = ep->ld_dact_y;
@@ -1144,35 +1162,42 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
     const bool fills = wtiles < 148 ? wtiles >= wide_min_tiles : (double)wtiles / (148.0 * ((wtiles + 147) / 148)) >= wide_min_fill;
     const bool wide = g_tf32_wide && K >= wide_min_k && N >= 256 && (N % 256 == 0 || N >= 1024) && fills;
     static const int use_2cta = getenv("GO1_TF32_2CTA") ? atoi(getenv("GO1_TF32_2CTA")) : 1;      // cta_group::2 pairs for the wide shapes
-    const bool two_cta = use_2cta && wide && M >= 256;
-    const int BN = wide ? 256 : ((N > 64) ? 128 : (N > 32 ? 64 : 32));
-    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const bool two_cta = use_2cta && wide && M >= 256 && nprob == 1;
+    const int BN = (wide && nprob == 1) ? 256 : ((N > 64) ? 128 : (N > 32 ? 64 : 32));
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * nprob;
     int splits = 1;
     if (tiles < 148 && num_kb >= split_min_kb && g.nex == 0 && act != 2 && g.lead <= 0 && !g.colsum && g.nbx == 0) {      // one wave of 2 CTAs/SM, >= 16 k-blocks each
-        splits = split_ctas / tiles; if (splits > num_kb / split_min_kb) splits = num_kb / split_min_kb; if (splits < 1) splits = 1;
+        splits = (nprob > 1 ? 148 : split_ctas) / tiles;      // grouped: one CTA-unit per SM (fewer, longer partial sums: less same-address red traffic)
+        if (splits > num_kb / split_min_kb) splits = num_kb / split_min_kb; if (splits < 1) splits = 1;
     }
     g.kb_per_split = (num_kb + splits - 1) / splits;
     splits = (num_kb + g.kb_per_split - 1) / g.kb_per_split;
-    CUtensorMap ma, mb;
+    GemmMaps gm;
     // K-major: rows = M (or N), cols = K, box BK x tile rows.  MN-major: rows = K, cols = M (or N), box 32 mn x BK k-rows.
-    if (int e = amn ? make_map(&ma, A, K, M, lda, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) : make_map(&ma, A, M, K, lda, BM)) return e;
-    if (int e = bmn ? make_map(&mb, B, K, N, ldb, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) : make_map(&mb, B, N, K, ldb, two_cta ? 128 : BN)) return e;
+    for (int p = 0; p < nprob; p++) {
+        if (int e = amn ? make_map(&gm.a[p], As[p], K, M, lda, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) : make_map(&gm.a[p], As[p], M, K, lda, BM)) return e;
+        if (int e = bmn ? make_map(&gm.b[p], Bs[p], K, N, ldb, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) : make_map(&gm.b[p], Bs[p], N, K, ldb, two_cta ? 128 : BN)) return e;
+    }
+    for (int p = nprob; p < GEMM_MAXP; p++) { gm.a[p] = gm.a[0]; gm.b[p] = gm.b[0]; }
+    const CUtensorMap& ma = gm.a[0];
+    const CUtensorMap& mb = gm.b[0];
     if (splits > 1) {
-        if (!accumulate) { const size_t tot = (size_t)M * N; zero_strided<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cm, ldc, M, N); go1_count_launch(1); }
+        if (!accumulate)
+            for (int p = 0; p < nprob; p++) { const size_t tot = (size_t)M * N; zero_strided<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cs[p], ldc, M, N); go1_count_launch(1); }
         g.bias = nullptr; g.act = 0;
     }
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     const bool timed = g_time_on && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone;
     if (timed) {
-        cudaEventRecord(timing_event(), st); g_time_flop += 2.0 * (double)M * (double)N * (double)K;
-        g_time_recs.push_back({M, N, K, amn, bmn, act, g.nex, splits, two_cta ? 2 : BN, g.colsum ? 1 : 0});
+        cudaEventRecord(timing_event(), st); g_time_flop += 2.0 * (double)M * (double)N * (double)K * nprob;
+        g_time_recs.push_back({M * nprob, N, K, amn, bmn, act, g.nex, splits, two_cta ? 2 : BN, g.colsum ? 1 : 0});
     }
     int e;
     // staged epilogue (BN <= 128 kernels): C blocks through shared memory + TMA store, the ELU' operand through TMA loads
     static const int use_staged = getenv("GO1_TF32_STAGED") ? atoi(getenv("GO1_TF32_STAGED")) : 1;
     CUtensorMap mc = ma, my = ma;
     g.tma_store = g.tma_aux = 0;
-    if (use_staged && !two_cta && BN <= 128 && splits == 1 && !accumulate && N >= 32 && (ldc & 3) == 0 && (((uintptr_t)Cm) & 15) == 0) {
+    if (use_staged && !two_cta && nprob == 1 && BN <= 128 && splits == 1 && !accumulate && N >= 32 && (ldc & 3) == 0 && (((uintptr_t)Cm) & 15) == 0) {
         if (int e2 = make_map(&mc, Cm, M, N, ldc, 32)) return e2;
         g.tma_store = 1;
         if (g.act == 2 && (g.ldaux & 3) == 0 && (((uintptr_t)g.aux) & 15) == 0) {
@@ -1181,16 +1206,32 @@ extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const 
         }
     }
     if (two_cta) e = launch_2cta<6, 4>(ma, mb, g, splits, st);
-    else if (BN == 256) e = launch_persistent<256, 4, false>(ma, mb, mc, my, g, splits, st);
-    else if (BN == 128) e = launch_persistent<128, 4, true>(ma, mb, mc, my, g, splits, st);
-    else if (BN == 64) e = launch_persistent<64, 2, true>(ma, mb, mc, my, g, splits, st);
-    else e = launch_persistent<32, 1, true>(ma, mb, mc, my, g, splits, st);
+    else if (BN == 256) e = launch_persistent<256, 4, false>(gm, mc, my, g, splits, st);
+    else if (BN == 128) e = launch_persistent<128, 4, true>(gm, mc, my, g, splits, st);
+    else if (BN == 64) e = launch_persistent<64, 2, true>(gm, mc, my, g, splits, st);
+    else e = launch_persistent<32, 1, true>(gm, mc, my, g, splits, st);
     if (e) return e;
-    if (splits > 1 && (bias || act)) { const size_t tot = (size_t)M * N; bias_act_strided<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cm, ldc, bias, M, N, act); go1_count_launch(1); }
+    if (splits > 1 && (bias || act))
+        for (int p = 0; p < nprob; p++) { const size_t tot = (size_t)M * N; bias_act_strided<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(Cs[p], ldc, bias, M, N, act); go1_count_launch(1); }
     if (timed) cudaEventRecord(timing_event(), st);
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return go1_set_error(cudaGetErrorString(ce));
     return 0;
+}
+
+extern "C" int go1_gemm_tf32(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                             float* Cm, int ldc, const Go1GemmEpilogue* ep, cudaStream_t st) {
+    return gemm_tf32_impl(transA, transB, M, N, K, 1, &A, lda, &B, ldb, &Cm, ldc, ep, st);
+}
+// nprob (<= 4) products of the same shape and operand strides in ONE grid: C[p] (+)= op(A[p]) op(B[p]).  Meant for the equal-shape
+// split-K wgrads of the three MLPs (128 x 256 x 24576 three times, 256 x 512 x 24576 twice per optimizer step): one launch fills the
+// SMs that a single two-tile product leaves idle.  No fused epilogue operands.
+extern "C" int go1_gemm_grouped(int transA, int transB, int M, int N, int K, int nprob, const float* const* A, int lda, const float* const* B, int ldb,
+                                float* const* C, int ldc, int accumulate, void* stream) {
+    if (!A || !B || !C || nprob < 1 || nprob > GEMM_MAXP || M <= 0 || N <= 0 || K <= 0) return go1_set_error("go1_gemm_grouped: 1..4 problems");
+    Go1GemmEpilogue ep = {};
+    ep.accumulate = accumulate;
+    return gemm_tf32_impl(transA, transB, M, N, K, nprob, A, lda, B, ldb, C, ldc, &ep, (cudaStream_t)stream);
 }
 
 // dst[c][r] = src[r][c]  (32x32 smem tiles): brings dgrad/wgrad operands into the K-major form the tcgen05 kernel reads

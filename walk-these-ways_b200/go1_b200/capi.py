@@ -185,6 +185,7 @@ def lib():
         "go1_skinny_dgrad": ([vp, ip, vp, ip, vp, ip, vp, ip, ip, ip, ip, vp], ip),
         "go1_skinny_dgrad_ex": ([vp, ip, vp, ip, vp, ip, vp, ip, vp, ip, ip, ip, vp], ip),
         "go1_skinny_wgrad_ex": ([vp, ip, vp, ip, vp, ip, vp, ip, ip, ip, ip, vp], ip),
+        "go1_gemm_grouped": ([ip, ip, ip, ip, ip, ip, C.POINTER(vp), ip, C.POINTER(vp), ip, C.POINTER(vp), ip, ip, vp], ip),
         "go1_copy_segments": ([C.POINTER(Go1CopySeg), ip, vp], ip),
         "go1_skinny_forward": ([vp, ip, vp, ip, vp, vp, ip, ip, ip, ip, vp], ip),
         "go1_skinny_wgrad": ([vp, ip, vp, ip, vp, ip, ip, ip, ip, ip, vp], ip),

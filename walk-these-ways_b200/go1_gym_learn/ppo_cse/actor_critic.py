@@ -259,7 +259,11 @@ class _Net:
                 tc = impl == 1 and M >= 64 and K >= 8 and self._tma_ok(dz, ldz) and self._tma_ok(inp, ld_in)
                 # into a gradient buffer the caller has already zeroed the split-K partial tiles can accumulate directly (no zeroing pass)
                 acc_w = 1 if (accumulate or (tc and self.owner.grads_prezeroed)) else 0
-                self._gemm(1, 0, o, K, M, dz, ldz, inp, ld_in, gW, i, None, 0, acc_w, 1 if tc else 0)
+                q = self.owner._wgrad_queue
+                if q is not None and tc and acc_w:      # deferred: ActorCritic launches the equal-shape wgrads of its MLPs as grouped products
+                    q.append((o, K, M, ldz, ld_in, i, dz, inp, gW))
+                else:
+                    self._gemm(1, 0, o, K, M, dz, ldz, inp, ld_in, gW, i, None, 0, acc_w, 1 if tc else 0)
             if li == 0 and extra is not None and not extra_done:
                 E = i - K0
                 if want_dextra:
@@ -271,7 +275,7 @@ class _Net:
                 dprev = dz1_out if (li == 1 and dz1_out is not None) else self._buf((tag, "d", li - 1), M, i)
                 ldp = dprev.stride(0)
                 yprev = outs[li - 1]
-                if impl == 1 and self._tma_ok(dz, ldz) and self._tma_ok(W, i) and M >= 64:
+                if impl == 1 and o > 16 and self._tma_ok(dz, ldz) and self._tma_ok(W, i) and M >= 64:      # (narrow heads: the skinny pass below)
                     # W read MN-major in place; the bias gradient of layer li-1 (column sums of dprev) rides in the epilogue
                     pwo, pbo, po, pi = self.specs[li - 1]
                     gb_prev = self.grad[pbo:pbo + po]
@@ -342,10 +346,12 @@ class ActorCritic(nn.Module):
         self._counter_dev = None
         self.force_repack = False     # (kept for callers that set it; packing is never part of a graph any more, see ensure_packed)
         self._packed_version = -1
+        self._wgrad_queue = None      # list while backward_ppo collects the tensor-core wgrads of the layers behind the first ones
         self.sample_seed = 0
         self.injected_eps = None      # parity tests inject the N(0,1) draws
         self.weights_version = 0      # bumped by every optimizer step / load: invalidates the packed first-layer weight copies
         import os
+        self.group_wgrads = os.environ.get("GO1_GROUP_WGRADS", "1") != "0"          # equal-shape wgrads of the three MLPs as grouped products
         self.fuse_bias_grad = os.environ.get("GO1_FUSE_BIAS_GRAD", "1") != "0"     # bias gradients reduced in the dgrad GEMM epilogues
         self.update_streams = os.environ.get("GO1_UPDATE_STREAMS", "1") != "0"     # critic chain on a second stream during the update (measured -1.3 ms / iteration)
         self._side = None
@@ -625,6 +631,24 @@ class ActorCritic(nn.Module):
         return self._nets["adapt"].forward(h, h.stride(0), self.num_obs_history, None, h.shape[0], self._impl(), "latent")[-1]
 
     # ------------------------------------------------------------------ explicit backward passes (ppo.py:154-189)
+    def _flush_wgrads(self):
+        """Launch the queued wgrads: equal shapes (same M, N, K and operand strides) as ONE grouped product (go1_gemm_grouped: up to four
+        problems in one grid), the rest one by one.  All of them accumulate into the pre-zeroed flat gradient buffer."""
+        import ctypes as C
+        q, self._wgrad_queue = self._wgrad_queue, None
+        groups = {}
+        for it in q:
+            groups.setdefault(it[:6], []).append(it)
+        L, st = capi.lib(), capi.stream_ptr()
+        for (o, K, M, ldz, ld_in, i), items in groups.items():
+            for k0 in range(0, len(items), 4):
+                chunk = items[k0:k0 + 4]
+                n = len(chunk)
+                A = (C.c_void_p * n)(*[it[6].data_ptr() for it in chunk])
+                B = (C.c_void_p * n)(*[it[7].data_ptr() for it in chunk])
+                Cc = (C.c_void_p * n)(*[it[8].data_ptr() for it in chunk])
+                capi.check(L.go1_gemm_grouped(1, 0, o, K, M, n, A, ldz, B, ld_in, Cc, i, 1, st), "go1_gemm_grouped")
+
     def backward_ppo(self, h, priv, dmean, dvalue, dstd, aug=False):
         """Gradients of the PPO loss into flat_grads (overwrites). h/priv are the minibatch inputs of the forward
         pass just run with tag='train'; dmean [M,A], dvalue [M,1], dstd [A].
@@ -648,6 +672,8 @@ class ActorCritic(nn.Module):
             if aug:
                 h_ext = h.as_strided((M, KA), (h.stride(0), 1))
                 capi.copy_segments([(h_ext[:, K0 + 1 + E:], self._latent)])
+            if self.group_wgrads and self.grads_prezeroed:
+                self._wgrad_queue = []
             side = self._side_stream(M)
             if side is not None:    # critic chain beside actor -> adaptation chain
                 self._fork(side)
@@ -660,6 +686,8 @@ class ActorCritic(nn.Module):
             nets["adapt"].backward(h, h.stride(0), K0, None, self._a_out, dlat, M, impl, 0, tag="train", dz1_out=dz1[:, :oa], aug_first=aug)
             if side is not None:
                 self._join(side)
+            if self._wgrad_queue is not None:
+                self._flush_wgrads()
             n0 = nets["adapt"]
             KP = (KA + 31) // 32 * 32
             gcat = n0._buf(("train", "gWcat"), oa + op + oc, KP)
