@@ -132,7 +132,8 @@ class Runner:
             W = capi.NUM_EPISODE_SUMS + 1
             with torch.inference_mode(False):
                 st = dict(slot=torch.zeros(1, dtype=torch.int32, device=dev), acc=torch.zeros(W, device=dev),
-                          acc_hist=torch.zeros(T, W, device=dev), graphs={}, warm={0: 0, 1: 0}, W=W, T=T)
+                          acc_hist=torch.zeros(T, W, device=dev), graphs={}, warm={0: 0, 1: 0}, W=W, T=T,
+                          fork=os.environ.get("GO1_STEP_FORK", "1") != "0")
         self._sg = st
         return st
 
@@ -147,17 +148,37 @@ class Runner:
         core, dc, L, sp = base.core, base._dev_cur, capi.lib(), capi.stream_ptr
         hist, obs, priv = env.obs_history, core.obs, core.priv_obs
         N = core.N
+        # Two independent pieces run on a side stream (forks / joins become edges of the captured graph): the periodic command resample of
+        # this step beside the policy evaluation (it writes commands and curriculum state, the policy reads histories), and the storage of
+        # the transition beside the history roll (both only read what the kernels before them produced; the roll writes the other buffer).
+        fork = sg.get("fork", True) and not dc.shared
+        main = torch.cuda.current_stream()
+        side = sg.get("side") if fork else None
+        if fork and side is None:
+            side = sg["side"] = torch.cuda.Stream()
+        if fork:
+            e0 = torch.cuda.Event(); e0.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(e0)
+                dc.resample(1)
+                e1 = torch.cuda.Event(); e1.record(side)
         actions, values = alg._act_eager(hist, priv)
         capi.check(L.go1_rollout_store_observations(capi.ptr(obs), capi.ptr(priv) if core.num_priv else None, capi.ptr(stg.observations),
                                                     capi.ptr(stg.privileged_observations) if core.num_priv else None, capi.ptr(sg["slot"]), N,
                                                     core.num_obs, core.num_priv, sp()), "go1_rollout_store_observations")
-        dc.resample(1)
+        if fork:
+            main.wait_event(e1)
+        else:
+            dc.resample(1)
         core.step(actions, common_step=0, mode=0)
         dc.gather()
         sg["acc"].zero_()
         dc.resample(0)
         dc.reset_envs(actions, True, 0, sg["acc"])
-        env._roll(core.obs)
+        if fork:
+            e2 = torch.cuda.Event(); e2.record(main)
+        else:
+            env._roll(core.obs)
         send_to = bool(base.cfg.env.send_timeouts)
         ins = [None, None, hist, actions, core.rew, values, ac._logp, ac._mean, ac.std.data, dc.env_bins_f32]
         outs = [stg.observations, stg.privileged_observations, stg.observation_histories, stg.actions, stg.rewards, stg.values, stg.actions_log_prob,
@@ -165,12 +186,24 @@ class Runner:
         for x in ins[2:]:
             assert x.is_contiguous() and x.dtype == torch.float32
         from .ppo import PPO_Args
-        capi.check(L.go1_rollout_store_transition((C.c_void_p * 10)(*[x.data_ptr() if x is not None else None for x in ins]), capi.ptr(core.reset_u8),
-                                                  capi.ptr(dc.time_outs_u8) if send_to else None, (C.c_void_p * 10)(*[x.data_ptr() for x in outs]),
-                                                  capi.ptr(stg.dones), capi.ptr(sg["slot"]), N, core.num_obs, core.num_priv, hist.shape[1],
-                                                  actions.shape[1], float(PPO_Args.gamma), sp()), "go1_rollout_store_transition")
-        capi.check(L.go1_rollout_advance(capi.ptr(sg["acc"]), capi.ptr(sg["acc_hist"]), sg["W"], sg["T"], capi.ptr(sg["slot"]), capi.ptr(core.step_dev), sp()),
-                   "go1_rollout_advance")
+
+        def store_and_advance():
+            capi.check(L.go1_rollout_store_transition((C.c_void_p * 10)(*[x.data_ptr() if x is not None else None for x in ins]), capi.ptr(core.reset_u8),
+                                                      capi.ptr(dc.time_outs_u8) if send_to else None, (C.c_void_p * 10)(*[x.data_ptr() for x in outs]),
+                                                      capi.ptr(stg.dones), capi.ptr(sg["slot"]), N, core.num_obs, core.num_priv, hist.shape[1],
+                                                      actions.shape[1], float(PPO_Args.gamma), sp()), "go1_rollout_store_transition")
+            capi.check(L.go1_rollout_advance(capi.ptr(sg["acc"]), capi.ptr(sg["acc_hist"]), sg["W"], sg["T"], capi.ptr(sg["slot"]), capi.ptr(core.step_dev), sp()),
+                       "go1_rollout_advance")
+
+        if fork:
+            with torch.cuda.stream(side):
+                side.wait_event(e2)
+                store_and_advance()
+                e3 = torch.cuda.Event(); e3.record(side)
+            env._roll(core.obs)
+            main.wait_event(e3)
+        else:
+            store_and_advance()
         return actions
 
     def _rollout_graphed(self, sg):
