@@ -452,7 +452,7 @@ extern "C" int go1_skinny_wgrad_ex(const float* dz, int lddz, const float* x, in
     }
     if ((K & 3) == 0 && (ldx & 3) == 0 && (((uintptr_t)x) & 15) == 0) {
         const int kb = (K + 127) / 128;
-        int rpb4 = (M * kb + 147) / 148;                 // about one block per SM
+        int rpb4 = (M * kb + 147) / 148;                 // about one block per SM (more blocks measured slower: the per-block reduction and atomics dominate)
         rpb4 = (rpb4 + 7) / 8 * 8; if (rpb4 < 8) rpb4 = 8;
         dim3 grid4(kb, (M + rpb4 - 1) / rpb4);
         if (o <= 2) skinny_wgrad4_kernel<2><<<grid4, 256, 0, st>>>(dz, lddz, x, ldx, gW, ldg, gb, M, o, K, rpb4);
@@ -834,14 +834,23 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const long lon
     const float* s = src + (size_t)idx[r] * width;
     float* d = dst + (size_t)r * ldd;
     if ((width & 3) == 0 && (ldd & 3) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
-        for (int c = threadIdx.x; c < width / 4; c += blockDim.x) reinterpret_cast<float4*>(d)[c] = reinterpret_cast<const float4*>(s)[c];
+        const int w4 = width / 4;
+        if (w4 <= 5 * (int)blockDim.x) {        // long rows (the 2100-float histories): all of a thread's loads in flight before its stores
+            float4 v[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) { const int c = threadIdx.x + k * blockDim.x; if (c < w4) v[k] = __ldg(reinterpret_cast<const float4*>(s) + c); }
+#pragma unroll
+            for (int k = 0; k < 5; k++) { const int c = threadIdx.x + k * blockDim.x; if (c < w4) reinterpret_cast<float4*>(d)[c] = v[k]; }
+        } else {
+            for (int c = threadIdx.x; c < w4; c += blockDim.x) reinterpret_cast<float4*>(d)[c] = reinterpret_cast<const float4*>(s)[c];
+        }
     } else {
         for (int c = threadIdx.x; c < width; c += blockDim.x) d[c] = s[c];
     }
 }
 extern "C" int go1_gather_rows(const float* src, const int64_t* idx, float* dst, int64_t rows, int width, int ldd, void* stream) {
     if (!src || !idx || !dst || rows <= 0 || width <= 0 || ldd < width) return go1_set_error("go1_gather_rows: bad arguments");
-    const int threads = width >= 1024 ? 256 : (width >= 128 ? 64 : 32);
+    const int threads = width >= 1024 ? 128 : (width >= 128 ? 64 : 32);
     gather_rows_kernel<<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(src, (const long long*)idx, dst, rows, width, ldd); go1_count_launch(1);
     return cuda_rc("go1_gather_rows");
 }
@@ -967,7 +976,7 @@ extern "C" int go1_skinny_dgrad_ex(const float* dz, int lddz, const float* W, in
                      ((((uintptr_t)W) | ((uintptr_t)dprev) | ((uintptr_t)(y_prev ? y_prev : W))) & 15) == 0;
     if (vec) {
         const int cb = (n + 127) / 128;
-        int rpb = (M * cb + 2 * 148 - 1) / (2 * 148);           // about two blocks per SM
+        int rpb = (M * cb + 2 * 148 - 1) / (2 * 148);           // about two blocks per SM (four measured slower)
         rpb = (rpb + 7) / 8 * 8; if (rpb < 8) rpb = 8;
         dim3 grid(cb, (M + rpb - 1) / rpb);
         if (o <= 2) skinny_dgrad4_kernel<2><<<grid, 256, 0, st>>>(dz, lddz, W, ldw, y_prev, ldy, dprev, lddp, colsum, M, o, n, rpb);

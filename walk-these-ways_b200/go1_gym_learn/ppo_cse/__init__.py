@@ -227,9 +227,14 @@ class Runner:
                 if g is None and sg["warm"][p] < 2:
                     sg["warm"][p] += 1
                     actions = self._graph_step_body(sg)
+                elif g is None and any(k[1] != key[1] for k in sg["graphs"]):
+                    # the flat weight buffer was rebuilt (ActorCritic.to()): drop the graphs captured against the old one and warm up again
+                    # (the eager steps also rebuild the packed weight copies the new graphs will read)
+                    sg["graphs"].clear()
+                    sg["warm"] = {0: 0, 1: 0}
+                    sg["warm"][p] += 1
+                    actions = self._graph_step_body(sg)
                 elif g is None:
-                    for stale in [k for k in sg["graphs"] if k[1] != key[1]]:
-                        del sg["graphs"][stale]
                     graph = torch.cuda.CUDAGraph()
                     ac.ensure_packed()
                     n0 = L.go1_kernel_launch_count()

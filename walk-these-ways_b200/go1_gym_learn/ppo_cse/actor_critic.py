@@ -275,7 +275,7 @@ class _Net:
                 dprev = dz1_out if (li == 1 and dz1_out is not None) else self._buf((tag, "d", li - 1), M, i)
                 ldp = dprev.stride(0)
                 yprev = outs[li - 1]
-                if impl == 1 and o > 16 and self._tma_ok(dz, ldz) and self._tma_ok(W, i) and M >= 64:      # (narrow heads: the skinny pass below)
+                if impl == 1 and self._tma_ok(dz, ldz) and self._tma_ok(W, i) and M >= 64:      # (the 12-wide actor head included: 19 us here, 22 us on the skinny pass)
                     # W read MN-major in place; the bias gradient of layer li-1 (column sums of dprev) rides in the epilogue
                     pwo, pbo, po, pi = self.specs[li - 1]
                     gb_prev = self.grad[pbo:pbo + po]
@@ -396,6 +396,7 @@ class ActorCritic(nn.Module):
             flat[o:o + n].copy_(p.data.reshape(-1))
             p.data = flat[o:o + n].view(p.shape)
         self._flat = flat
+        self._packed_version = -1             # new _Net objects below: their packed weight copies do not exist yet
         self._grad = torch.zeros_like(flat)
         self.n_params = total                 # length of the flat buffers (HEAD + 3,054,619 parameters + alignment padding)
         self._nets = {}
