@@ -151,7 +151,7 @@ class Runner:
         # Two independent pieces run on a side stream (forks / joins become edges of the captured graph): the periodic command resample of
         # this step beside the policy evaluation (it writes commands and curriculum state, the policy reads histories), and the storage of
         # the transition beside the history roll (both only read what the kernels before them produced; the roll writes the other buffer).
-        fork = sg.get("fork", True) and not dc.shared
+        fork = sg.get("fork", True) and (not dc.shared or os.environ.get("GO1_STEP_FORK_SHARED", "1") != "0")
         main = torch.cuda.current_stream()
         side = sg.get("side") if fork else None
         if fork and side is None:
