@@ -339,6 +339,15 @@ typedef struct Go1TailProblem {
     const float* W3; const float* b3; float* y3; int32_t ldy3; const float* Wh; const float* bh; int32_t nh; float* out; int32_t ldout;
 } Go1TailProblem;
 int go1_mlp_tail_forward_grouped(const Go1TailProblem* probs, int nprob, int M, int K1, int N2, int N3, void* stream);
+/* Backward of the same bodies, first half, for up to two problems in one grid (nn.Linear / nn.ELU autograd of actor_critic.py:38-77):
+ *   dz3 = (dout Wh) * ELU'(y3) [M][N3];  dz2 = (dz3 W3) * ELU'(y2) [M][N2];  gb3 += colsum(dz3);  gb2 += colsum(dz2)   (N3 = 128, N2 = 256, nh <= 12)
+ * dout is the gradient of the head's output [M][nh], Wh [nh][N3] and W3 [N3][N2] the nn.Linear weights, y3 / y2 the saved activations;
+ * dz3 never leaves the SM between the CUDA-core product and the tcgen05 product.  gb3 / gb2 are accumulated with atomics. */
+typedef struct Go1TailBwdProblem {
+    const float* dout; int32_t lddout, nh; const float* Wh; const float* y3; int32_t ldy3; const float* W3; const float* y2; int32_t ldy2;
+    float* dz3; int32_t lddz3; float* dz2; int32_t lddz2; float* gb3; float* gb2;
+} Go1TailBwdProblem;
+int go1_mlp_tail_backward_grouped(const Go1TailBwdProblem* probs, int nprob, int M, int N3, int N2, void* stream);
 
 /* Per-launch timing of the impl-1 (tcgen05) products for the roofline report: on = 1 starts collecting (CUDA events on the launch
  * stream around every call that is not being graph-captured), on = 0 stops and returns the summed kernel time, flops and count. */

@@ -409,7 +409,7 @@ def test_fused_first_layer_epilogue_lead_cols_and_extra_forward():
         capi.check(L.go1_gemm_ex(0, 1, M, lead + tail, K, capi.ptr(A), K, capi.ptr(W), K, capi.ptr(y), lead + tail, ep, 0, capi.stream_ptr()), "gemm_ex")
 
 
-@pytest.mark.parametrize("M", [512, 2304])
+@pytest.mark.parametrize("M", [512, 2304, 1000, 24576 + 300])      # the last one: several row blocks per CTA and a change of problem inside a CTA's sequence
 def test_fused_backward_epilogues_match_separate_kernels(M):
     """The bias gradients (column sums of dz) and the trailing-input gradients of the first layers (go1_mlp_extra_backward) reduced
     inside the dgrad GEMM epilogues must equal the separate bandwidth kernels: same flat gradient buffer up to the fp32 rounding of
@@ -453,7 +453,17 @@ def test_fused_backward_epilogues_match_separate_kernels(M):
     assert torch.equal(hb[:, NH + 1 + NP:NH + 1 + 2 * NP], ac._latent)          # the latent slot was filled
     # TF32 products instead of fp32 reductions for these few gradients: compare at TF32 accuracy against the fp32-reduced ones
     assert float((a - c).abs().max()) <= 3e-3 * float(scale) + 1e-7, float((a - c).abs().max())
-    b = c
+    # first half of the bodies' backward tails in one launch (go1_mlp_tail_backward_grouped): same operands, same products -> same gradients
+    # up to the order of the atomic bias-gradient sums
+    ac.fuse_tail_bwd = True
+    ac.flat_grads.zero_(); ac.grads_prezeroed = True
+    ac.forward_all(h2, priv, tag="train")
+    ac.backward_ppo(h2, priv, dmean, dvalue, dstd, aug=True)
+    torch.cuda.synchronize()
+    d = ac.flat_grads.clone()
+    ac.grads_prezeroed = False; ac.fuse_tail_bwd = False
+    assert float((c - d).abs().max()) <= 2e-5 * float(scale) + 1e-7, float((c - d).abs().max())
+    b = d
     # fp64 autograd of sum(mean * dmean) + sum(value * dvalue) through plain torch modules holding the same weights
     import copy
     ref = {k: copy.deepcopy(getattr(ac, k)).double() for k in ("adaptation_module", "actor_body", "critic_body")}

@@ -1086,6 +1086,247 @@ int launch_tail(const TailMaps& maps, const TailArgs& g, cudaStream_t st) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused MLP tail, backward (first half): for the bodies 512-256-128-head (actor_critic.py:38-77), from the gradient of the head's output,
+//     dz3 = (dout Wh) * ELU'(y3)   [M][128]     CUDA cores: K = nh <= 12
+//     dz2 = (dz3 W3) * ELU'(y2)    [M][256]     tensor core: A = the dz3 tile the epilogue warps laid out in shared memory, B = W3 (resident)
+// plus the bias gradients gb3 = colsum(dz3), gb2 = colsum(dz2), for up to two problems (actor + critic) in one grid.  This replaces, per
+// body, a skinny dgrad launch and a 24576 x 256 x 128 tcgen05 dgrad launch (which re-reads dz3 from memory and whose tiles are too
+// short to hide their epilogue): dz3 never leaves the SM between the two products.  The wgrads (dz3^T y2, dz2^T y1) and the last dgrad
+// (dz1) stay separate products.  One CTA (576 threads) per 128-row block:
+//   warp 0      loads W3 (128 KB, MN-major boxes) once per problem it meets
+//   warp 1      one product per block: 16 tcgen05.mma (M = 128, N = 256, K = 8) -> TMEM columns [0, 256)
+//   warps 2-17  (TMEM lane quarter q, column group grp): E0 builds dz3 chunk grp of the block from dout, Wh (shared memory) and y3,
+//               writes it swizzled into the A tile and sends it to global memory by TMA; E1 drains the accumulator chunks grp, grp + 4,
+//               multiplies by ELU'(y2), stages them in the warp's own (by then consumed) 4 KB block of the A tile and sends them by TMA.
+// Column sums meet in shared memory (atomics) and are flushed once per CTA.
+// ---------------------------------------------------------------------------------------------------------------
+struct TailBwdProb { const float* dout; const float* Wh; const float* y3; const float* y2; float* gb3; float* gb2; int lddout, nh, ldy3, ldy2; };
+struct TailBwdArgs { TailBwdProb p[TAIL_MAXP]; int nprob, M, tiles_per_prob, tiles; };
+struct TailBwdMaps { CUtensorMap w3[TAIL_MAXP], dz3[TAIL_MAXP], dz2[TAIL_MAXP]; };
+constexpr int TB_N3 = 128, TB_N2 = 256;
+constexpr int TB_W3_BYTES = TB_N3 * TB_N2 * 4;                 // 128 KB: 4 k-blocks x 8 boxes x 4 KB
+constexpr int TB_Z3_BYTES = BM * TB_N3 * 4;                    // 64 KB: 4 k-blocks x [128 rows][32 floats]
+constexpr int TB_SMEM = TB_W3_BYTES + TB_Z3_BYTES + (TAIL_MAXP * TAIL_HPW * TB_N3 + TAIL_MAXP * (TB_N3 + TB_N2)) * 4 + 8 * 8 + 16 + 1024;
+
+// column sums of a 32 x 32 block held one row per lane (v[j] = column j): 31 shuffles; lane l ends up with column l
+__device__ __forceinline__ float warp_colsum32(const float (&v)[32], const int lane) {
+    float sred[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) sred[j] = v[j];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < off; j++) {
+            const float send = upper ? sred[j] : sred[j + off];
+            const float keep = upper ? sred[j + off] : sred[j];
+            sred[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return sred[0];
+}
+
+__global__ void __launch_bounds__(64 + 128 * TAIL_G, 1) mlp_tail_bwd_kernel(const __grid_constant__ TailBwdMaps maps, const TailBwdArgs g) {
+    constexpr int G = TAIL_G;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* w3s = base;                                     // B operand: [4 k-blocks][8 boxes][32 k-rows][32 n-floats]
+    uint8_t* z3 = base + TB_W3_BYTES;                        // A operand: [4 k-blocks][128 rows][32 floats], 128B-swizzled
+    float* s_wh = (float*)(z3 + TB_Z3_BYTES);                // [MAXP][HPW][128]
+    float* s_cs = s_wh + TAIL_MAXP * TAIL_HPW * TB_N3;       // [MAXP][128 + 256] column sums (bias gradients)
+    uint64_t* w3_full = (uint64_t*)(s_cs + TAIL_MAXP * (TB_N3 + TB_N2));
+    uint64_t* w3_free = w3_full + 1;
+    uint64_t* z3_ready = w3_free + 1;
+    uint64_t* acc_full = z3_ready + 1;
+    uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int p = 0; p < g.nprob; p++) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w3[p]) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.dz3[p]) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.dz2[p]) : "memory");
+        }
+        mbar_init(w3_full, 1); mbar_init(w3_free, 1); mbar_init(z3_ready, 128 * G); mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < TAIL_MAXP * TAIL_HPW * TB_N3; i += blockDim.x) {
+        const int p = i / (TAIL_HPW * TB_N3), r = (i / TB_N3) % TAIL_HPW, k = i % TB_N3;
+        s_wh[i] = (p < g.nprob && r < g.p[p].nh) ? __ldg(g.p[p].Wh + (size_t)r * TB_N3 + k) : 0.f;
+    }
+    for (int i = threadIdx.x; i < TAIL_MAXP * (TB_N3 + TB_N2); i += blockDim.x) s_cs[i] = 0.f;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== W3 loader: the weights of the problem this CTA's blocks belong to stay resident; reloaded when the problem changes =====
+        if (elect_one()) {
+            int cur = -1, tl = 0;
+            for (int t = blockIdx.x; t < g.tiles; t += gridDim.x, tl++) {
+                const int p = t / g.tiles_per_prob;
+                // follow the products block by block (every phase of w3_free is consumed in order: a parity wait that skipped phases would
+                // alias and let this thread run two loads ahead): block tl - 1's product has read the weights
+                if (tl > 0) mbar_wait(w3_free, (tl - 1) & 1);
+                if (p == cur) continue;
+                cur = p;
+                mbar_expect_tx(w3_full, TB_W3_BYTES);
+                for (int kb = 0; kb < TB_N3 / BK; kb++)
+#pragma unroll
+                    for (int x = 0; x < TB_N2 / 32; x++) tma_load_2d(&maps.w3[p], w3_full, w3s + (size_t)kb * (TB_N2 * BK * 4) + (size_t)x * (32 * BK * 4), 32 * x, kb * BK);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: A = dz3 tile (K-major), B = W3 given as [K = 128][N = 256] (MN-major) =====
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(TB_N2 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        int cur = -1, nload = 0, tl = 0;
+        for (int t = blockIdx.x; t < g.tiles; t += gridDim.x, tl++) {
+            const int p = t / g.tiles_per_prob;
+            if (p != cur) { cur = p; mbar_wait(w3_full, nload & 1); nload++; }
+            mbar_wait(z3_ready, tl & 1);                                   // the dz3 tile is in shared memory; the previous accumulator has been drained
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+#pragma unroll
+                for (int kb = 0; kb < TB_N3 / BK; kb++) {
+                    const uint64_t da = make_desc(z3 + (size_t)kb * (BM * BK * 4)), db = make_desc_mn(w3s + (size_t)kb * (TB_N2 * BK * 4));
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; k++) umma_tf32(tmem_base, da + 2 * k, db + (uint64_t)(1024 >> 4) * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(acc_full);
+                umma_commit(w3_free);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue warps =====
+        const int ew = warp - 2, q = warp & 3, grp = ew >> 2;
+        uint8_t* myblk = z3 + (size_t)(4 * grp + q) * 4096;           // chunk grp, rows 32 q .. 32 q + 31 of the A tile; later this warp's staging
+        int tl = 0;
+        for (int t = blockIdx.x; t < g.tiles; t += gridDim.x, tl++) {
+            const int p = t / g.tiles_per_prob, m0 = (t - p * g.tiles_per_prob) * BM;
+            const TailBwdProb& pr = g.p[p];
+            const int row = m0 + 32 * q + lane;
+            const bool row_ok = row < g.M;
+            float* cs = s_cs + p * (TB_N3 + TB_N2);
+            // ---- E0: dz3 chunk grp = (dout Wh)[.., 32 grp ..] * ELU'(y3)
+            {
+                float4 y[8];
+                const float4* yrow = reinterpret_cast<const float4*>(pr.y3 + (size_t)(row_ok ? row : 0) * pr.ldy3 + 32 * grp);
+#pragma unroll
+                for (int j = 0; j < 8; j++) y[j] = __ldg(yrow + j);
+                float d[TAIL_HPW];
+#pragma unroll
+                for (int n = 0; n < TAIL_HPW; n++) d[n] = (row_ok && n < pr.nh) ? __ldg(pr.dout + (size_t)row * pr.lddout + n) : 0.f;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = 0.f;
+                const float* wh = s_wh + (size_t)p * TAIL_HPW * TB_N3 + 32 * grp;
+#pragma unroll
+                for (int n = 0; n < TAIL_HPW; n++) {
+                    if (n < pr.nh) {
+                        const float4* w = reinterpret_cast<const float4*>(wh + n * TB_N3);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const float4 ww = w[j];
+                            v[4 * j] = fmaf(d[n], ww.x, v[4 * j]); v[4 * j + 1] = fmaf(d[n], ww.y, v[4 * j + 1]);
+                            v[4 * j + 2] = fmaf(d[n], ww.z, v[4 * j + 2]); v[4 * j + 3] = fmaf(d[n], ww.w, v[4 * j + 3]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    v[4 * j] *= (y[j].x > 0.f ? 1.0f : y[j].x + 1.0f); v[4 * j + 1] *= (y[j].y > 0.f ? 1.0f : y[j].y + 1.0f);
+                    v[4 * j + 2] *= (y[j].z > 0.f ? 1.0f : y[j].z + 1.0f); v[4 * j + 3] *= (y[j].w > 0.f ? 1.0f : y[j].w + 1.0f);
+                }
+                if (!row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = 0.f;
+                }
+                const float c3 = warp_colsum32(v, lane);
+                atomicAdd(cs + 32 * grp + lane, c3);
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the previous block's dz2 store has left this warp's block
+                __syncwarp();
+                uint8_t* trow = myblk + (size_t)lane * 128;
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    *reinterpret_cast<float4*>(trow + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&maps.dz3[p], myblk, 32 * grp, m0 + 32 * q);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(z3_ready);
+            }
+            // ---- E1: dz2 chunks grp, grp + 4 = accumulator * ELU'(y2)
+            {
+                float4 y[8];
+                const float4* yrow = reinterpret_cast<const float4*>(pr.y2 + (size_t)(row_ok ? row : 0) * pr.ldy2 + 32 * grp);
+#pragma unroll
+                for (int j = 0; j < 8; j++) y[j] = __ldg(yrow + j);                 // in flight while the product runs
+                mbar_wait(acc_full, tl & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                for (int c = grp; c < TB_N2 / 32; c += G) {
+                    if (c != grp) {
+                        const float4* yr2 = reinterpret_cast<const float4*>(pr.y2 + (size_t)(row_ok ? row : 0) * pr.ldy2 + 32 * c);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) y[j] = __ldg(yr2 + j);
+                    }
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), r);
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        v[4 * j] = __uint_as_float(r[4 * j]) * (y[j].x > 0.f ? 1.0f : y[j].x + 1.0f);
+                        v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) * (y[j].y > 0.f ? 1.0f : y[j].y + 1.0f);
+                        v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) * (y[j].z > 0.f ? 1.0f : y[j].z + 1.0f);
+                        v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) * (y[j].w > 0.f ? 1.0f : y[j].w + 1.0f);
+                    }
+                    if (!row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) v[j] = 0.f;
+                    }
+                    const float c2 = warp_colsum32(v, lane);
+                    atomicAdd(cs + TB_N3 + 32 * c + lane, c2);
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // dz3 store (first chunk) / previous dz2 store has read the block
+                    __syncwarp();
+                    uint8_t* trow = myblk + (size_t)lane * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        *reinterpret_cast<float4*>(trow + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&maps.dz2[p], myblk, 32 * c, m0 + 32 * q);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    }
+    // bias gradients: one set of atomics per CTA
+    for (int i = threadIdx.x; i < g.nprob * (TB_N3 + TB_N2); i += blockDim.x) {
+        const int p = i / (TB_N3 + TB_N2), c = i - p * (TB_N3 + TB_N2);
+        const float vsum = s_cs[p * (TB_N3 + TB_N2) + c];
+        if (vsum != 0.f) atomicAdd(c < TB_N3 ? g.p[p].gb3 + c : g.p[p].gb2 + (c - TB_N3), vsum);
+    }
+}
+
 }  // namespace
 
 static int g_tf32_wide = 1;   // wide = 128 x 256 tiles / cta_group::2 pairs where the heuristic in go1_gemm_tf32 says they pay
@@ -1118,7 +1359,7 @@ extern "C" int go1_gemm_timing(int on, double* total_ms, double* total_flop, lon
         if (csv && i / 2 < g_time_recs.size()) {
             const TimeRec& r = g_time_recs[i / 2];
             fprintf(csv, "%d,%d,%d,%d,%d,%d,%d,%d,%s,%d,%.2f\n", r.M, r.N, r.K, r.amn, r.bmn, r.act, r.nex, r.splits,
-                    r.kern >= 1000 ? (r.kern == 1003 ? "tail3" : "tail2") : r.kern == 2 ? "2cta" : (r.kern == 256 ? "p256" : (r.kern == 128 ? "p128" : (r.kern == 64 ? "p64" : "p32"))), r.colsum, 1e3 * t);
+                    r.kern >= 1000 ? (r.kern == 1004 ? "tailbwd" : (r.kern == 1003 ? "tail3" : "tail2")) : r.kern == 2 ? "2cta" : (r.kern == 256 ? "p256" : (r.kern == 128 ? "p128" : (r.kern == 64 ? "p64" : "p32"))), r.colsum, 1e3 * t);
         }
     }
     if (csv) fclose(csv);
@@ -1309,4 +1550,52 @@ extern "C" int go1_mlp_tail_forward(const float* x, int ldx, int M, int K1, cons
     Go1TailProblem q;
     q.x = x; q.ldx = ldx; q.W2 = W2; q.b2 = b2; q.y2 = y2; q.ldy2 = ldy2; q.W3 = W3; q.b3 = b3; q.y3 = y3; q.ldy3 = ldy3; q.Wh = Wh; q.bh = bh; q.nh = nh; q.out = out; q.ldout = ldout;
     return go1_mlp_tail_forward_grouped(&q, 1, M, K1, N2, N3, stream);
+}
+
+// ---- fused MLP tail (backward, first half), see mlp_tail_bwd_kernel
+extern "C" int go1_mlp_tail_backward_grouped(const Go1TailBwdProblem* probs, int nprob, int M, int N3, int N2, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!probs || nprob < 1 || nprob > TAIL_MAXP || M <= 0) return go1_set_error("go1_mlp_tail_backward: 1 or 2 problems of the same shape");
+    if (N3 != TB_N3 || N2 != TB_N2) return go1_set_error("go1_mlp_tail_backward: the supported tail is ...-256-128-head");
+    TailBwdMaps maps;
+    TailBwdArgs g;
+    g.nprob = nprob; g.M = M; g.tiles_per_prob = (M + BM - 1) / BM; g.tiles = g.tiles_per_prob * nprob;
+    for (int p = 0; p < nprob; p++) {
+        const Go1TailBwdProblem& q = probs[p];
+        if (!q.dout || !q.Wh || !q.y3 || !q.W3 || !q.y2 || !q.dz3 || !q.dz2 || !q.gb3 || !q.gb2 || q.nh < 1 || q.nh > TAIL_HPW || q.lddout < q.nh)
+            return go1_set_error("go1_mlp_tail_backward: bad arguments (head width 1..12)");
+        if ((q.ldy3 & 3) || (q.ldy2 & 3) || (q.lddz3 & 3) || (q.lddz2 & 3) ||
+            ((((uintptr_t)q.y3 | (uintptr_t)q.y2 | (uintptr_t)q.W3 | (uintptr_t)q.dz3 | (uintptr_t)q.dz2) & 15) != 0))
+            return go1_set_error("go1_mlp_tail_backward: operands must be 16-byte aligned with row strides that are multiples of 4 floats");
+        if (int e = make_map(&maps.w3[p], q.W3, N3, N2, N2, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
+        if (int e = make_map(&maps.dz3[p], q.dz3, M, N3, q.lddz3, 32)) return e;
+        if (int e = make_map(&maps.dz2[p], q.dz2, M, N2, q.lddz2, 32)) return e;
+        TailBwdProb& d = g.p[p];
+        d.dout = q.dout; d.Wh = q.Wh; d.y3 = q.y3; d.y2 = q.y2; d.gb3 = q.gb3; d.gb2 = q.gb2; d.lddout = q.lddout; d.nh = q.nh; d.ldy3 = q.ldy3; d.ldy2 = q.ldy2;
+    }
+    for (int p = nprob; p < TAIL_MAXP; p++) { maps.w3[p] = maps.w3[0]; maps.dz3[p] = maps.dz3[0]; maps.dz2[p] = maps.dz2[0]; g.p[p] = g.p[0]; }
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_tail_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB_SMEM);
+        if (e != cudaSuccess) return go1_set_error(cudaGetErrorString(e));
+        configured = true;
+    }
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    const bool timed = g_time_on && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone;
+    if (timed) {
+        cudaEventRecord(timing_event(), st);
+        double fl = 0.0;
+        for (int p = 0; p < nprob; p++) fl += 2.0 * (double)M * ((double)N3 * N2 + (double)probs[p].nh * N3);
+        g_time_flop += fl;
+        g_time_recs.push_back({M * nprob, N2, N3, 0, 1, 2, 0, 1, 1004, 1});
+    }
+    const int grid = g.tiles < sms ? g.tiles : sms;
+    mlp_tail_bwd_kernel<<<grid, 64 + 128 * TAIL_G, TB_SMEM, st>>>(maps, g);
+    go1_count_launch(1);
+    if (timed) cudaEventRecord(timing_event(), st);
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return go1_set_error(cudaGetErrorString(ce));
+    return 0;
 }

@@ -218,7 +218,32 @@ class _Net:
         capi.check(capi.lib().go1_mlp_tail_forward_grouped(arr, 1, M, k1, n2, n3, capi.stream_ptr()), "go1_mlp_tail_forward")
         return outs
 
-    def backward(self, x, ldx, K0, extra, outs, dout, M, impl, accumulate, want_dextra=False, tag="a", dz1_out=None, aug_first=False):
+    def tail_bwd_ok(self, outs, dout):
+        """This body is a ...-256-128-head one whose backward first half go1_mlp_tail_backward_grouped supports (launches nothing)."""
+        sp = self.specs
+        if len(sp) != 4 or sp[2][2] != 128 or sp[2][3] != 256 or sp[1][2] != 256 or sp[3][2] > 12 or not self.owner.grads_prezeroed:
+            return False
+        y3, y2 = outs[2], outs[1]
+        return self._tma_ok(y3, y3.stride(0)) and self._tma_ok(y2, y2.stride(0)) and ((self.flat.data_ptr() + 4 * sp[2][0]) & 15) == 0 and dout.stride(1) == 1
+
+    def tail_bwd_problem(self, outs, dout, M, tag):
+        """Launches the head's wgrad (+ bias gradient) of this body and returns (Go1TailBwdProblem, dz3, dz2) for the fused backward first
+        half (go1_mlp_tail_backward_grouped).  Call only if tail_bwd_ok()."""
+        sp = self.specs
+        (wo3, bo3, n3, n2), (woh, boh, nh, _), (wo2, bo2, _, _) = sp[2], sp[3], sp[1]
+        y3, y2 = outs[2], outs[1]
+        L, st = capi.lib(), capi.stream_ptr()
+        gWh, gbh = self.grad[woh:woh + nh * n3], self.grad[boh:boh + nh]
+        capi.check(L.go1_skinny_wgrad_ex(capi.ptr(dout), dout.stride(0), capi.ptr(y3), y3.stride(0), gWh.data_ptr(), n3, gbh.data_ptr(), M, nh, n3, 1, st), "skinny_wgrad")
+        dz3, dz2 = self._buf((tag, "d", 2), M, n3), self._buf((tag, "d", 1), M, n2)
+        q = capi.Go1TailBwdProblem()
+        q.dout, q.lddout, q.nh, q.Wh = dout.data_ptr(), dout.stride(0), nh, self.flat.data_ptr() + 4 * woh
+        q.y3, q.ldy3, q.W3, q.y2, q.ldy2 = y3.data_ptr(), y3.stride(0), self.flat.data_ptr() + 4 * wo3, y2.data_ptr(), y2.stride(0)
+        q.dz3, q.lddz3, q.dz2, q.lddz2 = dz3.data_ptr(), dz3.stride(0), dz2.data_ptr(), dz2.stride(0)
+        q.gb3, q.gb2 = self.grad.data_ptr() + 4 * bo3, self.grad.data_ptr() + 4 * bo2
+        return q, dz3, dz2
+
+    def backward(self, x, ldx, K0, extra, outs, dout, M, impl, accumulate, want_dextra=False, tag="a", dz1_out=None, aug_first=False, pre=None):
         """dout: gradient w.r.t. the network output [M][out] (the last layer has no activation).  Writes weight/bias grads
         into the flat grad buffer.  dz of every hidden layer comes out of the dgrad GEMM already multiplied by ELU'
         (fused epilogue).  dz1_out: optional [M][o1] strided view; when given the first layer's dz is written there and its wgrad is
@@ -231,7 +256,10 @@ class _Net:
         dextra = None
         bias_done = False      # this layer's bias gradient was already reduced in the epilogue of the dgrad product that made its dz
         extra_done = False     # likewise the trailing-input gradients of the first layer
-        for li in range(n - 1, -1, -1):
+        start = n - 1
+        if pre is not None:    # (dz of layer n-2, dz of layer n-3) from go1_mlp_tail_backward_grouped, which also reduced their bias gradients;
+            dz, start, bias_done = pre[0], n - 2, True      # the head's wgrad was launched by tail_bwd_problem
+        for li in range(start, -1, -1):
             wo, bo, o, i = self.specs[li]
             W = self.flat[wo:wo + o * i]
             gW, gb = self.grad[wo:wo + o * i], self.grad[bo:bo + o]
@@ -271,6 +299,9 @@ class _Net:
                 capi.check(L.go1_mlp_extra_backward(capi.ptr(dz), ldz, capi.ptr(extra), extra.stride(0), W.data_ptr() + 4 * K0, i, gW.data_ptr() + 4 * K0, i,
                                                     capi.ptr(dextra) if want_dextra else None, E, M, o, E, accumulate, st), "extra_backward")
             # ---- dgrad (+ fused ELU'): dz_prev[M][i] = (dz[M][o] W[o][i]) * ELU'(y_prev)
+            if pre is not None and li == n - 2:
+                dz, bias_done = pre[1], True            # produced (with its bias gradient) by the fused kernel
+                continue
             if li > 0:
                 dprev = dz1_out if (li == 1 and dz1_out is not None) else self._buf((tag, "d", li - 1), M, i)
                 ldp = dprev.stride(0)
@@ -352,6 +383,7 @@ class ActorCritic(nn.Module):
         self.weights_version = 0      # bumped by every optimizer step / load: invalidates the packed first-layer weight copies
         import os
         self.group_wgrads = os.environ.get("GO1_GROUP_WGRADS", "1") != "0"          # equal-shape wgrads of the three MLPs as grouped products
+        self.fuse_tail_bwd = os.environ.get("GO1_FUSE_TAIL_BWD", "0") != "0"        # first half of the bodies' backward tails in one launch (go1_mlp_tail_backward_grouped)
         self.fuse_bias_grad = os.environ.get("GO1_FUSE_BIAS_GRAD", "1") != "0"     # bias gradients reduced in the dgrad GEMM epilogues
         self.update_streams = os.environ.get("GO1_UPDATE_STREAMS", "1") != "0"     # critic chain on a second stream during the update (measured -1.3 ms / iteration)
         self._side = None
@@ -675,15 +707,22 @@ class ActorCritic(nn.Module):
                 capi.copy_segments([(h_ext[:, K0 + 1 + E:], self._latent)])
             if self.group_wgrads and self.grads_prezeroed:
                 self._wgrad_queue = []
+            pre_p = pre_c = None
+            if self.fuse_tail_bwd:      # first half of both bodies' backward tails in ONE grid (dz3, dz2 and their bias gradients)
+                if nets["actor"].tail_bwd_ok(self._p_out, dmean) and nets["critic"].tail_bwd_ok(self._c_out, dvalue):
+                    tp, tc = nets["actor"].tail_bwd_problem(self._p_out, dmean, M, "train"), nets["critic"].tail_bwd_problem(self._c_out, dvalue, M, "train")
+                    arr = (capi.Go1TailBwdProblem * 2)(tp[0], tc[0])
+                    capi.check(capi.lib().go1_mlp_tail_backward_grouped(arr, 2, M, 128, 256, capi.stream_ptr()), "go1_mlp_tail_backward")
+                    pre_p, pre_c = tp[1:], tc[1:]
             side = self._side_stream(M)
             if side is not None:    # critic chain beside actor -> adaptation chain
                 self._fork(side)
                 with torch.cuda.stream(side):
-                    nets["critic"].backward(h, h.stride(0), K0, priv, self._c_out, dvalue, M, impl, 0, tag="train", dz1_out=dz1[:, oa + op:], aug_first=aug)
+                    nets["critic"].backward(h, h.stride(0), K0, priv, self._c_out, dvalue, M, impl, 0, tag="train", dz1_out=dz1[:, oa + op:], aug_first=aug, pre=pre_c)
             dlat = nets["actor"].backward(h, h.stride(0), K0, self._latent, self._p_out, dmean, M, impl, 0, want_dextra=True, tag="train", dz1_out=dz1[:, oa:oa + op],
-                                          aug_first=aug)
+                                          aug_first=aug, pre=pre_p)
             if side is None:
-                nets["critic"].backward(h, h.stride(0), K0, priv, self._c_out, dvalue, M, impl, 0, tag="train", dz1_out=dz1[:, oa + op:], aug_first=aug)
+                nets["critic"].backward(h, h.stride(0), K0, priv, self._c_out, dvalue, M, impl, 0, tag="train", dz1_out=dz1[:, oa + op:], aug_first=aug, pre=pre_c)
             nets["adapt"].backward(h, h.stride(0), K0, None, self._a_out, dlat, M, impl, 0, tag="train", dz1_out=dz1[:, :oa], aug_first=aug)
             if side is not None:
                 self._join(side)
