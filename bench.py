@@ -2,10 +2,11 @@
 """bench.py — Go1 env-steps/s at 4096 envs per GPU (BASELINE.json metric), one JSON line on rank 0.
 
 A "step" is one training iteration of scripts/train.py's configuration: a 24-step rollout of 4096 envs
-(policy inference + fused sim step + host curriculum) followed by compute_returns and the full PPO update
-(5 epochs x 4 minibatches + adaptation steps).  value = env-steps of all ranks / device time (CUDA events,
-max over ranks); e2e = the same through the public API by host wall clock, including every host<->device
-copy of the path (event lists down, new commands up, loss read-back).
+(policy inference + fused sim step + device-resident command curriculum, one CUDA graph replay per env step)
+followed by compute_returns and the full PPO update (5 epochs x 4 minibatches + adaptation steps).
+value = env-steps of all ranks / device time (CUDA events, max over ranks); e2e = the same through the public
+API by host wall clock, including every host<->device copy of the path (with the device curriculum: the
+read-back of the loss scalars, 28 bytes per iteration -- nothing else of this on-device RL loop crosses PCIe).
 
     python bench.py --gpus 1 --steps 3 --warmup 3
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
