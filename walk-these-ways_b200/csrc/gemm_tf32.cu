@@ -1390,10 +1390,10 @@ static int gemm_tf32_impl(int transA, int transB, int M, int N, int K, int nprob
     if (g.nex < 0 || g.nex > 4) return go1_set_error("go1_gemm_ex: num_extra must be 0..4");
     if (act == 2 && !g.aux) return go1_set_error("go1_gemm_ex: act 2 needs dact_y");
     const int num_kb = (K + BK - 1) / BK;
-    // 128 x 256 tiles (one CTA per SM, 4-stage ring of 48 KB) raise the flop/byte ratio of the L2-bound big products by 1.33x
-    // 128 x 256 tiles (one CTA per SM, 4-stage ring of 48 KB) cut the L2->SM bytes per flop to 0.75x of the 128 x 128 tiling; the big
-    // products sit at the chip's TMA/L2 throughput cap (ncu: 11.4 TB/s), so that is what they are worth -- when the tile count
-    // still fills the 148 SMs evenly (a 160-tile product would run two half-empty rounds) and K is long enough to hide the epilogue
+    // Tile selection.  The products with fp32 operands sit at the chip's L2 -> SM throughput cap (ncu: 11.4 TB/s), so bytes per flop decide:
+    // "wide" shapes (K >= 1024, N >= 256) run as cta_group::2 256 x 256 tile pairs (0.5x the bytes of the 128 x 128 tiling; 128 x 256
+    // single-CTA tiles when M < 256) -- when the tile count still fills the SMs evenly (a 160-tile product would run two half-empty rounds)
+    // or split-K makes up for it; everything else runs 128 x BN tiles on the persistent kernel with the staged epilogue.
     static const int wide_min_k = getenv("GO1_TF32_WIDE_MINK") ? atoi(getenv("GO1_TF32_WIDE_MINK")) : 1024;
     static const int wide_min_tiles = getenv("GO1_TF32_WIDE_MINTILES") ? atoi(getenv("GO1_TF32_WIDE_MINTILES")) : 9;      // 9: the 256 x 2100 x 24576 adaptation wgrad takes cta_group::2 pairs + split-K (74 -> 62 us)
     static const int split_ctas = getenv("GO1_TF32_SPLIT_CTAS") ? atoi(getenv("GO1_TF32_SPLIT_CTAS")) : 2 * 148;
@@ -1407,7 +1407,7 @@ static int gemm_tf32_impl(int transA, int transB, int M, int N, int K, int nprob
     const int BN = (wide && nprob == 1) ? 256 : ((N > 64) ? 128 : (N > 32 ? 64 : 32));
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * nprob;
     int splits = 1;
-    if (tiles < 148 && num_kb >= split_min_kb && g.nex == 0 && act != 2 && g.lead <= 0 && !g.colsum && g.nbx == 0) {      // one wave of 2 CTAs/SM, >= 16 k-blocks each
+    if (tiles < 148 && num_kb >= split_min_kb && g.nex == 0 && act != 2 && g.lead <= 0 && !g.colsum && g.nbx == 0) {      // split-K: about two CTA-units per SM, >= 16 k-blocks each
         splits = (nprob > 1 ? 148 : split_ctas) / tiles;      // grouped: one CTA-unit per SM (fewer, longer partial sums: less same-address red traffic)
         if (splits > num_kb / split_min_kb) splits = num_kb / split_min_kb; if (splits < 1) splits = 1;
     }
